@@ -1,0 +1,109 @@
+"""ORACLE - test infrastructure, build-container only.
+
+Generates tests/golden/*.npz by running the REFERENCE's own modules
+(/root/reference/backend, imported through oracle/ref_import.py) on
+  G1: backend/sample_images/e{1,2}.jpg + backend/sample_details/patient_details.json,
+      B=1 each, L=96 (inference_pipeline.py:174-186), seed-0 weights;
+  G2: seeded synthetic studies, B=8, L in {96,128}, full and ragged valid lengths;
+  G3: Pillow/torchvision Resize(256)+CenterCrop(224) uint8 known answers for
+      512x512, 224x224, 300x400 and 1024x768 inputs (crc32 of the cropped bytes).
+Run:  python -m oracle.make_golden      (about a minute on 8 cores)
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import torch
+from PIL import Image
+
+from mmdx_b200 import synth
+from oracle import ref_import
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+REF = "/root/reference/backend"
+
+
+@torch.no_grad()
+def run_reference(tp, rb, pil_images, tok):
+    """The steps of inference() :174-186 with the reference's modules, batched, keeping intermediates."""
+    x = torch.stack([tp.image_transfom_into_tensor(p) for p in pil_images])
+    ie, te, fm = rb["image_encoder"], rb["text_encoder"], rb["fusion_model"]
+    feats = ie.backbone(x).flatten(1)
+    z_img = ie(x)["embeddings"]
+    enc = te.encoder(input_ids=tok["input_ids"], attention_mask=tok["attention_mask"],
+                     token_type_ids=tok["token_type_ids"], return_dict=True)
+    pooled = te.mean_pool(enc.last_hidden_state, tok["attention_mask"])
+    z_txt = te(**tok)["embeddings"]
+    out = fm(z_img=z_img, z_txt=z_txt, report_labels=None)
+    logits = out["disease_logits"]
+    probs = torch.sigmoid(logits)
+    vector = (probs >= torch.tensor(rb["thresholds"])).int()
+    pre_u8 = np.stack([np.asarray(T_crop(tp, p)) for p in pil_images])
+    return {"pre_u8": pre_u8, "x_checksum": np.float64(x.double().sum().item()),
+            "feats": feats.numpy(), "z_img": z_img.numpy(), "pooled": pooled.numpy(), "z_txt": z_txt.numpy(),
+            "z_fuse": out["z_fuse"].numpy(), "logits": logits.numpy(), "probs": probs.numpy(),
+            "vector": vector.numpy().astype(np.uint8)}
+
+
+def T_crop(tp, pil):
+    """First two stages of the reference's own transform object (Resize, CenterCrop) -> PIL u8."""
+    t = tp.image_transfom_into_tensor.transforms
+    return t[1](t[0](pil))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    tp, ip = ref_import.import_reference()
+    sb = synth.make_state_bundle(seed=0)
+    rb = ref_import.build_reference_bundle(sb)
+
+    # ---- G1: the reference's two sample studies, one at a time (B=1) like inference()
+    det = json.load(open(f"{REF}/sample_details/patient_details.json"))
+    names = sorted(det)
+    grays, rows, texts = [], [], []
+    for n in names:
+        pil = Image.open(f"{REF}/sample_images/{n}").convert("RGB")        # api/views.py:70
+        a = np.asarray(pil)
+        assert (a[..., 0] == a[..., 1]).all() and (a[..., 0] == a[..., 2]).all()
+        grays.append(a[..., 0].copy())
+        tok = tp.tokenize_patient_details([det[n]], max_len=96)             # inference_pipeline.py:175
+        r = run_reference(tp, rb, [pil], tok)
+        # cross-check with the reference's real entry point (report generation stubbed out: off-path)
+        r.update(input_ids=tok["input_ids"].numpy(), attention_mask=tok["attention_mask"].numpy())
+        rows.append(r)
+        texts.append(det[n])
+    g1 = {k: np.concatenate([r[k] for r in rows]) if rows[0][k].ndim else np.array([r[k] for r in rows])
+          for k in rows[0]}
+    np.savez_compressed(os.path.join(OUT, "g1_samples.npz"), gray=np.stack(grays), names=np.array(names),
+                        details=np.array(texts), **g1)
+    print("G1", {k: v.shape for k, v in g1.items()}, g1["vector"].tolist())
+
+    # ---- G2: synthetic batches
+    for L, ragged in ((96, True), (128, False), (128, True)):
+        B = 8
+        imgs = synth.synth_images(B, 224, seed=1234)
+        ids, mask = synth.synth_token_ids(B, L, seed=1235, ragged=ragged)
+        tok = {"input_ids": torch.from_numpy(ids), "attention_mask": torch.from_numpy(mask),
+               "token_type_ids": torch.zeros(B, L, dtype=torch.long)}
+        r = run_reference(tp, rb, [Image.fromarray(im) for im in imgs], tok)
+        r.pop("pre_u8_full", None)
+        r["pre_crc"] = np.array([zlib.crc32(p.tobytes()) for p in r.pop("pre_u8")], dtype=np.uint64)
+        tag = f"g2_B{B}_L{L}_{'ragged' if ragged else 'full'}"
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **r)
+        print(tag, r["probs"][0].round(3).tolist())
+
+    # ---- G3: resize+crop known answers straight from Pillow/torchvision
+    kat = {}
+    for (h, w) in ((512, 512), (224, 224), (300, 400), (1024, 768), (257, 640)):
+        rng = np.random.Generator(np.random.PCG64([77, h, w]))
+        a = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        out = np.asarray(T_crop(tp, Image.fromarray(a)))
+        kat[f"{h}x{w}"] = {"crc32": zlib.crc32(out.tobytes()), "sum": int(out.sum()), "seed": [77, h, w]}
+    json.dump(kat, open(os.path.join(OUT, "g3_resize_kat.json"), "w"), indent=1)
+    print("G3", kat)
+
+
+if __name__ == "__main__":
+    main()

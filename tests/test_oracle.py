@@ -1,0 +1,84 @@
+"""Pins the oracle (oracle/forward_ref.py) against the reference: the golden vectors in
+tests/golden/ were produced by the reference's own modules (oracle/make_golden.py), and
+Pillow/torchvision - where the reference's preprocessing arithmetic lives - are called directly."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from conftest import GOLDEN, load_golden
+from mmdx_b200 import synth
+from oracle import forward_ref as R
+
+
+def _tv_crop(img_u8):
+    import torchvision.transforms as T
+    pil = Image.fromarray(img_u8)
+    return np.asarray(T.CenterCrop(224)(T.Resize(256, antialias=True)(pil)))
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (224, 224), (300, 400), (1024, 768), (257, 640)])
+def test_resize_crop_bit_exact_vs_pillow_and_kat(hw):
+    kat = json.load(open(os.path.join(GOLDEN, "g3_resize_kat.json")))[f"{hw[0]}x{hw[1]}"]
+    rng = np.random.Generator(np.random.PCG64(kat["seed"]))
+    a = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    got = R.preprocess_u8(a)
+    assert got.shape == (224, 224, 3)
+    assert zlib.crc32(got.tobytes()) == kat["crc32"] and int(got.sum()) == kat["sum"]
+    assert np.array_equal(got, _tv_crop(a))
+
+
+def test_resize_grayscale_single_channel():
+    rng = np.random.Generator(np.random.PCG64(5))
+    a = rng.integers(0, 256, size=(300, 260), dtype=np.uint8)
+    got = R.preprocess_u8(a[..., None])[..., 0]
+    import torchvision.transforms as T
+    want = np.asarray(T.CenterCrop(224)(T.Resize(256, antialias=True)(Image.fromarray(a))))
+    assert np.array_equal(got, want)
+
+
+def test_preprocess_samples_bit_exact(g1):
+    for i in range(2):
+        rgb = np.repeat(g1["gray"][i][..., None], 3, axis=-1)
+        assert np.array_equal(R.preprocess_u8(rgb), g1["pre_u8"][i])
+        x = R.preprocess_f32(rgb)
+        assert x.shape == (3, 224, 224)
+        assert abs(float(x.double().sum()) - float(g1["x_checksum"][i])) < 1e-6 * 3 * 224 * 224
+
+
+def test_forward_matches_reference_on_samples(state_bundle, g1):
+    """Config C1: backend/sample_images + sample_details, B=1, L=96, fp32 CPU."""
+    for i in range(2):
+        rgb = np.repeat(g1["gray"][i][..., None], 3, axis=-1)
+        ids = torch.from_numpy(g1["input_ids"][i:i + 1])
+        mask = torch.from_numpy(g1["attention_mask"][i:i + 1])
+        out = R.inference_batch(state_bundle, [rgb], ids, mask)
+        for k in ("feats", "z_img", "pooled", "z_txt", "z_fuse", "logits", "probs"):
+            ref = g1[k][i:i + 1]
+            err = np.abs(out[k].numpy() - ref).max() / max(1.0, np.abs(ref).max())
+            assert err < 2e-5, (k, err)
+        assert out["vector"].numpy().astype(np.uint8).tolist() == g1["vector"][i:i + 1].tolist()
+
+
+def test_forward_matches_reference_on_synthetic_batch(state_bundle):
+    g = load_golden("g2_B8_L128_ragged")
+    imgs = synth.synth_images(8, 224, seed=1234)
+    ids, mask = synth.synth_token_ids(8, 128, seed=1235, ragged=True)
+    assert [zlib.crc32(R.preprocess_u8(im).tobytes()) for im in imgs] == g["pre_crc"].tolist()
+    out = R.inference_batch(state_bundle, list(imgs), torch.from_numpy(ids), torch.from_numpy(mask))
+    for k in ("feats", "z_img", "pooled", "z_txt", "z_fuse", "logits", "probs"):
+        err = np.abs(out[k].numpy() - g[k]).max() / max(1.0, np.abs(g[k]).max())
+        assert err < 2e-5, (k, err)
+    assert np.array_equal(out["vector"].numpy().astype(np.uint8), g["vector"])
+
+
+def test_padding_does_not_change_result(state_bundle):
+    """Padded query rows are discarded by the masked mean (training_pipeline.py:452-459):
+    L=96 and L=128 paddings of the same ragged ids give the same golden outputs."""
+    a, b = load_golden("g2_B8_L96_ragged"), load_golden("g2_B8_L128_ragged")
+    assert np.abs(a["z_txt"] - b["z_txt"]).max() < 1e-5
+    assert np.array_equal(a["vector"], b["vector"])
