@@ -1,0 +1,119 @@
+/* mmdx.h - C ABI of the B200-native batched multimodal inference forward.
+ *
+ * The reference (PravCoder/Multi-Modal-Medical-Imaging-and-Report-ML-Diagnosis-System) has no
+ * FFI/plugin interface: its boundary is the Python function
+ *     inference(model_bundle, image_pil, patient_details, device=None, gen_kwargs=None)
+ *     backend/ml/pipelines/inference_pipeline.py:150-206   (called from backend/api/views.py:85)
+ * and the three nn.Modules it drives (backend/ml/pipelines/training_pipeline.py:157-311,
+ * :348-508, :516-618).  This header is what a ctypes binding behind that function binds
+ * (see INTEGRATION.md); each entry point names the reference step it replaces.
+ *
+ * Conventions: plain pointers and sizes only; `d_` = device pointer, `h_` = host pointer;
+ * every call returns 0 on success, non-zero on failure with the message available from
+ * mmdx_last_error() (thread-local).  `stream` is a cudaStream_t passed as void*.
+ * There is NO CPU fallback: without a CUDA device mmdx_create fails.
+ */
+#ifndef MMDX_H
+#define MMDX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmdx_engine mmdx_engine;
+
+typedef struct mmdx_config {
+  int32_t device;         /* CUDA device ordinal */
+  int32_t resize_short;   /* T.Resize(256)      training_pipeline.py:113 ; 0 = no resize */
+  int32_t crop;           /* T.CenterCrop(224)  training_pipeline.py:114 ; 0 = no crop (needs resize_short==0) */
+  int32_t n_heads;        /* BERT attention heads (12) */
+  float   mean[3];        /* T.Normalize mean   training_pipeline.py:117 */
+  float   std[3];         /* T.Normalize std */
+} mmdx_config;
+
+const char* mmdx_last_error(void);
+const char* mmdx_version(void);
+
+/* Host-only helper (no GPU needed): Pillow ImagingResample bilinear coefficients for output
+ * indices [out_first, out_first+n) of an axis resized in_size -> out_size.  `weights` is
+ * [n][ksize] int32 in 22-bit fixed point.  Returns ksize (>0) or -1. */
+int mmdx_resample_coeffs(int in_size, int out_size, int out_first, int n, int32_t* first, int32_t* count,
+                         int32_t* weights, int weights_capacity);
+/* torchvision Resize(int) output size + CenterCrop offsets (functional.py:353-384, :592-594). */
+int mmdx_resize_geometry(int h, int w, int resize_short, int crop, int* out_h, int* out_w, int* top, int* left);
+
+/* ---- lifetime / weights: replaces api/views.py:216-234 (build modules + load_state_dict) ---- */
+int mmdx_create(const mmdx_config* cfg, mmdx_engine** out);
+void mmdx_destroy(mmdx_engine* e);
+/* One call per state_dict tensor, fp32 host data, names prefixed "image." / "text." / "fusion."
+ * followed by the reference's state_dict key. */
+int mmdx_load_tensor(mmdx_engine* e, const char* name, const float* h_data, int ndim, const int64_t* shape);
+/* Fold BatchNorm into conv weights+bias, fuse Q/K/V, cast to bf16, lay out K-major for TMA, upload. */
+int mmdx_finalize_weights(mmdx_engine* e);
+int mmdx_num_sms(mmdx_engine* e);
+/* dims read from the loaded weights: d_img, d_txt, d_fuse_hidden, n_disease, hidden, n_layers */
+int mmdx_dims(mmdx_engine* e, int32_t out[6]);
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* image_transfom_into_tensor (training_pipeline.py:112-119) + ImageEncoderCNN.forward (:306-311).
+ * d_images: uint8 [B,H,W,C] (C = 1 or 3).  Outputs nullable: d_feats fp32 [B,2048], d_z_img fp32 [B,d_img]. */
+int mmdx_image_encode(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, float* d_feats,
+                      float* d_z_img, void* stream);
+/* TextEncoderTransformer.forward (:503-508) over packed (unpadded) tokens: d_ids/d_pos/d_tt int32 [T],
+ * d_cu_seqlens int32 [B+1].  Outputs nullable: d_pooled fp32 [B,768], d_z_txt fp32 [B,d_txt]. */
+int mmdx_text_encode(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt,
+                     const int32_t* d_cu_seqlens, int B, int T, int max_len, float* d_pooled, float* d_z_txt,
+                     void* stream);
+/* FusionTransformerModel.forward with report_labels=None (:584-592) + sigmoid/threshold
+ * (inference_pipeline.py:185-186) on the embeddings left in the engine by the two calls above. */
+int mmdx_head(mmdx_engine* e, int B, const float* d_thresholds, float* d_z_fuse, float* d_logits, float* d_probs,
+              uint8_t* d_vector, void* stream);
+/* All three, device buffers. */
+int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
+                 const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu_seqlens, int T, int max_len,
+                 const float* d_thresholds, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream);
+/* Same with HOST buffers (pinned recommended): H2D copies, forward, D2H copies, stream sync. */
+int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
+                      const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu_seqlens, int T, int max_len,
+                      const float* h_thresholds, float* h_logits, float* h_probs, uint8_t* h_vector, void* stream);
+/* kernels launched by this engine since creation (bench.py's gpu_launches) */
+int64_t mmdx_launch_count(mmdx_engine* e);
+
+/* ---- single-kernel entry points (parity tests call the hot kernels one at a time) ---------- */
+/* out[M,N] = act(A[M,K] * Wt[N,K]^T + bias (+ residual)); bf16 A/Wt/residual, bf16 or fp32 out. */
+int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
+                 const void* d_residual, int64_t ldr, void* d_out, int64_t ldc, int M, int N, int K, int act,
+                 int out_f32, int bn, void* stream);
+/* NHWC conv k in {1,3}, stride in {1,2}, pad k/2; weights packed [Cout][k*k][Cin] bf16 (BN folded). */
+int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
+                 const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride, int act,
+                 void* stream);
+/* 7x7/2 stem over the padded 4-channel image written by mmdx_op_preprocess; weights [64][7][8][4] bf16. */
+int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
+                 const float* d_bias, void* d_out, void* stream);
+int mmdx_padded_dims(int H, int W, int* hp, int* wp);
+int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, void* d_out_padded,
+                       int* out_h, int* out_w, void* stream);
+int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,
+                        void* stream);
+int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, int W, int C, void* d_out, void* stream);
+int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, int C, void* d_out_bf16, float* d_out_f32,
+                    void* stream);
+int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int N, const float* d_gamma, const float* d_beta,
+                      float eps, void* d_y, void* stream);
+int mmdx_op_embed_ln(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt, int rows,
+                     const void* d_word, const void* d_ptab, const void* d_ttab, const float* d_gamma,
+                     const float* d_beta, float eps, void* d_y, void* stream);
+int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu_seqlens, int n_seq, int max_len,
+                      int n_heads, int hidden, void* d_ctx, void* stream);
+int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int32_t* d_cu_seqlens, int n_seq, int hidden,
+                          void* d_out_bf16, float* d_out_f32, void* stream);
+int mmdx_op_head_tail(mmdx_engine* e, const float* d_hidden, int B, int D, const float* d_ln_g, const float* d_ln_b,
+                      float eps, const float* d_w, const float* d_b, int n_cls, const float* d_thresholds,
+                      float* d_z_fuse, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDX_H */

@@ -1,0 +1,1147 @@
+// Engine + C ABI (include/mmdx.h): weight packing (BN fold, QKV fuse, bf16, K-major), per-shape
+// launch plans (tensor maps + workspace), and the forward: K_pre -> stem/maxpool/16 bottlenecks/avgpool
+// -> BERT-base over packed tokens -> fused head.  All compute is in hand-written sm_100a kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mmdx.h"
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+using namespace mmdx;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" +  \
+                  std::to_string(__LINE__));                                                             \
+  } while (0)
+#define REQUIRE(cond, msg)                                                            \
+  do {                                                                                \
+    if (!(cond)) return fail(std::string("mmdx: ") + msg + " [" #cond "]");           \
+  } while (0)
+#define TRY(expr)                  \
+  do {                             \
+    int _r = (expr);               \
+    if (_r != 0) return _r;        \
+  } while (0)
+
+extern "C" const char* mmdx_last_error(void) { return g_err.c_str(); }
+extern "C" const char* mmdx_version(void) { return "mmdx-b200 0.1 (sm_100a, tcgen05/TMA)"; }
+
+// ------------------------------------------------------------------------------------------ Pillow tables
+extern "C" int mmdx_resample_coeffs(int in_size, int out_size, int out_first, int n, int32_t* first, int32_t* count,
+                                    int32_t* weights, int weights_capacity) {
+  // Pillow ImagingResample precompute_coeffs + normalize_coeffs_8bpc, triangle filter (support 1.0)
+  if (in_size <= 0 || out_size <= 0 || n < 0) return -1;
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double fs = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * fs;
+  const int ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  if (static_cast<long long>(n) * ksize > weights_capacity) return -1;
+  const double ss = 1.0 / fs;
+  std::vector<double> k(ksize);
+  for (int i = 0; i < n; ++i) {
+    const int xx = out_first + i;
+    const double center = (xx + 0.5) * scale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    first[i] = xmin;
+    count[i] = xmax;
+    for (int x = 0; x < ksize; ++x) {
+      int32_t q = 0;
+      if (x < xmax) q = k[x] < 0 ? static_cast<int32_t>(-0.5 + k[x] * (1 << 22)) : static_cast<int32_t>(0.5 + k[x] * (1 << 22));
+      weights[static_cast<size_t>(i) * ksize + x] = q;
+    }
+  }
+  return ksize;
+}
+
+extern "C" int mmdx_resize_geometry(int h, int w, int resize_short, int crop, int* out_h, int* out_w, int* top,
+                                    int* left) {
+  int oh = h, ow = w;
+  if (resize_short > 0) {
+    const int s = w <= h ? w : h, l = w <= h ? h : w;
+    const int ns = resize_short, nl = static_cast<int>(static_cast<double>(resize_short) * l / s);
+    if (w <= h) { ow = ns; oh = nl; } else { ow = nl; oh = ns; }
+  }
+  *out_h = oh; *out_w = ow;
+  if (crop > 0) {
+    if (oh < crop || ow < crop) return 1;
+    *top = static_cast<int>(std::nearbyint((oh - crop) / 2.0));    // Python round(): half-to-even
+    *left = static_cast<int>(std::nearbyint((ow - crop) / 2.0));
+  } else { *top = 0; *left = 0; }
+  return 0;
+}
+
+extern "C" int mmdx_padded_dims(int H, int W, int* hp, int* wp) {
+  *hp = H + 8 + (H & 1);
+  *wp = W + 8 + (W & 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ engine types
+struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int ensure(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    bytes = n;
+    return 0;
+  }
+};
+
+struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; };
+
+struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
+  bf16* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1;
+};
+struct LinW { bf16* w = nullptr; float* bias = nullptr; int nin = 0, nout = 0; };
+struct LnW { float* g = nullptr; float* b = nullptr; };
+struct BertLayerW { LinW qkv, ao, ff1, ff2; LnW ln1, ln2; };
+struct Bottleneck { ConvW c1, c2, c3, ds; bool has_ds = false; };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ImagePlan {
+  int B = 0, H = 0, W = 0, C = 0;
+  int crop_h = 0, crop_w = 0, hp = 0, wp = 0;
+  int has_x = 0, has_y = 0, off_x = 0, off_y = 0;
+  ResampleTable tx{}, ty{};
+  bf16* in_pad = nullptr; bf16* stem_out = nullptr; bf16* pool_out = nullptr;
+  int sh = 0, sw = 0, ph = 0, pw = 0;   // stem / pool output sizes
+  struct Step { int kind; GemmLaunch g; };   // kind 0 = gemm
+  std::vector<GemmLaunch> convs;            // stem first, then bottleneck convs in launch order
+  bf16* last = nullptr; int last_hw = 0;
+  size_t in_pad_bytes = 0;
+  DevBuf tables;        // Pillow coefficient tables of this geometry
+};
+struct TextPlan {
+  int T = 0, B = 0;
+  std::vector<GemmLaunch> gemms;   // per layer: qkv, ao, ff1, ff2
+};
+struct HeadPlan { int B = 0; GemmLaunch proj_img, proj_txt, fuse; };
+
+struct mmdx_engine {
+  mmdx_config cfg{};
+  int num_sms = 148;
+  EncodeTiledFn encode = nullptr;
+  std::mutex mu;
+  int64_t launches = 0;
+  std::map<std::string, HostTensor> host;
+  bool finalized = false;
+  // dims
+  int d_img = 0, d_txt = 0, d_fuse = 0, n_cls = 0, hidden = 0, n_layers = 0, ffn = 0, feat_dim = 2048;
+  // weights (one arena)
+  DevBuf warena; size_t wused = 0;
+  ConvW stem; std::vector<Bottleneck> blocks;
+  bf16 *word = nullptr, *ptab = nullptr, *ttab = nullptr; LnW emb_ln; std::vector<BertLayerW> layers;
+  LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
+  // workspaces
+  DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
+  std::map<std::string, std::unique_ptr<ImagePlan>> img_plans;
+  ImagePlan* img_last = nullptr;   // plan whose zero borders currently sit in img_ws
+  std::map<std::string, std::unique_ptr<TextPlan>> txt_plans;
+  std::map<int, std::unique_ptr<HeadPlan>> head_plans;
+  // head-side persistent buffers (capacity B)
+  int head_cap = 0;
+  bf16* feats_bf = nullptr; bf16* pooled_bf = nullptr; bf16* zcat = nullptr; float* fuse_h = nullptr;
+  float* thr_default = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------ tensor maps
+static int make_tmap(mmdx_engine* e, CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+             rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return fail(buf);
+  }
+  return 0;
+}
+
+static int pick_bn(mmdx_engine* e, long long m_tiles, int N, int bn_req) {
+  if (bn_req == 64 || bn_req == 128 || bn_req == 256) return (N % bn_req == 0) ? bn_req : 0;
+  const int cands[3] = {256, 128, 64};
+  for (int c : cands)
+    if (N % c == 0 && m_tiles * (N / c) >= 2LL * e->num_sms) return c;
+  for (int c : {128, 64})      // small problems: prefer more, smaller tiles
+    if (N % c == 0) return c;
+  return 0;
+}
+
+static void fill_epilogue(GemmParams& p, const float* bias, const bf16* residual, long long ldr, void* out,
+                          long long ldc, int act, int out_f32) {
+  p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
+}
+
+// C[M,N] = A[M,K] * W[N,K]^T
+static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long lda, const bf16* Wt, int M, int N, int K,
+                      int bn_req) {
+  REQUIRE(K % 64 == 0 && N % 64 == 0 && M > 0, "gemm needs K%64==0, N%64==0");
+  REQUIRE(lda % 8 == 0, "gemm lda must be a multiple of 8 elements");
+  GemmParams& p = g.p;
+  memset(&p, 0, sizeof p);
+  const long long m_tiles = (M + 127) / 128;
+  g.bn = pick_bn(e, m_tiles, N, bn_req);
+  REQUIRE(g.bn != 0, "no BN tile divides N");
+  g.bk = 64;
+  const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+  const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M, (uint64_t)lda * 2 * (uint64_t)M};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  TRY(make_tmap(e, &p.tmA[0], A, 4, dims, str, box, 128));
+  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  const uint64_t bd[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t bs[1] = {(uint64_t)K * 2};
+  const uint32_t bb[2] = {64, (uint32_t)g.bn};
+  TRY(make_tmap(e, &p.tmB, Wt, 2, bd, bs, bb, 128));
+  p.num_k_blocks = K / 64; p.kb_per_tap = K / 64; p.a_box_bytes = 128 * 64 * 2;
+  p.n_tiles = N / g.bn; p.num_tiles = (int)(m_tiles * p.n_tiles);
+  p.tiles_w = (int)m_tiles; p.tiles_h = 1;
+  p.Wb = 128; p.Hb = 1; p.Nb = 1; p.OW = M; p.OH = 1; p.NB = 1;
+  return 0;
+}
+
+// choose a spatial tile (Wb x Hb pixels x Nb images, <=128 rows) that minimises the number of tiles
+static void pick_tile(int OW, int OH, int NB, int& Wb, int& Hb, int& Nb) {
+  long long best = -1; Wb = 1; Hb = 1; Nb = 1;
+  for (int w = 1; w <= OW && w <= 128; ++w) {
+    for (int h = 1; h <= OH && w * h <= 128; ++h) {
+      int n = 128 / (w * h);
+      if (n > NB) n = NB;
+      if (n < 1) continue;
+      const long long tiles = (long long)((OW + w - 1) / w) * ((OH + h - 1) / h) * ((NB + n - 1) / n);
+      // tie-break: wider rows (longer contiguous runs for TMA)
+      if (best < 0 || tiles < best || (tiles == best && w > Wb)) { best = tiles; Wb = w; Hb = h; Nb = n; }
+    }
+  }
+}
+
+// NHWC conv as implicit GEMM.  in [NB,H,W,Cin], w [Cout][k*k][Cin], out [NB,OH,OW,Cout]
+static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int H, int W, int Cin, const bf16* w,
+                      int Cout, int k, int stride) {
+  REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2), "conv supports k in {1,3}, stride in {1,2}");
+  REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv channels must be multiples of 64");
+  const int pad = k / 2;
+  const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+  if (k == 1 && stride == 1) return build_gemm(e, g, in, Cin, w, NB * H * W, Cout, Cin, 0);
+  GemmParams& p = g.p;
+  memset(&p, 0, sizeof p);
+  int Wb, Hb, Nb;
+  pick_tile(OW, OH, NB, Wb, Hb, Nb);
+  const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
+  g.bn = pick_bn(e, m_tiles, Cout, 0);
+  REQUIRE(g.bn != 0, "no BN tile divides Cout");
+  g.bk = 64;
+  const uint32_t box[4] = {64, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
+  if (stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    TRY(make_tmap(e, &p.tmA[0], in, 4, dims, str, box, 128));
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const int Hh = (H - ph + 1) / 2, Wh = (W - pw + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)(Wh > 0 ? Wh : 1), (uint64_t)(Hh > 0 ? Hh : 1), (uint64_t)NB};
+        const uint64_t str[3] = {(uint64_t)2 * Cin * 2, (uint64_t)2 * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        TRY(make_tmap(e, &p.tmA[ph * 2 + pw], in + ((size_t)ph * W + pw) * Cin, 4, dims, str, box, 128));
+      }
+  }
+  int t = 0;
+  for (int r = 0; r < k; ++r)
+    for (int s = 0; s < k; ++s, ++t) {
+      if (stride == 1) { p.tap_map[t] = 0; p.tap_dh[t] = (signed char)(r - pad); p.tap_dw[t] = (signed char)(s - pad); }
+      else {
+        // input index = 2*o + r - pad ; parity view index = floor((2*o + r - pad)/2)
+        const int rr = r - pad, sr = s - pad;
+        const int phh = ((rr % 2) + 2) % 2, pww = ((sr % 2) + 2) % 2;
+        p.tap_map[t] = (signed char)(phh * 2 + pww);
+        p.tap_dh[t] = (signed char)((rr - phh) / 2);
+        p.tap_dw[t] = (signed char)((sr - pww) / 2);
+      }
+    }
+  const uint64_t bd[2] = {(uint64_t)k * k * Cin, (uint64_t)Cout};
+  const uint64_t bs[1] = {(uint64_t)k * k * Cin * 2};
+  const uint32_t bb[2] = {64, (uint32_t)g.bn};
+  TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 128));
+  p.kb_per_tap = Cin / 64; p.num_k_blocks = k * k * p.kb_per_tap; p.a_box_bytes = Wb * Hb * Nb * 64 * 2;
+  p.n_tiles = Cout / g.bn; p.num_tiles = (int)(m_tiles * p.n_tiles);
+  p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
+  p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
+  return 0;
+}
+
+// 7x7/2 pad 3 stem over the zero-bordered 4-channel image [NB,hp,wp,4] (image origin at (3,3)).
+static int build_stem(mmdx_engine* e, GemmLaunch& g, const bf16* in_pad, int NB, int H, int W, const bf16* w) {
+  int hp, wp;
+  mmdx_padded_dims(H, W, &hp, &wp);
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  GemmParams& p = g.p;
+  memset(&p, 0, sizeof p);
+  int Wb, Hb, Nb;
+  pick_tile(OW, OH, NB, Wb, Hb, Nb);
+  g.bn = 64; g.bk = 32;
+  const uint32_t box[4] = {32, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
+  for (int par = 0; par < 2; ++par) {
+    const uint64_t dims[4] = {32, (uint64_t)OW, (uint64_t)((hp - par) / 2), (uint64_t)NB};
+    const uint64_t str[3] = {16, (uint64_t)2 * wp * 8, (uint64_t)hp * wp * 8};   // W advances 2 pixels: overlapping windows
+    TRY(make_tmap(e, &p.tmA[par], in_pad + (size_t)par * wp * 4, 4, dims, str, box, 64));
+  }
+  p.tmA[2] = p.tmA[0]; p.tmA[3] = p.tmA[1];
+  for (int r = 0; r < 7; ++r) { p.tap_map[r] = (signed char)(r & 1); p.tap_dw[r] = 0; p.tap_dh[r] = (signed char)(r >> 1); }
+  const uint64_t bd[2] = {224, 64};
+  const uint64_t bs[1] = {224 * 2};
+  const uint32_t bb[2] = {32, 64};
+  TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 64));
+  p.kb_per_tap = 1; p.num_k_blocks = 7; p.a_box_bytes = Wb * Hb * Nb * 32 * 2;
+  const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
+  p.n_tiles = 1; p.num_tiles = (int)m_tiles;
+  p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
+  p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
+  return 0;
+}
+
+template <int BN, int BK, int ST>
+static int launch_inst(const GemmLaunch& g, int grid, cudaStream_t s) {
+  static bool attr_set = false;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST>;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BK, ST>::TOTAL));
+    attr_set = true;
+  }
+  kfn<<<grid, 192, GemmSmem<BN, BK, ST>::TOTAL, s>>>(g.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
+  const int grid = g.p.num_tiles < e->num_sms ? g.p.num_tiles : e->num_sms;
+  e->launches++;
+  if (g.bk == 32) return launch_inst<64, 32, 8>(g, grid, s);
+  switch (g.bn) {
+    case 256: return launch_inst<256, 64, 4>(g, grid, s);
+    case 128: return launch_inst<128, 64, 6>(g, grid, s);
+    case 64: return launch_inst<64, 64, 8>(g, grid, s);
+  }
+  return fail("mmdx: bad BN");
+}
+
+// ------------------------------------------------------------------------------------------ create / weights
+extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
+  REQUIRE(cfg && out, "null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(std::string("mmdx: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+  REQUIRE(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail("mmdx: this library is built for sm_100a (B200) only; found sm_" +
+                                    std::to_string(prop.major) + std::to_string(prop.minor));
+  std::unique_ptr<mmdx_engine> e(new mmdx_engine());
+  e->cfg = *cfg;
+  if (e->cfg.n_heads <= 0) e->cfg.n_heads = 12;
+  e->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = e.release();
+  return 0;
+}
+
+extern "C" void mmdx_destroy(mmdx_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+extern "C" int mmdx_num_sms(mmdx_engine* e) { return e ? e->num_sms : 0; }
+extern "C" int64_t mmdx_launch_count(mmdx_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int mmdx_load_tensor(mmdx_engine* e, const char* name, const float* h_data, int ndim, const int64_t* shape) {
+  REQUIRE(e && name && h_data && ndim >= 0 && ndim <= 4, "bad argument");
+  REQUIRE(!e->finalized, "weights already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(h_data, h_data + n);
+  e->host[name] = std::move(t);
+  return 0;
+}
+
+static const HostTensor* get(mmdx_engine* e, const std::string& k) {
+  auto it = e->host.find(k);
+  return it == e->host.end() ? nullptr : &it->second;
+}
+#define GET(var, key)                                                       \
+  const HostTensor* var = get(e, key);                                      \
+  if (!var) return fail(std::string("mmdx: missing weight tensor ") + (key))
+
+template <typename T>
+static int upload(mmdx_engine* e, const std::vector<T>& v, T** out) {
+  const size_t bytes = (v.size() * sizeof(T) + 255) & ~size_t(255);
+  REQUIRE(e->wused + bytes <= e->warena.bytes, "weight arena overflow");
+  T* p = reinterpret_cast<T*>(static_cast<char*>(e->warena.p) + e->wused);
+  CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  e->wused += bytes;
+  *out = p;
+  return 0;
+}
+
+// conv weight [Cout,Cin,k,k] + BN(eval) -> bf16 [Cout][k*k][Cin] with scale folded, fp32 bias
+static int pack_conv(mmdx_engine* e, const std::string& wkey, const std::string& bnkey, int stride, ConvW* out) {
+  GET(w, wkey + ".weight"); GET(g, bnkey + ".weight"); GET(b, bnkey + ".bias");
+  GET(m, bnkey + ".running_mean"); GET(v, bnkey + ".running_var");
+  REQUIRE(w->shape.size() == 4, "conv weight rank");
+  const int cout = (int)w->shape[0], cin = (int)w->shape[1], k = (int)w->shape[2];
+  std::vector<bf16> pw((size_t)cout * k * k * cin);
+  std::vector<float> bias(cout);
+  for (int o = 0; o < cout; ++o) {
+    const float sc = g->data[o] / std::sqrt(v->data[o] + 1e-5f);     // BatchNorm2d eps 1e-5, running stats
+    bias[o] = b->data[o] - m->data[o] * sc;
+    for (int c = 0; c < cin; ++c)
+      for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s)
+          pw[((size_t)o * k * k + r * k + s) * cin + c] =
+              __float2bfloat16(w->data[(((size_t)o * cin + c) * k + r) * k + s] * sc);
+  }
+  out->cin = cin; out->cout = cout; out->k = k; out->stride = stride;
+  TRY(upload(e, pw, &out->w));
+  TRY(upload(e, bias, &out->bias));
+  return 0;
+}
+
+static int pack_linear(mmdx_engine* e, const std::string& key, LinW* out) {
+  GET(w, key + ".weight"); GET(b, key + ".bias");
+  REQUIRE(w->shape.size() == 2, "linear weight rank");
+  out->nout = (int)w->shape[0]; out->nin = (int)w->shape[1];
+  std::vector<bf16> pw(w->data.size());
+  for (size_t i = 0; i < pw.size(); ++i) pw[i] = __float2bfloat16(w->data[i]);
+  TRY(upload(e, pw, &out->w));
+  TRY(upload(e, b->data, &out->bias));
+  return 0;
+}
+static int pack_ln(mmdx_engine* e, const std::string& key, LnW* out) {
+  GET(g, key + ".weight"); GET(b, key + ".bias");
+  TRY(upload(e, g->data, &out->g));
+  TRY(upload(e, b->data, &out->b));
+  return 0;
+}
+static int pack_table(mmdx_engine* e, const std::string& key, bf16** out) {
+  GET(w, key);
+  std::vector<bf16> pw(w->data.size());
+  for (size_t i = 0; i < pw.size(); ++i) pw[i] = __float2bfloat16(w->data[i]);
+  return upload(e, pw, out);
+}
+
+extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
+  REQUIRE(e && !e->finalized, "bad engine state");
+  CK(cudaSetDevice(e->cfg.device));
+  size_t total = 0;
+  for (auto& kv : e->host) total += kv.second.data.size() * 4 + 512;
+  TRY(e->warena.ensure(total + (1 << 20)));
+  e->wused = 0;
+  // ---- image encoder: stem
+  {
+    GET(w, "image.backbone.0.weight"); GET(g, "image.backbone.1.weight"); GET(b, "image.backbone.1.bias");
+    GET(m, "image.backbone.1.running_mean"); GET(v, "image.backbone.1.running_var");
+    REQUIRE(w->shape.size() == 4 && w->shape[0] == 64 && w->shape[1] == 3 && w->shape[2] == 7, "stem shape");
+    std::vector<bf16> pw((size_t)64 * 224, __float2bfloat16(0.f));
+    std::vector<float> bias(64);
+    for (int o = 0; o < 64; ++o) {
+      const float sc = g->data[o] / std::sqrt(v->data[o] + 1e-5f);
+      bias[o] = b->data[o] - m->data[o] * sc;
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s)
+            pw[(size_t)o * 224 + r * 32 + s * 4 + c] = __float2bfloat16(w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + s] * sc);
+    }
+    e->stem.cin = 3; e->stem.cout = 64; e->stem.k = 7; e->stem.stride = 2;
+    TRY(upload(e, pw, &e->stem.w));
+    TRY(upload(e, bias, &e->stem.bias));
+  }
+  const int nblocks[4] = {3, 4, 6, 3};
+  e->blocks.clear();
+  for (int li = 0; li < 4; ++li)
+    for (int bi = 0; bi < nblocks[li]; ++bi) {
+      const std::string pfx = "image.backbone." + std::to_string(4 + li) + "." + std::to_string(bi);
+      Bottleneck bk;
+      const int s = (bi == 0 && li > 0) ? 2 : 1;
+      TRY(pack_conv(e, pfx + ".conv1", pfx + ".bn1", 1, &bk.c1));
+      TRY(pack_conv(e, pfx + ".conv2", pfx + ".bn2", s, &bk.c2));      // v1.5: stride on the 3x3
+      TRY(pack_conv(e, pfx + ".conv3", pfx + ".bn3", 1, &bk.c3));
+      if (get(e, pfx + ".downsample.0.weight")) {
+        bk.has_ds = true;
+        TRY(pack_conv(e, pfx + ".downsample.0", pfx + ".downsample.1", s, &bk.ds));
+      }
+      e->blocks.push_back(bk);
+    }
+  e->feat_dim = e->blocks.back().c3.cout;
+  TRY(pack_linear(e, "image.proj", &e->proj_img));
+  e->d_img = e->proj_img.nout;
+  // ---- text encoder
+  {
+    const std::string eb = "text.encoder.embeddings.";
+    TRY(pack_table(e, eb + "word_embeddings.weight", &e->word));
+    TRY(pack_table(e, eb + "position_embeddings.weight", &e->ptab));
+    TRY(pack_table(e, eb + "token_type_embeddings.weight", &e->ttab));
+    TRY(pack_ln(e, eb + "LayerNorm", &e->emb_ln));
+    e->hidden = (int)get(e, eb + "word_embeddings.weight")->shape[1];
+    e->layers.clear();
+    for (int l = 0;; ++l) {
+      const std::string p = "text.encoder.encoder.layer." + std::to_string(l) + ".";
+      if (!get(e, p + "attention.self.query.weight")) break;
+      BertLayerW L;
+      {   // fuse Q,K,V -> [3H, H]
+        GET(q, p + "attention.self.query.weight"); GET(k, p + "attention.self.key.weight");
+        GET(v, p + "attention.self.value.weight"); GET(qb, p + "attention.self.query.bias");
+        GET(kb, p + "attention.self.key.bias"); GET(vb, p + "attention.self.value.bias");
+        const size_t n = q->data.size();
+        std::vector<bf16> pw(3 * n);
+        for (size_t i = 0; i < n; ++i) {
+          pw[i] = __float2bfloat16(q->data[i]); pw[n + i] = __float2bfloat16(k->data[i]);
+          pw[2 * n + i] = __float2bfloat16(v->data[i]);
+        }
+        std::vector<float> bias;
+        bias.insert(bias.end(), qb->data.begin(), qb->data.end());
+        bias.insert(bias.end(), kb->data.begin(), kb->data.end());
+        bias.insert(bias.end(), vb->data.begin(), vb->data.end());
+        L.qkv.nin = e->hidden; L.qkv.nout = 3 * e->hidden;
+        TRY(upload(e, pw, &L.qkv.w));
+        TRY(upload(e, bias, &L.qkv.bias));
+      }
+      TRY(pack_linear(e, p + "attention.output.dense", &L.ao));
+      TRY(pack_ln(e, p + "attention.output.LayerNorm", &L.ln1));
+      TRY(pack_linear(e, p + "intermediate.dense", &L.ff1));
+      TRY(pack_linear(e, p + "output.dense", &L.ff2));
+      TRY(pack_ln(e, p + "output.LayerNorm", &L.ln2));
+      e->layers.push_back(L);
+    }
+    e->n_layers = (int)e->layers.size();
+    REQUIRE(e->n_layers > 0, "no BERT layers found");
+    e->ffn = e->layers[0].ff1.nout;
+    REQUIRE(e->hidden == 768 || e->hidden == 1024 || e->hidden == 512 || e->hidden == 256, "unsupported hidden size");
+    REQUIRE(e->hidden == e->cfg.n_heads * 64, "head dim must be 64");
+    TRY(pack_linear(e, "text.proj", &e->proj_txt));
+    e->d_txt = e->proj_txt.nout;
+  }
+  // ---- fusion head
+  TRY(pack_linear(e, "fusion.fusion_mlp.0", &e->fuse));
+  TRY(pack_ln(e, "fusion.fusion_mlp.3", &e->fuse_ln));
+  e->d_fuse = e->fuse.nout;
+  REQUIRE(e->fuse.nin == e->d_img + e->d_txt, "fusion_mlp.0 input width != d_img + d_txt");
+  {
+    GET(w, "fusion.disease_head.weight"); GET(b, "fusion.disease_head.bias");
+    e->n_cls = (int)w->shape[0];
+    TRY(upload(e, w->data, &e->head_w));
+    TRY(upload(e, b->data, &e->head_b));
+    std::vector<float> thr(e->n_cls, 0.5f);
+    TRY(upload(e, thr, &e->thr_default));
+  }
+  e->host.clear();
+  e->finalized = true;
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int mmdx_dims(mmdx_engine* e, int32_t out[6]) {
+  REQUIRE(e && e->finalized, "weights not finalized");
+  out[0] = e->d_img; out[1] = e->d_txt; out[2] = e->d_fuse; out[3] = e->n_cls; out[4] = e->hidden; out[5] = e->n_layers;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ preprocessing
+struct PreGeom { int oh, ow, top, left, crop_h, crop_w, has_x, has_y; };
+
+static int pre_geometry(mmdx_engine* e, int H, int W, PreGeom* g) {
+  int rc = mmdx_resize_geometry(H, W, e->cfg.resize_short, e->cfg.crop, &g->oh, &g->ow, &g->top, &g->left);
+  REQUIRE(rc == 0, "image too small for the crop");
+  g->crop_h = e->cfg.crop > 0 ? e->cfg.crop : g->oh;
+  g->crop_w = e->cfg.crop > 0 ? e->cfg.crop : g->ow;
+  g->has_x = g->ow != W; g->has_y = g->oh != H;
+  return 0;
+}
+
+// builds the two device coefficient tables inside `buf`
+static int build_tables(mmdx_engine* e, DevBuf& buf, int H, int W, const PreGeom& g, ResampleTable* tx,
+                        ResampleTable* ty) {
+  std::vector<int32_t> host;
+  size_t off_x[3] = {0, 0, 0}, off_y[3] = {0, 0, 0};
+  int kx = 0, ky = 0;
+  auto add = [&](int in, int out, int first, int n, size_t* off, int* ks) -> int {
+    const double sc = (double)in / out;
+    const int ksize = (int)std::ceil(sc < 1.0 ? 1.0 : sc) * 2 + 1;
+    std::vector<int32_t> f(n), c(n), w((size_t)n * ksize);
+    if (mmdx_resample_coeffs(in, out, first, n, f.data(), c.data(), w.data(), (int)w.size()) != ksize) return 1;
+    off[0] = host.size(); host.insert(host.end(), f.begin(), f.end());
+    off[1] = host.size(); host.insert(host.end(), c.begin(), c.end());
+    off[2] = host.size(); host.insert(host.end(), w.begin(), w.end());
+    *ks = ksize;
+    return 0;
+  };
+  if (g.has_x) REQUIRE(add(W, g.ow, g.left, g.crop_w, off_x, &kx) == 0, "coefficient table");
+  if (g.has_y) REQUIRE(add(H, g.oh, g.top, g.crop_h, off_y, &ky) == 0, "coefficient table");
+  if (host.empty()) host.push_back(0);
+  TRY(buf.ensure(host.size() * 4));
+  CK(cudaMemcpy(buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  const int* base = static_cast<const int*>(buf.p);
+  *tx = ResampleTable{base + off_x[0], base + off_x[1], base + off_x[2], kx};
+  *ty = ResampleTable{base + off_y[0], base + off_y[1], base + off_y[2], ky};
+  return 0;
+}
+
+static int launch_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const PreGeom& g,
+                             const ResampleTable& tx, const ResampleTable& ty, bf16* out, int hp, int wp,
+                             cudaStream_t s) {
+  dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
+  const float3 sc = make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]);
+  const float3 sh = make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]);
+  e->launches++;
+  if (C == 3)
+    preprocess_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                               g.top, out, hp, wp, 3, 3, sc, sh);
+  else if (C == 1)
+    preprocess_kernel<1><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                               g.top, out, hp, wp, 3, 3, sc, sh);
+  else
+    return fail("mmdx: images must have 1 or 3 channels");
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ plans
+static size_t al(size_t n) { return (n + 1023) & ~size_t(1023); }
+
+static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan** out) {
+  char key[96];
+  snprintf(key, sizeof key, "%d_%d_%d_%d", B, H, W, C);
+  auto it = e->img_plans.find(key);
+  if (it != e->img_plans.end()) { *out = it->second.get(); return 0; }
+  std::unique_ptr<ImagePlan> pl(new ImagePlan());
+  pl->B = B; pl->H = H; pl->W = W; pl->C = C;
+  PreGeom g;
+  TRY(pre_geometry(e, H, W, &g));
+  pl->crop_h = g.crop_h; pl->crop_w = g.crop_w; pl->has_x = g.has_x; pl->has_y = g.has_y; pl->off_x = g.left; pl->off_y = g.top;
+  mmdx_padded_dims(g.crop_h, g.crop_w, &pl->hp, &pl->wp);
+  const int IH = g.crop_h, IW = g.crop_w;
+  pl->sh = (IH - 1) / 2 + 1; pl->sw = (IW - 1) / 2 + 1;
+  pl->ph = (pl->sh - 1) / 2 + 1; pl->pw = (pl->sw - 1) / 2 + 1;
+  // workspace layout: in_pad | stem_out | pool_out/X | Y | O1 | O2 | DS
+  const size_t in_pad_b = al((size_t)B * pl->hp * pl->wp * 4 * 2);
+  const size_t stem_b = al((size_t)B * pl->sh * pl->sw * 64 * 2);
+  const size_t act_b = al((size_t)B * pl->ph * pl->pw * 256 * 2);      // largest bottleneck tensor (layer1 output)
+  const size_t total = in_pad_b + stem_b + 5 * act_b;
+  char* old = static_cast<char*>(e->img_ws.p);
+  TRY(e->img_ws.ensure(total));
+  if (old != e->img_ws.p) { e->img_plans.clear(); e->img_last = nullptr; }   // buffers moved: cached tensor maps are stale
+  char* base = static_cast<char*>(e->img_ws.p);
+  pl->in_pad = reinterpret_cast<bf16*>(base);
+  pl->stem_out = reinterpret_cast<bf16*>(base + in_pad_b);
+  bf16* bufs[5];
+  for (int i = 0; i < 5; ++i) bufs[i] = reinterpret_cast<bf16*>(base + in_pad_b + stem_b + i * act_b);
+  pl->in_pad_bytes = in_pad_b;
+  TRY(build_tables(e, pl->tables, H, W, g, &pl->tx, &pl->ty));
+  pl->convs.clear();
+  GemmLaunch gl;
+  TRY(build_stem(e, gl, pl->in_pad, B, IH, IW, e->stem.w));
+  fill_epilogue(gl.p, e->stem.bias, nullptr, 0, pl->stem_out, 64, ACT_RELU, 0);
+  pl->convs.push_back(gl);
+  pl->pool_out = bufs[0];
+  bf16* x = bufs[0];
+  bf16* y = bufs[1];
+  bf16* o1 = bufs[2];
+  bf16* o2 = bufs[3];
+  bf16* ds = bufs[4];
+  int h = pl->ph, w = pl->pw;
+  for (const Bottleneck& bk : e->blocks) {
+    const int s = bk.c2.stride;
+    const int oh = (h - 1) / s + 1, ow = (w - 1) / s + 1;
+    TRY(build_conv(e, gl, x, B, h, w, bk.c1.cin, bk.c1.w, bk.c1.cout, 1, 1));
+    fill_epilogue(gl.p, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0);
+    pl->convs.push_back(gl);
+    TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
+    fill_epilogue(gl.p, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0);
+    pl->convs.push_back(gl);
+    const bf16* idt = x;
+    if (bk.has_ds) {
+      TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
+      fill_epilogue(gl.p, bk.ds.bias, nullptr, 0, ds, bk.ds.cout, ACT_NONE, 0);
+      pl->convs.push_back(gl);
+      idt = ds;
+    }
+    TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
+    fill_epilogue(gl.p, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0);
+    pl->convs.push_back(gl);
+    bf16* t = x; x = y; y = t;
+    h = oh; w = ow;
+  }
+  pl->last = x; pl->last_hw = h * w;
+  *out = pl.get();
+  e->img_plans[key] = std::move(pl);
+  return 0;
+}
+
+static int ensure_head_buffers(mmdx_engine* e, int B) {
+  if (B <= e->head_cap) return 0;
+  const size_t f = al((size_t)B * e->feat_dim * 2), p = al((size_t)B * e->hidden * 2),
+               z = al((size_t)B * (e->d_img + e->d_txt) * 2), h = al((size_t)B * e->d_fuse * 4);
+  TRY(e->head_ws.ensure(f + p + z + h));
+  char* b = static_cast<char*>(e->head_ws.p);
+  e->feats_bf = reinterpret_cast<bf16*>(b);
+  e->pooled_bf = reinterpret_cast<bf16*>(b + f);
+  e->zcat = reinterpret_cast<bf16*>(b + f + p);
+  e->fuse_h = reinterpret_cast<float*>(b + f + p + z);
+  e->head_cap = B;
+  e->head_plans.clear();
+  return 0;
+}
+
+static int get_head_plan(mmdx_engine* e, int B, HeadPlan** out) {
+  TRY(ensure_head_buffers(e, B));
+  auto it = e->head_plans.find(B);
+  if (it != e->head_plans.end()) { *out = it->second.get(); return 0; }
+  std::unique_ptr<HeadPlan> pl(new HeadPlan());
+  pl->B = B;
+  const int dz = e->d_img + e->d_txt;
+  TRY(build_gemm(e, pl->proj_img, e->feats_bf, e->feat_dim, e->proj_img.w, B, e->d_img, e->feat_dim, 0));
+  fill_epilogue(pl->proj_img.p, e->proj_img.bias, nullptr, 0, e->zcat, dz, ACT_NONE, 0);
+  TRY(build_gemm(e, pl->proj_txt, e->pooled_bf, e->hidden, e->proj_txt.w, B, e->d_txt, e->hidden, 0));
+  fill_epilogue(pl->proj_txt.p, e->proj_txt.bias, nullptr, 0, e->zcat + e->d_img, dz, ACT_NONE, 0);
+  TRY(build_gemm(e, pl->fuse, e->zcat, dz, e->fuse.w, B, e->d_fuse, dz, 0));
+  fill_epilogue(pl->fuse.p, e->fuse.bias, nullptr, 0, e->fuse_h, e->d_fuse, ACT_GELU, 1);
+  *out = pl.get();
+  e->head_plans[B] = std::move(pl);
+  return 0;
+}
+
+struct TextBufs { bf16 *hid, *qkv, *ctx, *pre, *ffn, *hid2; };
+
+static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs* tb) {
+  const int H = e->hidden;
+  const size_t hb = al((size_t)T * H * 2), qb = al((size_t)T * 3 * H * 2), fb = al((size_t)T * e->ffn * 2);
+  const size_t total = 4 * hb + qb + fb;
+  char* old = static_cast<char*>(e->txt_ws.p);
+  TRY(e->txt_ws.ensure(total));
+  if (old != e->txt_ws.p) e->txt_plans.clear();
+  // layout depends on T; plans are keyed by T and laid out from the arena base
+  char* base = static_cast<char*>(e->txt_ws.p);
+  tb->hid = reinterpret_cast<bf16*>(base);
+  tb->hid2 = reinterpret_cast<bf16*>(base + hb);
+  tb->ctx = reinterpret_cast<bf16*>(base + 2 * hb);
+  tb->pre = reinterpret_cast<bf16*>(base + 3 * hb);
+  tb->qkv = reinterpret_cast<bf16*>(base + 4 * hb);
+  tb->ffn = reinterpret_cast<bf16*>(base + 4 * hb + qb);
+  char key[48];
+  snprintf(key, sizeof key, "%d", T);
+  auto it = e->txt_plans.find(key);
+  if (it != e->txt_plans.end()) { *out = it->second.get(); return 0; }
+  if (e->txt_plans.size() > 64) e->txt_plans.clear();
+  std::unique_ptr<TextPlan> pl(new TextPlan());
+  pl->T = T; pl->B = B;
+  for (int l = 0; l < e->n_layers; ++l) {
+    const BertLayerW& L = e->layers[l];
+    GemmLaunch g;
+    TRY(build_gemm(e, g, tb->hid, H, L.qkv.w, T, 3 * H, H, 0));
+    fill_epilogue(g.p, L.qkv.bias, nullptr, 0, tb->qkv, 3 * H, ACT_NONE, 0);
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->ctx, H, L.ao.w, T, H, H, 0));
+    fill_epilogue(g.p, L.ao.bias, tb->hid, H, tb->pre, H, ACT_NONE, 0);       // + residual (pre-LN)
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->hid2, H, L.ff1.w, T, e->ffn, H, 0));
+    fill_epilogue(g.p, L.ff1.bias, nullptr, 0, tb->ffn, e->ffn, ACT_GELU, 0);
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->ffn, e->ffn, L.ff2.w, T, H, e->ffn, 0));
+    fill_epilogue(g.p, L.ff2.bias, tb->hid2, H, tb->pre, H, ACT_NONE, 0);     // + residual (pre-LN)
+    pl->gemms.push_back(g);
+  }
+  *out = pl.get();
+  e->txt_plans[key] = std::move(pl);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ launch helpers
+static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float* g, const float* b, float eps, bf16* y,
+                     cudaStream_t s) {
+  const int grid = (rows + 7) / 8;
+  e->launches++;
+  switch (N) {
+    case 256: layernorm_kernel<256, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 512: layernorm_kernel<512, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 768: layernorm_kernel<768, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 1024: layernorm_kernel<1024, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    default: return fail("mmdx: layernorm width must be 256/512/768/1024");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const int* tt, int rows, int N, const bf16* word,
+                        const bf16* ptab, const bf16* ttab, const float* g, const float* b, float eps, bf16* y,
+                        cudaStream_t s) {
+  const int grid = (rows + 7) / 8;
+  e->launches++;
+  switch (N) {
+    case 256: layernorm_kernel<256, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 512: layernorm_kernel<512, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 768: layernorm_kernel<768, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 1024: layernorm_kernel<1024, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    default: return fail("mmdx: hidden width must be 256/512/768/1024");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int n_seq, int max_len, int heads, int hidden,
+                            bf16* ctx, cudaStream_t s) {
+  REQUIRE(hidden == heads * 64, "attention head dim must be 64");
+  dim3 grid((max_len + ATT_BQ - 1) / ATT_BQ, heads, n_seq);
+  e->launches++;
+  attention_kernel<<<grid, 128, 0, s>>>(qkv, cu, hidden, ctx, 0.125f * 1.4426950408889634f);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, long long ld, int rows, int cols, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+  out[i] = __bfloat162float(in[r * ld + c]);
+}
+static int launch_cvt(mmdx_engine* e, const bf16* in, long long ld, int rows, int cols, float* out, cudaStream_t s) {
+  const long long n = (long long)rows * cols;
+  e->launches++;
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, ld, rows, cols, out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ hot path
+static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, float* d_feats,
+                               float* d_z_img, cudaStream_t s) {
+  REQUIRE(e->finalized, "weights not finalized");
+  REQUIRE(B > 0 && H > 0 && W > 0, "bad image batch");
+  TRY(ensure_head_buffers(e, B));
+  ImagePlan* pl;
+  TRY(get_image_plan(e, B, H, W, C, &pl));
+  PreGeom g{0, 0, pl->off_y, pl->off_x, pl->crop_h, pl->crop_w, pl->has_x, pl->has_y};
+  if (e->img_last != pl) {   // another geometry used the arena: restore the zero border + zero 4th channel
+    CK(cudaMemsetAsync(pl->in_pad, 0, pl->in_pad_bytes, s));
+    e->img_last = pl;
+  }
+  TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->in_pad, pl->hp, pl->wp, s));
+  TRY(launch_gemm(e, pl->convs[0], s));
+  {
+    const long long total = (long long)B * pl->ph * pl->pw * 8;
+    e->launches++;
+    maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pl->stem_out, B, pl->sh, pl->sw, 64, pl->pool_out,
+                                                                        pl->ph, pl->pw);
+    CK(cudaGetLastError());
+  }
+  for (size_t i = 1; i < pl->convs.size(); ++i) TRY(launch_gemm(e, pl->convs[i], s));
+  {
+    const int n = B * (e->feat_dim / 8);
+    e->launches++;
+    avgpool_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->last, B, pl->last_hw, e->feat_dim, e->feats_bf, d_feats);
+    CK(cudaGetLastError());
+  }
+  HeadPlan* hp;
+  TRY(get_head_plan(e, B, &hp));
+  TRY(launch_gemm(e, hp->proj_img, s));
+  if (d_z_img) TRY(launch_cvt(e, e->zcat, e->d_img + e->d_txt, B, e->d_img, d_z_img, s));
+  return 0;
+}
+
+static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt,
+                              const int32_t* d_cu, int B, int T, int max_len, float* d_pooled, float* d_z_txt,
+                              cudaStream_t s) {
+  REQUIRE(e->finalized, "weights not finalized");
+  REQUIRE(B > 0 && T > 0 && max_len > 0, "bad token batch");
+  TRY(ensure_head_buffers(e, B));
+  TextPlan* pl;
+  TextBufs tb;
+  TRY(get_text_plan(e, T, B, &pl, &tb));
+  const int H = e->hidden;
+  TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s));
+  for (int l = 0; l < e->n_layers; ++l) {
+    const BertLayerW& L = e->layers[l];
+    TRY(launch_gemm(e, pl->gemms[4 * l + 0], s));                                         // QKV
+    TRY(launch_attention(e, tb.qkv, d_cu, B, max_len, e->cfg.n_heads, H, tb.ctx, s));
+    TRY(launch_gemm(e, pl->gemms[4 * l + 1], s));                                         // out-proj + residual
+    TRY(launch_ln(e, tb.pre, T, H, L.ln1.g, L.ln1.b, 1e-12f, tb.hid2, s));
+    TRY(launch_gemm(e, pl->gemms[4 * l + 2], s));                                         // FFN1 + GELU
+    TRY(launch_gemm(e, pl->gemms[4 * l + 3], s));                                         // FFN2 + residual
+    TRY(launch_ln(e, tb.pre, T, H, L.ln2.g, L.ln2.b, 1e-12f, tb.hid, s));
+  }
+  e->launches++;
+  seq_mean_pool_kernel<<<B, 128, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
+  CK(cudaGetLastError());
+  HeadPlan* hp;
+  TRY(get_head_plan(e, B, &hp));
+  TRY(launch_gemm(e, hp->proj_txt, s));
+  if (d_z_txt) TRY(launch_cvt(e, e->zcat + e->d_img, e->d_img + e->d_txt, B, e->d_txt, d_z_txt, s));
+  return 0;
+}
+
+static int head_locked(mmdx_engine* e, int B, const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs,
+                       uint8_t* d_vector, cudaStream_t s) {
+  REQUIRE(e->finalized && B > 0 && B <= e->head_cap, "head called before the encoders");
+  REQUIRE(d_logits && d_probs && d_vector, "null output");
+  HeadPlan* hp;
+  TRY(get_head_plan(e, B, &hp));
+  TRY(launch_gemm(e, hp->fuse, s));
+  e->launches++;
+  head_tail_kernel<<<B, 256, e->d_fuse * sizeof(float), s>>>(e->fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f,
+                                                             e->head_w, e->head_b, e->n_cls,
+                                                             d_thr ? d_thr : e->thr_default, d_z_fuse, d_logits, d_probs,
+                                                             d_vector);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmdx_image_encode(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, float* d_feats,
+                                 float* d_z_img, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  return image_encode_locked(e, d_images, B, H, W, C, d_feats, d_z_img, (cudaStream_t)stream);
+}
+extern "C" int mmdx_text_encode(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt,
+                                const int32_t* d_cu, int B, int T, int max_len, float* d_pooled, float* d_z_txt,
+                                void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  return text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, d_pooled, d_z_txt, (cudaStream_t)stream);
+}
+extern "C" int mmdx_head(mmdx_engine* e, int B, const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs,
+                         uint8_t* d_vector, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  return head_locked(e, B, d_thr, d_z_fuse, d_logits, d_probs, d_vector, (cudaStream_t)stream);
+}
+extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
+                            const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu, int T, int max_len,
+                            const float* d_thr, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(image_encode_locked(e, d_images, B, H, W, C, nullptr, nullptr, s));
+  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, s));
+  return head_locked(e, B, d_thr, nullptr, d_logits, d_probs, d_vector, s);
+}
+
+extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C,
+                                 const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu,
+                                 int T, int max_len, const float* h_thr, float* h_logits, float* h_probs,
+                                 uint8_t* h_vector, void* stream) {
+  REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  REQUIRE(e->finalized, "weights not finalized");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img_b = al((size_t)B * H * W * C), tok_b = al((size_t)T * 4), cu_b = al((size_t)(B + 1) * 4);
+  const size_t out_f = al((size_t)B * e->n_cls * 4), out_u = al((size_t)B * e->n_cls), thr_b = al((size_t)e->n_cls * 4);
+  TRY(e->io_ws.ensure(img_b + 3 * tok_b + cu_b + 2 * out_f + out_u + thr_b));
+  char* b = static_cast<char*>(e->io_ws.p);
+  uint8_t* d_img = reinterpret_cast<uint8_t*>(b); b += img_b;
+  int32_t* d_ids = reinterpret_cast<int32_t*>(b); b += tok_b;
+  int32_t* d_pos = reinterpret_cast<int32_t*>(b); b += tok_b;
+  int32_t* d_tt = reinterpret_cast<int32_t*>(b); b += tok_b;
+  int32_t* d_cu = reinterpret_cast<int32_t*>(b); b += cu_b;
+  float* d_logits = reinterpret_cast<float*>(b); b += out_f;
+  float* d_probs = reinterpret_cast<float*>(b); b += out_f;
+  uint8_t* d_vec = reinterpret_cast<uint8_t*>(b); b += out_u;
+  float* d_thr = reinterpret_cast<float*>(b);
+  CK(cudaMemcpyAsync(d_img, h_images, (size_t)B * H * W * C, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (h_thr) CK(cudaMemcpyAsync(d_thr, h_thr, (size_t)e->n_cls * 4, cudaMemcpyHostToDevice, s));
+  TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
+  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, s));
+  TRY(head_locked(e, B, h_thr ? d_thr : nullptr, nullptr, d_logits, d_probs, d_vec, s));
+  CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_vector, d_vec, (size_t)B * e->n_cls, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ single-op entry points
+extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
+                            const void* d_residual, int64_t ldr, void* d_out, int64_t ldc, int M, int N, int K, int act,
+                            int out_f32, int bn, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  GemmLaunch g;
+  TRY(build_gemm(e, g, static_cast<const bf16*>(d_a), lda, static_cast<const bf16*>(d_w), M, N, K, bn));
+  fill_epilogue(g.p, d_bias, static_cast<const bf16*>(d_residual), ldr, d_out, ldc, act, out_f32);
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
+                            const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride,
+                            int act, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  GemmLaunch g;
+  TRY(build_conv(e, g, static_cast<const bf16*>(d_in), NB, H, W, Cin, static_cast<const bf16*>(d_w), Cout, k, stride));
+  fill_epilogue(g.p, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0);
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
+                            const float* d_bias, void* d_out, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  GemmLaunch g;
+  TRY(build_stem(e, g, static_cast<const bf16*>(d_in_padded), NB, H, W, static_cast<const bf16*>(d_w)));
+  fill_epilogue(g.p, d_bias, nullptr, 0, d_out, 64, ACT_RELU, 0);
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C,
+                                  void* d_out_padded, int* out_h, int* out_w, void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  PreGeom g;
+  TRY(pre_geometry(e, H, W, &g));
+  ResampleTable tx, ty;
+  TRY(build_tables(e, e->tab_ws, H, W, g, &tx, &ty));
+  int hp, wp;
+  mmdx_padded_dims(g.crop_h, g.crop_w, &hp, &wp);
+  if (out_h) *out_h = g.crop_h;
+  if (out_w) *out_w = g.crop_w;
+  return launch_preprocess(e, d_images, B, H, W, C, g, tx, ty, static_cast<bf16*>(d_out_padded), hp, wp,
+                           (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,
+                                   void* stream) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  PreGeom g;
+  TRY(pre_geometry(e, H, W, &g));
+  ResampleTable tx, ty;
+  TRY(build_tables(e, e->tab_ws, H, W, g, &tx, &ty));
+  dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
+  e->launches++;
+  if (C == 3)
+    resample_u8_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
+                                                                   g.has_y, g.left, g.top, d_out);
+  else if (C == 1)
+    resample_u8_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
+                                                                   g.has_y, g.left, g.top, d_out);
+  else
+    return fail("mmdx: images must have 1 or 3 channels");
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, int W, int C, void* d_out, void* stream) {
+  REQUIRE(e && C % 8 == 0, "maxpool needs C%8==0");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const long long total = (long long)B * OH * OW * (C / 8);
+  e->launches++;
+  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const bf16*>(d_in), B, H, W, C, static_cast<bf16*>(d_out), OH, OW);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, int C, void* d_out_bf16,
+                               float* d_out_f32, void* stream) {
+  REQUIRE(e && C % 8 == 0, "avgpool needs C%8==0");
+  const int n = B * (C / 8);
+  e->launches++;
+  avgpool_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_in), B, HW, C,
+                                                                    static_cast<bf16*>(d_out_bf16), d_out_f32);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int N, const float* d_gamma,
+                                 const float* d_beta, float eps, void* d_y, void* stream) {
+  REQUIRE(e, "null engine");
+  return launch_ln(e, static_cast<const bf16*>(d_x), rows, N, d_gamma, d_beta, eps, static_cast<bf16*>(d_y),
+                   (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_embed_ln(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt, int rows,
+                                const void* d_word, const void* d_ptab, const void* d_ttab, const float* d_gamma,
+                                const float* d_beta, float eps, void* d_y, void* stream) {
+  REQUIRE(e, "null engine");
+  return launch_embed(e, d_ids, d_pos, d_tt, rows, 768, static_cast<const bf16*>(d_word), static_cast<const bf16*>(d_ptab),
+                      static_cast<const bf16*>(d_ttab), d_gamma, d_beta, eps, static_cast<bf16*>(d_y), (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu, int n_seq, int max_len,
+                                 int n_heads, int hidden, void* d_ctx, void* stream) {
+  REQUIRE(e, "null engine");
+  return launch_attention(e, static_cast<const bf16*>(d_qkv), d_cu, n_seq, max_len, n_heads, hidden,
+                          static_cast<bf16*>(d_ctx), (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int32_t* d_cu, int n_seq, int hidden,
+                                     void* d_out_bf16, float* d_out_f32, void* stream) {
+  REQUIRE(e && hidden % 8 == 0, "hidden % 8");
+  e->launches++;
+  seq_mean_pool_kernel<<<n_seq, 128, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_h), d_cu, hidden,
+                                                               static_cast<bf16*>(d_out_bf16), hidden, d_out_f32);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mmdx_op_head_tail(mmdx_engine* e, const float* d_hidden, int B, int D, const float* d_ln_g,
+                                 const float* d_ln_b, float eps, const float* d_w, const float* d_b, int n_cls,
+                                 const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs, uint8_t* d_vector,
+                                 void* stream) {
+  REQUIRE(e && D <= 8192, "head width");
+  e->launches++;
+  head_tail_kernel<<<B, 256, D * sizeof(float), (cudaStream_t)stream>>>(d_hidden, D, d_ln_g, d_ln_b, eps, d_w, d_b, n_cls,
+                                                                        d_thr, d_z_fuse, d_logits, d_probs, d_vector);
+  CK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,540 @@
+// HBM-bound and small kernels of the path: preprocessing, pooling, embedding+LayerNorm,
+// LayerNorm, attention, masked mean pooling and the final head (LN + 13-way linear + sigmoid).
+#pragma once
+#include "ptx.cuh"
+
+namespace mmdx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_pre: uint8 HWC image -> Pillow-exact Resize(short side 256, bilinear, antialias) ->
+// CenterCrop(224) -> /255 -> (x-mean)/std -> bf16, written into the zero-bordered 4-channel
+// NHWC buffer the stem's implicit GEMM reads  (reference: training_pipeline.py:112-119).
+// Pillow runs the horizontal pass first, rounds to uint8, then the vertical pass; coefficient
+// tables (first tap, tap count, 22-bit fixed-point weights) are precomputed on the host in
+// float64 for the cropped window only.  One thread per output pixel (all channels).
+// ---------------------------------------------------------------------------------------------
+struct ResampleTable {   // device pointers, one table per axis, `n` entries (crop size)
+  const int* first;      // first input index
+  const int* count;      // taps
+  const int* weight;     // [n][ksize] int32 (sum = 1<<22)
+  int ksize;
+};
+
+__device__ __forceinline__ int clip8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+template <int C>
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ in, int B, int H, int W,
+                                                         ResampleTable tx, ResampleTable ty, int crop_h, int crop_w,
+                                                         int has_x, int has_y, int off_x, int off_y,
+                                                         __nv_bfloat16* __restrict__ out, int out_hp, int out_wp,
+                                                         int pad_top, int pad_left, float3 scale, float3 shift) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  const int b = blockIdx.z;
+  if (ox >= crop_w) return;
+  const uint8_t* img = in + static_cast<size_t>(b) * H * W * C;
+  int acc[C];
+  // horizontal taps for this output column
+  int x0, nx;
+  const int* wx;
+  if (has_x) { x0 = tx.first[ox]; nx = tx.count[ox]; wx = tx.weight + ox * tx.ksize; }
+  else { x0 = ox + off_x; nx = 1; wx = nullptr; }
+  int y0, ny;
+  const int* wy;
+  if (has_y) { y0 = ty.first[oy]; ny = ty.count[oy]; wy = ty.weight + oy * ty.ksize; }
+  else { y0 = oy + off_y; ny = 1; wy = nullptr; }
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 1 << 21;
+  for (int ky = 0; ky < ny; ++ky) {
+    const uint8_t* row = img + (static_cast<size_t>(y0 + ky) * W + x0) * C;
+    int hval[C];
+    if (has_x) {
+      int h[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) h[c] = 1 << 21;
+      for (int kx = 0; kx < nx; ++kx) {
+        const int wgt = __ldg(wx + kx);
+#pragma unroll
+        for (int c = 0; c < C; ++c) h[c] += static_cast<int>(__ldg(row + kx * C + c)) * wgt;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) hval[c] = clip8(h[c] >> 22);   // uint8 intermediate between the passes
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) hval[c] = __ldg(row + c);
+    }
+    if (has_y) {
+      const int wgt = __ldg(wy + ky);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] += hval[c] * wgt;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = hval[c];
+    }
+  }
+  int px[3];
+  if (has_y) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = clip8(acc[c] >> 22);
+  }
+  if (C == 1) { px[0] = px[1] = px[2] = acc[0]; }          // T.Lambda: gray -> 3 channels (:116)
+  else { px[0] = acc[0]; px[1] = acc[C > 1 ? 1 : 0]; px[2] = acc[C > 2 ? 2 : 0]; }
+  // ToTensor (/255) then Normalize ((x-mean)/std), in fp32 like the reference
+  const float r = (static_cast<float>(px[0]) / 255.0f - shift.x) / scale.x;
+  const float g = (static_cast<float>(px[1]) / 255.0f - shift.y) / scale.y;
+  const float bl = (static_cast<float>(px[2]) / 255.0f - shift.z) / scale.z;
+  uint2 o;
+  o.x = pack_bf16(r, g);
+  o.y = pack_bf16(bl, 0.0f);
+  __nv_bfloat16* dst = out + ((static_cast<size_t>(b) * out_hp + (oy + pad_top)) * out_wp + (ox + pad_left)) * 4;
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+// Same resample, uint8 out (test hook: bit-exact comparison with Pillow at the integer stage).
+template <int C>
+__global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restrict__ in, int B, int H, int W,
+                                                          ResampleTable tx, ResampleTable ty, int crop_h, int crop_w,
+                                                          int has_x, int has_y, int off_x, int off_y,
+                                                          uint8_t* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y;
+  const int b = blockIdx.z;
+  if (ox >= crop_w) return;
+  const uint8_t* img = in + static_cast<size_t>(b) * H * W * C;
+  int x0, nx, y0, ny;
+  const int *wx, *wy;
+  if (has_x) { x0 = tx.first[ox]; nx = tx.count[ox]; wx = tx.weight + ox * tx.ksize; }
+  else { x0 = ox + off_x; nx = 1; wx = nullptr; }
+  if (has_y) { y0 = ty.first[oy]; ny = ty.count[oy]; wy = ty.weight + oy * ty.ksize; }
+  else { y0 = oy + off_y; ny = 1; wy = nullptr; }
+  int acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 1 << 21;
+  for (int ky = 0; ky < ny; ++ky) {
+    const uint8_t* row = img + (static_cast<size_t>(y0 + ky) * W + x0) * C;
+    int hval[C];
+    if (has_x) {
+      int h[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) h[c] = 1 << 21;
+      for (int kx = 0; kx < nx; ++kx) {
+        const int wgt = __ldg(wx + kx);
+#pragma unroll
+        for (int c = 0; c < C; ++c) h[c] += static_cast<int>(__ldg(row + kx * C + c)) * wgt;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) hval[c] = clip8(h[c] >> 22);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) hval[c] = __ldg(row + c);
+    }
+    if (has_y) {
+      const int wgt = __ldg(wy + ky);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] += hval[c] * wgt;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = hval[c];
+    }
+  }
+  uint8_t* dst = out + ((static_cast<size_t>(b) * crop_h + oy) * crop_w + ox) * C;
+#pragma unroll
+  for (int c = 0; c < C; ++c) dst[c] = static_cast<uint8_t>(has_y ? clip8(acc[c] >> 22) : acc[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool 3x3 stride 2 pad 1, NHWC bf16, 8 channels (16 B) per thread.  (torchvision resnet maxpool)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W,
+                                                           int C, __nv_bfloat16* __restrict__ out, int OH, int OW) {
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(B) * OH * OW * cv;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cv);
+  long long t = idx / cv;
+  const int ow = static_cast<int>(t % OW); t /= OW;
+  const int oh = static_cast<int>(t % OH);
+  const int b = static_cast<int>(t / OH);
+  __nv_bfloat162 m[4];
+  const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = ninf;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int ih = oh * 2 - 1 + dy;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int iw = ow * 2 - 1 + dx;
+      if (iw < 0 || iw >= W) continue;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + ih) * W + iw) * C) + c8);
+      const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], v[i]);
+    }
+  }
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&m[0]); o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+  o.z = *reinterpret_cast<uint32_t*>(&m[2]); o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+  reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + oh) * OW + ow) * C)[c8] = o;
+}
+
+// Global average pool NHWC [B,HW,C] -> bf16 [B,C] (+ optional fp32 copy); 8 channels per thread.
+__global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int HW, int C,
+                                                      __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+  const int cv = C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * cv) return;
+  const int b = idx / cv, c8 = idx % cv;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(b) * HW * C) + c8;
+  for (int i = 0; i < HW; ++i) {
+    const uint4 u = __ldg(src + static_cast<size_t>(i) * cv);
+    float2 f;
+    f = unpack_bf16(u.x); s[0] += f.x; s[1] += f.y;
+    f = unpack_bf16(u.y); s[2] += f.x; s[3] += f.y;
+    f = unpack_bf16(u.z); s[4] += f.x; s[5] += f.y;
+    f = unpack_bf16(u.w); s[6] += f.x; s[7] += f.y;
+  }
+  const float inv = 1.0f / static_cast<float>(HW);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] *= inv;
+  reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * C)[c8] =
+      make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+  if (out_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(b) * C + c8 * 8);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over rows of width N (N % 256 == 0, N <= 1024): one warp per row, 16-byte loads,
+// fp32 statistics by warp shuffles (two-pass in registers), bf16 in/out.
+// EMBED variant: row = word[id] + position[pos] + type[tt]  (HF BertEmbeddings, eps 1e-12).
+// ---------------------------------------------------------------------------------------------
+template <int N, bool EMBED>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ y,
+                                                        const int* __restrict__ ids, const int* __restrict__ pos,
+                                                        const int* __restrict__ tts,
+                                                        const __nv_bfloat16* __restrict__ word,
+                                                        const __nv_bfloat16* __restrict__ ptab,
+                                                        const __nv_bfloat16* __restrict__ ttab) {
+  constexpr int CH = N / 256;   // 16-byte chunks per lane
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[CH][8];
+  if (EMBED) {
+    const uint4* w = reinterpret_cast<const uint4*>(word + static_cast<size_t>(ids[row]) * N);
+    const uint4* pp = reinterpret_cast<const uint4*>(ptab + static_cast<size_t>(pos[row]) * N);
+    const uint4* tt = reinterpret_cast<const uint4*>(ttab + static_cast<size_t>(tts[row]) * N);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint4 a = __ldg(w + c * 32 + lane), b = __ldg(pp + c * 32 + lane), d = __ldg(tt + c * 32 + lane);
+      const uint32_t* ua = &a.x; const uint32_t* ub = &b.x; const uint32_t* ud = &d.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack_bf16(ua[j]), fb = unpack_bf16(ub[j]), fd = unpack_bf16(ud[j]);
+        v[c][2 * j] = fa.x + fd.x + fb.x;       // word + type + position (HF order)
+        v[c][2 * j + 1] = fa.y + fd.y + fb.y;
+      }
+    }
+  } else {
+    const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * N);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint4 a = __ldg(src + c * 32 + lane);
+      const uint32_t* ua = &a.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(ua[j]);
+        v[c][2 * j] = f.x; v[c][2 * j + 1] = f.y;
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  const float mean = warp_sum(s) * (1.0f / N);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / N) + eps);
+  uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * N);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    float o[8];
+    o[0] = (v[c][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[c][1] - mean) * rstd * g0.y + b0.y;
+    o[2] = (v[c][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[c][3] - mean) * rstd * g0.w + b0.w;
+    o[4] = (v[c][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[c][5] - mean) * rstd * g1.y + b1.y;
+    o[6] = (v[c][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[c][7] - mean) * rstd * g1.w + b1.w;
+    dst[c * 32 + lane] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                    pack_bf16(o[6], o[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-attention over packed (unpadded) tokens: softmax(Q K^T / sqrt(64)) V per (sequence, head).
+// qkv: bf16 [T, 3*HID] rows = tokens, columns [Q | K | V], head h at columns h*64.
+// Grid (q_blocks, heads, sequences); 4 warps x 16 query rows; keys streamed in blocks of 64 through
+// shared memory; mma.sync m16n8k16 bf16 with fp32 online softmax in registers (warp-shuffle row
+// reductions).  Padded keys never exist here (tokens are packed), which equals the reference's
+// additive -inf key mask (modeling_bert.py eager_attention_forward).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int ATT_D = 64;       // head dim
+constexpr int ATT_BQ = 64;      // query rows per CTA
+constexpr int ATT_BK = 64;      // keys per smem block
+constexpr int ATT_PITCH = 72;   // smem row pitch (elements): 144 B -> conflict-free ldmatrix
+
+__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                        const int* __restrict__ cu_seqlens, int hidden,
+                                                        __nv_bfloat16* __restrict__ ctx, float scale_log2) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[ATT_BQ * ATT_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sK[ATT_BK * ATT_PITCH];
+  __shared__ __align__(16) __nv_bfloat16 sV[ATT_BK * ATT_PITCH];
+  const int seq = blockIdx.z, head = blockIdx.y, qb = blockIdx.x;
+  const int tok0 = cu_seqlens[seq];
+  const int len = cu_seqlens[seq + 1] - tok0;
+  const int q0 = qb * ATT_BQ;
+  if (q0 >= len) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t ld = static_cast<size_t>(3) * hidden;
+  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(tok0) * ld + head * ATT_D;
+  const __nv_bfloat16* kbase = qbase + hidden;
+  const __nv_bfloat16* vbase = qbase + 2 * hidden;
+
+  // Q tile -> smem (zero rows beyond the sequence)
+  for (int i = tid; i < ATT_BQ * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (q0 + r < len) u = __ldg(reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld) + c);
+    *reinterpret_cast<uint4*>(&sQ[r * ATT_PITCH + c * 8]) = u;
+  }
+  __syncthreads();
+  uint32_t qf[4][4];   // A fragments of this warp's 16 query rows, 4 k-steps of 16
+  {
+    const int r = warp * 16 + (lane & 15);
+    const int cofs = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ldsm_x4(smem_u32(&sQ[r * ATT_PITCH + ks * 16 + cofs]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
+
+  for (int k0 = 0; k0 < len; k0 += ATT_BK) {
+    __syncthreads();   // previous block fully consumed
+    for (int i = tid; i < ATT_BK * 8; i += 128) {
+      const int r = i >> 3, c = i & 7;
+      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
+      if (k0 + r < len) {
+        uk = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k0 + r) * ld) + c);
+        uv = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k0 + r) * ld) + c);
+      }
+      *reinterpret_cast<uint4*>(&sK[r * ATT_PITCH + c * 8]) = uk;
+      *reinterpret_cast<uint4*>(&sV[r * ATT_PITCH + c * 8]) = uv;
+    }
+    __syncthreads();
+
+    // S = Q K^T : 16 x 64 per warp
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {       // pairs of 8-key tiles
+        const int mid = lane >> 3;
+        const int key = np * 16 + (mid >> 1) * 8 + (lane & 7);
+        const int d = ks * 16 + (mid & 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(&sK[key * ATT_PITCH + d]), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+      }
+    }
+    // scale, mask keys beyond the sequence, online softmax
+    const int t4 = (lane & 3) * 2;
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = k0 + i * 8 + t4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (key + (e & 1)) < len;
+        s[i][e] = ok ? s[i][e] * scale_log2 : -INFINITY;
+      }
+      bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);   // finite: every block has >=1 valid key
+    const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
+    m0 = nm0; m1 = nm1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pf[4][4];    // P as A fragments: 4 k-steps of 16 keys
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float p0 = exp2f(s[i][0] - nm0), p1 = exp2f(s[i][1] - nm0);
+      const float p2 = exp2f(s[i][2] - nm1), p3 = exp2f(s[i][3] - nm1);
+      rs0 += p0 + p1; rs1 += p2 + p3;
+      pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+    // O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {         // 16 keys per step
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {       // pairs of 8-wide d tiles
+        const int mid = lane >> 3;
+        const int key = ks * 16 + (mid & 1) * 8 + (lane & 7);
+        const int d = dp * 16 + (mid >> 1) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(&sV[key * ATT_PITCH + d]), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], pf[ks], b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], pf[ks], b2, b3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int g = lane >> 2, t4 = (lane & 3) * 2;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = head * ATT_D + i * 8 + t4;
+    if (r0 < len)
+      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(tok0 + r0) * hidden + col) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
+    if (r1 < len)
+      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(tok0 + r1) * hidden + col) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+  }
+}
+
+// Masked mean pool over each sequence's packed tokens (training_pipeline.py:452-459):
+// sum / clamp(count, 1e-6).  One block per sequence, 8 columns per thread.
+__global__ void __launch_bounds__(128) seq_mean_pool_kernel(const __nv_bfloat16* __restrict__ h,
+                                                            const int* __restrict__ cu_seqlens, int hidden,
+                                                            __nv_bfloat16* __restrict__ out, long long ldo,
+                                                            float* __restrict__ out_f32) {
+  const int seq = blockIdx.x;
+  const int t0 = cu_seqlens[seq], t1 = cu_seqlens[seq + 1];
+  for (int c8 = threadIdx.x; c8 < hidden / 8; c8 += blockDim.x) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = t0; t < t1; ++t) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + static_cast<size_t>(t) * hidden) + c8);
+      float2 f;
+      f = unpack_bf16(u.x); s[0] += f.x; s[1] += f.y;
+      f = unpack_bf16(u.y); s[2] += f.x; s[3] += f.y;
+      f = unpack_bf16(u.z); s[4] += f.x; s[5] += f.y;
+      f = unpack_bf16(u.w); s[6] += f.x; s[7] += f.y;
+    }
+    const float inv = 1.0f / fmaxf(static_cast<float>(t1 - t0), 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] *= inv;
+    reinterpret_cast<uint4*>(out + static_cast<size_t>(seq) * ldo)[c8] =
+        make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+    if (out_f32 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(seq) * hidden + c8 * 8);
+      o[0] = make_float4(s[0], s[1], s[2], s[3]);
+      o[1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head tail: LayerNorm(eps 1e-5) of the GELU'd fusion hidden -> z_fuse; disease_head Linear(1024->13);
+// sigmoid; vector = probs >= thresholds  (training_pipeline.py:589-592, inference_pipeline.py:185-186).
+// One block (256 threads) per study; hidden width D <= 4096, D % 4 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict__ hdn, int D,
+                                                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                        float eps, const float* __restrict__ w_head,
+                                                        const float* __restrict__ b_head, int n_cls,
+                                                        const float* __restrict__ thresholds,
+                                                        float* __restrict__ z_fuse, float* __restrict__ logits,
+                                                        float* __restrict__ probs, uint8_t* __restrict__ vec) {
+  extern __shared__ float sz[];        // D floats
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* x = hdn + static_cast<size_t>(b) * D;
+  float s = 0.f;
+  for (int i = tid; i < D; i += 256) { const float v = x[i]; sz[i] = v; s += v; }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float mean = tot / D;
+  __syncthreads();
+  float q = 0.f;
+  for (int i = tid; i < D; i += 256) { const float d = sz[i] - mean; q += d * d; }
+  q = warp_sum(q);
+  if (lane == 0) red[warp] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / D + eps);
+  for (int i = tid; i < D; i += 256) {
+    const float z = (sz[i] - mean) * rstd * ln_g[i] + ln_b[i];
+    sz[i] = z;
+    if (z_fuse != nullptr) z_fuse[static_cast<size_t>(b) * D + i] = z;
+  }
+  __syncthreads();
+  for (int c = warp; c < n_cls; c += 8) {
+    const float* w = w_head + static_cast<size_t>(c) * D;
+    float acc = 0.f;
+    for (int i = lane; i < D; i += 32) acc += sz[i] * __ldg(w + i);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float lg = acc + b_head[c];
+      const float pr = 1.0f / (1.0f + expf(-lg));
+      logits[b * n_cls + c] = lg;
+      probs[b * n_cls + c] = pr;
+      vec[b * n_cls + c] = pr >= thresholds[c] ? 1 : 0;
+    }
+  }
+}
+
+}  // namespace mmdx

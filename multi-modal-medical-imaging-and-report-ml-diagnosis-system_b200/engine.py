@@ -1,0 +1,172 @@
+"""Python host side of the engine: weight import from the reference's state_dicts, token packing,
+and thin wrappers over the C ABI (`include/mmdx.h`).  PyTorch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, MmdxError, check, lib
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # training_pipeline.py:117
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_tokens(input_ids, attention_mask, token_type_ids=None):
+    """Host-side unpadding: keep the tokens with attention_mask==1 (padded keys are masked to -inf and
+    padded query rows are dropped by the masked mean in the reference, training_pipeline.py:452-459, so
+    computing only valid tokens is results-identical).  Returns int32 numpy arrays
+    (ids[T], pos[T], tt[T], cu_seqlens[B+1]) and max_len."""
+    ids = np.asarray(input_ids)
+    mask = np.asarray(attention_mask).astype(bool)
+    B, L = ids.shape
+    tt = np.zeros_like(ids) if token_type_ids is None else np.asarray(token_type_ids)
+    lens = mask.sum(1)
+    if (lens == 0).any():
+        raise ValueError("every study needs at least one unmasked token")
+    pos = np.broadcast_to(np.arange(L, dtype=np.int32), (B, L))
+    cu = np.zeros(B + 1, np.int32)
+    np.cumsum(lens, out=cu[1:])
+    return (np.ascontiguousarray(ids[mask], dtype=np.int32), np.ascontiguousarray(pos[mask], dtype=np.int32),
+            np.ascontiguousarray(tt[mask], dtype=np.int32), cu, int(lens.max()))
+
+
+class Engine:
+    """One engine per process/GPU.  `states` = {"image": sd, "text": sd, "fusion": sd} with the reference's
+    state_dict key names."""
+
+    def __init__(self, states: dict, device: int | None = None, resize_short: int = 256, crop: int = 224,
+                 n_heads: int = 12):
+        if not torch.cuda.is_available():
+            raise MmdxError("mmdx needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        cfg = Config(self.device, resize_short, crop, n_heads, (C.c_float * 3)(*IMAGENET_MEAN),
+                     (C.c_float * 3)(*IMAGENET_STD))
+        self._h = C.c_void_p()
+        check(lib().mmdx_create(C.byref(cfg), C.byref(self._h)))
+        skip = ("num_batches_tracked", "report_model.", "classifier.", "pooler.", "position_ids", "cond_proj.")
+        for prefix, sd in states.items():
+            for k, v in sd.items():
+                if any(s in k for s in skip):
+                    continue   # dead at inference (I3, T6, T9) or off the named path (T5)
+                t = v.detach().to(dtype=torch.float32, device="cpu").contiguous()
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                check(lib().mmdx_load_tensor(self._h, f"{prefix}.{k}".encode(), C.c_void_p(t.data_ptr()), t.dim(), shape))
+        check(lib().mmdx_finalize_weights(self._h))
+        d = (C.c_int32 * 6)()
+        check(lib().mmdx_dims(self._h, d))
+        self.d_img, self.d_txt, self.d_fuse, self.n_cls, self.hidden, self.n_layers = list(d)
+        self.feat_dim = 2048
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().mmdx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().mmdx_launch_count(self._h))
+
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    # ---- the hot path on device tensors -------------------------------------------------------
+    def image_encode(self, images_u8: torch.Tensor, want_feats=True):
+        """images_u8: uint8 [B,H,W,C] on the device -> (feats fp32 [B,2048] | None, z_img fp32 [B,d_img])."""
+        assert images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.is_cuda and images_u8.is_contiguous()
+        B, H, W, Cc = images_u8.shape
+        feats = torch.empty(B, self.feat_dim, dtype=torch.float32, device=self._dev()) if want_feats else None
+        z = torch.empty(B, self.d_img, dtype=torch.float32, device=self._dev())
+        check(lib().mmdx_image_encode(self._h, _ptr(images_u8), B, H, W, Cc, _ptr(feats), _ptr(z), _stream()))
+        return feats, z
+
+    def text_encode(self, ids, pos, tt, cu, max_len, want_pooled=True):
+        """Packed int32 device tensors -> (pooled fp32 [B,hidden] | None, z_txt fp32 [B,d_txt])."""
+        B, T = cu.numel() - 1, ids.numel()
+        pooled = torch.empty(B, self.hidden, dtype=torch.float32, device=self._dev()) if want_pooled else None
+        z = torch.empty(B, self.d_txt, dtype=torch.float32, device=self._dev())
+        check(lib().mmdx_text_encode(self._h, _ptr(ids), _ptr(pos), _ptr(tt), _ptr(cu), B, T, int(max_len), _ptr(pooled),
+                                     _ptr(z), _stream()))
+        return pooled, z
+
+    def head(self, B, thresholds=None, want_z_fuse=True):
+        dev = self._dev()
+        z_fuse = torch.empty(B, self.d_fuse, dtype=torch.float32, device=dev) if want_z_fuse else None
+        logits = torch.empty(B, self.n_cls, dtype=torch.float32, device=dev)
+        probs = torch.empty_like(logits)
+        vec = torch.empty(B, self.n_cls, dtype=torch.uint8, device=dev)
+        check(lib().mmdx_head(self._h, B, _ptr(thresholds), _ptr(z_fuse), _ptr(logits), _ptr(probs), _ptr(vec), _stream()))
+        return z_fuse, logits, probs, vec
+
+    def forward(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None):
+        """Whole path, device in / device out: (logits, probs, vector)."""
+        B, H, W, Cc = images_u8.shape
+        dev = self._dev()
+        logits = torch.empty(B, self.n_cls, dtype=torch.float32, device=dev)
+        probs = torch.empty_like(logits)
+        vec = torch.empty(B, self.n_cls, dtype=torch.uint8, device=dev)
+        check(lib().mmdx_forward(self._h, _ptr(images_u8), B, H, W, Cc, _ptr(ids), _ptr(pos), _ptr(tt), _ptr(cu),
+                                 ids.numel(), int(max_len), _ptr(thresholds), _ptr(logits), _ptr(probs), _ptr(vec),
+                                 _stream()))
+        return logits, probs, vec
+
+    def forward_host(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None, out=None):
+        """Whole path with HOST tensors (pinned recommended): H2D, forward, D2H, sync inside the C call."""
+        B, H, W, Cc = images_u8.shape
+        if out is None:
+            out = (torch.empty(B, self.n_cls, dtype=torch.float32).pin_memory(),
+                   torch.empty(B, self.n_cls, dtype=torch.float32).pin_memory(),
+                   torch.empty(B, self.n_cls, dtype=torch.uint8).pin_memory())
+        logits, probs, vec = out
+        check(lib().mmdx_forward_host(self._h, _ptr(images_u8), B, H, W, Cc, _ptr(ids), _ptr(pos), _ptr(tt), _ptr(cu),
+                                      ids.numel(), int(max_len), _ptr(thresholds), _ptr(logits), _ptr(probs), _ptr(vec),
+                                      _stream()))
+        return logits, probs, vec
+
+
+class RawHandle:
+    """An engine handle without weights: enough for the single-kernel entry points (`mmdx_op_*`)."""
+
+    def __init__(self, device: int | None = None, resize_short: int = 256, crop: int = 224, n_heads: int = 12):
+        if not torch.cuda.is_available():
+            raise MmdxError("mmdx needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        cfg = Config(self.device, resize_short, crop, n_heads, (C.c_float * 3)(*IMAGENET_MEAN),
+                     (C.c_float * 3)(*IMAGENET_STD))
+        self._h = C.c_void_p()
+        check(lib().mmdx_create(C.byref(cfg), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h.value:
+            lib().mmdx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,175 @@
+"""Drop-in for the reference's `backend/ml/pipelines/inference_pipeline.py` hot path.
+
+`inference(model_bundle, image_pil, patient_details, device=None, gen_kwargs=None)` keeps the
+reference's signature, argument meaning, error behaviour and result dict
+(inference_pipeline.py:150-206); the work between `image_transfom_into_tensor` (:174) and the
+sigmoid/threshold (:185-186) runs in hand-written sm_100a kernels through the C ABI (include/mmdx.h).
+`inference_batch` is the batch extension (the reference is hard-wired to B=1: `.unsqueeze(0)` :174).
+
+Differences a maintainer must know (also in INTEGRATION.md):
+  * there is no CPU path: `device=None` means the current CUDA device (the reference means "cpu");
+  * report generation (T5 beam search, :190-196) is off the accelerated path: when the bundle carries
+    the reference's `fusion_model` module and `t5_tok`, `report_text` is produced by that module's own
+    `generate` from our embeddings; pass `gen_kwargs=False` to skip it (`report_text` = "").
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+
+from .engine import Engine, pack_tokens
+
+_ENGINES: dict = {}
+_LOCK = threading.Lock()
+
+
+def _parse_device(device):
+    # same accepted types / same TypeError as inference_pipeline.py:152-159
+    if isinstance(device, torch.device):
+        dev = device
+    elif isinstance(device, str):
+        dev = torch.device(device)
+    elif device is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+    else:
+        raise TypeError(f"'device' must be str|torch.device|None, got {type(device)}")
+    if dev.type != "cuda":
+        raise RuntimeError("mmdx_b200 runs on CUDA (B200) only - there is no CPU fallback; got device=%r" % (device,))
+    return dev
+
+
+def _states_from_bundle(model_bundle: dict) -> dict:
+    """Accepts the serving bundle of api/views.py:247-257 (nn.Modules) or the on-disk
+    `model_bundle.pt` layout of training_pipeline.py:783-791 (state dicts)."""
+    out = {}
+    for prefix, mod_key, sd_key in (("image", "image_encoder", "image_state"), ("text", "text_encoder", "text_state"),
+                                    ("fusion", "fusion_model", "fusion_state")):
+        if model_bundle.get(mod_key) is not None:
+            out[prefix] = model_bundle[mod_key].state_dict()
+        elif model_bundle.get(sd_key) is not None:
+            out[prefix] = model_bundle[sd_key]
+        else:
+            raise ValueError(f"Bundle missing '{mod_key}' / '{sd_key}'")
+    return out
+
+
+def get_engine(model_bundle: dict, device=None) -> Engine:
+    """Weights are packed to the device once per bundle identity and device, never per call."""
+    dev = _parse_device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (id(model_bundle), idx)
+    with _LOCK:
+        hit = _ENGINES.get(key)
+        if hit is not None and hit[1] is model_bundle:
+            return hit[0]
+        with torch.cuda.device(idx):
+            eng = Engine(_states_from_bundle(model_bundle), device=idx)
+        _ENGINES[key] = (eng, model_bundle)
+        return eng
+
+
+def clear_engines():
+    """Counterpart of api/views.py:260-263 `clear_model_bundle`."""
+    with _LOCK:
+        for eng, _ in _ENGINES.values():
+            eng.close()
+        _ENGINES.clear()
+
+
+def _to_u8(img) -> np.ndarray:
+    if isinstance(img, np.ndarray):
+        a = img
+    elif isinstance(img, torch.Tensor):
+        a = img.cpu().numpy()
+    else:                                  # PIL image (api/views.py:70 hands over `.convert("RGB")`)
+        a = np.asarray(img)
+    if a.ndim == 2:
+        a = a[..., None]
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] not in (1, 3):
+        raise ValueError("images must be 8-bit with 1 or 3 channels (PIL mode L/RGB or uint8 HWC)")
+    return np.ascontiguousarray(a)
+
+
+def tokenize(model_bundle, text_list, max_len=96):
+    """tokenize_patient_details (training_pipeline.py:335-342) with the bundle's BERT tokenizer."""
+    tok = model_bundle.get("bert_tok")
+    if tok is None:
+        raise ValueError("Bundle missing 'bert_tok'")
+    return tok(list(text_list), padding="max_length", truncation=True, return_tensors="np", max_length=max_len)
+
+
+@torch.no_grad()
+def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=False, max_len=96, tokens=None):
+    """Batched `inference`: images = list of PIL / uint8 HWC arrays (any sizes), details = list[str]
+    (or `tokens` = dict with input_ids / attention_mask / token_type_ids [B,L] already tokenized).
+    Returns a list of result dicts in input order."""
+    dev = _parse_device(device)
+    eng = get_engine(model_bundle, dev)
+    class_names = model_bundle["class_names"]
+    imgs = [_to_u8(im) for im in images]
+    B = len(imgs)
+    if tokens is None:
+        if details is None or len(details) != B:
+            raise ValueError("need one patient_details string per image")
+        tokens = tokenize(model_bundle, details, max_len)
+    ids_all = np.asarray(tokens["input_ids"])
+    mask_all = np.asarray(tokens["attention_mask"])
+    tt_all = np.asarray(tokens["token_type_ids"]) if tokens.get("token_type_ids") is not None else np.zeros_like(ids_all)
+    if ids_all.shape[0] != B:
+        raise ValueError("tokens and images disagree on the batch size")
+    thr = torch.tensor(model_bundle["thresholds"], dtype=torch.float32)
+
+    probs_out = np.zeros((B, eng.n_cls), np.float32)
+    vec_out = np.zeros((B, eng.n_cls), np.uint8)
+    z_img_out = np.zeros((B, eng.d_img), np.float32)
+    z_txt_out = np.zeros((B, eng.d_txt), np.float32)
+    groups: dict = {}
+    for i, a in enumerate(imgs):
+        groups.setdefault(a.shape, []).append(i)
+    want_report = gen_kwargs is not False and model_bundle.get("fusion_model") is not None \
+        and model_bundle.get("t5_tok") is not None
+    with torch.cuda.device(dev):
+        thr_d = thr.to(dev)
+        for shape, idxs in groups.items():
+            batch = torch.from_numpy(np.stack([imgs[i] for i in idxs])).pin_memory().to(dev, non_blocking=True)
+            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs])
+            t = [torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (ids, pos, tt, cu)]
+            _, z_img = eng.image_encode(batch, want_feats=False)
+            _, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen, want_pooled=False)
+            _, _, probs, vec = eng.head(len(idxs), thr_d, want_z_fuse=False)
+            probs_out[idxs] = probs.cpu().numpy()
+            vec_out[idxs] = vec.cpu().numpy()
+            if want_report:
+                z_img_out[idxs] = z_img.cpu().numpy()
+                z_txt_out[idxs] = z_txt.cpu().numpy()
+
+    reports = [""] * B
+    if want_report:
+        # inference_pipeline.py:190-196, unchanged, on the reference's own module (off the accelerated path)
+        t5_tok = model_bundle["t5_tok"]
+        fusion = model_bundle["fusion_model"].to(dev)
+        gen_attributes = dict(max_new_tokens=180, min_new_tokens=150, num_beams=4, no_repeat_ngram_size=3,
+                              length_penalty=1.1, early_stopping=True, eos_token_id=t5_tok.eos_token_id,
+                              pad_token_id=t5_tok.pad_token_id)
+        if gen_kwargs:
+            gen_attributes.update(gen_kwargs)
+        gen_ids = fusion.generate(torch.from_numpy(z_img_out).to(dev), torch.from_numpy(z_txt_out).to(dev), **gen_attributes)
+        reports = t5_tok.batch_decode(gen_ids, skip_special_tokens=True)
+
+    return [{
+        "report_text": reports[i],
+        "disease_probs": {class_names[j]: float(probs_out[i, j]) for j in range(len(class_names))},
+        "disease_vector": [int(v) for v in vec_out[i]],
+        "model_version": model_bundle["version"],
+    } for i in range(B)]
+
+
+@torch.no_grad()
+def inference(model_bundle, image_pil, patient_details, device=None, gen_kwargs=None):
+    """Same contract as the reference's inference() (inference_pipeline.py:150-206):
+    returns {report_text, disease_probs{class: float}, disease_vector[0/1], model_version}."""
+    _parse_device(device)   # TypeError before any work, like the reference
+    return inference_batch(model_bundle, [image_pil], [patient_details], device=device, gen_kwargs=gen_kwargs,
+                           max_len=96)[0]

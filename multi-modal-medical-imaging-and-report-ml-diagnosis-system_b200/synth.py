@@ -157,19 +157,22 @@ def make_state_bundle(seed: int = 0, d_img: int = 1024, d_txt: int = 512, d_fuse
 
 def synth_images(batch: int, size: int = 224, seed: int = 1234) -> np.ndarray:
     """Chest-X-ray-shaped uint8 images [B, size, size, 3], R=G=B: a smooth
-    low-frequency field (bilinear-upsampled 14x14 U[0,255]) plus N(0,8) noise."""
-    rng = np.random.Generator(np.random.PCG64(seed))
+    low-frequency field (bilinear-upsampled 14x14 U[0,255]) plus N(0,8) noise.
+    Study i depends only on (seed, i), so any batch is a prefix of a larger one."""
     g = 14
-    base = rng.random(size=(batch, g, g), dtype=np.float32) * 255.0
     pos = (np.arange(size, dtype=np.float32) + 0.5) * (g / size) - 0.5
     i0 = np.clip(np.floor(pos).astype(np.int64), 0, g - 1)
     i1 = np.clip(i0 + 1, 0, g - 1)
     f = np.clip(pos - np.floor(pos), 0, 1).astype(np.float32)
-    rows = base[:, i0, :] * (1 - f)[None, :, None] + base[:, i1, :] * f[None, :, None]
-    img = rows[:, :, i0] * (1 - f)[None, None, :] + rows[:, :, i1] * f[None, None, :]
-    img = img + rng.standard_normal(size=img.shape, dtype=np.float32) * 8.0
-    gray = np.clip(np.rint(img), 0, 255).astype(np.uint8)
-    return np.ascontiguousarray(np.repeat(gray[..., None], 3, axis=-1))
+    out = np.empty((batch, size, size, 3), np.uint8)
+    for b in range(batch):
+        rng = np.random.Generator(np.random.PCG64([seed, b]))
+        base = rng.random(size=(g, g), dtype=np.float32) * 255.0
+        rows = base[i0, :] * (1 - f)[:, None] + base[i1, :] * f[:, None]
+        img = rows[:, i0] * (1 - f)[None, :] + rows[:, i1] * f[None, :]
+        img = img + rng.standard_normal(size=img.shape, dtype=np.float32) * 8.0
+        out[b] = np.clip(np.rint(img), 0, 255).astype(np.uint8)[..., None]
+    return out
 
 
 def synth_token_ids(batch: int, seq_len: int = 128, seed: int = 1235, ragged: bool = False):
@@ -177,18 +180,19 @@ def synth_token_ids(batch: int, seq_len: int = 128, seed: int = 1235, ragged: bo
 
     Returns (input_ids int64 [B,L], attention_mask int64 [B,L]).  With `ragged`
     each row gets a valid length U{16..40} (the size the reference's
-    patient-details grammar produces) and is padded with [PAD]=0 to L."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    lens = rng.integers(16, 41, size=batch)                     # drawn first: independent of seq_len
-    ids = np.ascontiguousarray(rng.integers(1000, 30522, size=(batch, 512), dtype=np.int64)[:, :seq_len])
-    mask = np.ones((batch, seq_len), dtype=np.int64)
-    lens = np.minimum(lens, seq_len) if ragged else np.full(batch, seq_len)
+    patient-details grammar produces) and is padded with [PAD]=0 to L.
+    Row i depends only on (seed, i): independent of batch size and seq_len."""
+    ids = np.zeros((batch, seq_len), np.int64)
+    mask = np.zeros((batch, seq_len), np.int64)
     for b in range(batch):
-        n = int(lens[b])
+        rng = np.random.Generator(np.random.PCG64([seed, b]))
+        n = int(rng.integers(16, 41))
+        row = rng.integers(1000, 30522, size=512, dtype=np.int64)
+        n = min(n, seq_len) if ragged else seq_len
+        ids[b, :n] = row[:n]
         ids[b, 0] = 101
         ids[b, n - 1] = 102
-        ids[b, n:] = 0
-        mask[b, n:] = 0
+        mask[b, :n] = 1
     return ids, mask
 
 

@@ -1,0 +1,143 @@
+"""End-to-end parity on the B200: the CUDA path (through the C ABI / the drop-in `inference`) against
+(a) the golden vectors produced by the reference's own modules (tests/golden, oracle/make_golden.py) and
+(b) the CPU oracle run here on the same seeded inputs.
+Tolerances (BASELINE.json north_star): thresholded labels identical; probabilities within 1e-2 absolute
+in bf16.  Intermediates are held to a relative error of 3e-2 of the tensor's max magnitude."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden                      # noqa: E402
+from mmdx_b200 import engine, synth                   # noqa: E402
+from mmdx_b200 import inference_pipeline as ip        # noqa: E402
+from oracle import forward_ref as R                   # noqa: E402
+
+PROB_TOL = 1e-2
+REL_TOL = 3e-2
+
+
+@pytest.fixture(scope="module")
+def bundle(state_bundle):
+    b = dict(state_bundle)
+    b["bert_tok"] = synth.make_bert_tokenizer()
+    return b
+
+
+@pytest.fixture(scope="module")
+def eng(bundle):
+    return ip.get_engine(bundle, "cuda")
+
+
+def _rel(got, ref):
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6))
+
+
+def _run_stages(eng, imgs_u8, ids, mask):
+    d = torch.from_numpy(np.ascontiguousarray(imgs_u8)).cuda()
+    pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+    t = [torch.from_numpy(x).cuda() for x in (pi, pp, pt, cu)]
+    feats, z_img = eng.image_encode(d)
+    pooled, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen)
+    z_fuse, logits, probs, vec = eng.head(d.shape[0])
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in dict(feats=feats, z_img=z_img, pooled=pooled, z_txt=z_txt, z_fuse=z_fuse,
+                                                logits=logits, probs=probs, vector=vec).items()}
+
+
+def _check(out, ref, safe_margin=0.0):
+    for k in ("feats", "z_img", "pooled", "z_txt", "z_fuse"):
+        assert _rel(out[k], ref[k]) < REL_TOL, (k, _rel(out[k], ref[k]))
+    assert np.abs(out["probs"] - ref["probs"]).max() < PROB_TOL
+    decided = np.abs(ref["probs"] - 0.5) > safe_margin
+    assert np.array_equal(out["vector"][decided], ref["vector"][decided])
+
+
+def test_samples_match_reference_goldens(eng, g1):
+    """Config C1: backend/sample_images e1/e2 + sample_details, one study at a time (B=1, L=96)."""
+    for i in range(2):
+        rgb = np.repeat(g1["gray"][i][None, ..., None], 3, axis=-1)
+        out = _run_stages(eng, rgb, g1["input_ids"][i:i + 1], g1["attention_mask"][i:i + 1])
+        ref = {k: g1[k][i:i + 1] for k in out}
+        _check(out, ref)
+        assert out["vector"].tolist() == g1["vector"][i:i + 1].tolist()          # labels identical, no margin
+
+
+@pytest.mark.parametrize("name,L,ragged", [("g2_B8_L128_full", 128, False), ("g2_B8_L128_ragged", 128, True),
+                                            ("g2_B8_L96_ragged", 96, True)])
+def test_synthetic_batches_match_reference_goldens(eng, name, L, ragged):
+    g = load_golden(name)
+    imgs = synth.synth_images(8, 224, seed=1234)
+    ids, mask = synth.synth_token_ids(8, L, seed=1235, ragged=ragged)
+    out = _run_stages(eng, imgs, ids, mask)
+    _check(out, g, safe_margin=2e-3)
+
+
+def test_forward_entry_points_agree(eng):
+    """mmdx_forward (device buffers) == mmdx_forward_host (host buffers) == the staged calls."""
+    B, L = 16, 128
+    imgs = synth.synth_images(B, 224, seed=99)
+    ids, mask = synth.synth_token_ids(B, L, seed=98, ragged=True)
+    staged = _run_stages(eng, imgs, ids, mask)
+    pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+    host = [torch.from_numpy(x).pin_memory() for x in (np.ascontiguousarray(imgs), pi, pp, pt, cu)]
+    lg, pr, vec = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen)
+    dev = [x.cuda() for x in host]
+    lg2, pr2, vec2 = eng.forward(dev[0], dev[1], dev[2], dev[3], dev[4], mlen)
+    torch.cuda.synchronize()
+    assert np.array_equal(pr.numpy(), staged["probs"]) and np.array_equal(pr2.cpu().numpy(), staged["probs"])
+    assert np.array_equal(vec.numpy(), staged["vector"]) and np.array_equal(lg.numpy(), lg2.cpu().numpy())
+
+
+def test_batch_vs_oracle_high_res_and_mixed_sizes(bundle, eng):
+    """The drop-in batch call on mixed image sizes against the CPU oracle on the same inputs."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    sizes = [(512, 512), (300, 400), (224, 224), (512, 512), (640, 480)]
+    imgs = [np.repeat(rng.integers(0, 256, size=(h, w, 1), dtype=np.uint8), 3, axis=-1) for h, w in sizes]
+    details = synth.synth_details(len(imgs), seed=7)
+    res = ip.inference_batch(bundle, imgs, details, device="cuda", max_len=96)
+    tok = ip.tokenize(bundle, details, 96)
+    ref = R.inference_batch(bundle, imgs, torch.from_numpy(tok["input_ids"]), torch.from_numpy(tok["attention_mask"]),
+                            torch.from_numpy(tok["token_type_ids"]))
+    for i, r in enumerate(res):
+        p = np.array([r["disease_probs"][c] for c in bundle["class_names"]])
+        assert np.abs(p - ref["probs"][i].numpy()).max() < PROB_TOL
+        decided = np.abs(ref["probs"][i].numpy() - 0.5) > 2e-3
+        assert np.array_equal(np.array(r["disease_vector"])[decided], ref["vector"][i].numpy()[decided])
+
+
+def test_inference_drop_in_contract(bundle, g1):
+    """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
+    from PIL import Image
+    pil = Image.fromarray(np.repeat(g1["gray"][0][..., None], 3, axis=-1))
+    res = ip.inference(bundle, pil, str(g1["details"][0]), device="cuda", gen_kwargs=False)
+    assert set(res) == {"report_text", "disease_probs", "disease_vector", "model_version"}
+    assert list(res["disease_probs"]) == bundle["class_names"] and res["model_version"] == bundle["version"]
+    assert all(isinstance(v, float) for v in res["disease_probs"].values())
+    assert res["disease_vector"] == g1["vector"][0].tolist()
+    p = np.array(list(res["disease_probs"].values()))
+    assert np.abs(p - g1["probs"][0]).max() < PROB_TOL
+    with pytest.raises(TypeError):
+        ip.inference(bundle, pil, "x", device=0)
+    # same bundle -> same engine (weights packed once)
+    assert ip.get_engine(bundle, "cuda") is ip.get_engine(bundle, torch.device("cuda"))
+
+
+def test_full_size_properties(eng):
+    """BASELINE config C2 size (B=256, L=128): size-independent properties instead of the slow oracle:
+    a study's result does not depend on its batch neighbours or its position (batch independence), and
+    padding length does not change it."""
+    B, L = 256, 128
+    imgs = synth.synth_images(B, 224, seed=1234)
+    ids, mask = synth.synth_token_ids(B, L, seed=1235, ragged=False)
+    big = _run_stages(eng, imgs, ids, mask)
+    assert np.isfinite(big["probs"]).all()
+    sel = [0, 17, 255]
+    small = _run_stages(eng, imgs[sel], ids[sel], mask[sel])
+    assert np.abs(big["probs"][sel] - small["probs"]).max() < 4e-3
+    perm = np.random.Generator(np.random.PCG64(1)).permutation(B)
+    shuf = _run_stages(eng, imgs[perm], ids[perm], mask[perm])
+    assert np.abs(shuf["probs"] - big["probs"][perm]).max() < 4e-3
+    g = load_golden("g2_B8_L128_full")       # first 8 studies are the golden batch
+    assert np.abs(big["probs"][:8] - g["probs"]).max() < PROB_TOL

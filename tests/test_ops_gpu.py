@@ -1,0 +1,285 @@
+"""Single-kernel parity tests (B200 only): every hot kernel is called through the C ABI
+(`mmdx_op_*`, include/mmdx.h) and compared with a plain fp32 torch evaluation of the same op on the
+same bf16-rounded inputs, or - for the integer resample - bit-exactly with the numpy oracle / Pillow."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from mmdx_b200 import _lib, engine            # noqa: E402
+from oracle import forward_ref as R           # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def h():
+    hd = engine.RawHandle()
+    yield hd
+    hd.close()
+
+
+def P(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def S():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel_err(got, ref):
+    return float((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,act,res,f32,bn", [
+    (128, 64, 64, 0, False, False, 64),
+    (128, 128, 64, 0, False, False, 128),
+    (128, 256, 128, 0, False, False, 256),
+    (256, 128, 256, 0, False, False, 0),
+    (1000, 768, 768, 0, True, False, 0),
+    (4096, 2304, 768, 0, False, False, 256),
+    (300, 3072, 768, 2, False, False, 0),
+    (513, 768, 3072, 0, True, False, 128),
+    (20000, 768, 768, 0, True, False, 256),
+    (1, 1024, 2048, 0, False, False, 0),
+    (5, 512, 768, 0, False, True, 0),
+    (256, 1024, 1536, 2, False, True, 0),
+    (777, 64, 64, 1, False, False, 0),
+])
+def test_gemm_tcgen05(h, M, N, K, act, res, f32, bn):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5))
+    bias = torch.randn(N, device="cuda", generator=g)
+    r = bf(torch.randn(M, N, device="cuda", generator=g)) if res else None
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(r), N, P(out), N, M, N, K, act, int(f32), bn, S()))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    if res:
+        ref = ref + r.float()
+    if act == 1:
+        ref = F.relu(ref)
+    elif act == 2:
+        ref = F.gelu(ref)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < (2e-5 if f32 else 1e-2) + 2e-3
+
+
+def test_gemm_strided_output_and_no_bias(h):
+    M, N, K = 200, 512, 768
+    a = bf(torch.randn(M, K, device="cuda"))
+    w = bf(torch.randn(N, K, device="cuda") * (K ** -0.5))
+    buf = torch.zeros(M, 1536, device="cuda", dtype=torch.bfloat16)
+    out = buf[:, 1024:]
+    _lib.check(_lib.lib().mmdx_op_gemm(h.handle, P(a), K, P(w), None, None, 0, P(out), 1536, M, N, K, 0, 0, 0, S()))
+    torch.cuda.synchronize()
+    assert rel_err(out, a.float() @ w.float().t()) < 1e-2
+    assert float(buf[:, :1024].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------- conv
+def _conv_case(h, NB, H, W, Cin, Cout, k, stride, act, res, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + NB + H + Cin + Cout + k + stride)
+    x = bf(torch.randn(NB, H, W, Cin, device="cuda", generator=g))
+    w = bf(torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * ((Cin * k * k) ** -0.5))
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    pad = k // 2
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    r = bf(torch.randn(NB, OH, OW, Cout, device="cuda", generator=g)) if res else None
+    wp = w.permute(0, 2, 3, 1).contiguous()       # [Cout][k][k][Cin]
+    out = torch.full((NB, OH, OW, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_conv(h.handle, P(x), NB, H, W, Cin, P(wp), P(bias), P(r), P(out), Cout, k, stride, act, S()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    if act == 1:
+        ref = F.relu(ref)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1.2e-2
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,act,res", [
+    (2, 56, 56, 64, 64, 1, 1, 1, False),       # layer1 conv1
+    (2, 56, 56, 64, 64, 3, 1, 1, False),       # layer1 conv2
+    (3, 56, 56, 64, 256, 1, 1, 1, True),       # layer1 conv3 + residual
+    (2, 56, 56, 128, 128, 3, 2, 1, False),     # layer2.0 conv2 (stride 2)
+    (2, 56, 56, 256, 512, 1, 2, 0, False),     # layer2.0 downsample
+    (4, 28, 28, 128, 128, 3, 1, 1, False),     # layer2 conv2
+    (5, 14, 14, 256, 256, 3, 1, 1, False),     # layer3 conv2
+    (2, 14, 14, 512, 512, 3, 2, 1, False),     # layer4.0 conv2
+    (3, 7, 7, 512, 512, 3, 1, 1, False),       # layer4 conv2, small batch
+    (130, 7, 7, 512, 512, 3, 1, 1, False),     # layer4 conv2, (1,1,128)-style tiles
+    (1, 7, 7, 512, 2048, 1, 1, 1, True),       # layer4 conv3, batch 1
+    (2, 15, 13, 64, 64, 3, 1, 0, False),       # odd sizes
+    (2, 15, 13, 64, 128, 3, 2, 0, False),      # odd sizes, stride 2
+    (2, 15, 13, 64, 128, 1, 2, 0, False),
+])
+def test_conv_implicit_gemm(h, NB, H, W, Cin, Cout, k, stride, act, res):
+    _conv_case(h, NB, H, W, Cin, Cout, k, stride, act, res)
+
+
+def _pad_nhwc4(x_nchw):
+    """fp32 [B,3,H,W] -> bf16 zero-bordered [B,hp,wp,4] with the image at (3,3) (what K_pre writes)."""
+    B, _, H, W = x_nchw.shape
+    hp, wp = C.c_int(), C.c_int()
+    _lib.lib().mmdx_padded_dims(H, W, C.byref(hp), C.byref(wp))
+    buf = torch.zeros(B, hp.value, wp.value, 4, device="cuda", dtype=torch.bfloat16)
+    buf[:, 3:3 + H, 3:3 + W, :3] = bf(x_nchw.permute(0, 2, 3, 1))
+    return buf
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 224, 224), (1, 64, 96), (3, 30, 34)])
+def test_stem_conv7x7(h, B, H, W):
+    g = torch.Generator(device="cuda").manual_seed(B + H)
+    x = bf(torch.randn(B, 3, H, W, device="cuda", generator=g)).float()
+    w = bf(torch.randn(64, 3, 7, 7, device="cuda", generator=g) * (147 ** -0.5))
+    bias = torch.randn(64, device="cuda", generator=g)
+    wp = torch.zeros(64, 7, 8, 4, device="cuda", dtype=torch.bfloat16)
+    wp[:, :, :7, :3] = w.permute(0, 2, 3, 1)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, OH, OW, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    xin = _pad_nhwc4(x)
+    _lib.check(_lib.lib().mmdx_op_stem(h.handle, P(xin), B, H, W, P(wp), P(bias), P(out), S()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x, w.float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1.2e-2
+
+
+# ---------------------------------------------------------------------------------------- preprocessing
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 512, 512, 3), (3, 224, 224, 3), (1, 300, 400, 3), (1, 1024, 768, 3),
+                                      (2, 257, 640, 1), (1, 256, 256, 3), (1, 256, 300, 3)])
+def test_resample_u8_bit_exact(h, B, H, W, Cc):
+    rng = np.random.Generator(np.random.PCG64([3, H, W]))
+    a = rng.integers(0, 256, size=(B, H, W, Cc), dtype=np.uint8)
+    d = torch.from_numpy(a).cuda()
+    out = torch.zeros(B, 224, 224, Cc, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().mmdx_op_resample_u8(h.handle, P(d), B, H, W, Cc, P(out), S()))
+    torch.cuda.synchronize()
+    want = np.stack([R.preprocess_u8(a[i]) for i in range(B)])
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 512, 512, 3), (2, 224, 224, 3), (1, 300, 400, 1)])
+def test_preprocess_normalized_bf16(h, B, H, W, Cc):
+    rng = np.random.Generator(np.random.PCG64([4, H, W]))
+    a = rng.integers(0, 256, size=(B, H, W, Cc), dtype=np.uint8)
+    d = torch.from_numpy(a).cuda()
+    hp, wp = C.c_int(), C.c_int()
+    _lib.lib().mmdx_padded_dims(224, 224, C.byref(hp), C.byref(wp))
+    out = torch.zeros(B, hp.value, wp.value, 4, dtype=torch.bfloat16, device="cuda")
+    oh, ow = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().mmdx_op_preprocess(h.handle, P(d), B, H, W, Cc, P(out), C.byref(oh), C.byref(ow), S()))
+    torch.cuda.synchronize()
+    assert (oh.value, ow.value) == (224, 224)
+    want = torch.stack([R.preprocess_f32(a[i]) for i in range(B)]).permute(0, 2, 3, 1)       # fp32 NHWC
+    got = out[:, 3:227, 3:227, :3].float().cpu()
+    assert torch.equal(got, want.to(torch.bfloat16).float())       # exactly the bf16 rounding of the fp32 reference
+    o = out.float()
+    assert float(o[..., 3].abs().max()) == 0 and float(o[:, :3].abs().max()) == 0 and float(o[:, :, :3].abs().max()) == 0
+    assert float(o[:, 227:].abs().max()) == 0 and float(o[:, :, 227:].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------- pooling / norms
+def test_maxpool_avgpool(h):
+    x = bf(torch.randn(3, 30, 34, 64, device="cuda"))
+    out = torch.zeros(3, 15, 17, 64, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_maxpool(h.handle, P(x), 3, 30, 34, 64, P(out), S()))
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out.float(), ref)
+    y = bf(torch.randn(5, 49, 2048, device="cuda"))
+    ob = torch.zeros(5, 2048, device="cuda", dtype=torch.bfloat16)
+    of = torch.zeros(5, 2048, device="cuda")
+    _lib.check(_lib.lib().mmdx_op_avgpool(h.handle, P(y), 5, 49, 2048, P(ob), P(of), S()))
+    torch.cuda.synchronize()
+    ref = y.float().mean(1)
+    assert (of - ref).abs().max() < 1e-5 and rel_err(ob, ref) < 5e-3
+
+
+@pytest.mark.parametrize("rows,N,eps", [(1000, 768, 1e-12), (7, 1024, 1e-5), (64, 256, 1e-12)])
+def test_layernorm(h, rows, N, eps):
+    x = bf(torch.randn(rows, N, device="cuda") * 3 + 0.5)
+    g = torch.rand(N, device="cuda") + 0.5
+    b = torch.randn(N, device="cuda") * 0.1
+    y = torch.zeros_like(x)
+    _lib.check(_lib.lib().mmdx_op_layernorm(h.handle, P(x), rows, N, P(g), P(b), eps, P(y), S()))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (N,), g, b, eps)
+    assert rel_err(y, ref) < 6e-3
+
+
+def test_embed_layernorm(h):
+    T, N = 777, 768
+    word = bf(torch.randn(30522, N, device="cuda") * 0.05)
+    ptab = bf(torch.randn(512, N, device="cuda") * 0.05)
+    ttab = bf(torch.randn(2, N, device="cuda") * 0.05)
+    ids = torch.randint(0, 30522, (T,), device="cuda", dtype=torch.int32)
+    pos = torch.randint(0, 512, (T,), device="cuda", dtype=torch.int32)
+    tt = torch.randint(0, 2, (T,), device="cuda", dtype=torch.int32)
+    g = torch.rand(N, device="cuda") + 0.5
+    b = torch.randn(N, device="cuda") * 0.1
+    y = torch.zeros(T, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_embed_ln(h.handle, P(ids), P(pos), P(tt), T, P(word), P(ptab), P(ttab), P(g), P(b), 1e-12, P(y), S()))
+    torch.cuda.synchronize()
+    ref = F.layer_norm(word[ids.long()].float() + ttab[tt.long()].float() + ptab[pos.long()].float(), (N,), g, b, 1e-12)
+    assert rel_err(y, ref) < 6e-3
+
+
+@pytest.mark.parametrize("lens", [[128, 128, 128], [17, 64, 65, 1, 40], [512, 300], [96] * 4])
+def test_attention_varlen(h, lens):
+    heads, hid = 12, 768
+    T = sum(lens)
+    qkv = bf(torch.randn(T, 3 * hid, device="cuda"))
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    ctx = torch.full((T, hid), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_attention(h.handle, P(qkv), P(cu), len(lens), max(lens), heads, hid, P(ctx), S()))
+    torch.cuda.synchronize()
+    ref = torch.empty(T, hid, device="cuda")
+    o = 0
+    for n in lens:
+        q, k, v = [qkv[o:o + n, i * hid:(i + 1) * hid].float().view(n, heads, 64).transpose(0, 1) for i in range(3)]
+        s = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1)
+        ref[o:o + n] = (s @ v).transpose(0, 1).reshape(n, hid)
+        o += n
+    assert torch.isfinite(ctx.float()).all()
+    assert rel_err(ctx, ref) < 1.5e-2
+
+
+def test_seq_mean_pool_and_head_tail(h):
+    lens = [5, 128, 33]
+    T, hid = sum(lens), 768
+    x = bf(torch.randn(T, hid, device="cuda"))
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    ob = torch.zeros(3, hid, device="cuda", dtype=torch.bfloat16)
+    of = torch.zeros(3, hid, device="cuda")
+    _lib.check(_lib.lib().mmdx_op_seq_mean_pool(h.handle, P(x), P(cu), 3, hid, P(ob), P(of), S()))
+    torch.cuda.synchronize()
+    ref = torch.stack([x[cu[i]:cu[i + 1]].float().mean(0) for i in range(3)])
+    assert (of - ref).abs().max() < 1e-5
+    # head tail
+    B, D, nc = 6, 1024, 13
+    hd = torch.randn(B, D, device="cuda")
+    g = torch.rand(D, device="cuda") + 0.5
+    b = torch.randn(D, device="cuda") * 0.1
+    w = torch.randn(nc, D, device="cuda") * 0.06
+    bb = torch.randn(nc, device="cuda") * 0.3
+    thr = torch.full((nc,), 0.5, device="cuda")
+    zf = torch.zeros(B, D, device="cuda"); lg = torch.zeros(B, nc, device="cuda"); pr = torch.zeros(B, nc, device="cuda")
+    vec = torch.zeros(B, nc, device="cuda", dtype=torch.uint8)
+    _lib.check(_lib.lib().mmdx_op_head_tail(h.handle, P(hd), B, D, P(g), P(b), 1e-5, P(w), P(bb), nc, P(thr), P(zf), P(lg), P(pr), P(vec), S()))
+    torch.cuda.synchronize()
+    z = F.layer_norm(hd, (D,), g, b, 1e-5)
+    l = F.linear(z, w, bb)
+    assert (zf - z).abs().max() < 1e-4 and (lg - l).abs().max() < 1e-4
+    assert (pr - torch.sigmoid(l)).abs().max() < 1e-5
+    assert torch.equal(vec, (pr >= thr).to(torch.uint8))
