@@ -79,6 +79,11 @@ int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int
                       const float* h_thresholds, float* h_logits, float* h_probs, uint8_t* h_vector, void* stream);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t mmdx_launch_count(mmdx_engine* e);
+/* Per-kernel-class device time: between begin and end every launch is bracketed by CUDA events on its
+ * stream.  Classes: 0 preprocess, 1 stem conv, 2 pooling, 3 bottleneck convs, 4 text GEMMs, 5 attention,
+ * 6 layernorm/embedding, 7 head, 8 other.  mmdx_profile_end returns the number of classes (9) on success, 1 on error. */
+int mmdx_profile_begin(mmdx_engine* e);
+int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_class, int n_classes);
 
 /* ---- single-kernel entry points (parity tests call the hot kernels one at a time) ---------- */
 /* out[M,N] = act(A[M,K] * Wt[N,K]^T + bias (+ residual)); bf16 A/Wt/residual, bf16 or fp32 out. */

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mmdx_forward": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_launch_count": [_p],
+    "mmdx_profile_begin": [_p],
+    "mmdx_profile_end": [_p, _p, _p, _i],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mmdx_op_stem": [_p, _p, _i, _i, _i, _p, _p, _p, _p],

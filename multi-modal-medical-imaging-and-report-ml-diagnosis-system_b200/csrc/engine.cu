@@ -159,6 +159,12 @@ struct mmdx_engine {
   EncodeTiledFn encode = nullptr;
   std::mutex mu;
   int64_t launches = 0;
+  // optional per-kernel-class timing (bench.py roofline): CUDA events around every launch
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  int cur_cls = 8;
+  cudaStream_t cur_stream = nullptr;
   std::map<std::string, HostTensor> host;
   bool finalized = false;
   // dims
@@ -178,6 +184,14 @@ struct mmdx_engine {
   int head_cap = 0;
   bf16* feats_bf = nullptr; bf16* pooled_bf = nullptr; bf16* zcat = nullptr; float* fuse_h = nullptr;
   float* thr_default = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------ profiling
+enum { CLS_PRE = 0, CLS_STEM, CLS_POOL, CLS_CONV, CLS_GEMM_TEXT, CLS_ATTN, CLS_LN, CLS_HEAD, CLS_MISC, CLS_COUNT };
+struct ProfScope {       // counts the launch; in profiling mode brackets it with CUDA events on the launch stream
+  mmdx_engine* e; cudaEvent_t a = nullptr, b = nullptr;
+  explicit ProfScope(mmdx_engine* e_);
+  ~ProfScope();
 };
 
 // ------------------------------------------------------------------------------------------ tensor maps
@@ -200,6 +214,18 @@ static int make_tmap(mmdx_engine* e, CUtensorMap* m, const void* base, int rank,
     return fail(buf);
   }
   return 0;
+}
+
+ProfScope::ProfScope(mmdx_engine* e_) : e(e_) {
+  e->launches++;
+  if (!e->profiling) return;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, e->cur_stream);
+}
+ProfScope::~ProfScope() {
+  if (!a) return;
+  cudaEventRecord(b, e->cur_stream);
+  e->prof.push_back({e->cur_cls, a, b});
 }
 
 static int pick_bn(mmdx_engine* e, long long m_tiles, int N, int bn_req) {
@@ -359,7 +385,7 @@ static int launch_inst(const GemmLaunch& g, int grid, cudaStream_t s) {
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   const int grid = g.p.num_tiles < e->num_sms ? g.p.num_tiles : e->num_sms;
-  e->launches++;
+  ProfScope _ps(e);
   if (g.bk == 32) return launch_inst<64, 32, 8>(g, grid, s);
   switch (g.bn) {
     case 256: return launch_inst<256, 64, 4>(g, grid, s);
@@ -643,7 +669,7 @@ static int launch_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int
   dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
   const float3 sc = make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]);
   const float3 sh = make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]);
-  e->launches++;
+  ProfScope _ps(e);
   if (C == 3)
     preprocess_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
                                                g.top, out, hp, wp, 3, 3, sc, sh);
@@ -810,7 +836,7 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
 static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float* g, const float* b, float eps, bf16* y,
                      cudaStream_t s) {
   const int grid = (rows + 7) / 8;
-  e->launches++;
+  ProfScope _ps(e);
   switch (N) {
     case 256: layernorm_kernel<256, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
     case 512: layernorm_kernel<512, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
@@ -825,7 +851,7 @@ static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const in
                         const bf16* ptab, const bf16* ttab, const float* g, const float* b, float eps, bf16* y,
                         cudaStream_t s) {
   const int grid = (rows + 7) / 8;
-  e->launches++;
+  ProfScope _ps(e);
   switch (N) {
     case 256: layernorm_kernel<256, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
     case 512: layernorm_kernel<512, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
@@ -840,7 +866,7 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
                             bf16* ctx, cudaStream_t s) {
   REQUIRE(hidden == heads * 64, "attention head dim must be 64");
   dim3 grid((max_len + ATT_BQ - 1) / ATT_BQ, heads, n_seq);
-  e->launches++;
+  ProfScope _ps(e);
   attention_kernel<<<grid, 128, 0, s>>>(qkv, cu, hidden, ctx, 0.125f * 1.4426950408889634f);
   CK(cudaGetLastError());
   return 0;
@@ -854,7 +880,7 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, long long ld, in
 }
 static int launch_cvt(mmdx_engine* e, const bf16* in, long long ld, int rows, int cols, float* out, cudaStream_t s) {
   const long long n = (long long)rows * cols;
-  e->launches++;
+  ProfScope _ps(e);
   bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, ld, rows, cols, out);
   CK(cudaGetLastError());
   return 0;
@@ -869,26 +895,32 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   ImagePlan* pl;
   TRY(get_image_plan(e, B, H, W, C, &pl));
   PreGeom g{0, 0, pl->off_y, pl->off_x, pl->crop_h, pl->crop_w, pl->has_x, pl->has_y};
+  e->cur_stream = s; e->cur_cls = CLS_PRE;
   if (e->img_last != pl) {   // another geometry used the arena: restore the zero border + zero 4th channel
     CK(cudaMemsetAsync(pl->in_pad, 0, pl->in_pad_bytes, s));
     e->img_last = pl;
   }
   TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->in_pad, pl->hp, pl->wp, s));
+  e->cur_cls = CLS_STEM;
   TRY(launch_gemm(e, pl->convs[0], s));
+  e->cur_cls = CLS_POOL;
   {
     const long long total = (long long)B * pl->ph * pl->pw * 8;
-    e->launches++;
+    ProfScope _ps(e);
     maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pl->stem_out, B, pl->sh, pl->sw, 64, pl->pool_out,
                                                                         pl->ph, pl->pw);
     CK(cudaGetLastError());
   }
+  e->cur_cls = CLS_CONV;
   for (size_t i = 1; i < pl->convs.size(); ++i) TRY(launch_gemm(e, pl->convs[i], s));
+  e->cur_cls = CLS_POOL;
   {
     const int n = B * (e->feat_dim / 8);
-    e->launches++;
+    ProfScope _ps(e);
     avgpool_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->last, B, pl->last_hw, e->feat_dim, e->feats_bf, d_feats);
     CK(cudaGetLastError());
   }
+  e->cur_cls = CLS_HEAD;
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
   TRY(launch_gemm(e, hp->proj_img, s));
@@ -906,20 +938,31 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   TextBufs tb;
   TRY(get_text_plan(e, T, B, &pl, &tb));
   const int H = e->hidden;
+  e->cur_stream = s; e->cur_cls = CLS_LN;
   TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s));
   for (int l = 0; l < e->n_layers; ++l) {
     const BertLayerW& L = e->layers[l];
+    e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 0], s));                                         // QKV
+    e->cur_cls = CLS_ATTN;
     TRY(launch_attention(e, tb.qkv, d_cu, B, max_len, e->cfg.n_heads, H, tb.ctx, s));
+    e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 1], s));                                         // out-proj + residual
+    e->cur_cls = CLS_LN;
     TRY(launch_ln(e, tb.pre, T, H, L.ln1.g, L.ln1.b, 1e-12f, tb.hid2, s));
+    e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 2], s));                                         // FFN1 + GELU
     TRY(launch_gemm(e, pl->gemms[4 * l + 3], s));                                         // FFN2 + residual
+    e->cur_cls = CLS_LN;
     TRY(launch_ln(e, tb.pre, T, H, L.ln2.g, L.ln2.b, 1e-12f, tb.hid, s));
   }
-  e->launches++;
-  seq_mean_pool_kernel<<<B, 128, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
-  CK(cudaGetLastError());
+  e->cur_cls = CLS_POOL;
+  {
+    ProfScope _ps(e);
+    seq_mean_pool_kernel<<<B, 128, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
+    CK(cudaGetLastError());
+  }
+  e->cur_cls = CLS_HEAD;
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
   TRY(launch_gemm(e, hp->proj_txt, s));
@@ -931,10 +974,11 @@ static int head_locked(mmdx_engine* e, int B, const float* d_thr, float* d_z_fus
                        uint8_t* d_vector, cudaStream_t s) {
   REQUIRE(e->finalized && B > 0 && B <= e->head_cap, "head called before the encoders");
   REQUIRE(d_logits && d_probs && d_vector, "null output");
+  e->cur_stream = s; e->cur_cls = CLS_HEAD;
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
   TRY(launch_gemm(e, hp->fuse, s));
-  e->launches++;
+  ProfScope _ps(e);
   head_tail_kernel<<<B, 256, e->d_fuse * sizeof(float), s>>>(e->fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f,
                                                              e->head_w, e->head_b, e->n_cls,
                                                              d_thr ? d_thr : e->thr_default, d_z_fuse, d_logits, d_probs,
@@ -1019,6 +1063,7 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
 extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
                             const void* d_residual, int64_t ldr, void* d_out, int64_t ldc, int M, int N, int K, int act,
                             int out_f32, int bn, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
@@ -1030,6 +1075,7 @@ extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const 
 extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
                             const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride,
                             int act, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
@@ -1040,6 +1086,7 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
 }
 extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
                             const float* d_bias, void* d_out, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
@@ -1050,6 +1097,7 @@ extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int
 }
 extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C,
                                   void* d_out_padded, int* out_h, int* out_w, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
@@ -1066,6 +1114,7 @@ extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B
 }
 extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,
                                    void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
@@ -1074,7 +1123,7 @@ extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int 
   ResampleTable tx, ty;
   TRY(build_tables(e, e->tab_ws, H, W, g, &tx, &ty));
   dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
-  e->launches++;
+  ProfScope _ps(e);
   if (C == 3)
     resample_u8_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
                                                                    g.has_y, g.left, g.top, d_out);
@@ -1087,10 +1136,11 @@ extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int 
   return 0;
 }
 extern "C" int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, int W, int C, void* d_out, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && C % 8 == 0, "maxpool needs C%8==0");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
   const long long total = (long long)B * OH * OW * (C / 8);
-  e->launches++;
+  ProfScope _ps(e);
   maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       static_cast<const bf16*>(d_in), B, H, W, C, static_cast<bf16*>(d_out), OH, OW);
   CK(cudaGetLastError());
@@ -1098,9 +1148,10 @@ extern "C" int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, i
 }
 extern "C" int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, int C, void* d_out_bf16,
                                float* d_out_f32, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && C % 8 == 0, "avgpool needs C%8==0");
   const int n = B * (C / 8);
-  e->launches++;
+  ProfScope _ps(e);
   avgpool_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_in), B, HW, C,
                                                                     static_cast<bf16*>(d_out_bf16), d_out_f32);
   CK(cudaGetLastError());
@@ -1108,6 +1159,7 @@ extern "C" int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, 
 }
 extern "C" int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int N, const float* d_gamma,
                                  const float* d_beta, float eps, void* d_y, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   return launch_ln(e, static_cast<const bf16*>(d_x), rows, N, d_gamma, d_beta, eps, static_cast<bf16*>(d_y),
                    (cudaStream_t)stream);
@@ -1115,20 +1167,23 @@ extern "C" int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int 
 extern "C" int mmdx_op_embed_ln(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt, int rows,
                                 const void* d_word, const void* d_ptab, const void* d_ttab, const float* d_gamma,
                                 const float* d_beta, float eps, void* d_y, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   return launch_embed(e, d_ids, d_pos, d_tt, rows, 768, static_cast<const bf16*>(d_word), static_cast<const bf16*>(d_ptab),
                       static_cast<const bf16*>(d_ttab), d_gamma, d_beta, eps, static_cast<bf16*>(d_y), (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu, int n_seq, int max_len,
                                  int n_heads, int hidden, void* d_ctx, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
   return launch_attention(e, static_cast<const bf16*>(d_qkv), d_cu, n_seq, max_len, n_heads, hidden,
                           static_cast<bf16*>(d_ctx), (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int32_t* d_cu, int n_seq, int hidden,
                                      void* d_out_bf16, float* d_out_f32, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && hidden % 8 == 0, "hidden % 8");
-  e->launches++;
+  ProfScope _ps(e);
   seq_mean_pool_kernel<<<n_seq, 128, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_h), d_cu, hidden,
                                                                static_cast<bf16*>(d_out_bf16), hidden, d_out_f32);
   CK(cudaGetLastError());
@@ -1138,10 +1193,38 @@ extern "C" int mmdx_op_head_tail(mmdx_engine* e, const float* d_hidden, int B, i
                                  const float* d_ln_b, float eps, const float* d_w, const float* d_b, int n_cls,
                                  const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs, uint8_t* d_vector,
                                  void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && D <= 8192, "head width");
-  e->launches++;
+  ProfScope _ps(e);
   head_tail_kernel<<<B, 256, D * sizeof(float), (cudaStream_t)stream>>>(d_hidden, D, d_ln_g, d_ln_b, eps, d_w, d_b, n_cls,
                                                                         d_thr, d_z_fuse, d_logits, d_probs, d_vector);
   CK(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ profiling API
+extern "C" int mmdx_profile_begin(mmdx_engine* e) {
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->profiling = true;
+  return 0;
+}
+extern "C" int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_class, int n_classes) {
+  REQUIRE(e && ms_by_class && launches_by_class && n_classes >= CLS_COUNT, "bad argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0.f; launches_by_class[i] = 0; }
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_class[r.cls] += ms;
+    launches_by_class[r.cls] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  e->prof.clear();
+  e->profiling = false;
+  return CLS_COUNT;
 }
