@@ -238,9 +238,32 @@ static int pick_bn(mmdx_engine* e, long long m_tiles, int N, int bn_req) {
   return 0;
 }
 
-static void fill_epilogue(GemmParams& p, const float* bias, const bf16* residual, long long ldr, void* out,
-                          long long ldc, int act, int out_f32) {
+// Epilogue wiring.  Must be called after build_gemm/build_conv/build_stem (needs the tile geometry).
+// bf16 outputs with 16-byte-aligned pitches go through the TMA-staged epilogue; fp32 outputs use direct stores.
+static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const bf16* residual, long long ldr, void* out,
+                         long long ldc, int act, int out_f32) {
+  GemmParams& p = g.p;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
+  const bool aligned = (ldc % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                       (!residual || ((ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(residual) % 16 == 0)));
+  p.epi_mode = (!out_f32 && aligned) ? EPI_TMA : EPI_DIRECT;
+  p.c_box_bytes = p.Wb * p.Hb * p.Nb * kEpiCW * 2;
+  if (p.epi_mode == EPI_TMA) {
+    const uint64_t N = (uint64_t)p.n_tiles * g.bn;
+    const uint64_t dims[4] = {N, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)p.NB};
+    const uint32_t box[4] = {(uint32_t)kEpiCW, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    const uint64_t cs[3] = {(uint64_t)ldc * 2, (uint64_t)p.OW * ldc * 2, (uint64_t)p.OH * p.OW * ldc * 2};
+    TRY(make_tmap(e, &p.tmC, out, 4, dims, cs, box, 64));
+    if (residual) {
+      const uint64_t rs[3] = {(uint64_t)ldr * 2, (uint64_t)p.OW * ldr * 2, (uint64_t)p.OH * p.OW * ldr * 2};
+      TRY(make_tmap(e, &p.tmR, residual, 4, dims, rs, box, 64));
+    } else {
+      p.tmR = p.tmC;
+    }
+  } else {
+    p.tmC = p.tmB; p.tmR = p.tmB;     // valid descriptors, never used
+  }
+  return 0;
 }
 
 // C[M,N] = A[M,K] * W[N,K]^T
@@ -378,7 +401,7 @@ static int launch_inst(const GemmLaunch& g, int grid, cudaStream_t s) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BK, ST>::TOTAL));
     attr_set = true;
   }
-  kfn<<<grid, 192, GemmSmem<BN, BK, ST>::TOTAL, s>>>(g.p);
+  kfn<<<grid, kGemmThreads, GemmSmem<BN, BK, ST>::TOTAL, s>>>(g.p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -717,7 +740,7 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   pl->convs.clear();
   GemmLaunch gl;
   TRY(build_stem(e, gl, pl->in_pad, B, IH, IW, e->stem.w));
-  fill_epilogue(gl.p, e->stem.bias, nullptr, 0, pl->stem_out, 64, ACT_RELU, 0);
+  TRY(fill_epilogue(e, gl, e->stem.bias, nullptr, 0, pl->stem_out, 64, ACT_RELU, 0));
   pl->convs.push_back(gl);
   pl->pool_out = bufs[0];
   bf16* x = bufs[0];
@@ -730,20 +753,20 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
     const int s = bk.c2.stride;
     const int oh = (h - 1) / s + 1, ow = (w - 1) / s + 1;
     TRY(build_conv(e, gl, x, B, h, w, bk.c1.cin, bk.c1.w, bk.c1.cout, 1, 1));
-    fill_epilogue(gl.p, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0);
+    TRY(fill_epilogue(e, gl, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0));
     pl->convs.push_back(gl);
     TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
-    fill_epilogue(gl.p, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0);
+    TRY(fill_epilogue(e, gl, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0));
     pl->convs.push_back(gl);
     const bf16* idt = x;
     if (bk.has_ds) {
       TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
-      fill_epilogue(gl.p, bk.ds.bias, nullptr, 0, ds, bk.ds.cout, ACT_NONE, 0);
+      TRY(fill_epilogue(e, gl, bk.ds.bias, nullptr, 0, ds, bk.ds.cout, ACT_NONE, 0));
       pl->convs.push_back(gl);
       idt = ds;
     }
     TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
-    fill_epilogue(gl.p, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0);
+    TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
     pl->convs.push_back(gl);
     bf16* t = x; x = y; y = t;
     h = oh; w = ow;
@@ -777,11 +800,11 @@ static int get_head_plan(mmdx_engine* e, int B, HeadPlan** out) {
   pl->B = B;
   const int dz = e->d_img + e->d_txt;
   TRY(build_gemm(e, pl->proj_img, e->feats_bf, e->feat_dim, e->proj_img.w, B, e->d_img, e->feat_dim, 0));
-  fill_epilogue(pl->proj_img.p, e->proj_img.bias, nullptr, 0, e->zcat, dz, ACT_NONE, 0);
+  TRY(fill_epilogue(e, pl->proj_img, e->proj_img.bias, nullptr, 0, e->zcat, dz, ACT_NONE, 0));
   TRY(build_gemm(e, pl->proj_txt, e->pooled_bf, e->hidden, e->proj_txt.w, B, e->d_txt, e->hidden, 0));
-  fill_epilogue(pl->proj_txt.p, e->proj_txt.bias, nullptr, 0, e->zcat + e->d_img, dz, ACT_NONE, 0);
+  TRY(fill_epilogue(e, pl->proj_txt, e->proj_txt.bias, nullptr, 0, e->zcat + e->d_img, dz, ACT_NONE, 0));
   TRY(build_gemm(e, pl->fuse, e->zcat, dz, e->fuse.w, B, e->d_fuse, dz, 0));
-  fill_epilogue(pl->fuse.p, e->fuse.bias, nullptr, 0, e->fuse_h, e->d_fuse, ACT_GELU, 1);
+  TRY(fill_epilogue(e, pl->fuse, e->fuse.bias, nullptr, 0, e->fuse_h, e->d_fuse, ACT_GELU, 1));
   *out = pl.get();
   e->head_plans[B] = std::move(pl);
   return 0;
@@ -815,16 +838,16 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
     const BertLayerW& L = e->layers[l];
     GemmLaunch g;
     TRY(build_gemm(e, g, tb->hid, H, L.qkv.w, T, 3 * H, H, 0));
-    fill_epilogue(g.p, L.qkv.bias, nullptr, 0, tb->qkv, 3 * H, ACT_NONE, 0);
+    TRY(fill_epilogue(e, g, L.qkv.bias, nullptr, 0, tb->qkv, 3 * H, ACT_NONE, 0));
     pl->gemms.push_back(g);
     TRY(build_gemm(e, g, tb->ctx, H, L.ao.w, T, H, H, 0));
-    fill_epilogue(g.p, L.ao.bias, tb->hid, H, tb->pre, H, ACT_NONE, 0);       // + residual (pre-LN)
+    TRY(fill_epilogue(e, g, L.ao.bias, tb->hid, H, tb->pre, H, ACT_NONE, 0));      // + residual (pre-LN)
     pl->gemms.push_back(g);
     TRY(build_gemm(e, g, tb->hid2, H, L.ff1.w, T, e->ffn, H, 0));
-    fill_epilogue(g.p, L.ff1.bias, nullptr, 0, tb->ffn, e->ffn, ACT_GELU, 0);
+    TRY(fill_epilogue(e, g, L.ff1.bias, nullptr, 0, tb->ffn, e->ffn, ACT_GELU, 0));
     pl->gemms.push_back(g);
     TRY(build_gemm(e, g, tb->ffn, e->ffn, L.ff2.w, T, H, e->ffn, 0));
-    fill_epilogue(g.p, L.ff2.bias, tb->hid2, H, tb->pre, H, ACT_NONE, 0);     // + residual (pre-LN)
+    TRY(fill_epilogue(e, g, L.ff2.bias, tb->hid2, H, tb->pre, H, ACT_NONE, 0));    // + residual (pre-LN)
     pl->gemms.push_back(g);
   }
   *out = pl.get();
@@ -1069,7 +1092,7 @@ extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const 
   CK(cudaSetDevice(e->cfg.device));
   GemmLaunch g;
   TRY(build_gemm(e, g, static_cast<const bf16*>(d_a), lda, static_cast<const bf16*>(d_w), M, N, K, bn));
-  fill_epilogue(g.p, d_bias, static_cast<const bf16*>(d_residual), ldr, d_out, ldc, act, out_f32);
+  TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), ldr, d_out, ldc, act, out_f32));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
@@ -1081,7 +1104,7 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
   CK(cudaSetDevice(e->cfg.device));
   GemmLaunch g;
   TRY(build_conv(e, g, static_cast<const bf16*>(d_in), NB, H, W, Cin, static_cast<const bf16*>(d_w), Cout, k, stride));
-  fill_epilogue(g.p, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0);
+  TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
@@ -1092,7 +1115,7 @@ extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int
   CK(cudaSetDevice(e->cfg.device));
   GemmLaunch g;
   TRY(build_stem(e, g, static_cast<const bf16*>(d_in_padded), NB, H, W, static_cast<const bf16*>(d_w)));
-  fill_epilogue(g.p, d_bias, nullptr, 0, d_out, 64, ACT_RELU, 0);
+  TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, 64, ACT_RELU, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C,

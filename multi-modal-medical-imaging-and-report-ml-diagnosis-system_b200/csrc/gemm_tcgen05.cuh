@@ -8,10 +8,16 @@
 //     (8 pixels x 4 channels = 32 contiguous bf16), fetched through a tensor map whose
 //     W dimension advances by 2 pixels (16 B) - overlapping windows, no im2col buffer.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/act/residual -> global).
+// Roles (384 threads): warp 0 = TMA producer (A/B ring), warp 1 = TMEM allocator + single-thread MMA
+// issuer, warp 2 = residual-tile TMA loader, warps 4..11 = epilogue in two groups of four
+// (group g owns the 32-column chunks with index = g mod 2; each warp reads its TMEM lane quarter).
+// Epilogue data path (EPI_TMA): TMEM -> registers (+bias, +residual read from the swizzled staging
+// buffer the loader filled by TMA, activation) -> bf16 -> same staging buffer -> TMA store.  Both
+// global transfers are full-line bulk copies; the output box is the same (Wb x Hb x Nb) spatial tile
+// as the A operand, so image borders and ragged M are clipped by the TMA unit.
 // Pipelines: smem ring full/empty (TMA <-> MMA), double-buffered TMEM accumulator full/empty
-// (MMA <-> epilogue), static persistent tile schedule (tile = blockIdx.x + i*gridDim.x).
+// (MMA <-> epilogue), staging ring rfull/rempty (loader <-> epilogue/store), static persistent
+// tile schedule (tile = blockIdx.x + i*gridDim.x).
 #pragma once
 #include "ptx.cuh"
 
@@ -19,20 +25,29 @@ namespace mmdx {
 
 constexpr int kMaxTaps = 12;
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum : int { EPI_DIRECT = 0, EPI_TMA = 1 };
+constexpr int kEpiCW = 32;                    // epilogue chunk width (columns): 64-byte bf16 rows, SWIZZLE_64B
+constexpr int kEpiStages = 4;                 // staging buffers (2 per epilogue group)
+constexpr int kEpiBufBytes = 128 * kEpiCW * 2;
+constexpr int kGemmThreads = 384;
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmC;    // output  [.., N] bf16, box (32, Wb, Hb, Nb), SWIZZLE_64B   (EPI_TMA)
+  CUtensorMap tmR;    // residual, same geometry                                  (EPI_TMA, optional)
   int num_k_blocks;   // taps * kb_per_tap
   int kb_per_tap;     // channel chunks per filter tap (K/BK for a plain GEMM)
   int a_box_bytes;    // bytes one A box load lands (Wb*Hb*Nb*BK*2)
+  int c_box_bytes;    // bytes one residual box load lands (Wb*Hb*Nb*32*2)
   int num_tiles;      // m_tiles * n_tiles
   int n_tiles;
   int tiles_w, tiles_h;        // spatial tile grid (tiles over batch follow)
   int Wb, Hb, Nb;              // tile = Wb x Hb pixels x Nb images (<=128 rows)
   int OW, OH, NB;              // valid output extents (plain GEMM: OW=M, OH=NB=1)
   int act;                     // ACT_*
-  int out_f32;                 // 0: bf16 output, 1: fp32 output
+  int out_f32;                 // 0: bf16 output, 1: fp32 output (EPI_DIRECT only)
+  int epi_mode;                // EPI_*
   long long ldc, ldr;          // output / residual row pitch in elements
   const float* bias;           // [N] or null
   const __nv_bfloat16* residual;   // [M, ldr] or null
@@ -45,40 +60,71 @@ struct GemmSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = kEpiStages * kEpiBufBytes;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int TOTAL = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+  static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
 };
 
+struct TileCoord { int n_t, w0, h0, n0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.n_t = tile % p.n_tiles;
+  const int m_t = tile / p.n_tiles;
+  const int tiles_hw = p.tiles_w * p.tiles_h;
+  const int tn = m_t / tiles_hw;
+  const int rem = m_t - tn * tiles_hw;
+  const int th = rem / p.tiles_w;
+  const int tw = rem - th * p.tiles_w;
+  t.w0 = tw * p.Wb; t.h0 = th * p.Hb; t.n0 = tn * p.Nb;
+  return t;
+}
+
 template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using L = GemmSmem<BN, BK, STAGES>;
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
   constexpr uint32_t IDESC = make_idesc_bf16(128, BN);
   constexpr uint32_t TMEM_COLS = 2 * BN;      // double-buffered fp32 accumulator
-  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  constexpr int NC = BN / kEpiCW;             // epilogue chunks per tile (even)
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert(BK == 64 || BK == 32, "BK");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint8_t* stg = smem + L::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + L::STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + kEpiStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kEpiStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool has_res = p.residual != nullptr;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&p.tmA[i]);
     prefetch_tensormap(&p.tmB);
+    if (p.epi_mode == EPI_TMA) {
+      prefetch_tensormap(&p.tmC);
+      if (has_res) prefetch_tensormap(&p.tmR);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    for (int s = 0; s < kEpiStages; ++s) {
+      mbar_init(&rfull_bar[s], 1);
+      mbar_init(&rempty_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -91,30 +137,22 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_hw = p.tiles_w * p.tiles_h;
-
   if (warp == 0) {
     if (lane == 0) {
-      // ================= TMA producer =================
+      // ================= TMA producer: A/B ring =================
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_t = tile % p.n_tiles;
-        const int m_t = tile / p.n_tiles;
-        const int tn = m_t / tiles_hw;
-        const int rem = m_t - tn * tiles_hw;
-        const int th = rem / p.tiles_w;
-        const int tw = rem - th * p.tiles_w;
-        const int w0 = tw * p.Wb, h0 = th * p.Hb, n0 = tn * p.Nb;
+        const TileCoord t = decode_tile(p, tile);
         int tap = 0, cc = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes + L::B_BYTES));
-          tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[stage], cc * BK, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
-                      n0);
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, n_t * BN);
+          tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[stage], cc * BK, t.w0 + p.tap_dw[tap],
+                      t.h0 + p.tap_dh[tap], t.n0);
+          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, t.n_t * BN);
           if (++cc == p.kb_per_tap) { cc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -148,42 +186,58 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
         }
       }
     }
-  } else {
-    // ================= epilogue warps 2..5 =================
+  } else if (warp == 2) {
+    if (lane == 0 && p.epi_mode == EPI_TMA) {
+      // ================= staging-buffer producer: residual tiles by TMA (or just grants the buffer) =================
+      int kc = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int c = 0; c < NC; ++c, ++kc) {
+          const int s = kc % kEpiStages;
+          const uint32_t ph = (kc / kEpiStages) & 1;
+          mbar_wait(&rempty_bar[s], ph ^ 1);          // previous TMA store out of this buffer has read it
+          if (has_res) {
+            mbar_arrive_expect_tx(&rfull_bar[s], static_cast<uint32_t>(p.c_box_bytes));
+            tma_load_4d(stg + s * kEpiBufBytes, &p.tmR, &rfull_bar[s], t.n_t * BN + c * kEpiCW, t.w0, t.h0, t.n0);
+          } else {
+            mbar_arrive(&rfull_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue warps 4..11 =================
+    const int e = warp - 4;
+    const int g = e >> 2;                   // group: chunks c with (c & 1) == g
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // row inside the 128-row tile
-    const int rows_valid = p.Wb * p.Hb * p.Nb;
-    const int wi = r % p.Wb;
-    const int hi = (r / p.Wb) % p.Hb;
-    const int ni = r / (p.Wb * p.Hb);
+    const bool issuer = (e & 3) == 0 && lane == 0;
+    int prev_s = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int n_t = tile % p.n_tiles;
-      const int m_t = tile / p.n_tiles;
-      const int tn = m_t / tiles_hw;
-      const int rem = m_t - tn * tiles_hw;
-      const int th = rem / p.tiles_w;
-      const int tw = rem - th * p.tiles_w;
-      const int w = tw * p.Wb + wi, h = th * p.Hb + hi, n = tn * p.Nb + ni;
-      const bool valid = (r < rows_valid) && (w < p.OW) && (h < p.OH) && (n < p.NB);
-      const long long orow = (static_cast<long long>(n) * p.OH + h) * p.OW + w;
-
+      const TileCoord t = decode_tile(p, tile);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+
+      if (p.epi_mode == EPI_TMA) {
+        uint8_t* my_row_base;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + c * 32, v);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {             // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
-        if (valid) {
-          const int col0 = n_t * BN + c * 32;
+        for (int c = g; c < NC; c += 2) {
+          const int kc = it * NC + c;
+          const int s = kc % kEpiStages;
+          const uint32_t ph = (kc / kEpiStages) & 1;
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + c * kEpiCW, v);
+          tmem_ld_wait();
+          if (c == NC - 2 + g) {              // this warp's last read of the accumulator: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          const int col0 = t.n_t * BN + c * kEpiCW;
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
@@ -195,11 +249,13 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
               x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
             }
           }
-          if (p.residual != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col0);
+          mbar_wait(&rfull_bar[s], ph);       // staging buffer granted (and residual landed)
+          my_row_base = stg + s * kEpiBufBytes + r * 64;
+          const int sw = (r >> 1) & 3;        // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(r4 + j);
+              const uint4 u = *reinterpret_cast<const uint4*>(my_row_base + ((j ^ sw) << 4));
               float2 f;
               f = unpack_bf16(u.x); x[8 * j + 0] += f.x; x[8 * j + 1] += f.y;
               f = unpack_bf16(u.y); x[8 * j + 2] += f.x; x[8 * j + 3] += f.y;
@@ -214,20 +270,90 @@ __global__ void __launch_bounds__(192, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
           }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldc + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col0);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_row_base + ((j ^ sw) << 4)) =
+                make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                           pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+          fence_proxy_async();                // make the generic-proxy smem writes visible to the TMA unit
+          named_bar_sync(1 + g, 128);
+          if (issuer) {
+            tma_store_4d(&p.tmC, stg + s * kEpiBufBytes, col0, t.w0, t.h0, t.n0);
+            tma_store_commit();
+            if (prev_s >= 0) {                // the group's previous store has finished reading its buffer
+              tma_store_wait_read<1>();
+              mbar_arrive(&rempty_bar[prev_s]);
+            }
+            prev_s = s;
+          }
+        }
+      } else {
+        // ---------- EPI_DIRECT: per-thread row-contiguous global I/O (fp32 outputs, unaligned pitches) ----------
+        const int rows_valid = p.Wb * p.Hb * p.Nb;
+        const int wi = r % p.Wb;
+        const int hi = (r / p.Wb) % p.Hb;
+        const int ni = r / (p.Wb * p.Hb);
+        const int w = t.w0 + wi, h = t.h0 + hi, n = t.n0 + ni;
+        const bool valid = (r < rows_valid) && (w < p.OW) && (h < p.OH) && (n < p.NB);
+        const long long orow = (static_cast<long long>(n) * p.OH + h) * p.OW + w;
+#pragma unroll 1
+        for (int c = g; c < NC; c += 2) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + c * kEpiCW, v);
+          tmem_ld_wait();
+          if (c == NC - 2 + g) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          if (valid) {
+            const int col0 = t.n_t * BN + c * kEpiCW;
+            float x[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o4[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
-                                 pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+              }
+            }
+            if (has_res) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = __ldg(r4 + j);
+                float2 f;
+                f = unpack_bf16(u.x); x[8 * j + 0] += f.x; x[8 * j + 1] += f.y;
+                f = unpack_bf16(u.y); x[8 * j + 2] += f.x; x[8 * j + 3] += f.y;
+                f = unpack_bf16(u.z); x[8 * j + 4] += f.x; x[8 * j + 5] += f.y;
+                f = unpack_bf16(u.w); x[8 * j + 6] += f.x; x[8 * j + 7] += f.y;
+              }
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+            } else if (p.act == ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            }
+            if (p.out_f32) {
+              float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+              uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
+                                   pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
+            }
           }
         }
       }
     }
+    if (issuer && p.epi_mode == EPI_TMA) tma_store_wait_all<0>();   // all output bytes are in global memory
   }
 
   tc_fence_before();
