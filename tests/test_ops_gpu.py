@@ -73,6 +73,23 @@ def test_gemm_tcgen05(h, M, N, K, act, res, f32, bn):
     assert rel_err(out, ref) < (2e-5 if f32 else 1e-2) + 2e-3
 
 
+def test_gelu_epilogue_matches_erf_form(h):
+    """The epilogue's branch-free GELU against torch's erf GELU, isolated with an identity weight
+    (fp32 output, so only the activation's own error is seen): |err| < 1e-6 absolute."""
+    M, K = 4096, 64
+    x = bf(torch.linspace(-9, 9, M * K, device="cuda").view(M, K))
+    w = bf(torch.eye(K, device="cuda"))
+    out = torch.empty(M, K, device="cuda", dtype=torch.float32)
+    _lib.check(_lib.lib().mmdx_op_gemm(h.handle, P(x), K, P(w), None, None, 0, P(out), K, M, K, K, 2, 1, 0, S()))
+    torch.cuda.synchronize()
+    ref = F.gelu(x.double()).float()
+    assert float((out - ref).abs().max()) < 1e-6
+    ob = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)      # TMA epilogue path, bf16 output
+    _lib.check(_lib.lib().mmdx_op_gemm(h.handle, P(x), K, P(w), None, None, 0, P(ob), K, M, K, K, 2, 0, 0, S()))
+    torch.cuda.synchronize()
+    assert torch.equal(ob, out.to(torch.bfloat16))
+
+
 def test_gemm_strided_output_and_no_bias(h):
     M, N, K = 200, 512, 768
     a = bf(torch.randn(M, K, device="cuda"))
