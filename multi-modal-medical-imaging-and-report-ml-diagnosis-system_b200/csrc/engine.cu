@@ -174,6 +174,8 @@ struct mmdx_engine {
   ConvW stem; std::vector<Bottleneck> blocks;
   bf16 *word = nullptr, *ptab = nullptr, *ttab = nullptr; LnW emb_ln; std::vector<BertLayerW> layers;
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
+  DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
+  CUtensorMap tm_ident{};
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
   std::map<std::string, std::unique_ptr<ImagePlan>> img_plans;
@@ -244,24 +246,25 @@ static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const
                          long long ldc, int act, int out_f32) {
   GemmParams& p = g.p;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.out = out; p.ldc = ldc; p.act = act; p.out_f32 = out_f32;
-  const bool aligned = (ldc % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
-                       (!residual || ((ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(residual) % 16 == 0)));
-  p.epi_mode = (!out_f32 && aligned) ? EPI_TMA : EPI_DIRECT;
-  p.c_box_bytes = p.Wb * p.Hb * p.Nb * kEpiCW * 2;
+  const bool out_aligned = (ldc % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  const bool res_aligned = residual && (ldr % 8 == 0) && (reinterpret_cast<uintptr_t>(residual) % 16 == 0);
+  p.epi_mode = (!out_f32 && out_aligned) ? EPI_TMA : EPI_DIRECT;
+  const uint64_t N = (uint64_t)p.n_tiles * g.bn;
+  const uint64_t dims[4] = {N, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)p.NB};
+  p.tmC = p.tmB; p.tmR = p.tmB; p.tmI = e->tm_ident;     // always valid descriptors
+  p.res_blocks = 0;
   if (p.epi_mode == EPI_TMA) {
-    const uint64_t N = (uint64_t)p.n_tiles * g.bn;
-    const uint64_t dims[4] = {N, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)p.NB};
     const uint32_t box[4] = {(uint32_t)kEpiCW, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
     const uint64_t cs[3] = {(uint64_t)ldc * 2, (uint64_t)p.OW * ldc * 2, (uint64_t)p.OH * p.OW * ldc * 2};
     TRY(make_tmap(e, &p.tmC, out, 4, dims, cs, box, 64));
-    if (residual) {
-      const uint64_t rs[3] = {(uint64_t)ldr * 2, (uint64_t)p.OW * ldr * 2, (uint64_t)p.OH * p.OW * ldr * 2};
-      TRY(make_tmap(e, &p.tmR, residual, 4, dims, rs, box, 64));
-    } else {
-      p.tmR = p.tmC;
-    }
-  } else {
-    p.tmC = p.tmB; p.tmR = p.tmB;     // valid descriptors, never used
+  }
+  if (res_aligned && g.bk == 64) {      // residual added by the tensor core: D += R * I (see gemm_tcgen05.cuh)
+    const uint32_t rbox[4] = {64, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    const uint64_t rs[3] = {(uint64_t)ldr * 2, (uint64_t)p.OW * ldr * 2, (uint64_t)p.OH * p.OW * ldr * 2};
+    TRY(make_tmap(e, &p.tmR, residual, 4, dims, rs, rbox, 128));
+    p.res_blocks = g.bn / 64;
+  } else if (residual) {
+    REQUIRE(p.epi_mode == EPI_DIRECT, "unaligned residual needs the direct epilogue (fp32 or unaligned output)");
   }
   return 0;
 }
@@ -440,6 +443,16 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
   e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  {
+    std::vector<bf16> id(64 * 64, __float2bfloat16(0.f));
+    for (int i = 0; i < 64; ++i) id[i * 64 + i] = __float2bfloat16(1.f);
+    TRY(e->ident.ensure(id.size() * 2));
+    CK(cudaMemcpy(e->ident.p, id.data(), id.size() * 2, cudaMemcpyHostToDevice));
+    const uint64_t d[2] = {64, 64};
+    const uint64_t st[1] = {128};
+    const uint32_t bx[2] = {64, 64};
+    TRY(make_tmap(e.get(), &e->tm_ident, e->ident.p, 2, d, st, bx, 128));
+  }
   *out = e.release();
   return 0;
 }

@@ -9,15 +9,19 @@
 //     W dimension advances by 2 pixels (16 B) - overlapping windows, no im2col buffer.
 //
 // Roles (384 threads): warp 0 = TMA producer (A/B ring), warp 1 = TMEM allocator + single-thread MMA
-// issuer, warp 2 = residual-tile TMA loader, warps 4..11 = epilogue in two groups of four
-// (group g owns the 32-column chunks with index = g mod 2; each warp reads its TMEM lane quarter).
-// Epilogue data path (EPI_TMA): TMEM -> registers (+bias, +residual read from the swizzled staging
-// buffer the loader filled by TMA, activation) -> bf16 -> same staging buffer -> TMA store.  Both
-// global transfers are full-line bulk copies; the output box is the same (Wb x Hb x Nb) spatial tile
-// as the A operand, so image borders and ragged M are clipped by the TMA unit.
+// issuer, warps 4..11 = epilogue in two groups of four (group g owns the 32-column chunks with
+// index = g mod 2; each warp reads its TMEM lane quarter).
+// Residual add (bottleneck shortcut, BERT skip connections) rides the MMA pipeline: after the main K loop
+// the producer streams the residual tile through the same smem ring as extra A blocks (128 rows x 64
+// columns) next to a 64x64 identity B block, and the issuer accumulates D[:, 64j:64j+64] += R_j * I
+// with N=64 MMAs.  bf16 x 1.0 is exact in the fp32 accumulator, the loads are prefetched as deep as the
+// ring, and the epilogue never touches the residual.
+// Epilogue data path (EPI_TMA): TMEM -> registers (+bias, activation) -> bf16 -> swizzled staging buffer
+// -> TMA store.  The output box is the same (Wb x Hb x Nb) spatial tile as the A operand, so image
+// borders and ragged M are clipped by the TMA unit.
 // Pipelines: smem ring full/empty (TMA <-> MMA), double-buffered TMEM accumulator full/empty
-// (MMA <-> epilogue), staging ring rfull/rempty (loader <-> epilogue/store), static persistent
-// tile schedule (tile = blockIdx.x + i*gridDim.x).
+// (MMA <-> epilogue), one staging buffer per epilogue group guarded by bulk-group waits + named
+// barriers, static persistent tile schedule (tile = blockIdx.x + i*gridDim.x).
 #pragma once
 #include "ptx.cuh"
 
@@ -27,7 +31,8 @@ constexpr int kMaxTaps = 12;
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 enum : int { EPI_DIRECT = 0, EPI_TMA = 1 };
 constexpr int kEpiCW = 32;                    // epilogue chunk width (columns): 64-byte bf16 rows, SWIZZLE_64B
-constexpr int kEpiStages = 4;                 // staging buffers (2 per epilogue group)
+constexpr int kEpiStages = 2;                 // staging buffers (one per epilogue group)
+constexpr int kIdentBytes = 64 * 64 * 2;      // resident 64x64 identity (B operand of the residual MMAs)
 constexpr int kEpiBufBytes = 128 * kEpiCW * 2;
 constexpr int kGemmThreads = 384;
 
@@ -35,11 +40,12 @@ struct alignas(64) GemmParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
   CUtensorMap tmC;    // output  [.., N] bf16, box (32, Wb, Hb, Nb), SWIZZLE_64B   (EPI_TMA)
-  CUtensorMap tmR;    // residual, same geometry                                  (EPI_TMA, optional)
+  CUtensorMap tmR;    // residual as an A operand: box (64, Wb, Hb, Nb), SWIZZLE_128B (res_blocks > 0)
+  CUtensorMap tmI;    // 64x64 bf16 identity, box (64, 64), SWIZZLE_128B
   int num_k_blocks;   // taps * kb_per_tap
   int kb_per_tap;     // channel chunks per filter tap (K/BK for a plain GEMM)
   int a_box_bytes;    // bytes one A box load lands (Wb*Hb*Nb*BK*2)
-  int c_box_bytes;    // bytes one residual box load lands (Wb*Hb*Nb*32*2)
+  int res_blocks;     // residual k-blocks per tile (BN/64) when the residual is added by the tensor core, else 0
   int num_tiles;      // m_tiles * n_tiles
   int n_tiles;
   int tiles_w, tiles_h;        // spatial tile grid (tiles over batch follow)
@@ -61,7 +67,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = kEpiStages * kEpiBufBytes;
+  static constexpr int STG_BYTES = kEpiStages * kEpiBufBytes + kIdentBytes;
   static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
@@ -99,21 +105,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* rfull_bar = tempty_bar + 2;
-  uint64_t* rempty_bar = rfull_bar + kEpiStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kEpiStages);
+  uint64_t* ident_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
+  uint8_t* ident = stg + kEpiStages * kEpiBufBytes;      // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool has_res = p.residual != nullptr;
+  const bool res_direct = p.residual != nullptr && p.res_blocks == 0;   // EPI_DIRECT fallback only
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&p.tmA[i]);
     prefetch_tensormap(&p.tmB);
-    if (p.epi_mode == EPI_TMA) {
-      prefetch_tensormap(&p.tmC);
-      if (has_res) prefetch_tensormap(&p.tmR);
-    }
+    if (p.epi_mode == EPI_TMA) prefetch_tensormap(&p.tmC);
+    if (p.res_blocks > 0) { prefetch_tensormap(&p.tmR); prefetch_tensormap(&p.tmI); }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -122,10 +126,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8);
     }
-    for (int s = 0; s < kEpiStages; ++s) {
-      mbar_init(&rfull_bar[s], 1);
-      mbar_init(&rempty_bar[s], 1);
-    }
+    mbar_init(ident_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -142,6 +143,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       // ================= TMA producer: A/B ring =================
       int stage = 0;
       uint32_t phase = 0;
+      if (BK == 64 && p.res_blocks > 0) {               // identity block: loaded once, stays resident
+        mbar_arrive_expect_tx(ident_bar, kIdentBytes);
+        tma_load_2d(ident, &p.tmI, ident_bar, 0, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         int tap = 0, cc = 0;
@@ -156,6 +161,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (++cc == p.kb_per_tap) { cc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if constexpr (BK == 64) {
+          for (int j = 0; j < p.res_blocks; ++j) {      // residual tile as extra A blocks + identity B block
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes));
+            tma_load_4d(sa, &p.tmR, &full_bar[stage], t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -164,6 +178,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
+      const uint32_t sid = smem_u32(ident);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -181,26 +197,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                       (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs finish
-          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (kb == p.num_k_blocks - 1 && p.res_blocks == 0) umma_commit(&tfull_bar[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-      }
-    }
-  } else if (warp == 2) {
-    if (lane == 0 && p.epi_mode == EPI_TMA) {
-      // ================= staging-buffer producer: residual tiles by TMA (or just grants the buffer) =================
-      int kc = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int c = 0; c < NC; ++c, ++kc) {
-          const int s = kc % kEpiStages;
-          const uint32_t ph = (kc / kEpiStages) & 1;
-          mbar_wait(&rempty_bar[s], ph ^ 1);          // previous TMA store out of this buffer has read it
-          if (has_res) {
-            mbar_arrive_expect_tx(&rfull_bar[s], static_cast<uint32_t>(p.c_box_bytes));
-            tma_load_4d(stg + s * kEpiBufBytes, &p.tmR, &rfull_bar[s], t.n_t * BN + c * kEpiCW, t.w0, t.h0, t.n0);
-          } else {
-            mbar_arrive(&rfull_bar[s]);
+        if constexpr (BK == 64) {
+          constexpr uint32_t IDESC64 = make_idesc_bf16(128, 64);
+          for (int j = 0; j < p.res_blocks; ++j) {      // D[:, 64j:64j+64] += R_j * I64
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_d + j * 64, make_sdesc<128>(sa + k * 32), make_sdesc<128>(sid + k * 32), IDESC64, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (j == p.res_blocks - 1) umma_commit(&tfull_bar[as]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -212,7 +223,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // row inside the 128-row tile
     const bool issuer = (e & 3) == 0 && lane == 0;
-    int prev_s = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -223,12 +233,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 
       if (p.epi_mode == EPI_TMA) {
-        uint8_t* my_row_base;
+        const int sw = (r >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
 #pragma unroll 1
         for (int c = g; c < NC; c += 2) {
-          const int kc = it * NC + c;
-          const int s = kc % kEpiStages;
-          const uint32_t ph = (kc / kEpiStages) & 1;
+          uint8_t* buf = stg + g * kEpiBufBytes;
           uint32_t v[32];
           tmem_ld_32x32(tbase + c * kEpiCW, v);
           tmem_ld_wait();
@@ -249,20 +257,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
               x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
             }
           }
-          mbar_wait(&rfull_bar[s], ph);       // staging buffer granted (and residual landed)
-          my_row_base = stg + s * kEpiBufBytes + r * 64;
-          const int sw = (r >> 1) & 3;        // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-          if (has_res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = *reinterpret_cast<const uint4*>(my_row_base + ((j ^ sw) << 4));
-              float2 f;
-              f = unpack_bf16(u.x); x[8 * j + 0] += f.x; x[8 * j + 1] += f.y;
-              f = unpack_bf16(u.y); x[8 * j + 2] += f.x; x[8 * j + 3] += f.y;
-              f = unpack_bf16(u.z); x[8 * j + 4] += f.x; x[8 * j + 5] += f.y;
-              f = unpack_bf16(u.w); x[8 * j + 6] += f.x; x[8 * j + 7] += f.y;
-            }
-          }
           if (p.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
@@ -270,21 +264,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
           }
+          if (issuer) tma_store_wait_read<0>();   // the group's previous store has finished reading `buf`
+          named_bar_sync(1 + g, 128);
+          uint8_t* my_row = buf + r * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(my_row_base + ((j ^ sw) << 4)) =
+            *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
                 make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
                            pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
           fence_proxy_async();                // make the generic-proxy smem writes visible to the TMA unit
           named_bar_sync(1 + g, 128);
           if (issuer) {
-            tma_store_4d(&p.tmC, stg + s * kEpiBufBytes, col0, t.w0, t.h0, t.n0);
+            tma_store_4d(&p.tmC, buf, col0, t.w0, t.h0, t.n0);
             tma_store_commit();
-            if (prev_s >= 0) {                // the group's previous store has finished reading its buffer
-              tma_store_wait_read<1>();
-              mbar_arrive(&rempty_bar[prev_s]);
-            }
-            prev_s = s;
           }
         }
       } else {
@@ -319,7 +311,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
               }
             }
-            if (has_res) {
+            if (res_direct) {
               const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
