@@ -110,7 +110,8 @@ int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int N, const fl
 int mmdx_op_embed_ln(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt, int rows,
                      const void* d_word, const void* d_ptab, const void* d_ttab, const float* d_gamma,
                      const float* d_beta, float eps, void* d_y, void* stream);
-int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu_seqlens, int n_seq, int max_len,
+/* softmax(Q K^T / 8) V over packed tokens: d_qkv bf16 [T, 3*hidden] (16-byte aligned), d_ctx bf16 [T, hidden]. */
+int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu_seqlens, int n_seq, int T, int max_len,
                       int n_heads, int hidden, void* d_ctx, void* stream);
 int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int32_t* d_cu_seqlens, int n_seq, int hidden,
                           void* d_out_bf16, float* d_out_f32, void* stream);

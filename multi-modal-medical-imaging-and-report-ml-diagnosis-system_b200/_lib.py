@@ -65,7 +65,7 @@ SIGNATURES = {
     "mmdx_op_avgpool": [_p, _p, _i, _i, _i, _p, _p, _p],
     "mmdx_op_layernorm": [_p, _p, _i, _i, _p, _p, _f, _p, _p],
     "mmdx_op_embed_ln": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _f, _p, _p],
-    "mmdx_op_attention": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "mmdx_op_attention": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "mmdx_op_seq_mean_pool": [_p, _p, _p, _i, _i, _p, _p, _p],
     "mmdx_op_head_tail": [_p, _p, _i, _i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p],
 }

@@ -4,8 +4,11 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libmmdx.so
-if [ "$OUT" -nt engine.cu ] && [ "$OUT" -nt kernels.cuh ] && [ "$OUT" -nt gemm_tcgen05.cuh ] && [ "$OUT" -nt ptx.cuh ] \
-   && [ "$OUT" -nt ../../include/mmdx.h ] && [ "${FORCE:-0}" != "1" ]; then
+stale=0
+for f in engine.cu *.cuh ../../include/mmdx.h build.sh; do
+  if [ ! -e "$OUT" ] || [ "$f" -nt "$OUT" ]; then stale=1; fi
+done
+if [ "$stale" = "0" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "libmmdx.so up to date"; exit 0
 fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr \

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/mmdx.h"
+#include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 
@@ -186,6 +187,8 @@ struct mmdx_engine {
   int head_cap = 0;
   bf16* feats_bf = nullptr; bf16* pooled_bf = nullptr; bf16* zcat = nullptr; float* fuse_h = nullptr;
   float* thr_default = nullptr;
+  // attention: tensor map over the packed qkv buffer, rebuilt when (pointer, T, hidden) changes
+  const void* attn_qkv = nullptr; int attn_T = 0, attn_hidden = 0; CUtensorMap attn_tm{};
 };
 
 // ------------------------------------------------------------------------------------------ profiling
@@ -898,12 +901,29 @@ static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const in
   CK(cudaGetLastError());
   return 0;
 }
-static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int n_seq, int max_len, int heads, int hidden,
-                            bf16* ctx, cudaStream_t s) {
+static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int n_seq, int T, int max_len, int heads,
+                            int hidden, bf16* ctx, cudaStream_t s) {
   REQUIRE(hidden == heads * 64, "attention head dim must be 64");
-  dim3 grid((max_len + ATT_BQ - 1) / ATT_BQ, heads, n_seq);
+  REQUIRE(n_seq > 0 && T > 0 && max_len > 0, "bad attention batch");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    attr_set = true;
+  }
+  if (e->attn_qkv != qkv || e->attn_T != T || e->attn_hidden != hidden) {
+    const uint64_t dims[2] = {(uint64_t)3 * hidden, (uint64_t)T};
+    const uint64_t str[1] = {(uint64_t)3 * hidden * 2};
+    const uint32_t box[2] = {64, 128};
+    TRY(make_tmap(e, &e->attn_tm, qkv, 2, dims, str, box, 128));
+    e->attn_qkv = qkv; e->attn_T = T; e->attn_hidden = hidden;
+  }
+  AttnParams p;
+  p.tm = e->attn_tm; p.cu_seqlens = cu; p.ctx = ctx; p.n_seq = n_seq; p.heads = heads; p.hidden = hidden;
+  p.nqb = (max_len + 127) / 128; p.num_units = n_seq * heads * p.nqb;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
   ProfScope _ps(e);
-  attention_kernel<<<grid, 128, 0, s>>>(qkv, cu, hidden, ctx, 0.125f * 1.4426950408889634f);
+  attention_tcgen05_kernel<<<grid, ATC_THREADS, ATC_SMEM, s>>>(p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -981,7 +1001,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
     e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 0], s));                                         // QKV
     e->cur_cls = CLS_ATTN;
-    TRY(launch_attention(e, tb.qkv, d_cu, B, max_len, e->cfg.n_heads, H, tb.ctx, s));
+    TRY(launch_attention(e, tb.qkv, d_cu, B, T, max_len, e->cfg.n_heads, H, tb.ctx, s));
     e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 1], s));                                         // out-proj + residual
     e->cur_cls = CLS_LN;
@@ -1208,11 +1228,13 @@ extern "C" int mmdx_op_embed_ln(mmdx_engine* e, const int32_t* d_ids, const int3
   return launch_embed(e, d_ids, d_pos, d_tt, rows, 768, static_cast<const bf16*>(d_word), static_cast<const bf16*>(d_ptab),
                       static_cast<const bf16*>(d_ttab), d_gamma, d_beta, eps, static_cast<bf16*>(d_y), (cudaStream_t)stream);
 }
-extern "C" int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu, int n_seq, int max_len,
+extern "C" int mmdx_op_attention(mmdx_engine* e, const void* d_qkv, const int32_t* d_cu, int n_seq, int T, int max_len,
                                  int n_heads, int hidden, void* d_ctx, void* stream) {
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e, "null engine");
-  return launch_attention(e, static_cast<const bf16*>(d_qkv), d_cu, n_seq, max_len, n_heads, hidden,
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  return launch_attention(e, static_cast<const bf16*>(d_qkv), d_cu, n_seq, T, max_len, n_heads, hidden,
                           static_cast<bf16*>(d_ctx), (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int32_t* d_cu, int n_seq, int hidden,

@@ -259,7 +259,7 @@ def test_attention_varlen(h, lens):
     qkv = bf(torch.randn(T, 3 * hid, device="cuda"))
     cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
     ctx = torch.full((T, hid), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().mmdx_op_attention(h.handle, P(qkv), P(cu), len(lens), max(lens), heads, hid, P(ctx), S()))
+    _lib.check(_lib.lib().mmdx_op_attention(h.handle, P(qkv), P(cu), len(lens), T, max(lens), heads, hid, P(ctx), S()))
     torch.cuda.synchronize()
     ref = torch.empty(T, hid, device="cuda")
     o = 0
