@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tm);
-    for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < ATC_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }   // both MMA threads release a stage
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1); mbar_init(&o_free[g], 4);
     }
@@ -127,7 +127,17 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
         if (!attn_unit(p, id, u)) continue;
         const int nkb = (u.len + 127) >> 7;
         const bool mine = (nvalid++ & 1) == g;
-        if (!mine) { blk += nkb; continue; }
+        if (!mine) {
+          // The ring is shared by both groups.  A parity wait is only unambiguous while the waiter is never a whole
+          // phase away from the barrier, so this thread observes the other group's blocks too and co-signs their
+          // release: the producer cannot recycle a stage before BOTH MMA threads have seen it filled.
+          for (int kb = 0; kb < nkb; ++kb, ++blk) {
+            const int stage = blk % ATC_STAGES;
+            mbar_wait(&kv_full[stage], (blk / ATC_STAGES) & 1);
+            mbar_arrive(&kv_empty[stage]);
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb, ++blk, ++n) {
           const int stage = blk % ATC_STAGES;
           const uint32_t ph = (blk / ATC_STAGES) & 1;

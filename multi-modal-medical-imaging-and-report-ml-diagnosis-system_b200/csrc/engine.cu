@@ -3,6 +3,7 @@
 // -> BERT-base over packed tokens -> fused head.  All compute is in hand-written sm_100a kernels.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -121,7 +122,7 @@ struct DevBuf {
   }
 };
 
-struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; };
+struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; int cg = 1; };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
   bf16* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1;
@@ -177,6 +178,8 @@ struct mmdx_engine {
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
+  CUtensorMap tm_ident_half{};   // same identity, box of 32 rows: each CTA of a pair holds half of the B operand
+  int force_cg = 0;      // MMDX_CG=1|2 pins the CTA-group size of every eligible GEMM (experiments); 0 = heuristic
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
   std::map<std::string, std::unique_ptr<ImagePlan>> img_plans;
@@ -243,6 +246,14 @@ static int pick_bn(mmdx_engine* e, long long m_tiles, int N, int bn_req) {
   return 0;
 }
 
+// CTA pairs (cta_group::2) halve the B-operand traffic per SM; worth it once every pair has >= 2 tiles of work.
+static int pick_cg(mmdx_engine* e, long long m_tiles, int n_tiles, int bn, int bk) {
+  if (bn < 128 || bk != 64 || m_tiles < 2) return 1;
+  if (e->force_cg == 1 || e->force_cg == 2) return e->force_cg;
+  const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
+  return pair_tiles >= 2LL * (e->num_sms / 2) ? 2 : 1;
+}
+
 // Epilogue wiring.  Must be called after build_gemm/build_conv/build_stem (needs the tile geometry).
 // bf16 outputs with 16-byte-aligned pitches go through the TMA-staged epilogue; fp32 outputs use direct stores.
 static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const bf16* residual, long long ldr, void* out,
@@ -254,7 +265,7 @@ static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const
   p.epi_mode = (!out_f32 && out_aligned) ? EPI_TMA : EPI_DIRECT;
   const uint64_t N = (uint64_t)p.n_tiles * g.bn;
   const uint64_t dims[4] = {N, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)p.NB};
-  p.tmC = p.tmB; p.tmR = p.tmB; p.tmI = e->tm_ident;     // always valid descriptors
+  p.tmC = p.tmB; p.tmR = p.tmB; p.tmI = g.cg == 2 ? e->tm_ident_half : e->tm_ident;     // always valid descriptors
   p.res_blocks = 0;
   if (p.epi_mode == EPI_TMA) {
     const uint32_t box[4] = {(uint32_t)kEpiCW, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
@@ -283,6 +294,7 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   g.bn = pick_bn(e, m_tiles, N, bn_req);
   REQUIRE(g.bn != 0, "no BN tile divides N");
   g.bk = 64;
+  g.cg = pick_cg(e, m_tiles, N / g.bn, g.bn, 64);
   const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
   const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M, (uint64_t)lda * 2 * (uint64_t)M};
   const uint32_t box[4] = {64, 128, 1, 1};
@@ -290,10 +302,10 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   const uint64_t bd[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t bs[1] = {(uint64_t)K * 2};
-  const uint32_t bb[2] = {64, (uint32_t)g.bn};
+  const uint32_t bb[2] = {64, (uint32_t)(g.bn / g.cg)};
   TRY(make_tmap(e, &p.tmB, Wt, 2, bd, bs, bb, 128));
   p.num_k_blocks = K / 64; p.kb_per_tap = K / 64; p.a_box_bytes = 128 * 64 * 2;
-  p.n_tiles = N / g.bn; p.num_tiles = (int)(m_tiles * p.n_tiles);
+  p.n_tiles = N / g.bn; p.cg = g.cg; p.num_tiles = (int)(((m_tiles + g.cg - 1) / g.cg) * p.n_tiles);
   p.tiles_w = (int)m_tiles; p.tiles_h = 1;
   p.Wb = 128; p.Hb = 1; p.Nb = 1; p.OW = M; p.OH = 1; p.NB = 1;
   return 0;
@@ -330,6 +342,7 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
   g.bn = pick_bn(e, m_tiles, Cout, 0);
   REQUIRE(g.bn != 0, "no BN tile divides Cout");
   g.bk = 64;
+  g.cg = pick_cg(e, m_tiles, Cout / g.bn, g.bn, 64);
   const uint32_t box[4] = {64, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
   if (stride == 1) {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -360,10 +373,10 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
     }
   const uint64_t bd[2] = {(uint64_t)k * k * Cin, (uint64_t)Cout};
   const uint64_t bs[1] = {(uint64_t)k * k * Cin * 2};
-  const uint32_t bb[2] = {64, (uint32_t)g.bn};
+  const uint32_t bb[2] = {64, (uint32_t)(g.bn / g.cg)};
   TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 128));
   p.kb_per_tap = Cin / 64; p.num_k_blocks = k * k * p.kb_per_tap; p.a_box_bytes = Wb * Hb * Nb * 64 * 2;
-  p.n_tiles = Cout / g.bn; p.num_tiles = (int)(m_tiles * p.n_tiles);
+  p.n_tiles = Cout / g.bn; p.cg = g.cg; p.num_tiles = (int)(((m_tiles + g.cg - 1) / g.cg) * p.n_tiles);
   p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
   p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
   return 0;
@@ -378,7 +391,7 @@ static int build_stem(mmdx_engine* e, GemmLaunch& g, const bf16* in_pad, int NB,
   memset(&p, 0, sizeof p);
   int Wb, Hb, Nb;
   pick_tile(OW, OH, NB, Wb, Hb, Nb);
-  g.bn = 64; g.bk = 32;
+  g.bn = 64; g.bk = 32; g.cg = 1;
   const uint32_t box[4] = {32, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
   for (int par = 0; par < 2; ++par) {
     const uint64_t dims[4] = {32, (uint64_t)OW, (uint64_t)((hp - par) / 2), (uint64_t)NB};
@@ -393,33 +406,66 @@ static int build_stem(mmdx_engine* e, GemmLaunch& g, const bf16* in_pad, int NB,
   TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 64));
   p.kb_per_tap = 1; p.num_k_blocks = 7; p.a_box_bytes = Wb * Hb * Nb * 32 * 2;
   const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
-  p.n_tiles = 1; p.num_tiles = (int)m_tiles;
+  p.n_tiles = 1; p.cg = 1; p.num_tiles = (int)m_tiles;
   p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
   p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
   return 0;
 }
 
-template <int BN, int BK, int ST>
-static int launch_inst(const GemmLaunch& g, int grid, cudaStream_t s) {
+template <int BN, int BK, int ST, int CG>
+static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
-  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST>;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST, CG>;
+  constexpr int SMEM = GemmSmem<BN, BK, ST, CG>::TOTAL;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, BK, ST>::TOTAL));
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  kfn<<<grid, kGemmThreads, GemmSmem<BN, BK, ST>::TOTAL, s>>>(g.p);
+  if (CG == 1) {
+    kfn<<<groups, kGemmThreads, SMEM, s>>>(g.p);
+  } else {     // CTA pairs: clusters of two along x
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)groups * CG, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    // The schedule is static and persistent: every cluster must be resident at once, or the stragglers run as a
+    // second wave.  Not every SM can be paired (GPCs with an odd number of enabled SMs), so ask the driver.
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      int n = 0;
+      CK(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
+      REQUIRE(n > 0, "no CTA pair fits on this device");
+      max_clusters = n;
+      if (getenv("MMDX_DEBUG")) fprintf(stderr, "mmdx: gemm<%d,%d,%d,%d> max active clusters %d\n", BN, BK, ST, CG, n);
+    }
+    if (groups > max_clusters) { groups = max_clusters; cfg.gridDim = dim3((unsigned)groups * CG, 1, 1); }
+    CK(cudaLaunchKernelEx(&cfg, kfn, g.p));
+  }
   CK(cudaGetLastError());
   return 0;
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
-  const int grid = g.p.num_tiles < e->num_sms ? g.p.num_tiles : e->num_sms;
+  const int max_groups = e->num_sms / g.cg;
+  const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
-  if (g.bk == 32) return launch_inst<64, 32, 8>(g, grid, s);
+  if (g.bk == 32) return launch_inst<64, 32, 8, 1>(g, groups, s);
+  if (g.cg == 2) {
+    switch (g.bn) {
+      case 256: return launch_inst<256, 64, 6, 2>(g, groups, s);
+      case 128: return launch_inst<128, 64, 8, 2>(g, groups, s);
+    }
+    return fail("mmdx: bad BN for a CTA pair");
+  }
   switch (g.bn) {
-    case 256: return launch_inst<256, 64, 4>(g, grid, s);
-    case 128: return launch_inst<128, 64, 6>(g, grid, s);
-    case 64: return launch_inst<64, 64, 8>(g, grid, s);
+    case 256: return launch_inst<256, 64, 4, 1>(g, groups, s);
+    case 128: return launch_inst<128, 64, 6, 1>(g, groups, s);
+    case 64: return launch_inst<64, 64, 8, 1>(g, groups, s);
   }
   return fail("mmdx: bad BN");
 }
@@ -455,7 +501,10 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     const uint64_t st[1] = {128};
     const uint32_t bx[2] = {64, 64};
     TRY(make_tmap(e.get(), &e->tm_ident, e->ident.p, 2, d, st, bx, 128));
+    const uint32_t bh[2] = {64, 32};
+    TRY(make_tmap(e.get(), &e->tm_ident_half, e->ident.p, 2, d, st, bh, 128));
   }
+  if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
   *out = e.release();
   return 0;
 }

@@ -19,6 +19,14 @@
 // Epilogue data path (EPI_TMA): TMEM -> registers (+bias, activation) -> bf16 -> swizzled staging buffer
 // -> TMA store.  The output box is the same (Wb x Hb x Nb) spatial tile as the A operand, so image
 // borders and ragged M are clipped by the TMA unit.
+// CTA pairs (CG = 2, launched as clusters of two): the pair computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 issued by the leader (cluster rank 0) only.  Each CTA TMA-loads its own 128 A rows
+// and HALF of the B tile (BN/2 weight rows) into its own smem - 32 KB instead of 48 KB of L2 traffic per
+// k-block at BN = 256, which is what bounds the single-CTA tiles - and owns the accumulator rows of its
+// A half in its own TMEM, so the epilogue is unchanged.  Completion bytes of both CTAs' loads are posted to
+// the leader's full barrier; the leader's commits are multicast to both CTAs' empty / accumulator-full
+// barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.  Only the leader arms
+// the full barriers (expect_tx of both CTAs' bytes): no cluster-scope release (a MEMBAR.ALL.GPU) in the loop.
 // Pipelines: smem ring full/empty (TMA <-> MMA), double-buffered TMEM accumulator full/empty
 // (MMA <-> epilogue), one staging buffer per epilogue group guarded by bulk-group waits + named
 // barriers, static persistent tile schedule (tile = blockIdx.x + i*gridDim.x).
@@ -41,13 +49,14 @@ struct alignas(64) GemmParams {
   CUtensorMap tmB;
   CUtensorMap tmC;    // output  [.., N] bf16, box (32, Wb, Hb, Nb), SWIZZLE_64B   (EPI_TMA)
   CUtensorMap tmR;    // residual as an A operand: box (64, Wb, Hb, Nb), SWIZZLE_128B (res_blocks > 0)
-  CUtensorMap tmI;    // 64x64 bf16 identity, box (64, 64), SWIZZLE_128B
+  CUtensorMap tmI;    // 64x64 bf16 identity, box (64, 64 / CG), SWIZZLE_128B
   int num_k_blocks;   // taps * kb_per_tap
   int kb_per_tap;     // channel chunks per filter tap (K/BK for a plain GEMM)
   int a_box_bytes;    // bytes one A box load lands (Wb*Hb*Nb*BK*2)
   int res_blocks;     // residual k-blocks per tile (BN/64) when the residual is added by the tensor core, else 0
-  int num_tiles;      // m_tiles * n_tiles
+  int num_tiles;      // work items: ceil(m_tiles / CG) * n_tiles   (CG = 2: one item = two consecutive m-tiles)
   int n_tiles;
+  int cg;             // CTAs per tile group (1, or 2 = cta_group::2 pair)
   int tiles_w, tiles_h;        // spatial tile grid (tiles over batch follow)
   int Wb, Hb, Nb;              // tile = Wb x Hb pixels x Nb images (<=128 rows)
   int OW, OH, NB;              // valid output extents (plain GEMM: OW=M, OH=NB=1)
@@ -61,10 +70,10 @@ struct alignas(64) GemmParams {
   signed char tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
 };
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int CG>
 struct GemmSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;     // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STG_BYTES = kEpiStages * kEpiBufBytes + kIdentBytes;
@@ -75,10 +84,11 @@ struct GemmSmem {
 
 struct TileCoord { int n_t, w0, h0, n0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int rank) {
   TileCoord t;
   t.n_t = tile % p.n_tiles;
-  const int m_t = tile / p.n_tiles;
+  const int m_t = (tile / p.n_tiles) * p.cg + rank;   // past-the-end m-tiles of an odd pair land out of bounds:
+                                                      // TMA zero-fills the loads and clips the stores
   const int tiles_hw = p.tiles_w * p.tiles_h;
   const int tn = m_t / tiles_hw;
   const int rem = m_t - tn * tiles_hw;
@@ -88,11 +98,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   return t;
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using L = GemmSmem<BN, BK, STAGES>;
+  using L = GemmSmem<BN, BK, STAGES, CG>;
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
-  constexpr uint32_t IDESC = make_idesc_bf16(128, BN);
+  constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BN);
+  static_assert(CG == 1 || (CG == 2 && BK == 64 && BN >= 128), "CTA pairs: BK 64, BN >= 128");
   constexpr uint32_t TMEM_COLS = 2 * BN;      // double-buffered fp32 accumulator
   constexpr int NC = BN / kEpiCW;             // epilogue chunks per tile (even)
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
@@ -112,6 +123,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool res_direct = p.residual != nullptr && p.res_blocks == 0;   // EPI_DIRECT fallback only
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;  // 0 = leader (issues the MMAs)
+  const int group = blockIdx.x / CG;            // persistent schedule: item = group + i * num_groups
+  const int num_groups = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) prefetch_tensormap(&p.tmA[i]);
@@ -119,45 +133,62 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     if (p.epi_mode == EPI_TMA) prefetch_tensormap(&p.tmC);
     if (p.res_blocks > 0) { prefetch_tensormap(&p.tmR); prefetch_tensormap(&p.tmI); }
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);               // armed by the leader's producer with the bytes of the whole group
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 8 * CG);        // epilogue warps of every CTA of the group
     }
     mbar_init(ident_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ================= TMA producer: A/B ring =================
+      // ================= TMA producer: A/B ring (every CTA loads its own A rows and its share of B) =================
       int stage = 0;
       uint32_t phase = 0;
-      if (BK == 64 && p.res_blocks > 0) {               // identity block: loaded once, stays resident
-        mbar_arrive_expect_tx(ident_bar, kIdentBytes);
-        tma_load_2d(ident, &p.tmI, ident_bar, 0, 0);
+      // CG = 2: completion is tracked by the LEADER's full barriers (shared::cluster addresses of rank 0)
+      const uint32_t full0 = CG == 2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0;
+      if (BK == 64 && p.res_blocks > 0) {               // identity block (this CTA's rows of it): loaded once, stays resident
+        if constexpr (CG == 2) {
+          if (rank == 0) mbar_arrive_expect_tx(ident_bar, kIdentBytes);      // both halves
+          tma_load_2d_pair(ident, &p.tmI, mapa_rank(smem_u32(ident_bar), 0), 0, rank * 32);
+        } else {
+          mbar_arrive_expect_tx(ident_bar, kIdentBytes);
+          tma_load_2d(ident, &p.tmI, ident_bar, 0, 0);
+        }
       }
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = group; tile < p.num_tiles; tile += num_groups) {
+        const TileCoord t = decode_tile(p, tile, rank);
         int tap = 0, cc = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes + L::B_BYTES));
-          tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[stage], cc * BK, t.w0 + p.tap_dw[tap],
-                      t.h0 + p.tap_dh[tap], t.n0);
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, t.n_t * BN);
+          if constexpr (CG == 2) {
+            // The leader arms its barrier with the bytes of BOTH CTAs; the peer only issues its loads.  Peer bytes
+            // that land before the leader's expect_tx just drive the tx-count negative for a moment: the phase
+            // cannot complete before the (single) pending arrival.
+            const uint32_t fb = full0 + stage * 8;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.a_box_bytes + L::B_BYTES));
+            tma_load_4d_pair(sa, &p.tmA[p.tap_map[tap]], fb, cc * BK, t.w0 + p.tap_dw[tap], t.h0 + p.tap_dh[tap], t.n0);
+            tma_load_2d_pair(sb, &p.tmB, fb, kb * BK, t.n_t * BN + rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes + L::B_BYTES));
+            tma_load_4d(sa, &p.tmA[p.tap_map[tap]], &full_bar[stage], cc * BK, t.w0 + p.tap_dw[tap],
+                        t.h0 + p.tap_dh[tap], t.n0);
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, t.n_t * BN);
+          }
           if (++cc == p.kb_per_tap) { cc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -165,52 +196,63 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int j = 0; j < p.res_blocks; ++j) {      // residual tile as extra A blocks + identity B block
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes));
-            tma_load_4d(sa, &p.tmR, &full_bar[stage], t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+            if constexpr (CG == 2) {
+              const uint32_t fb = full0 + stage * 8;
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.a_box_bytes));
+              tma_load_4d_pair(sa, &p.tmR, fb, t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes));
+              tma_load_4d(sa, &p.tmR, &full_bar[stage], t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer (one thread) =================
+    if (lane == 0 && rank == 0) {
+      // ================= MMA issuer (one thread of the leader CTA) =================
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if constexpr (CG == 2) umma_bf16_pair(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       if (BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
       const uint32_t sid = smem_u32(ident);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);     // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[as], aphase ^ 1);     // the epilogue (of both CTAs) has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);         // TMA bytes have landed
+          mbar_wait(&full_bar[stage], phase);         // TMA bytes (of both CTAs) have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_d, make_sdesc<SWZ>(sa + k * 32), make_sdesc<SWZ>(sb + k * 32), IDESC,
-                      (kb | k) != 0 ? 1u : 0u);
+            mma(tmem_d, make_sdesc<SWZ>(sa + k * 32), make_sdesc<SWZ>(sb + k * 32), IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs finish
-          if (kb == p.num_k_blocks - 1 && p.res_blocks == 0) umma_commit(&tfull_bar[as]);
+          commit(&empty_bar[stage]);                  // frees the smem slot (in both CTAs) when these MMAs finish
+          if (kb == p.num_k_blocks - 1 && p.res_blocks == 0) commit(&tfull_bar[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (BK == 64) {
-          constexpr uint32_t IDESC64 = make_idesc_bf16(128, 64);
+          constexpr uint32_t IDESC64 = make_idesc_bf16(128 * CG, 64);
           for (int j = 0; j < p.res_blocks; ++j) {      // D[:, 64j:64j+64] += R_j * I64
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_d + j * 64, make_sdesc<128>(sa + k * 32), make_sdesc<128>(sid + k * 32), IDESC64, 1u);
-            umma_commit(&empty_bar[stage]);
-            if (j == p.res_blocks - 1) umma_commit(&tfull_bar[as]);
+              mma(tmem_d + j * 64, make_sdesc<128>(sa + k * 32), make_sdesc<128>(sid + k * 32), IDESC64, 1u);
+            commit(&empty_bar[stage]);
+            if (j == p.res_blocks - 1) commit(&tfull_bar[as]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -223,11 +265,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // row inside the 128-row tile
     const bool issuer = (e & 3) == 0 && lane == 0;
+    // accumulator-empty barriers live in the leader CTA (its MMA thread waits on them)
+    const uint32_t tempty0 = CG == 2 ? mapa_rank(smem_u32(&tempty_bar[0]), 0) : 0;
+    auto release_acc = [&](int as) {
+      if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + as * 8); else mbar_arrive(&tempty_bar[as]);
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = decode_tile(p, tile, rank);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -243,7 +290,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (c == NC - 2 + g) {              // this warp's last read of the accumulator: hand it back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) release_acc(as);
           }
           const int col0 = t.n_t * BN + c * kEpiCW;
           float x[32];
@@ -296,7 +343,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (c == NC - 2 + g) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) release_acc(as);
           }
           if (valid) {
             const int col0 = t.n_t * BN + c * kEpiCW;
@@ -349,10 +396,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer may still signal this CTA's barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -114,14 +114,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-// arrive / arrive+expect_tx on an mbarrier given by its shared::cluster address (own or peer CTA)
+// arrive on an mbarrier given by its shared::cluster address (own or peer CTA).  Default semantics
+// (release at CTA scope): an explicit .release.cluster costs a MEMBAR.ALL.GPU per arrive, and nothing but
+// tcgen05-fenced TMEM state is handed over through these barriers.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
-               "r"(bytes)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in this CTA's smem, completion bytes are posted to the barrier at
 // `bar_cluster_addr`, which may live in the peer (leader) CTA.

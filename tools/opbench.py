@@ -1,0 +1,125 @@
+"""Single-kernel timings at the C2 sizes (B=256, L=128) through the C ABI: CUDA events on the launch stream,
+L2 flushed between repetitions (a 256 MB memset).  Usage on the GPU box:
+    python tools/opbench.py attention gemm conv ln            # any subset; no argument = everything
+    MMDX_CG=1 python tools/opbench.py gemm                    # pin the CTA-group size
+Prints one line per case: name, microseconds (median of reps), achieved TFLOP/s or GB/s."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmdx_b200 import _lib, engine  # noqa: E402
+
+
+def P(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def S():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_flush = None
+
+
+def timeit(fn, reps=7):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(reps):
+        _flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    return float(np.median(ts))
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def bench_attention(h, lib):
+    for B, L in [(256, 128), (64, 512), (256, 32)]:
+        T, hid = B * L, 768
+        qkv = bf(torch.randn(T, 3 * hid, device="cuda"))
+        cu = torch.arange(0, T + 1, L, dtype=torch.int32, device="cuda")
+        ctx = torch.empty(T, hid, device="cuda", dtype=torch.bfloat16)
+        us = timeit(lambda: _lib.check(lib.mmdx_op_attention(h.handle, P(qkv), P(cu), B, T, L, 12, hid, P(ctx), S())))
+        fl = 4.0 * B * 12 * L * L * 64
+        by = T * hid * 2 * 4
+        print(f"attention B={B} L={L}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
+
+
+def bench_gemm(h, lib):
+    M = 32768
+    for name, N, K, act, res in [("qkv", 2304, 768, 0, False), ("attn_out+res", 768, 768, 0, True),
+                                 ("ffn1+gelu", 3072, 768, 2, False), ("ffn2+res", 768, 3072, 0, True)]:
+        a = bf(torch.randn(M, K, device="cuda"))
+        w = bf(torch.randn(N, K, device="cuda") * K ** -0.5)
+        bias = torch.randn(N, device="cuda")
+        r = bf(torch.randn(M, N, device="cuda")) if res else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        us = timeit(lambda: _lib.check(lib.mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(r), N, P(out), N, M, N, K, act, 0, 0, S())))
+        print(f"gemm {name:14s} M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+
+
+def bench_conv(h, lib):
+    NB = 256
+    cases = [("l1.c1", 56, 256, 64, 1, 1, False), ("l1.c2", 56, 64, 64, 3, 1, False), ("l1.c3+res", 56, 64, 256, 1, 1, True),
+             ("l2.c1", 28, 512, 128, 1, 1, False), ("l2.c2", 28, 128, 128, 3, 1, False), ("l2.c3+res", 28, 128, 512, 1, 1, True),
+             ("l2.c2s2", 56, 128, 128, 3, 2, False),
+             ("l3.c1", 14, 1024, 256, 1, 1, False), ("l3.c2", 14, 256, 256, 3, 1, False), ("l3.c3+res", 14, 256, 1024, 1, 1, True),
+             ("l4.c1", 7, 2048, 512, 1, 1, False), ("l4.c2", 7, 512, 512, 3, 1, False), ("l4.c3+res", 7, 512, 2048, 1, 1, True)]
+    for name, HW, Cin, Cout, k, s, res in cases:
+        x = bf(torch.randn(NB, HW, HW, Cin, device="cuda"))
+        w = bf(torch.randn(Cout, k * k, Cin, device="cuda") * (k * k * Cin) ** -0.5)
+        bias = torch.randn(Cout, device="cuda")
+        OH = (HW + 2 * (k // 2) - k) // s + 1
+        r = bf(torch.randn(NB, OH, OH, Cout, device="cuda")) if res else None
+        out = torch.empty(NB, OH, OH, Cout, device="cuda", dtype=torch.bfloat16)
+        us = timeit(lambda: _lib.check(lib.mmdx_op_conv(h.handle, P(x), NB, HW, HW, Cin, P(w), P(bias), P(r), P(out), Cout, k, s, 1, S())))
+        fl = 2.0 * NB * OH * OH * Cout * Cin * k * k
+        by = 2.0 * (x.numel() + out.numel() * (2 if res else 1))
+        print(f"conv {name:10s} {HW}x{HW} {Cin}->{Cout} k{k} s{s}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
+
+
+def bench_ln(h, lib):
+    T, N = 32768, 768
+    x = bf(torch.randn(T, N, device="cuda"))
+    g = torch.rand(N, device="cuda") + 0.5
+    b = torch.randn(N, device="cuda")
+    y = torch.empty_like(x)
+    us = timeit(lambda: _lib.check(lib.mmdx_op_layernorm(h.handle, P(x), T, N, P(g), P(b), 1e-12, P(y), S())))
+    print(f"layernorm T={T} N={N}: {us:8.1f} us  {4.0 * T * N / us / 1e3:7.1f} GB/s", flush=True)
+
+
+def bench_pre(h, lib):
+    for B, HW in [(256, 224), (64, 512)]:
+        img = torch.randint(0, 256, (B, HW, HW, 3), dtype=torch.uint8, device="cuda")
+        hp, wp = C.c_int(), C.c_int()
+        lib.mmdx_padded_dims(224, 224, C.byref(hp), C.byref(wp))
+        out = torch.zeros(B, hp.value, wp.value, 4, device="cuda", dtype=torch.bfloat16)
+        oh, ow = C.c_int(), C.c_int()
+        us = timeit(lambda: _lib.check(lib.mmdx_op_preprocess(h.handle, P(img), B, HW, HW, 3, P(out), C.byref(oh), C.byref(ow), S())))
+        by = img.numel() + B * 224 * 224 * 4 * 2
+        print(f"preprocess B={B} {HW}x{HW}: {us:8.1f} us  {by / us / 1e3:7.1f} GB/s", flush=True)
+
+
+ALL = {"attention": bench_attention, "gemm": bench_gemm, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
+
+if __name__ == "__main__":
+    torch.cuda.set_device(0)
+    h = engine.RawHandle()
+    lib = _lib.lib()
+    for name in (sys.argv[1:] or list(ALL)):
+        ALL[name](h, lib)
+    h.close()
