@@ -292,4 +292,223 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
   }
 }
 
+
+// =================================================================================================================
+// Short-sequence variant (every sequence <= 128 tokens: the reference's own max_len = 96, and BASELINE C2's 128).
+// One unit = (sequence, head): a single 128-key block, so no online softmax.  Four units are in flight per SM:
+// unit i uses smem stage i%4 and TMEM region i%4 (128 columns), in which S, P and O alias each other:
+//     S = Q K^T   fp32, columns [0,128)                      tcgen05.mma, A/B K-major from smem
+//     P = softmax numerators, bf16 pairs, columns [0,64)     written in place by tcgen05.st as S is consumed
+//     O = P V     fp32, columns [64,128)                     tcgen05.mma with A = P read from TENSOR MEMORY
+// so the probabilities never touch shared memory.  Roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer
+// (software-pipelined: S of unit i, then P V of unit i-2), warp 2 TMEM allocator, warps 4-19 four softmax groups
+// (thread = query row).  Warps whose 32 rows are all padding skip the math and only keep the barriers moving;
+// key chunks beyond the sequence are neither exponentiated nor multiplied.
+// =================================================================================================================
+constexpr int ATS_THREADS = 640;
+constexpr int ATS_GROUPS = 4;
+constexpr int ATS_SMEM = ATS_GROUPS * ATC_STAGE_BYTES + ATC_BAR_BYTES + 1024;
+constexpr int ATS_LAG = 2;                         // P V of unit i-2 is issued after S of unit i
+
+struct AttnShortUnit { int tok0, len, head; };
+
+__device__ __forceinline__ AttnShortUnit attn_short_unit(const AttnParams& p, int id) {
+  AttnShortUnit u;
+  const int seq = id / p.heads;
+  u.head = id - seq * p.heads;
+  u.tok0 = __ldg(p.cu_seqlens + seq);
+  u.len = __ldg(p.cu_seqlens + seq + 1) - u.tok0;
+  return u;
+}
+
+__global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel(const __grid_constant__ AttnParams p) {
+  constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128);
+  constexpr uint32_t IDESC_PV = make_idesc_bf16(128, 64) | (1u << 16);    // B (= V) is MN-major
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(smem + ATS_GROUPS * ATC_STAGE_BYTES);
+  uint64_t* kv_empty = kv_full + ATS_GROUPS;
+  uint64_t* s_full = kv_empty + ATS_GROUPS;
+  uint64_t* p_full = s_full + ATS_GROUPS;
+  uint64_t* o_full = p_full + ATS_GROUPS;
+  uint64_t* o_free = o_full + ATS_GROUPS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + ATS_GROUPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = p.n_seq * p.heads;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.tm);
+    for (int g = 0; g < ATS_GROUPS; ++g) {
+      mbar_init(&kv_full[g], 1); mbar_init(&kv_empty[g], 1); mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1); mbar_init(&o_free[g], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int i = 0;
+      for (int id = blockIdx.x; id < num_units; id += gridDim.x, ++i) {
+        const AttnShortUnit u = attn_short_unit(p, id);
+        const int g = i & 3;
+        mbar_wait(&kv_empty[g], ((i >> 2) & 1) ^ 1);
+        uint8_t* st = smem + g * ATC_STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[g], ATC_STAGE_BYTES);
+        tma_load_2d(st, &p.tm, &kv_full[g], u.head * 64, u.tok0);
+        tma_load_2d(st + ATC_BOX, &p.tm, &kv_full[g], p.hidden + u.head * 64, u.tok0);
+        tma_load_2d(st + 2 * ATC_BOX, &p.tm, &kv_full[g], 2 * p.hidden + u.head * 64, u.tok0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      const int n_mine = blockIdx.x < num_units ? (num_units - 1 - blockIdx.x) / static_cast<int>(gridDim.x) + 1 : 0;
+      for (int i = 0; i < n_mine + ATS_LAG; ++i) {
+        if (i < n_mine) {                             // ---- S(i) = Q K^T into region i%4
+          const int g = i & 3;
+          const uint32_t ph = (i >> 2) & 1;
+          mbar_wait(&kv_full[g], ph);
+          if (i >= ATS_GROUPS) mbar_wait(&o_free[g], ph ^ 1);      // unit i-4's O has been read out of this region
+          tc_fence_after();
+          const uint32_t sQ = smem_u32(smem + g * ATC_STAGE_BYTES);
+          const uint32_t sK = sQ + ATC_BOX;
+          const uint32_t tS = tmem_base + g * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS, make_sdesc<128>(sQ + k * 32), make_sdesc<128>(sK + k * 32), IDESC_S, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        }
+        const int j = i - ATS_LAG;
+        if (j >= 0) {                                 // ---- O(j) = P V, P from tensor memory
+          const int g = j & 3;
+          const int id = blockIdx.x + j * static_cast<int>(gridDim.x);
+          const AttnShortUnit u = attn_short_unit(p, id);
+          const int nks = (min(u.len, 128) + 15) >> 4;             // 16-key steps that hold any valid key
+          mbar_wait(&p_full[g], (j >> 2) & 1);
+          tc_fence_after();
+          const uint32_t sV = smem_u32(smem + g * ATC_STAGE_BYTES) + 2 * ATC_BOX;
+          const uint32_t tP = tmem_base + g * 128;
+          const uint32_t tO = tP + 64;
+          for (int k = 0; k < nks; ++k)
+            umma_bf16_ts(tO, tP + k * 8, make_sdesc_mn128(sV + k * 2048), IDESC_PV, k != 0 ? 1u : 0u);
+          umma_commit(&o_full[g]);
+          umma_commit(&kv_empty[g]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= softmax groups =================
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128;
+    const uint32_t tO = tS + 64;
+    const int stride = ATS_GROUPS * static_cast<int>(gridDim.x);
+    int id = blockIdx.x + g * static_cast<int>(gridDim.x);
+    AttnShortUnit u{0, 0, 0};
+    if (id < num_units) u = attn_short_unit(p, id);
+    for (uint32_t n = 0; id < num_units; id += stride, ++n) {
+      AttnShortUnit nxt{0, 0, 0};
+      if (id + stride < num_units) nxt = attn_short_unit(p, id + stride);     // prefetch: off the critical path
+      const int len = min(u.len, 128);
+      const bool active = q * 32 < len;               // warp-uniform: any valid query row in this quarter
+      mbar_wait(&s_full[g], n & 1);
+      tc_fence_after();
+      float l = 0.f;
+      if (active) {
+        const int nch = (len + 31) >> 5;              // 32-key chunks holding valid keys
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tS + c * 32, v);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= len) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c * 32 + j < len) ? __uint_as_float(v[j]) : -INFINITY);
+          }
+        }
+        const float msc = mx * p.scale_log2;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          uint32_t pk[16];
+          tmem_ld_32x32(tS + c * 32, v);
+          tmem_ld_wait();
+          if (c * 32 + 32 <= len) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -msc));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -msc));
+              l += p0 + p1;
+              pk[j >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = (c * 32 + j < len) ? fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -msc)) : 0.f;
+              const float p1 = (c * 32 + j + 1 < len) ? fast_exp2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -msc)) : 0.f;
+              l += p0 + p1;
+              pk[j >> 1] = pack_bf16(p0, p1);
+            }
+          }
+          // keys [32c, 32c+32) -> packed columns [16c, 16c+16): inside S columns this thread has already consumed
+          tmem_st_32x16(tS + c * 16, pk);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      // ---- O = P V
+      mbar_wait(&o_full[g], n & 1);
+      tc_fence_after();
+      if (active) {
+        const float inv = 1.0f / l;
+        uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<size_t>(u.tok0 + r) * p.hidden + u.head * 64);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + c * 32, v);
+          tmem_ld_wait();
+          if (r < len) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[c * 4 + j] = make_uint4(
+                  pack_bf16(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv),
+                  pack_bf16(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv),
+                  pack_bf16(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv),
+                  pack_bf16(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      u = nxt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace mmdx

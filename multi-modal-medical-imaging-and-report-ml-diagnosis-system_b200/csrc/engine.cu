@@ -179,6 +179,7 @@ struct mmdx_engine {
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
   CUtensorMap tm_ident_half{};   // same identity, box of 32 rows: each CTA of a pair holds half of the B operand
+  bool attn_force_general = false;   // MMDX_ATTN=general: use the flash-style kernel for short sequences too (experiments)
   int force_cg = 0;      // MMDX_CG=1|2 pins the CTA-group size of every eligible GEMM (experiments); 0 = heuristic
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
@@ -505,6 +506,7 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     TRY(make_tmap(e.get(), &e->tm_ident_half, e->ident.p, 2, d, st, bh, 128));
   }
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
+  if (const char* v = getenv("MMDX_ATTN")) e->attn_force_general = (strcmp(v, "general") == 0);
   *out = e.release();
   return 0;
 }
@@ -957,6 +959,7 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    CK(cudaFuncSetAttribute(attention_short_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM));
     attr_set = true;
   }
   if (e->attn_qkv != qkv || e->attn_T != T || e->attn_hidden != hidden) {
@@ -970,9 +973,15 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
   p.tm = e->attn_tm; p.cu_seqlens = cu; p.ctx = ctx; p.n_seq = n_seq; p.heads = heads; p.hidden = hidden;
   p.nqb = (max_len + 127) / 128; p.num_units = n_seq * heads * p.nqb;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
-  const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
   ProfScope _ps(e);
-  attention_tcgen05_kernel<<<grid, ATC_THREADS, ATC_SMEM, s>>>(p);
+  if (max_len <= 128 && !e->attn_force_general) {       // one key block per sequence: the 4-deep TMEM-resident variant
+    const int units = n_seq * heads;
+    const int grid = units < e->num_sms ? units : e->num_sms;
+    attention_short_tcgen05_kernel<<<grid, ATS_THREADS, ATS_SMEM, s>>>(p);
+  } else {
+    const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
+    attention_tcgen05_kernel<<<grid, ATC_THREADS, ATC_SMEM, s>>>(p);
+  }
   CK(cudaGetLastError());
   return 0;
 }

@@ -252,7 +252,8 @@ def test_embed_layernorm(h):
     assert rel_err(y, ref) < 6e-3
 
 
-@pytest.mark.parametrize("lens", [[128, 128, 128], [17, 64, 65, 1, 40], [512, 300], [96] * 4])
+@pytest.mark.parametrize("lens", [[128, 128, 128], [17, 64, 65, 1, 40], [512, 300], [96] * 4, [129, 5, 128, 33, 257],
+                                  [31, 32, 33, 1, 16, 15, 127] * 30])
 def test_attention_varlen(h, lens):
     heads, hid = 12, 768
     T = sum(lens)
@@ -270,6 +271,17 @@ def test_attention_varlen(h, lens):
         o += n
     assert torch.isfinite(ctx.float()).all()
     assert rel_err(ctx, ref) < 1.5e-2
+
+
+def test_attention_general_kernel_on_short_sequences(monkeypatch):
+    """Sequences of <= 128 tokens normally take the 4-deep TMEM-resident kernel; MMDX_ATTN=general pins the
+    flash-style kernel so that it is also checked on ragged short inputs (both must agree with torch)."""
+    monkeypatch.setenv("MMDX_ATTN", "general")
+    hd = engine.RawHandle()
+    try:
+        test_attention_varlen(hd, [17, 64, 65, 1, 40, 128])
+    finally:
+        hd.close()
 
 
 def test_seq_mean_pool_and_head_tail(h):
