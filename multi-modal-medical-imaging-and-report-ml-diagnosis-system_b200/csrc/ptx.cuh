@@ -203,6 +203,32 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// Lean issue path: descriptors travel as (lo, hi) 32-bit words so the per-MMA K advance is one 32-bit add on
+// `lo` (start address >> 4 lives in its low 14 bits); PAIR selects cta_group::2.
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_words(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 // Instruction descriptor (kind::f16): fp32 accumulator, bf16 A/B, both K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
@@ -215,6 +241,13 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   constexpr uint64_t layout = (SWZ == 128) ? 2ull : (SWZ == 64 ? 4ull : 6ull);
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) |
          (static_cast<uint64_t>((8 * SWZ) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int SWZ>
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <int SWZ>
+__device__ __forceinline__ constexpr uint32_t sdesc_hi() {
+  return static_cast<uint32_t>((8 * SWZ) >> 4) | (1u << 14) | ((SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u)) << 29);
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base lane + i).
