@@ -98,6 +98,12 @@ int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin
 int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
                  const float* d_bias, void* d_out, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
+/* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
+ * d_w_packed: 7168 bf16 from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).
+ * d_out: bf16 [NB, OH, OW, 64] (pool == 0) or [NB, PH, PW, 64]; OH = (H-1)/2+1, PH = (OH-1)/2+1. */
+int mmdx_pack_stem_weights(const float* w_oihw, const float* scale, uint16_t* out_bf16);
+int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,
+                      const float* d_bias, void* d_out, int pool, void* stream);
 int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, void* d_out_padded,
                        int* out_h, int* out_w, void* stream);
 int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,

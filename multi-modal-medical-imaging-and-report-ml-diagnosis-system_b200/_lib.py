@@ -59,6 +59,8 @@ SIGNATURES = {
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "mmdx_op_stem": [_p, _p, _i, _i, _i, _p, _p, _p, _p],
+    "mmdx_pack_stem_weights": [_p, _p, _p],
+    "mmdx_op_stem_pool": [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p],
     "mmdx_op_preprocess": [_p, _p, _i, _i, _i, _i, _p, _ip, _ip, _p],
     "mmdx_op_resample_u8": [_p, _p, _i, _i, _i, _i, _p, _p],
     "mmdx_op_maxpool": [_p, _p, _i, _i, _i, _i, _p, _p],

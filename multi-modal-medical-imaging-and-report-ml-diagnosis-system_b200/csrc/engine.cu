@@ -14,6 +14,7 @@
 #include "../../include/mmdx.h"
 #include "attention_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
+#include "stem_tcgen05.cuh"
 #include "kernels.cuh"
 
 using namespace mmdx;
@@ -122,7 +123,7 @@ struct DevBuf {
   }
 };
 
-struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; int cg = 1; };
+struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1; };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
   bf16* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1;
@@ -144,7 +145,8 @@ struct ImagePlan {
   bf16* in_pad = nullptr; bf16* stem_out = nullptr; bf16* pool_out = nullptr;
   int sh = 0, sw = 0, ph = 0, pw = 0;   // stem / pool output sizes
   struct Step { int kind; GemmLaunch g; };   // kind 0 = gemm
-  std::vector<GemmLaunch> convs;            // stem first, then bottleneck convs in launch order
+  StemParams stem_p{};                      // fused conv1 + bn + relu + maxpool
+  std::vector<GemmLaunch> convs;            // stem (legacy GEMM form) first, then bottleneck convs in launch order
   bf16* last = nullptr; int last_hw = 0;
   size_t in_pad_bytes = 0;
   DevBuf tables;        // Pillow coefficient tables of this geometry
@@ -173,13 +175,17 @@ struct mmdx_engine {
   int d_img = 0, d_txt = 0, d_fuse = 0, n_cls = 0, hidden = 0, n_layers = 0, ffn = 0, feat_dim = 2048;
   // weights (one arena)
   DevBuf warena; size_t wused = 0;
-  ConvW stem; std::vector<Bottleneck> blocks;
+  ConvW stem; bf16* stem_w2 = nullptr;   // stem weights in the stem kernel's resident layout
+  std::vector<Bottleneck> blocks;
   bf16 *word = nullptr, *ptab = nullptr, *ttab = nullptr; LnW emb_ln; std::vector<BertLayerW> layers;
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D of the image batch overlaps the text branch (mmdx_forward_host)
+  cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
   CUtensorMap tm_ident_half{};   // same identity, box of 32 rows: each CTA of a pair holds half of the B operand
   bool attn_force_general = false;   // MMDX_ATTN=general: use the flash-style kernel for short sequences too (experiments)
+  int epi_bufs = 0;      // MMDX_EB=1|2 pins the staging buffers per epilogue group of the CTA-pair kernels; 0 = heuristic
   int force_cg = 0;      // MMDX_CG=1|2 pins the CTA-group size of every eligible GEMM (experiments); 0 = heuristic
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
@@ -281,6 +287,10 @@ static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const
   } else if (residual) {
     REQUIRE(p.epi_mode == EPI_DIRECT, "unaligned residual needs the direct epilogue (fp32 or unaligned output)");
   }
+  // CTA-pair kernels trade one ring stage for a second staging buffer per epilogue group.  Measured on one box
+  // (tools/opbench.py, MMDX_EB=1|2): that pays when the main loop is short and the tile is epilogue/HBM-bound
+  // (layer1/2 conv3: -10 / -4 us) and costs 2-4 us on the long-K text GEMMs.
+  g.eb = (e->epi_bufs == 1 || e->epi_bufs == 2) ? e->epi_bufs : ((p.num_k_blocks + p.res_blocks <= 6) ? 2 : 1);
   return 0;
 }
 
@@ -413,11 +423,11 @@ static int build_stem(mmdx_engine* e, GemmLaunch& g, const bf16* in_pad, int NB,
   return 0;
 }
 
-template <int BN, int BK, int ST, int CG>
+template <int BN, int BK, int ST, int CG, int EB>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
-  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST, CG>;
-  constexpr int SMEM = GemmSmem<BN, BK, ST, CG>::TOTAL;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST, CG, EB>;
+  constexpr int SMEM = GemmSmem<BN, BK, ST, CG, EB>::TOTAL;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
@@ -442,7 +452,7 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
       CK(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
       REQUIRE(n > 0, "no CTA pair fits on this device");
       max_clusters = n;
-      if (getenv("MMDX_DEBUG")) fprintf(stderr, "mmdx: gemm<%d,%d,%d,%d> max active clusters %d\n", BN, BK, ST, CG, n);
+      if (getenv("MMDX_DEBUG")) fprintf(stderr, "mmdx: gemm<%d,%d,%d,%d,%d> max active clusters %d\n", BN, BK, ST, CG, EB, n);
     }
     if (groups > max_clusters) { groups = max_clusters; cfg.gridDim = dim3((unsigned)groups * CG, 1, 1); }
     CK(cudaLaunchKernelEx(&cfg, kfn, g.p));
@@ -455,20 +465,89 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
-  if (g.bk == 32) return launch_inst<64, 32, 8, 1>(g, groups, s);
+  if (g.bk == 32) return launch_inst<64, 32, 8, 1, 2>(g, groups, s);
   if (g.cg == 2) {
     switch (g.bn) {
-      case 256: return launch_inst<256, 64, 6, 2>(g, groups, s);
-      case 128: return launch_inst<128, 64, 8, 2>(g, groups, s);
+      case 256: return g.eb == 1 ? launch_inst<256, 64, 6, 2, 1>(g, groups, s) : launch_inst<256, 64, 5, 2, 2>(g, groups, s);
+      case 128: return g.eb == 1 ? launch_inst<128, 64, 8, 2, 1>(g, groups, s) : launch_inst<128, 64, 7, 2, 2>(g, groups, s);
     }
     return fail("mmdx: bad BN for a CTA pair");
   }
   switch (g.bn) {
-    case 256: return launch_inst<256, 64, 4, 1>(g, groups, s);
-    case 128: return launch_inst<128, 64, 6, 1>(g, groups, s);
-    case 64: return launch_inst<64, 64, 8, 1>(g, groups, s);
+    case 256: return launch_inst<256, 64, 4, 1, 1>(g, groups, s);     // 4 x 48 KB ring leaves room for one buffer per group
+    case 128: return launch_inst<128, 64, 5, 1, 2>(g, groups, s);
+    case 64: return launch_inst<64, 64, 7, 1, 2>(g, groups, s);
   }
   return fail("mmdx: bad BN");
+}
+
+// ------------------------------------------------------------------------------------------ stem (conv1 + maxpool)
+// conv1 weight [64,3,7,7] (x optional per-output-channel scale = folded BN) -> bf16 in the layout the stem kernel
+// keeps resident: per filter row r, a [64 x 32] K-major operand (k = 4*s + c; tap s = 7 and channel c = 3 are zero)
+// stored as no-swizzle core matrices [k-chunk j][n-group g][row i][8 elements].
+extern "C" int mmdx_pack_stem_weights(const float* w_oihw, const float* scale, uint16_t* out_bf16) {
+  if (!w_oihw || !out_bf16) return 1;
+  for (int r = 0; r < 7; ++r)
+    for (int j = 0; j < 4; ++j)
+      for (int g = 0; g < 8; ++g)
+        for (int i = 0; i < 8; ++i)
+          for (int el = 0; el < 8; ++el) {
+            const int o = 8 * g + i, k = 8 * j + el, s = k >> 2, c = k & 3;
+            float v = 0.f;
+            if (s < 7 && c < 3) v = w_oihw[((o * 3 + c) * 7 + r) * 7 + s] * (scale ? scale[o] : 1.0f);
+            const bf16 b = __float2bfloat16(v);
+            out_bf16[(((r * 4 + j) * 8 + g) * 8 + i) * 8 + el] = *reinterpret_cast<const uint16_t*>(&b);
+          }
+  return 0;
+}
+
+static int plan_stem(mmdx_engine* e, StemParams& p, const bf16* in_pad, int B, int H, int W, const bf16* w,
+                     const float* bias, bf16* out, int pool) {
+  memset(&p, 0, sizeof p);
+  int hp, wp;
+  mmdx_padded_dims(H, W, &hp, &wp);
+  p.in_pad = in_pad; p.w = w; p.bias = bias; p.out = out; p.B = B; p.hp = hp; p.wp = wp; p.pool = pool;
+  p.OH = (H - 1) / 2 + 1; p.OW = (W - 1) / 2 + 1;
+  p.PH = (p.OH - 1) / 2 + 1; p.PW = (p.OW - 1) / 2 + 1;
+  const int pitch = wp * 8;
+  const int fixed = STEM_W_BYTES + STEM_ROWBUF_BYTES + 512 + 1024;
+  const int budget = (232448 - fixed) / 2 - 16 - STEM_SLACK;             // bytes of image rows per strip buffer
+  const int max_rows_in = budget / pitch;
+  REQUIRE(max_rows_in >= (pool ? 11 : 7), "image too wide for the stem kernel's shared-memory strip");
+  const int out_rows = pool ? p.PH : p.OH, out_cols = pool ? p.PW : p.OW;
+  p.cols_per_block = pool ? (out_cols < 63 ? out_cols : 63) : (out_cols < 128 ? out_cols : 128);
+  p.col_blocks = (out_cols + p.cols_per_block - 1) / p.cols_per_block;
+  // rows per strip: fewest waves x conv rows per strip (halo rows are recomputed)
+  int max_r = pool ? (max_rows_in - 7) / 4 : (max_rows_in - 5) / 2;
+  if (max_r > out_rows) max_r = out_rows;
+  long long best = -1; int best_r = 1;
+  for (int r = 1; r <= max_r; ++r) {
+    const long long units = (long long)B * ((out_rows + r - 1) / r) * p.col_blocks;
+    const long long waves = (units + e->num_sms - 1) / e->num_sms;
+    const long long cost = waves * (pool ? 2 * r + 1 : r);
+    if (best < 0 || cost < best || (cost == best && r > best_r)) { best = cost; best_r = r; }
+  }
+  p.rows_per_strip = best_r;
+  p.strips = (out_rows + best_r - 1) / best_r;
+  p.num_units = B * p.strips * p.col_blocks;
+  const int rows_in = pool ? 4 * best_r + 7 : 2 * best_r + 5;
+  p.in_buf_bytes = ((16 + rows_in * pitch + STEM_SLACK + 1023) / 1024) * 1024;
+  return 0;
+}
+
+static int launch_stem(mmdx_engine* e, const StemParams& p, cudaStream_t s) {
+  const int smem = 1024 + STEM_W_BYTES + STEM_ROWBUF_BYTES + 2 * p.in_buf_bytes + 512;
+  REQUIRE(smem <= 232448, "stem strip does not fit in shared memory");
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    CK(cudaFuncSetAttribute(stem_pool_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_smem = 232448;
+  }
+  const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
+  ProfScope _ps(e);
+  stem_pool_tcgen05_kernel<<<grid, STEM_THREADS, smem, s>>>(p);
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ create / weights
@@ -505,7 +584,11 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     const uint32_t bh[2] = {64, 32};
     TRY(make_tmap(e.get(), &e->tm_ident_half, e->ident.p, 2, d, st, bh, 128));
   }
+  CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->copy_ready, cudaEventDisableTiming));
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
+  if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
   if (const char* v = getenv("MMDX_ATTN")) e->attn_force_general = (strcmp(v, "general") == 0);
   *out = e.release();
   return 0;
@@ -515,6 +598,9 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->copy_done) cudaEventDestroy(e->copy_done);
+  if (e->copy_ready) cudaEventDestroy(e->copy_ready);
   delete e;
 }
 
@@ -622,6 +708,13 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     e->stem.cin = 3; e->stem.cout = 64; e->stem.k = 7; e->stem.stride = 2;
     TRY(upload(e, pw, &e->stem.w));
     TRY(upload(e, bias, &e->stem.bias));
+    std::vector<float> sc(64);
+    for (int o = 0; o < 64; ++o) sc[o] = g->data[o] / std::sqrt(v->data[o] + 1e-5f);
+    std::vector<uint16_t> w2(STEM_W_BYTES / 2);
+    REQUIRE(mmdx_pack_stem_weights(w->data.data(), sc.data(), w2.data()) == 0, "stem weight packing");
+    uint16_t* dw2 = nullptr;
+    TRY(upload(e, w2, &dw2));
+    e->stem_w2 = reinterpret_cast<bf16*>(dw2);
   }
   const int nblocks[4] = {3, 4, 6, 3};
   e->blocks.clear();
@@ -810,6 +903,7 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   TRY(fill_epilogue(e, gl, e->stem.bias, nullptr, 0, pl->stem_out, 64, ACT_RELU, 0));
   pl->convs.push_back(gl);
   pl->pool_out = bufs[0];
+  TRY(plan_stem(e, pl->stem_p, pl->in_pad, B, IH, IW, e->stem_w2, e->stem.bias, pl->pool_out, 1));
   bf16* x = bufs[0];
   bf16* y = bufs[1];
   bf16* o1 = bufs[2];
@@ -925,13 +1019,14 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
 // ------------------------------------------------------------------------------------------ launch helpers
 static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float* g, const float* b, float eps, bf16* y,
                      cudaStream_t s) {
-  const int grid = (rows + 7) / 8;
+  constexpr int R = 4;                          // rows per warp
+  const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: layernorm_kernel<256, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 512: layernorm_kernel<512, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 768: layernorm_kernel<768, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 1024: layernorm_kernel<1024, false><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 256: layernorm_kernel<256, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 512: layernorm_kernel<512, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 768: layernorm_kernel<768, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 1024: layernorm_kernel<1024, false, 2><<<(rows + 15) / 16, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -940,13 +1035,14 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
 static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const int* tt, int rows, int N, const bf16* word,
                         const bf16* ptab, const bf16* ttab, const float* g, const float* b, float eps, bf16* y,
                         cudaStream_t s) {
-  const int grid = (rows + 7) / 8;
+  constexpr int R = 2;
+  const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: layernorm_kernel<256, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 512: layernorm_kernel<512, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 768: layernorm_kernel<768, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 1024: layernorm_kernel<1024, true><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 256: layernorm_kernel<256, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 512: layernorm_kernel<512, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 768: layernorm_kernel<768, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 1024: layernorm_kernel<1024, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
     default: return fail("mmdx: hidden width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1016,15 +1112,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   }
   TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->in_pad, pl->hp, pl->wp, s));
   e->cur_cls = CLS_STEM;
-  TRY(launch_gemm(e, pl->convs[0], s));
-  e->cur_cls = CLS_POOL;
-  {
-    const long long total = (long long)B * pl->ph * pl->pw * 8;
-    ProfScope _ps(e);
-    maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pl->stem_out, B, pl->sh, pl->sw, 64, pl->pool_out,
-                                                                        pl->ph, pl->pw);
-    CK(cudaGetLastError());
-  }
+  TRY(launch_stem(e, pl->stem_p, s));                // conv1 + bn1 + relu + maxpool in one kernel
   e->cur_cls = CLS_CONV;
   for (size_t i = 1; i < pl->convs.size(); ++i) TRY(launch_gemm(e, pl->convs[i], s));
   e->cur_cls = CLS_POOL;
@@ -1073,7 +1161,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   e->cur_cls = CLS_POOL;
   {
     ProfScope _ps(e);
-    seq_mean_pool_kernel<<<B, 128, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
+    seq_mean_pool_kernel<<<dim3(B, (H + 63) / 64), 256, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
     CK(cudaGetLastError());
   }
   e->cur_cls = CLS_HEAD;
@@ -1157,14 +1245,20 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   float* d_probs = reinterpret_cast<float*>(b); b += out_f;
   uint8_t* d_vec = reinterpret_cast<uint8_t*>(b); b += out_u;
   float* d_thr = reinterpret_cast<float*>(b);
-  CK(cudaMemcpyAsync(d_img, h_images, (size_t)B * H * W * C, cudaMemcpyHostToDevice, s));
+  // The image batch (the bulk of the input bytes) is copied on the engine's copy stream while the text branch,
+  // whose inputs are a few hundred KB, already runs on `s`; the image branch waits for the copy event.
+  CK(cudaEventRecord(e->copy_ready, s));                       // previous work on `s` may still read d_img
+  CK(cudaStreamWaitEvent(e->copy_stream, e->copy_ready, 0));
+  CK(cudaMemcpyAsync(d_img, h_images, (size_t)B * H * W * C, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(e->copy_done, e->copy_stream));
   CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
   if (h_thr) CK(cudaMemcpyAsync(d_thr, h_thr, (size_t)e->n_cls * 4, cudaMemcpyHostToDevice, s));
-  TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
   TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, s));
+  CK(cudaStreamWaitEvent(s, e->copy_done, 0));
+  TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
   TRY(head_locked(e, B, h_thr ? d_thr : nullptr, nullptr, d_logits, d_probs, d_vec, s));
   CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
@@ -1208,6 +1302,17 @@ extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int
   TRY(build_stem(e, g, static_cast<const bf16*>(d_in_padded), NB, H, W, static_cast<const bf16*>(d_w)));
   TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, 64, ACT_RELU, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,
+                                 const float* d_bias, void* d_out, int pool, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
+  REQUIRE(e, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  StemParams p;
+  TRY(plan_stem(e, p, static_cast<const bf16*>(d_in_padded), NB, H, W, static_cast<const bf16*>(d_w_packed), d_bias,
+                static_cast<bf16*>(d_out), pool ? 1 : 0));
+  return launch_stem(e, p, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C,
                                   void* d_out_padded, int* out_h, int* out_w, void* stream) {
@@ -1300,7 +1405,7 @@ extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int3
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && hidden % 8 == 0, "hidden % 8");
   ProfScope _ps(e);
-  seq_mean_pool_kernel<<<n_seq, 128, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_h), d_cu, hidden,
+  seq_mean_pool_kernel<<<dim3(n_seq, (hidden + 63) / 64), 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_h), d_cu, hidden,
                                                                static_cast<bf16*>(d_out_bf16), hidden, d_out_f32);
   CK(cudaGetLastError());
   return 0;

@@ -39,7 +39,7 @@ constexpr int kMaxTaps = 12;
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 enum : int { EPI_DIRECT = 0, EPI_TMA = 1 };
 constexpr int kEpiCW = 32;                    // epilogue chunk width (columns): 64-byte bf16 rows, SWIZZLE_64B
-constexpr int kEpiStages = 2;                 // staging buffers (one per epilogue group)
+constexpr int kEpiGroups = 2;                 // epilogue groups (four warps each)
 constexpr int kIdentBytes = 64 * 64 * 2;      // resident 64x64 identity (B operand of the residual MMAs)
 constexpr int kEpiBufBytes = 128 * kEpiCW * 2;
 constexpr int kGemmThreads = 384;
@@ -70,13 +70,15 @@ struct alignas(64) GemmParams {
   signed char tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
 };
 
-template <int BN, int BK, int STAGES, int CG>
+// EB = staging buffers per epilogue group: with two, the TMA store of chunk c reads its buffer while chunk c+2
+// (same group) is already being converted and written into the other one.
+template <int BN, int BK, int STAGES, int CG, int EB>
 struct GemmSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;     // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = kEpiStages * kEpiBufBytes + kIdentBytes;
+  static constexpr int STG_BYTES = kEpiGroups * EB * kEpiBufBytes + kIdentBytes;
   static constexpr int BAR_BYTES = 512;
   static constexpr int TOTAL = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
   static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
@@ -98,9 +100,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return t;
 }
 
-template <int BN, int BK, int STAGES, int CG>
+template <int BN, int BK, int STAGES, int CG, int EB>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using L = GemmSmem<BN, BK, STAGES, CG>;
+  using L = GemmSmem<BN, BK, STAGES, CG, EB>;
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BN);
   static_assert(CG == 1 || (CG == 2 && BK == 64 && BN >= 128), "CTA pairs: BK 64, BN >= 128");
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* ident_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
-  uint8_t* ident = stg + kEpiStages * kEpiBufBytes;      // 1024-byte aligned
+  uint8_t* ident = stg + kEpiGroups * EB * kEpiBufBytes;      // 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if constexpr (CG == 2) mbar_arrive_cluster(tempty0 + as * 8); else mbar_arrive(&tempty_bar[as]);
     };
     int it = 0;
+    uint32_t nstore = 0;                    // TMA stores issued by this group so far (selects the staging buffer)
     for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -298,8 +301,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       if (p.epi_mode == EPI_TMA) {
         const int sw = (r >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
 #pragma unroll 1
-        for (int c = g; c < NC; c += 2) {
-          uint8_t* buf = stg + g * kEpiBufBytes;
+        for (int c = g; c < NC; c += 2, ++nstore) {
+          uint8_t* buf = stg + (g * EB + (EB == 2 ? (nstore & 1) : 0)) * kEpiBufBytes;
           uint32_t v[32];
           tmem_ld_32x32(tbase + c * kEpiCW, v);
           tmem_ld_wait();
@@ -325,9 +328,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
           } else if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf_x2(x[j], x[j + 1]);
           }
-          if (issuer) tma_store_wait_read<0>();   // the group's previous store has finished reading `buf`
+          if (issuer) tma_store_wait_read<EB - 1>();   // the store that last used `buf` has finished reading it
           named_bar_sync(1 + g, 128);
           uint8_t* my_row = buf + r * 64;
 #pragma unroll

@@ -220,8 +220,8 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __res
 // fp32 statistics by warp shuffles (two-pass in registers), bf16 in/out.
 // EMBED variant: row = word[id] + position[pos] + type[tt]  (HF BertEmbeddings, eps 1e-12).
 // ---------------------------------------------------------------------------------------------
-template <int N, bool EMBED>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows,
+template <int N, bool EMBED, int R>
+__global__ void __launch_bounds__(256, 2) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __nv_bfloat16* __restrict__ y,
                                                         const int* __restrict__ ids, const int* __restrict__ pos,
@@ -229,52 +229,83 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ word,
                                                         const __nv_bfloat16* __restrict__ ptab,
                                                         const __nv_bfloat16* __restrict__ ttab) {
-  constexpr int CH = N / 256;   // 16-byte chunks per lane
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // R rows per warp: all their 16-byte loads are issued before the first reduction (R * N / 256 loads in flight
+  // per lane), which is what an HBM/L2-bound row kernel needs.
+  constexpr int CH = N / 256;   // 16-byte chunks per lane and row
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  float v[CH][8];
+  if (row0 >= rows) return;
+  float v[R][CH][8];
   if (EMBED) {
-    const uint4* w = reinterpret_cast<const uint4*>(word + static_cast<size_t>(ids[row]) * N);
-    const uint4* pp = reinterpret_cast<const uint4*>(ptab + static_cast<size_t>(pos[row]) * N);
-    const uint4* tt = reinterpret_cast<const uint4*>(ttab + static_cast<size_t>(tts[row]) * N);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const uint4 a = __ldg(w + c * 32 + lane), b = __ldg(pp + c * 32 + lane), d = __ldg(tt + c * 32 + lane);
-      const uint32_t* ua = &a.x; const uint32_t* ub = &b.x; const uint32_t* ud = &d.x;
+    for (int r = 0; r < R; ++r) {
+      const int row = min(row0 + r, rows - 1);        // clamped duplicates are computed but not stored
+      const uint4* w = reinterpret_cast<const uint4*>(word + static_cast<size_t>(__ldg(ids + row)) * N);
+      const uint4* pp = reinterpret_cast<const uint4*>(ptab + static_cast<size_t>(__ldg(pos + row)) * N);
+      const uint4* tt = reinterpret_cast<const uint4*>(ttab + static_cast<size_t>(__ldg(tts + row)) * N);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 fa = unpack_bf16(ua[j]), fb = unpack_bf16(ub[j]), fd = unpack_bf16(ud[j]);
-        v[c][2 * j] = fa.x + fd.x + fb.x;       // word + type + position (HF order)
-        v[c][2 * j + 1] = fa.y + fd.y + fb.y;
+      for (int c = 0; c < CH; ++c) {
+        const uint4 a = __ldg(w + c * 32 + lane), b = __ldg(pp + c * 32 + lane), d = __ldg(tt + c * 32 + lane);
+        const uint32_t* ua = &a.x; const uint32_t* ub = &b.x; const uint32_t* ud = &d.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = unpack_bf16(ua[j]), fb = unpack_bf16(ub[j]), fd = unpack_bf16(ud[j]);
+          v[r][c][2 * j] = fa.x + fd.x + fb.x;       // word + type + position (HF order)
+          v[r][c][2 * j + 1] = fa.y + fd.y + fb.y;
+        }
       }
     }
   } else {
-    const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * N);
+    uint4 raw[R][CH];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const uint4 a = __ldg(src + c * 32 + lane);
-      const uint32_t* ua = &a.x;
+    for (int r = 0; r < R; ++r) {
+      const int row = min(row0 + r, rows - 1);
+      const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * N);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(ua[j]);
-        v[c][2 * j] = f.x; v[c][2 * j + 1] = f.y;
-      }
+      for (int c = 0; c < CH; ++c) raw[r][c] = __ldg(src + c * 32 + lane);
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const uint32_t* ua = &raw[r][c].x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(ua[j]);
+          v[r][c][2 * j] = f.x; v[r][c][2 * j + 1] = f.y;
+        }
+      }
   }
-  float s = 0.f;
+  float mean[R], rstd[R];
 #pragma unroll
-  for (int c = 0; c < CH; ++c)
+  for (int r = 0; r < R; ++r) {
+    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[c][j];
-  const float mean = warp_sum(s) * (1.0f / N);
-  float q = 0.f;
+    for (int c = 0; c < CH; ++c)
 #pragma unroll
-  for (int c = 0; c < CH; ++c)
+      for (int j = 0; j < 8; ++j) s += v[r][c][j];
+    mean[r] = s;
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / N) + eps);
-  uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * N);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    mean[r] *= (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[r][c][j] - mean[r]; q += d * d; }
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+  for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(rstd[r] * (1.0f / N) + eps);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int col = (c * 32 + lane) * 8;
@@ -282,13 +313,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-    float o[8];
-    o[0] = (v[c][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[c][1] - mean) * rstd * g0.y + b0.y;
-    o[2] = (v[c][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[c][3] - mean) * rstd * g0.w + b0.w;
-    o[4] = (v[c][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[c][5] - mean) * rstd * g1.y + b1.y;
-    o[6] = (v[c][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[c][7] - mean) * rstd * g1.w + b1.w;
-    dst[c * 32 + lane] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                    pack_bf16(o[6], o[7]));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row0 + r >= rows) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[r][c][j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+      reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * N)[c * 32 + lane] =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
   }
 }
 
@@ -451,32 +486,40 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
 }
 
 // Masked mean pool over each sequence's packed tokens (training_pipeline.py:452-459):
-// sum / clamp(count, 1e-6).  One block per sequence, 8 columns per thread.
-__global__ void __launch_bounds__(128) seq_mean_pool_kernel(const __nv_bfloat16* __restrict__ h,
+// sum / clamp(count, 1e-6).  Grid (sequence, 64-column slab); 256 threads = 32 token lanes x 8 column chunks of
+// 16 bytes, so a warp reads four full 128-byte row segments per step; partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16* __restrict__ h,
                                                             const int* __restrict__ cu_seqlens, int hidden,
                                                             __nv_bfloat16* __restrict__ out, long long ldo,
                                                             float* __restrict__ out_f32) {
+  __shared__ float part[32][64 + 1];
   const int seq = blockIdx.x;
+  const int c8 = threadIdx.x & 7, tl = threadIdx.x >> 3;
+  const int col = blockIdx.y * 64 + c8 * 8;
   const int t0 = cu_seqlens[seq], t1 = cu_seqlens[seq + 1];
-  for (int c8 = threadIdx.x; c8 < hidden / 8; c8 += blockDim.x) {
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0; t < t1; ++t) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + static_cast<size_t>(t) * hidden) + c8);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < hidden) {
+    for (int t = t0 + tl; t < t1; t += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + static_cast<size_t>(t) * hidden + col));
       float2 f;
       f = unpack_bf16(u.x); s[0] += f.x; s[1] += f.y;
       f = unpack_bf16(u.y); s[2] += f.x; s[3] += f.y;
       f = unpack_bf16(u.z); s[4] += f.x; s[5] += f.y;
       f = unpack_bf16(u.w); s[6] += f.x; s[7] += f.y;
     }
-    const float inv = 1.0f / fmaxf(static_cast<float>(t1 - t0), 1e-6f);
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] *= inv;
-    reinterpret_cast<uint4*>(out + static_cast<size_t>(seq) * ldo)[c8] =
-        make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
-    if (out_f32 != nullptr) {
-      float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(seq) * hidden + c8 * 8);
-      o[0] = make_float4(s[0], s[1], s[2], s[3]);
-      o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  for (int i = 0; i < 8; ++i) part[tl][c8 * 8 + i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.y * 64 + threadIdx.x;
+    if (c < hidden) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a += part[i][threadIdx.x];
+      a *= 1.0f / fmaxf(static_cast<float>(t1 - t0), 1e-6f);
+      out[static_cast<size_t>(seq) * ldo + c] = __float2bfloat16(a);
+      if (out_f32 != nullptr) out_f32[static_cast<size_t>(seq) * hidden + c] = a;
     }
   }
 }

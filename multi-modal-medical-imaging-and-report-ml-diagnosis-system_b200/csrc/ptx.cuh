@@ -79,6 +79,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// plain bulk copy: one contiguous global range (16-byte aligned, size % 16 == 0) -> shared memory
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // smem (swizzled box) -> global tensor; completion tracked by this thread's bulk async-group
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -304,6 +312,50 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * tc));
   return fmaf(-0.5f * t, e, fmaxf(x, 0.0f));
+}
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of fp32 math per instruction.
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf (below) on two values at once: the polynomial, the two products and the final FMA run as packed
+// f32x2 instructions - 16 instructions per pair instead of 24.  Same arithmetic, same rounding.
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const float t0 = fabsf(x0), t1 = fabsf(x1);
+  const uint64_t T = pack_f32x2(fminf(t0, 6.0f), fminf(t1, 6.0f));
+  uint64_t q = fma_f32x2(pack_f32x2(2.9927026844234206e-05f, 2.9927026844234206e-05f), T,
+                         pack_f32x2(-0.0007398975430987775f, -0.0007398975430987775f));
+  q = fma_f32x2(q, T, pack_f32x2(0.007977532222867012f, 0.007977532222867012f));
+  q = fma_f32x2(q, T, pack_f32x2(-0.05323828011751175f, -0.05323828011751175f));
+  q = fma_f32x2(q, T, pack_f32x2(-0.4589156210422516f, -0.4589156210422516f));
+  q = fma_f32x2(q, T, pack_f32x2(-1.1511471271514893f, -1.1511471271514893f));
+  float a0, a1;
+  unpack_f32x2(mul_f32x2(q, T), a0, a1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t r = fma_f32x2(mul_f32x2(pack_f32x2(t0, t1), pack_f32x2(-0.5f, -0.5f)), pack_f32x2(e0, e1),
+                               pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  unpack_f32x2(r, x0, x1);
 }
 __device__ __forceinline__ float fast_exp2(float x) {     // MUFU.EX2; exp2(-inf) = 0
   float e;

@@ -172,6 +172,38 @@ def test_stem_conv7x7(h, B, H, W):
     assert rel_err(out, ref) < 1.2e-2
 
 
+def _pack_stem(w):
+    out = np.zeros(7 * 4 * 8 * 8 * 8, dtype=np.uint16)
+    wf = np.ascontiguousarray(w.float().cpu().numpy())
+    assert _lib.lib().mmdx_pack_stem_weights(wf.ctypes.data_as(C.c_void_p), None, out.ctypes.data_as(C.c_void_p)) == 0
+    return torch.from_numpy(out.view(np.int16)).cuda().view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 224, 224), (1, 64, 96), (3, 30, 34), (5, 224, 224), (1, 512, 512), (2, 225, 231)])
+@pytest.mark.parametrize("pool", [0, 1])
+def test_stem_fused_kernel(h, B, H, W, pool):
+    """conv1 + bias + ReLU (+ MaxPool 3x3/2) straight from raw image rows in shared memory (stem_tcgen05.cuh)
+    against torch on the same bf16 inputs; the pooled output must equal max-pooling the bf16-rounded conv rows."""
+    g = torch.Generator(device="cuda").manual_seed(B + H + pool)
+    x = bf(torch.randn(B, 3, H, W, device="cuda", generator=g)).float()
+    w = bf(torch.randn(64, 3, 7, 7, device="cuda", generator=g) * (147 ** -0.5))
+    bias = torch.randn(64, device="cuda", generator=g)
+    wpk = _pack_stem(w)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    PH, PW = (OH - 1) // 2 + 1, (OW - 1) // 2 + 1
+    shape = (B, PH, PW, 64) if pool else (B, OH, OW, 64)
+    out = torch.full(shape, float("nan"), device="cuda", dtype=torch.bfloat16)
+    xin = _pad_nhwc4(x)
+    _lib.check(_lib.lib().mmdx_op_stem_pool(h.handle, P(xin), B, H, W, P(wpk), P(bias), P(out), pool, S()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x, w.float(), bias, stride=2, padding=3))
+    if pool:
+        ref = F.max_pool2d(ref, 3, 2, 1)
+    ref = ref.permute(0, 2, 3, 1)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1.2e-2
+
+
 # ---------------------------------------------------------------------------------------- preprocessing
 @pytest.mark.parametrize("B,H,W,Cc", [(2, 512, 512, 3), (3, 224, 224, 3), (1, 300, 400, 3), (1, 1024, 768, 3),
                                       (2, 257, 640, 1), (1, 256, 256, 3), (1, 256, 300, 3)])
