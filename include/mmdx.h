@@ -99,7 +99,7 @@ int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, 
                  const float* d_bias, void* d_out, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
- * d_w_packed: 7168 bf16 from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).
+ * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).
  * d_out: bf16 [NB, OH, OW, 64] (pool == 0) or [NB, PH, PW, 64]; OH = (H-1)/2+1, PH = (OH-1)/2+1. */
 int mmdx_pack_stem_weights(const float* w_oihw, const float* scale, uint16_t* out_bf16);
 int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,

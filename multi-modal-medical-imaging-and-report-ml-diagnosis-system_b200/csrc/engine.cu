@@ -243,22 +243,27 @@ ProfScope::~ProfScope() {
   e->prof.push_back({e->cur_cls, a, b});
 }
 
-static int pick_bn(mmdx_engine* e, long long m_tiles, int N, int bn_req) {
-  if (bn_req == 64 || bn_req == 128 || bn_req == 256) return (N % bn_req == 0) ? bn_req : 0;
-  const int cands[3] = {256, 128, 64};
-  for (int c : cands)
-    if (N % c == 0 && m_tiles * (N / c) >= 2LL * e->num_sms) return c;
-  for (int c : {128, 64})      // small problems: prefer more, smaller tiles
-    if (N % c == 0) return c;
-  return 0;
-}
-
-// CTA pairs (cta_group::2) halve the B-operand traffic per SM; worth it once every pair has >= 2 tiles of work.
-static int pick_cg(mmdx_engine* e, long long m_tiles, int n_tiles, int bn, int bk) {
-  if (bn < 128 || bk != 64 || m_tiles < 2) return 1;
-  if (e->force_cg == 1 || e->force_cg == 2) return e->force_cg;
-  const long long pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
-  return pair_tiles >= 2LL * (e->num_sms / 2) ? 2 : 1;
+// Tile shape (BN) and CTA-group size (cg) of one GEMM: minimise  waves x BN x penalty, where a wave is one tile per
+// CTA group (148 / cg groups) - i.e. the per-SM time of the persistent schedule including its last, partly empty
+// wave.  Penalties (from tools/opbench.py on B200): single-CTA tiles and BN < 192 are shared-memory-bandwidth bound
+// (A + B operand reads plus the TMA fill exceed 128 B/clk), CTA pairs with BN >= 192 are not.
+// e.g. N = 768 (attention output / FFN2, M = 32768): BN 256 -> 6 waves x 256, BN 192 -> 7 waves x 192 (10 % less).
+static void pick_tile_shape(mmdx_engine* e, long long m_tiles, int N, int bn_req, int* bn_out, int* cg_out) {
+  struct Cand { int bn, cg; double pen; };
+  const Cand cands[] = {{256, 2, 1.00}, {192, 2, 1.03}, {128, 2, 1.15}, {256, 1, 1.35}, {128, 1, 1.35}, {64, 1, 1.60}};
+  double best = -1.0; *bn_out = 0; *cg_out = 1;
+  for (const Cand& c : cands) {
+    if (N % c.bn != 0) continue;
+    if (bn_req != 0 && c.bn != bn_req) continue;
+    if (c.cg == 2 && m_tiles < 2) continue;
+    if (e->force_cg == 1 && c.cg != 1) continue;
+    if (e->force_cg == 2 && c.cg != 2 && m_tiles >= 2 && N % 128 == 0) continue;
+    const long long groups = e->num_sms / c.cg;
+    const long long tiles = ((m_tiles + c.cg - 1) / c.cg) * (N / c.bn);
+    const long long waves = (tiles + groups - 1) / groups;
+    const double cost = (double)waves * c.bn * c.pen;
+    if (best < 0 || cost < best) { best = cost; *bn_out = c.bn; *cg_out = c.cg; }
+  }
 }
 
 // Epilogue wiring.  Must be called after build_gemm/build_conv/build_stem (needs the tile geometry).
@@ -302,10 +307,9 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   GemmParams& p = g.p;
   memset(&p, 0, sizeof p);
   const long long m_tiles = (M + 127) / 128;
-  g.bn = pick_bn(e, m_tiles, N, bn_req);
+  pick_tile_shape(e, m_tiles, N, bn_req, &g.bn, &g.cg);
   REQUIRE(g.bn != 0, "no BN tile divides N");
   g.bk = 64;
-  g.cg = pick_cg(e, m_tiles, N / g.bn, g.bn, 64);
   const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
   const uint64_t str[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M, (uint64_t)lda * 2 * (uint64_t)M};
   const uint32_t box[4] = {64, 128, 1, 1};
@@ -350,10 +354,9 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
   int Wb, Hb, Nb;
   pick_tile(OW, OH, NB, Wb, Hb, Nb);
   const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
-  g.bn = pick_bn(e, m_tiles, Cout, 0);
+  pick_tile_shape(e, m_tiles, Cout, 0, &g.bn, &g.cg);
   REQUIRE(g.bn != 0, "no BN tile divides Cout");
   g.bk = 64;
-  g.cg = pick_cg(e, m_tiles, Cout / g.bn, g.bn, 64);
   const uint32_t box[4] = {64, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
   if (stride == 1) {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -469,6 +472,7 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   if (g.cg == 2) {
     switch (g.bn) {
       case 256: return g.eb == 1 ? launch_inst<256, 64, 6, 2, 1>(g, groups, s) : launch_inst<256, 64, 5, 2, 2>(g, groups, s);
+      case 192: return g.eb == 1 ? launch_inst<192, 64, 7, 2, 1>(g, groups, s) : launch_inst<192, 64, 6, 2, 2>(g, groups, s);
       case 128: return g.eb == 1 ? launch_inst<128, 64, 8, 2, 1>(g, groups, s) : launch_inst<128, 64, 7, 2, 2>(g, groups, s);
     }
     return fail("mmdx: bad BN for a CTA pair");

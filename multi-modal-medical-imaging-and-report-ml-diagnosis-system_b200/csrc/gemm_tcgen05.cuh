@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BN);
   static_assert(CG == 1 || (CG == 2 && BK == 64 && BN >= 128), "CTA pairs: BK 64, BN >= 128");
-  constexpr uint32_t TMEM_COLS = 2 * BN;      // double-buffered fp32 accumulator
+  constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // double-buffered fp32 accumulator, power of two
   constexpr int NC = BN / kEpiCW;             // epilogue chunks per tile (even)
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert(BK == 64 || BK == 32, "BK");

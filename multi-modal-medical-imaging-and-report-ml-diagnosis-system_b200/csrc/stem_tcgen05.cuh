@@ -18,13 +18,14 @@
 // conv rows 2py-1..2py+1 in registers, then the horizontal 3-max through a swizzled shared row buffer, and
 // 16-byte coalesced stores of the pooled row.  Out-of-range rows/columns contribute zeros, which equals the
 // -inf padding of MaxPool2d because every ReLU output is >= 0.
-// Roles (192 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue.
+// Roles (320 threads): warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 / 6-9 = two
+// epilogue groups, each owning 32 of the 64 output channels of every conv row (one warp per SMSP was the limiter).
 #pragma once
 #include "ptx.cuh"
 
 namespace mmdx {
 
-constexpr int STEM_THREADS = 192;
+constexpr int STEM_THREADS = 320;
 constexpr int STEM_W_BYTES = 7 * 64 * 32 * 2;          // 28 KB resident weights
 constexpr int STEM_ROWBUF_BYTES = 128 * 128;           // one conv row of vertical maxima: 128 columns x 64 ch bf16
 constexpr int STEM_SLACK = 2048;                       // window reads of columns past the row end stay inside smem
@@ -77,6 +78,11 @@ __device__ __forceinline__ uint32_t stem_desc_lo(uint32_t saddr, uint32_t lbo) {
 }
 __device__ __forceinline__ constexpr uint32_t stem_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
 
+// Row-buffer swizzle: a bijection of (m & 7) with bits 1 and 2 swapped.  Writers (8 consecutive rows, same chunk) hit
+// 8 distinct 16-byte positions; readers (rows mm and mm+2, the 4 chunks of one channel half) land in different
+// halves of the 128-byte row - both conflict-free.
+__device__ __forceinline__ int stem_swz(int m) { return (m & 1) | ((m & 2) << 1) | ((m & 4) >> 1); }
+
 __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(const __grid_constant__ StemParams p) {
   constexpr uint32_t IDESC = make_idesc_bf16(128, 64);
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
-    for (int i = 0; i < STEM_ACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < STEM_ACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
     constexpr uint32_t A_HI = stem_desc_hi(128), B_HI = stem_desc_hi(128);
     mbar_wait(w_bar, 0);
     const uint32_t w_lo = stem_desc_lo(smem_u32(wbuf), 1024);
+    const uint32_t p16 = static_cast<uint32_t>(pitch) >> 4;        // row pitch in descriptor units (pitch % 16 == 0)
     int n = 0;
     uint32_t row_ctr = 0;                                          // conv rows issued so far (TMEM slot ring)
     for (int id = blockIdx.x; id < p.num_units; id += gridDim.x, ++n) {
@@ -140,21 +147,18 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
       const int buf = n & 1;
       mbar_wait(&in_full[buf], (n >> 1) & 1);
       // lane 0 of the tile = conv column ox0: its window starts 16*ox0 bytes into the row (ox0 = -1: the slack)
-      const uint32_t a_base = smem_u32(inbuf0 + buf * p.in_buf_bytes + 16) + 16 * u.ox0;
-      for (int c = 0; c < u.c_count; ++c, ++row_ctr) {
+      uint32_t a_lo = stem_desc_lo(smem_u32(inbuf0 + buf * p.in_buf_bytes + 16) + 16 * u.ox0, 16);
+      for (int c = 0; c < u.c_count; ++c, ++row_ctr, a_lo += 2 * p16) {
         const int slot = row_ctr % STEM_ACC;
         mbar_wait(&acc_empty[slot], ((row_ctr / STEM_ACC) & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = tmem_base + slot * 64;
-          const uint32_t a_row = a_base + static_cast<uint32_t>(2 * c) * pitch;
+          uint32_t a = a_lo;
 #pragma unroll
-          for (int r = 0; r < 7; ++r) {
-            const uint32_t a_lo = stem_desc_lo(a_row + r * pitch, 16);
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2)
-              umma_bf16_words<false>(d, a_lo + 2 * k2, A_HI, w_lo + ((r * 4096 + k2 * 2048) >> 4), B_HI, IDESC,
-                                     (r | k2) != 0 ? 1u : 0u);
+          for (int r = 0; r < 7; ++r, a += p16) {
+            umma_bf16_words<false>(d, a, A_HI, w_lo + ((r * 4096) >> 4), B_HI, IDESC, r != 0 ? 1u : 0u);
+            umma_bf16_words<false>(d, a + 2, A_HI, w_lo + ((r * 4096 + 2048) >> 4), B_HI, IDESC, 1u);
           }
           umma_commit(&acc_full[slot]);
           if (c == u.c_count - 1) umma_commit(&in_empty[buf]);     // every MMA reading this strip has finished
@@ -163,56 +167,53 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
       }
     }
   } else {
-    // ================= epilogue warps 2..5: thread = conv column =================
+    // ================= epilogue warps 2..9: thread = (conv column, channel half) =================
+    const int hf = (warp - 2) >> 2;                                // channels [32*hf, 32*hf + 32)
     const int q = warp & 3;                                        // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;                                   // lane of the tile = conv column ox0 + m
-    const int et = (warp - 2) * 32 + lane;                         // 0..127 index among the epilogue threads
+    const int et = ((warp - 2) & 3) * 32 + lane;                   // 0..127 index inside the group
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    float bias[64];
+    float bias[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) bias[i] = __ldg(p.bias + i);
+    for (int i = 0; i < 32; ++i) bias[i] = __ldg(p.bias + hf * 32 + i);
     uint32_t row_ctr = 0;
     for (int id = blockIdx.x; id < p.num_units; id += gridDim.x) {
       const StemUnit u = stem_unit(p, id);
       const int ox = u.ox0 + m;
       const bool col_ok = ox >= 0 && ox < p.OW && (p.pool ? m <= 2 * p.cols_per_block : m < p.cols_per_block);
-      uint32_t cur[32];                                            // running vertical max, bf16 pairs
+      uint32_t cur[16];                                            // running vertical max, bf16 pairs
 #pragma unroll
-      for (int i = 0; i < 32; ++i) cur[i] = 0u;
+      for (int i = 0; i < 16; ++i) cur[i] = 0u;
       for (int c = 0; c < u.c_count; ++c, ++row_ctr) {
         const int slot = row_ctr % STEM_ACC;
         mbar_wait(&acc_full[slot], (row_ctr / STEM_ACC) & 1);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(tmem_base + lane_base + slot * 64, v0);
-        tmem_ld_32x32(tmem_base + lane_base + slot * 64 + 32, v1);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_base + slot * 64 + hf * 32, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
-        uint32_t row[32];
+        uint32_t row[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float a0 = col_ok ? fmaxf(__uint_as_float(v0[2 * i]) + bias[2 * i], 0.f) : 0.f;
-          const float a1 = col_ok ? fmaxf(__uint_as_float(v0[2 * i + 1]) + bias[2 * i + 1], 0.f) : 0.f;
-          const float b0 = col_ok ? fmaxf(__uint_as_float(v1[2 * i]) + bias[32 + 2 * i], 0.f) : 0.f;
-          const float b1 = col_ok ? fmaxf(__uint_as_float(v1[2 * i + 1]) + bias[32 + 2 * i + 1], 0.f) : 0.f;
+          const float a0 = col_ok ? fmaxf(__uint_as_float(v[2 * i]) + bias[2 * i], 0.f) : 0.f;
+          const float a1 = col_ok ? fmaxf(__uint_as_float(v[2 * i + 1]) + bias[2 * i + 1], 0.f) : 0.f;
           row[i] = pack_bf16(a0, a1);
-          row[16 + i] = pack_bf16(b0, b1);
         }
         const int oy = u.c_first + c;
         if (!p.pool) {
           if (col_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(u.b) * p.OH + oy) * p.OW + ox) * 64);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(u.b) * p.OH + oy) * p.OW + ox) * 64 + hf * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_uint4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
           }
           continue;
         }
         // ---- fused max-pool: rows j = 0,1,2 | 2,3,4 | ... of the strip's window sequence feed pooled rows 0,1,..
         const int j = u.j0 + c;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&cur[i]);
           const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&row[i]);
           const __nv_bfloat162 mx = __hmax2(a, b);
@@ -222,22 +223,22 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
         if ((j >= 2 && (j & 1) == 0) || (last_row && (j & 1) == 1)) {
           // conv row 2py+1 (or the bottom border) completes pooled row py
           const int py = (u.c_first - u.j0 + 1) / 2 + (j - 1) / 2;      // strip's first pooled row + index
-          named_bar_sync(1, 128);                                         // previous pooled row fully read
-          uint8_t* my = rowbuf + m * 128;
+          named_bar_sync(1 + hf, 128);                                    // the group has read the previous pooled row
+          uint8_t* my = rowbuf + m * 128;                                 // 128-byte row: 8 chunks, XOR-swizzled
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(my + ((i ^ (m & 7)) << 4)) =
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(my + (((hf * 4 + i) ^ stem_swz(m)) << 4)) =
                 make_uint4(cur[4 * i], cur[4 * i + 1], cur[4 * i + 2], cur[4 * i + 3]);
-          named_bar_sync(1, 128);
+          named_bar_sync(1 + hf, 128);
           const int px0 = u.cb * p.cols_per_block;
           const int nq = min(p.cols_per_block, p.PW - px0);
-          for (int t = et; t < nq * 8; t += 128) {
-            const int qq = t >> 3, ch = t & 7;
+          for (int t = et; t < nq * 4; t += 128) {
+            const int qq = t >> 2, ch = hf * 4 + (t & 3);
             __nv_bfloat162 acc[4];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
               const int mm = 2 * qq + d;
-              const uint4 val = *reinterpret_cast<const uint4*>(rowbuf + mm * 128 + ((ch ^ (mm & 7)) << 4));
+              const uint4 val = *reinterpret_cast<const uint4*>(rowbuf + mm * 128 + ((ch ^ stem_swz(mm)) << 4));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&val);
 #pragma unroll
               for (int i = 0; i < 4; ++i) acc[i] = d == 0 ? h2[i] : __hmax2(acc[i], h2[i]);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
             reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(u.b) * p.PH + py) * p.PW + px0 + qq) * 64)[ch] = o;
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cur[i] = row[i];                   // row 2py+1 is also row 2(py+1)-1
+          for (int i = 0; i < 16; ++i) cur[i] = row[i];                   // row 2py+1 is also row 2(py+1)-1
         }
       }
     }

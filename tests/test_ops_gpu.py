@@ -48,6 +48,9 @@ def bf(x):
     (300, 3072, 768, 2, False, False, 0),
     (513, 768, 3072, 0, True, False, 128),
     (20000, 768, 768, 0, True, False, 256),
+    (20000, 768, 768, 0, True, False, 192),
+    (32768, 768, 3072, 0, True, False, 0),
+    (4099, 1536, 128, 1, False, False, 192),
     (1, 1024, 2048, 0, False, False, 0),
     (5, 512, 768, 0, False, True, 0),
     (256, 1024, 1536, 2, False, True, 0),

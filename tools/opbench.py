@@ -114,7 +114,28 @@ def bench_pre(h, lib):
         print(f"preprocess B={B} {HW}x{HW}: {us:8.1f} us  {by / us / 1e3:7.1f} GB/s", flush=True)
 
 
-ALL = {"attention": bench_attention, "gemm": bench_gemm, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
+def bench_stem(h, lib):
+    B, HW = 256, 224
+    hp, wp = C.c_int(), C.c_int()
+    lib.mmdx_padded_dims(HW, HW, C.byref(hp), C.byref(wp))
+    x = torch.zeros(B, hp.value, wp.value, 4, device="cuda", dtype=torch.bfloat16)
+    x[:, 3:3 + HW, 3:3 + HW, :3] = torch.randn(B, HW, HW, 3, device="cuda").to(torch.bfloat16)
+    w = torch.randn(64, 3, 7, 7) * 147 ** -0.5
+    pk = np.zeros(7 * 4 * 8 * 8 * 8, dtype=np.uint16)
+    wf = np.ascontiguousarray(w.numpy())
+    lib.mmdx_pack_stem_weights(wf.ctypes.data_as(C.c_void_p), None, pk.ctypes.data_as(C.c_void_p))
+    wd = torch.from_numpy(pk.view(np.int16)).cuda()
+    bias = torch.randn(64, device="cuda")
+    for pool in (1, 0):
+        shape = (B, 56, 56, 64) if pool else (B, 112, 112, 64)
+        out = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+        us = timeit(lambda: _lib.check(lib.mmdx_op_stem_pool(h.handle, P(x), B, HW, HW, P(wd), P(bias), P(out), pool, S())))
+        fl = 2.0 * B * 112 * 112 * 64 * 147
+        by = 2.0 * (x.numel() + out.numel())
+        print(f"stem pool={pool} B={B} {HW}x{HW}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
+
+
+ALL = {"stem": bench_stem, "attention": bench_attention, "gemm": bench_gemm, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
