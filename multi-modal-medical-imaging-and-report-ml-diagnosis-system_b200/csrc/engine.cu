@@ -142,6 +142,7 @@ struct ImagePlan {
   int crop_h = 0, crop_w = 0, hp = 0, wp = 0;
   int has_x = 0, has_y = 0, off_x = 0, off_y = 0;
   ResampleTable tx{}, ty{};
+  PreStrip strip{};
   bf16* in_pad = nullptr; bf16* stem_out = nullptr; bf16* pool_out = nullptr;
   int sh = 0, sw = 0, ph = 0, pw = 0;   // stem / pool output sizes
   struct Step { int kind; GemmLaunch g; };   // kind 0 = gemm
@@ -181,6 +182,7 @@ struct mmdx_engine {
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of the image batch overlaps the text branch (mmdx_forward_host)
   cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
+  DevBuf pre_lut;        // 3 x 256 bf16: ((v / 255) - mean[c]) / std[c], the ToTensor + Normalize arithmetic per byte value
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
   CUtensorMap tm_ident_half{};   // same identity, box of 32 rows: each CTA of a pair holds half of the B operand
@@ -591,6 +593,14 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->copy_ready, cudaEventDisableTiming));
+  {
+    std::vector<bf16> lut(3 * 256);
+    for (int c = 0; c < 3; ++c)
+      for (int v = 0; v < 256; ++v)      // ToTensor (/255) then Normalize ((x - mean) / std), fp32 like the reference
+        lut[c * 256 + v] = __float2bfloat16((static_cast<float>(v) / 255.0f - e->cfg.mean[c]) / e->cfg.std[c]);
+    TRY(e->pre_lut.ensure(lut.size() * 2));
+    CK(cudaMemcpy(e->pre_lut.p, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
+  }
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
   if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
   if (const char* v = getenv("MMDX_ATTN")) e->attn_force_general = (strcmp(v, "general") == 0);
@@ -823,48 +833,90 @@ static int pre_geometry(mmdx_engine* e, int H, int W, PreGeom* g) {
 }
 
 // builds the two device coefficient tables inside `buf`
-static int build_tables(mmdx_engine* e, DevBuf& buf, int H, int W, const PreGeom& g, ResampleTable* tx,
-                        ResampleTable* ty) {
+static int build_tables(mmdx_engine* e, DevBuf& buf, int H, int W, int C, const PreGeom& g, ResampleTable* tx,
+                        ResampleTable* ty, PreStrip* strip) {
   std::vector<int32_t> host;
   size_t off_x[3] = {0, 0, 0}, off_y[3] = {0, 0, 0};
   int kx = 0, ky = 0;
-  auto add = [&](int in, int out, int first, int n, size_t* off, int* ks) -> int {
+  int maxc_x = 1, maxc_y = 1;
+  std::vector<int32_t> fx, cx, fy, cy;
+  auto add = [&](int in, int out, int first, int n, size_t* off, int* ks, int* maxc, std::vector<int32_t>& fo,
+                 std::vector<int32_t>& co) -> int {
     const double sc = (double)in / out;
     const int ksize = (int)std::ceil(sc < 1.0 ? 1.0 : sc) * 2 + 1;
     std::vector<int32_t> f(n), c(n), w((size_t)n * ksize);
     if (mmdx_resample_coeffs(in, out, first, n, f.data(), c.data(), w.data(), (int)w.size()) != ksize) return 1;
+    for (int v : c) if (v > *maxc) *maxc = v;
     off[0] = host.size(); host.insert(host.end(), f.begin(), f.end());
     off[1] = host.size(); host.insert(host.end(), c.begin(), c.end());
     off[2] = host.size(); host.insert(host.end(), w.begin(), w.end());
     *ks = ksize;
+    fo = f; co = c;
     return 0;
   };
-  if (g.has_x) REQUIRE(add(W, g.ow, g.left, g.crop_w, off_x, &kx) == 0, "coefficient table");
-  if (g.has_y) REQUIRE(add(H, g.oh, g.top, g.crop_h, off_y, &ky) == 0, "coefficient table");
+  if (g.has_x) REQUIRE(add(W, g.ow, g.left, g.crop_w, off_x, &kx, &maxc_x, fx, cx) == 0, "coefficient table");
+  if (g.has_y) REQUIRE(add(H, g.oh, g.top, g.crop_h, off_y, &ky, &maxc_y, fy, cy) == 0, "coefficient table");
   if (host.empty()) host.push_back(0);
   TRY(buf.ensure(host.size() * 4));
   CK(cudaMemcpy(buf.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
   const int* base = static_cast<const int*>(buf.p);
-  *tx = ResampleTable{base + off_x[0], base + off_x[1], base + off_x[2], kx};
-  *ty = ResampleTable{base + off_y[0], base + off_y[1], base + off_y[2], ky};
+  *tx = ResampleTable{base + off_x[0], base + off_x[1], base + off_x[2], kx, maxc_x};
+  *ty = ResampleTable{base + off_y[0], base + off_y[1], base + off_y[2], ky, maxc_y};
+  // strip geometry of the tiled kernel: x-span touched by the crop window, rows staged per strip
+  PreStrip st{};
+  const int xs = g.has_x ? fx.front() : g.left;
+  const int xe = g.has_x ? fx.back() + cx.back() : g.left + g.crop_w;
+  st.xs = xs; st.span_bytes = (xe - xs) * C;
+  st.in_pitch = ((st.span_bytes + 3 + 3) / 4) * 4 + 4;
+  st.h_pitch = ((g.crop_w * C + 3) / 4) * 4;
+  st.rows_per_block = 0;
+  for (int ty_rows = 16; ty_rows >= 1; ty_rows /= 2) {
+    int rows_in = 0;
+    for (int oy0 = 0; oy0 < g.crop_h; oy0 += ty_rows) {
+      const int oy1 = oy0 + ty_rows < g.crop_h ? oy0 + ty_rows : g.crop_h;
+      const int n = g.has_y ? fy[oy1 - 1] + cy[oy1 - 1] - fy[oy0] : oy1 - oy0;
+      if (n > rows_in) rows_in = n;
+    }
+    const size_t smem = (size_t)rows_in * (st.in_pitch + st.h_pitch) + 256 * 3 * 2 + 64;
+    if (rows_in <= 256 && smem <= 160 * 1024) { st.rows_per_block = ty_rows; st.max_rows_in = rows_in; break; }
+  }
+  *strip = st;
   return 0;
 }
 
 static int launch_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const PreGeom& g,
-                             const ResampleTable& tx, const ResampleTable& ty, bf16* out, int hp, int wp,
+                             const ResampleTable& tx, const ResampleTable& ty, const PreStrip& st, bf16* out, int hp, int wp,
                              cudaStream_t s) {
-  dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
-  const float3 sc = make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]);
-  const float3 sh = make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]);
+  REQUIRE(C == 1 || C == 3, "images must have 1 or 3 channels");
   ProfScope _ps(e);
-  if (C == 3)
-    preprocess_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
-                                               g.top, out, hp, wp, 3, 3, sc, sh);
-  else if (C == 1)
-    preprocess_kernel<1><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
-                                               g.top, out, hp, wp, 3, 3, sc, sh);
-  else
-    return fail("mmdx: images must have 1 or 3 channels");
+  if (st.rows_per_block > 0) {                  // strip-tiled two-pass kernel
+    const size_t smem = (size_t)st.max_rows_in * (st.in_pitch + st.h_pitch) + 256 * 3 * 2 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(preprocess_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 2048));
+      CK(cudaFuncSetAttribute(preprocess_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 2048));
+      attr_set = true;
+    }
+    dim3 grid((g.crop_h + st.rows_per_block - 1) / st.rows_per_block, B), block(256);
+    const size_t total = (size_t)B * H * W * C;
+    const bf16* lut = static_cast<const bf16*>(e->pre_lut.p);
+    if (C == 3)
+      preprocess_tiled_kernel<3><<<grid, block, smem, s>>>(d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
+                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3);
+    else
+      preprocess_tiled_kernel<1><<<grid, block, smem, s>>>(d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
+                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3);
+  } else {                                      // a strip does not fit in shared memory (extreme down-scaling)
+    const float3 sc = make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]);
+    const float3 sh = make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]);
+    dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
+    if (C == 3)
+      preprocess_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                                 g.top, out, hp, wp, 3, 3, sc, sh);
+    else
+      preprocess_kernel<1><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                                 g.top, out, hp, wp, 3, 3, sc, sh);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -900,7 +952,7 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   bf16* bufs[5];
   for (int i = 0; i < 5; ++i) bufs[i] = reinterpret_cast<bf16*>(base + in_pad_b + stem_b + i * act_b);
   pl->in_pad_bytes = in_pad_b;
-  TRY(build_tables(e, pl->tables, H, W, g, &pl->tx, &pl->ty));
+  TRY(build_tables(e, pl->tables, H, W, C, g, &pl->tx, &pl->ty, &pl->strip));
   pl->convs.clear();
   GemmLaunch gl;
   TRY(build_stem(e, gl, pl->in_pad, B, IH, IW, e->stem.w));
@@ -1029,7 +1081,7 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
   switch (N) {
     case 256: layernorm_kernel<256, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
     case 512: layernorm_kernel<512, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 768: layernorm_kernel<768, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 768: layernorm_kernel<768, false, 2, 3><<<(rows + 15) / 16, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
     case 1024: layernorm_kernel<1024, false, 2><<<(rows + 15) / 16, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
@@ -1114,7 +1166,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
     CK(cudaMemsetAsync(pl->in_pad, 0, pl->in_pad_bytes, s));
     e->img_last = pl;
   }
-  TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->in_pad, pl->hp, pl->wp, s));
+  TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->strip, pl->in_pad, pl->hp, pl->wp, s));
   e->cur_cls = CLS_STEM;
   TRY(launch_stem(e, pl->stem_p, s));                // conv1 + bn1 + relu + maxpool in one kernel
   e->cur_cls = CLS_CONV;
@@ -1327,12 +1379,13 @@ extern "C" int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B
   PreGeom g;
   TRY(pre_geometry(e, H, W, &g));
   ResampleTable tx, ty;
-  TRY(build_tables(e, e->tab_ws, H, W, g, &tx, &ty));
+  PreStrip strip;
+  TRY(build_tables(e, e->tab_ws, H, W, C, g, &tx, &ty, &strip));
   int hp, wp;
   mmdx_padded_dims(g.crop_h, g.crop_w, &hp, &wp);
   if (out_h) *out_h = g.crop_h;
   if (out_w) *out_w = g.crop_w;
-  return launch_preprocess(e, d_images, B, H, W, C, g, tx, ty, static_cast<bf16*>(d_out_padded), hp, wp,
+  return launch_preprocess(e, d_images, B, H, W, C, g, tx, ty, strip, static_cast<bf16*>(d_out_padded), hp, wp,
                            (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,
@@ -1344,7 +1397,8 @@ extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int 
   PreGeom g;
   TRY(pre_geometry(e, H, W, &g));
   ResampleTable tx, ty;
-  TRY(build_tables(e, e->tab_ws, H, W, g, &tx, &ty));
+  PreStrip strip;
+  TRY(build_tables(e, e->tab_ws, H, W, C, g, &tx, &ty, &strip));
   dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
   ProfScope _ps(e);
   if (C == 3)
