@@ -9,7 +9,8 @@ A "step" is one pass of the hot path over one batch of synthetic studies: BASELI
 
   value     studies/s, device-resident inputs (uint8 images + packed int32 ids already in HBM)
   e2e       studies/s through the public host-buffer call (pinned host -> H2D -> forward -> D2H each step)
-  roofline  the dominant kernel (gemm_tcgen05_kernel: every conv and Linear) against the measured bf16 peak
+  roofline  the dominant kernel (gemm_tcgen05_kernel: the 52 bottleneck convs and every Linear) against the measured
+            bf16 peak; kernel_rooflines = the same arithmetic for every other kernel class (tensor or HBM bound)
   cpu_baseline  the CPU oracle port (oracle/forward_ref.py) on this box's host cores, bounded sample
 
 `--impl reference` times the reference's algorithm on the host CPU (the oracle port: the reference is
@@ -39,12 +40,46 @@ CLASSES = ["preprocess", "stem_conv", "pooling", "bottleneck_convs", "text_gemms
            "head", "other"]
 
 
+STEM_FLOPS = 2 * 64 * 3 * 49 * 112 * 112          # conv1 7x7/2 @224: 236,027,904 FLOP per study (stem_pool_tcgen05_kernel)
+
+
 def flops_per_study(L=SEQ_LEN):
     """ResNet-50 convs @224 + img proj + BERT(L) + txt proj + fusion + head (2*MAC)."""
-    gemm_kernel = 8_174_272_512 + 4_194_304 + 169_869_312 * L + 786_432 + 3_145_728   # runs in gemm_tcgen05_kernel
-    attention = 36_864 * L * L                                                          # attention_kernel
+    gemm_kernel = (8_174_272_512 - STEM_FLOPS) + 4_194_304 + 169_869_312 * L + 786_432 + 3_145_728   # gemm_tcgen05_kernel
+    attention = 36_864 * L * L                                    # attention_*_tcgen05_kernel, all 12 layers
     head13 = 26_624
-    return gemm_kernel, attention, head13
+    return gemm_kernel, STEM_FLOPS, attention, head13
+
+
+def class_rooflines(by_class, B, L, peaks, hidden=768, layers=12):
+    """Algorithmic FLOPs or bytes per step of every non-GEMM kernel class / its device time, against the measured
+    peak that bounds it (DESIGN.md section 4 lists the per-unit figures)."""
+    T = B * L
+    work = {
+        # uint8 HWC in, bf16 NHWC4 out
+        "preprocess": ("hbm", B * (IMG * IMG * 3 + IMG * IMG * 4 * 2)),
+        # conv1+bn+relu+maxpool fused: padded bf16 image in, pooled 56x56x64 out; tensor-bound by FLOPs
+        "stem_conv": ("tensor", B * STEM_FLOPS),
+        # global avgpool (7x7x2048 bf16 in) + masked mean pool (T x 768 bf16 in)
+        "pooling": ("hbm", B * 49 * 2048 * 2 + T * hidden * 2),
+        "attention": ("tensor", B * 36_864 * L * L),
+        # 24 LayerNorms (read + write T x 768 bf16) + embedding gather/LN (3 table rows read, 1 row written per token)
+        "layernorm_embed": ("hbm", 2 * layers * 2 * T * hidden * 2 + 4 * T * hidden * 2),
+    }
+    out = {}
+    for name, (bound, amount) in work.items():
+        if name not in by_class or by_class[name]["ms_per_step"] <= 0:
+            continue
+        sec = by_class[name]["ms_per_step"] * 1e-3
+        if bound == "tensor":
+            ach, peak, unit = amount / sec / 1e12, peaks["bf16_sustained"], "TFLOP/s"
+        else:
+            ach, peak, unit = amount / sec / 1e9, peaks["hbm"], "GB/s"
+        out[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+    if "attention" in out:      # attention also moves qkv in / ctx out once per layer: report the HBM view as well
+        sec = by_class["attention"]["ms_per_step"] * 1e-3
+        out["attention"]["hbm_gbs"] = layers * T * hidden * 2 * 4 / sec / 1e9
+    return out
 
 
 def load_peaks():
@@ -270,13 +305,13 @@ def main():
     lib().mmdx_profile_end(eng.handle, ms_cls, n_cls, 16)
     by_class = {CLASSES[i]: {"ms_per_step": ms_cls[i] / prof_steps, "launches_per_step": n_cls[i] // prof_steps}
                 for i in range(len(CLASSES)) if n_cls[i]}
-    gemm_classes = ("stem_conv", "bottleneck_convs", "text_gemms", "head")
+    gemm_classes = ("bottleneck_convs", "text_gemms", "head")
     gemm_ms = sum(by_class[c]["ms_per_step"] for c in gemm_classes if c in by_class)
     gemm_launches = sum(by_class[c]["launches_per_step"] for c in gemm_classes if c in by_class) - 1   # head_tail is not a GEMM
-    f_gemm, f_attn, f_head = flops_per_study(L)
+    f_gemm, f_stem, f_attn, f_head = flops_per_study(L)
     peaks = load_peaks()
     achieved = f_gemm * B / (gemm_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all convs + Linear layers)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (52 bottleneck convs + every Linear layer)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16",
                 "traffic": None, "launches_per_step": gemm_launches,
@@ -299,6 +334,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "kernel_classes": by_class,
+        "kernel_rooflines": class_rooflines(by_class, B, L, peaks),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

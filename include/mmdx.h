@@ -94,9 +94,6 @@ int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, 
 int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
                  const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride, int act,
                  void* stream);
-/* 7x7/2 stem over the padded 4-channel image written by mmdx_op_preprocess; weights [64][7][8][4] bf16. */
-int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
-                 const float* d_bias, void* d_out, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
  * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).
@@ -108,7 +105,6 @@ int mmdx_op_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int H, in
                        int* out_h, int* out_w, void* stream);
 int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, uint8_t* d_out,
                         void* stream);
-int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, int W, int C, void* d_out, void* stream);
 int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, int C, void* d_out_bf16, float* d_out_f32,
                     void* stream);
 int mmdx_op_layernorm(mmdx_engine* e, const void* d_x, int rows, int N, const float* d_gamma, const float* d_beta,

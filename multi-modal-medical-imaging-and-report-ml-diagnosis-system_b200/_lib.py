@@ -58,12 +58,10 @@ SIGNATURES = {
     "mmdx_profile_end": [_p, _p, _p, _i],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "mmdx_op_stem": [_p, _p, _i, _i, _i, _p, _p, _p, _p],
     "mmdx_pack_stem_weights": [_p, _p, _p],
     "mmdx_op_stem_pool": [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p],
     "mmdx_op_preprocess": [_p, _p, _i, _i, _i, _i, _p, _ip, _ip, _p],
     "mmdx_op_resample_u8": [_p, _p, _i, _i, _i, _i, _p, _p],
-    "mmdx_op_maxpool": [_p, _p, _i, _i, _i, _i, _p, _p],
     "mmdx_op_avgpool": [_p, _p, _i, _i, _i, _p, _p, _p],
     "mmdx_op_layernorm": [_p, _p, _i, _i, _p, _p, _f, _p, _p],
     "mmdx_op_embed_ln": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _f, _p, _p],

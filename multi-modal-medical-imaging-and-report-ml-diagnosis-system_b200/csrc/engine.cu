@@ -143,11 +143,11 @@ struct ImagePlan {
   int has_x = 0, has_y = 0, off_x = 0, off_y = 0;
   ResampleTable tx{}, ty{};
   PreStrip strip{};
-  bf16* in_pad = nullptr; bf16* stem_out = nullptr; bf16* pool_out = nullptr;
+  bf16* in_pad = nullptr; bf16* pool_out = nullptr;
   int sh = 0, sw = 0, ph = 0, pw = 0;   // stem / pool output sizes
   struct Step { int kind; GemmLaunch g; };   // kind 0 = gemm
   StemParams stem_p{};                      // fused conv1 + bn + relu + maxpool
-  std::vector<GemmLaunch> convs;            // stem (legacy GEMM form) first, then bottleneck convs in launch order
+  std::vector<GemmLaunch> convs;            // the 52 bottleneck convolutions in launch order
   bf16* last = nullptr; int last_hw = 0;
   size_t in_pad_bytes = 0;
   DevBuf tables;        // Pillow coefficient tables of this geometry
@@ -398,36 +398,6 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
   return 0;
 }
 
-// 7x7/2 pad 3 stem over the zero-bordered 4-channel image [NB,hp,wp,4] (image origin at (3,3)).
-static int build_stem(mmdx_engine* e, GemmLaunch& g, const bf16* in_pad, int NB, int H, int W, const bf16* w) {
-  int hp, wp;
-  mmdx_padded_dims(H, W, &hp, &wp);
-  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
-  GemmParams& p = g.p;
-  memset(&p, 0, sizeof p);
-  int Wb, Hb, Nb;
-  pick_tile(OW, OH, NB, Wb, Hb, Nb);
-  g.bn = 64; g.bk = 32; g.cg = 1;
-  const uint32_t box[4] = {32, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
-  for (int par = 0; par < 2; ++par) {
-    const uint64_t dims[4] = {32, (uint64_t)OW, (uint64_t)((hp - par) / 2), (uint64_t)NB};
-    const uint64_t str[3] = {16, (uint64_t)2 * wp * 8, (uint64_t)hp * wp * 8};   // W advances 2 pixels: overlapping windows
-    TRY(make_tmap(e, &p.tmA[par], in_pad + (size_t)par * wp * 4, 4, dims, str, box, 64));
-  }
-  p.tmA[2] = p.tmA[0]; p.tmA[3] = p.tmA[1];
-  for (int r = 0; r < 7; ++r) { p.tap_map[r] = (signed char)(r & 1); p.tap_dw[r] = 0; p.tap_dh[r] = (signed char)(r >> 1); }
-  const uint64_t bd[2] = {224, 64};
-  const uint64_t bs[1] = {224 * 2};
-  const uint32_t bb[2] = {32, 64};
-  TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 64));
-  p.kb_per_tap = 1; p.num_k_blocks = 7; p.a_box_bytes = Wb * Hb * Nb * 32 * 2;
-  const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
-  p.n_tiles = 1; p.cg = 1; p.num_tiles = (int)m_tiles;
-  p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
-  p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
-  return 0;
-}
-
 template <int BN, int BK, int ST, int CG, int EB>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
@@ -470,7 +440,6 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
-  if (g.bk == 32) return launch_inst<64, 32, 8, 1, 2>(g, groups, s);
   if (g.cg == 2) {
     switch (g.bn) {
       case 256: return g.eb == 1 ? launch_inst<256, 64, 6, 2, 1>(g, groups, s) : launch_inst<256, 64, 5, 2, 2>(g, groups, s);
@@ -709,21 +678,13 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     GET(w, "image.backbone.0.weight"); GET(g, "image.backbone.1.weight"); GET(b, "image.backbone.1.bias");
     GET(m, "image.backbone.1.running_mean"); GET(v, "image.backbone.1.running_var");
     REQUIRE(w->shape.size() == 4 && w->shape[0] == 64 && w->shape[1] == 3 && w->shape[2] == 7, "stem shape");
-    std::vector<bf16> pw((size_t)64 * 224, __float2bfloat16(0.f));
-    std::vector<float> bias(64);
+    std::vector<float> bias(64), sc(64);
     for (int o = 0; o < 64; ++o) {
-      const float sc = g->data[o] / std::sqrt(v->data[o] + 1e-5f);
-      bias[o] = b->data[o] - m->data[o] * sc;
-      for (int c = 0; c < 3; ++c)
-        for (int r = 0; r < 7; ++r)
-          for (int s = 0; s < 7; ++s)
-            pw[(size_t)o * 224 + r * 32 + s * 4 + c] = __float2bfloat16(w->data[(((size_t)o * 3 + c) * 7 + r) * 7 + s] * sc);
+      sc[o] = g->data[o] / std::sqrt(v->data[o] + 1e-5f);          // BatchNorm2d eps 1e-5, running stats
+      bias[o] = b->data[o] - m->data[o] * sc[o];
     }
     e->stem.cin = 3; e->stem.cout = 64; e->stem.k = 7; e->stem.stride = 2;
-    TRY(upload(e, pw, &e->stem.w));
     TRY(upload(e, bias, &e->stem.bias));
-    std::vector<float> sc(64);
-    for (int o = 0; o < 64; ++o) sc[o] = g->data[o] / std::sqrt(v->data[o] + 1e-5f);
     std::vector<uint16_t> w2(STEM_W_BYTES / 2);
     REQUIRE(mmdx_pack_stem_weights(w->data.data(), sc.data(), w2.data()) == 0, "stem weight packing");
     uint16_t* dw2 = nullptr;
@@ -938,9 +899,9 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   const int IH = g.crop_h, IW = g.crop_w;
   pl->sh = (IH - 1) / 2 + 1; pl->sw = (IW - 1) / 2 + 1;
   pl->ph = (pl->sh - 1) / 2 + 1; pl->pw = (pl->sw - 1) / 2 + 1;
-  // workspace layout: in_pad | stem_out | pool_out/X | Y | O1 | O2 | DS
+  // workspace layout: in_pad | pool_out/X | Y | O1 | O2 | DS   (the conv1 output never reaches memory)
   const size_t in_pad_b = al((size_t)B * pl->hp * pl->wp * 4 * 2);
-  const size_t stem_b = al((size_t)B * pl->sh * pl->sw * 64 * 2);
+  const size_t stem_b = 0;
   const size_t act_b = al((size_t)B * pl->ph * pl->pw * 256 * 2);      // largest bottleneck tensor (layer1 output)
   const size_t total = in_pad_b + stem_b + 5 * act_b;
   char* old = static_cast<char*>(e->img_ws.p);
@@ -948,16 +909,12 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   if (old != e->img_ws.p) { e->img_plans.clear(); e->img_last = nullptr; }   // buffers moved: cached tensor maps are stale
   char* base = static_cast<char*>(e->img_ws.p);
   pl->in_pad = reinterpret_cast<bf16*>(base);
-  pl->stem_out = reinterpret_cast<bf16*>(base + in_pad_b);
   bf16* bufs[5];
   for (int i = 0; i < 5; ++i) bufs[i] = reinterpret_cast<bf16*>(base + in_pad_b + stem_b + i * act_b);
   pl->in_pad_bytes = in_pad_b;
   TRY(build_tables(e, pl->tables, H, W, C, g, &pl->tx, &pl->ty, &pl->strip));
   pl->convs.clear();
   GemmLaunch gl;
-  TRY(build_stem(e, gl, pl->in_pad, B, IH, IW, e->stem.w));
-  TRY(fill_epilogue(e, gl, e->stem.bias, nullptr, 0, pl->stem_out, 64, ACT_RELU, 0));
-  pl->convs.push_back(gl);
   pl->pool_out = bufs[0];
   TRY(plan_stem(e, pl->stem_p, pl->in_pad, B, IH, IW, e->stem_w2, e->stem.bias, pl->pool_out, 1));
   bf16* x = bufs[0];
@@ -1170,7 +1127,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   e->cur_cls = CLS_STEM;
   TRY(launch_stem(e, pl->stem_p, s));                // conv1 + bn1 + relu + maxpool in one kernel
   e->cur_cls = CLS_CONV;
-  for (size_t i = 1; i < pl->convs.size(); ++i) TRY(launch_gemm(e, pl->convs[i], s));
+  for (const GemmLaunch& g : pl->convs) TRY(launch_gemm(e, g, s));
   e->cur_cls = CLS_POOL;
   {
     const int n = B * (e->feat_dim / 8);
@@ -1348,17 +1305,6 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
   TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
-extern "C" int mmdx_op_stem(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w,
-                            const float* d_bias, void* d_out, void* stream) {
-  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
-  REQUIRE(e, "null engine");
-  std::lock_guard<std::mutex> lk(e->mu);
-  CK(cudaSetDevice(e->cfg.device));
-  GemmLaunch g;
-  TRY(build_stem(e, g, static_cast<const bf16*>(d_in_padded), NB, H, W, static_cast<const bf16*>(d_w)));
-  TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, 64, ACT_RELU, 0));
-  return launch_gemm(e, g, (cudaStream_t)stream);
-}
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,
                                  const float* d_bias, void* d_out, int pool, void* stream) {
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
@@ -1409,17 +1355,6 @@ extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int 
                                                                    g.has_y, g.left, g.top, d_out);
   else
     return fail("mmdx: images must have 1 or 3 channels");
-  CK(cudaGetLastError());
-  return 0;
-}
-extern "C" int mmdx_op_maxpool(mmdx_engine* e, const void* d_in, int B, int H, int W, int C, void* d_out, void* stream) {
-  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
-  REQUIRE(e && C % 8 == 0, "maxpool needs C%8==0");
-  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  const long long total = (long long)B * OH * OW * (C / 8);
-  ProfScope _ps(e);
-  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const bf16*>(d_in), B, H, W, C, static_cast<bf16*>(d_out), OH, OW);
   CK(cudaGetLastError());
   return 0;
 }

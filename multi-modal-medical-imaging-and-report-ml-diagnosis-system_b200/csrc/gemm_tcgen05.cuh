@@ -4,9 +4,7 @@
 //     (filter tap, 64-channel chunk); each step is one TMA box load of a spatial tile shifted
 //     by the tap offset, with TMA out-of-bounds zero fill providing the conv padding.
 //     Stride-2 convs read one of four "parity" views of the input (even/odd rows x even/odd cols).
-//   * The 7x7/2 stem over a zero-padded 4-channel image: K chunk = one filter row
-//     (8 pixels x 4 channels = 32 contiguous bf16), fetched through a tensor map whose
-//     W dimension advances by 2 pixels (16 B) - overlapping windows, no im2col buffer.
+//   (The 7x7/2 stem has its own kernel, stem_tcgen05.cuh.)
 //
 // Roles (384 threads): warp 0 = TMA producer (A/B ring), warp 1 = TMEM allocator + single-thread MMA
 // issuer, warps 4..11 = epilogue in two groups of four (group g owns the 32-column chunks with

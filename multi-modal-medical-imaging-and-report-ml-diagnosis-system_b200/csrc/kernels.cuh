@@ -1,5 +1,6 @@
-// HBM-bound and small kernels of the path: preprocessing, pooling, embedding+LayerNorm,
-// LayerNorm, attention, masked mean pooling and the final head (LN + 13-way linear + sigmoid).
+// HBM-bound and small kernels of the path: preprocessing, average pooling, embedding+LayerNorm,
+// LayerNorm, masked mean pooling and the final head (LN + 13-way linear + sigmoid).
+// (conv1+maxpool: stem_tcgen05.cuh; attention: attention_tcgen05.cuh; every other contraction: gemm_tcgen05.cuh)
 #pragma once
 #include "ptx.cuh"
 
@@ -312,44 +313,6 @@ __global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restr
   for (int c = 0; c < C; ++c) dst[c] = static_cast<uint8_t>(has_y ? clip8(acc[c] >> 22) : acc[c]);
 }
 
-// ---------------------------------------------------------------------------------------------
-// MaxPool 3x3 stride 2 pad 1, NHWC bf16, 8 channels (16 B) per thread.  (torchvision resnet maxpool)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W,
-                                                           int C, __nv_bfloat16* __restrict__ out, int OH, int OW) {
-  const int cv = C / 8;
-  const long long total = static_cast<long long>(B) * OH * OW * cv;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % cv);
-  long long t = idx / cv;
-  const int ow = static_cast<int>(t % OW); t /= OW;
-  const int oh = static_cast<int>(t % OH);
-  const int b = static_cast<int>(t / OH);
-  __nv_bfloat162 m[4];
-  const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) m[i] = ninf;
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int ih = oh * 2 - 1 + dy;
-    if (ih < 0 || ih >= H) continue;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int iw = ow * 2 - 1 + dx;
-      if (iw < 0 || iw >= W) continue;
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + ih) * W + iw) * C) + c8);
-      const __nv_bfloat162* v = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], v[i]);
-    }
-  }
-  uint4 o;
-  o.x = *reinterpret_cast<uint32_t*>(&m[0]); o.y = *reinterpret_cast<uint32_t*>(&m[1]);
-  o.z = *reinterpret_cast<uint32_t*>(&m[2]); o.w = *reinterpret_cast<uint32_t*>(&m[3]);
-  reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * OH + oh) * OW + ow) * C)[c8] = o;
-}
-
 // Global average pool NHWC [B,HW,C] -> bf16 [B,C] (+ optional fp32 copy); 8 channels per thread.
 __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int HW, int C,
                                                       __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
@@ -488,164 +451,6 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
       reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * N)[c * 32 + lane] =
           make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Self-attention over packed (unpadded) tokens: softmax(Q K^T / sqrt(64)) V per (sequence, head).
-// qkv: bf16 [T, 3*HID] rows = tokens, columns [Q | K | V], head h at columns h*64.
-// Grid (q_blocks, heads, sequences); 4 warps x 16 query rows; keys streamed in blocks of 64 through
-// shared memory; mma.sync m16n8k16 bf16 with fp32 online softmax in registers (warp-shuffle row
-// reductions).  Padded keys never exist here (tokens are packed), which equals the reference's
-// additive -inf key mask (modeling_bert.py eager_attention_forward).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int ATT_D = 64;       // head dim
-constexpr int ATT_BQ = 64;      // query rows per CTA
-constexpr int ATT_BK = 64;      // keys per smem block
-constexpr int ATT_PITCH = 72;   // smem row pitch (elements): 144 B -> conflict-free ldmatrix
-
-__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                        const int* __restrict__ cu_seqlens, int hidden,
-                                                        __nv_bfloat16* __restrict__ ctx, float scale_log2) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[ATT_BQ * ATT_PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sK[ATT_BK * ATT_PITCH];
-  __shared__ __align__(16) __nv_bfloat16 sV[ATT_BK * ATT_PITCH];
-  const int seq = blockIdx.z, head = blockIdx.y, qb = blockIdx.x;
-  const int tok0 = cu_seqlens[seq];
-  const int len = cu_seqlens[seq + 1] - tok0;
-  const int q0 = qb * ATT_BQ;
-  if (q0 >= len) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t ld = static_cast<size_t>(3) * hidden;
-  const __nv_bfloat16* qbase = qkv + static_cast<size_t>(tok0) * ld + head * ATT_D;
-  const __nv_bfloat16* kbase = qbase + hidden;
-  const __nv_bfloat16* vbase = qbase + 2 * hidden;
-
-  // Q tile -> smem (zero rows beyond the sequence)
-  for (int i = tid; i < ATT_BQ * 8; i += 128) {
-    const int r = i >> 3, c = i & 7;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (q0 + r < len) u = __ldg(reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld) + c);
-    *reinterpret_cast<uint4*>(&sQ[r * ATT_PITCH + c * 8]) = u;
-  }
-  __syncthreads();
-  uint32_t qf[4][4];   // A fragments of this warp's 16 query rows, 4 k-steps of 16
-  {
-    const int r = warp * 16 + (lane & 15);
-    const int cofs = (lane >> 4) * 8;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-      ldsm_x4(smem_u32(&sQ[r * ATT_PITCH + ks * 16 + cofs]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-  }
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
-
-  for (int k0 = 0; k0 < len; k0 += ATT_BK) {
-    __syncthreads();   // previous block fully consumed
-    for (int i = tid; i < ATT_BK * 8; i += 128) {
-      const int r = i >> 3, c = i & 7;
-      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < len) {
-        uk = __ldg(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(k0 + r) * ld) + c);
-        uv = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(k0 + r) * ld) + c);
-      }
-      *reinterpret_cast<uint4*>(&sK[r * ATT_PITCH + c * 8]) = uk;
-      *reinterpret_cast<uint4*>(&sV[r * ATT_PITCH + c * 8]) = uv;
-    }
-    __syncthreads();
-
-    // S = Q K^T : 16 x 64 per warp
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {       // pairs of 8-key tiles
-        const int mid = lane >> 3;
-        const int key = np * 16 + (mid >> 1) * 8 + (lane & 7);
-        const int d = ks * 16 + (mid & 1) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(smem_u32(&sK[key * ATT_PITCH + d]), b0, b1, b2, b3);
-        mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
-        mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
-      }
-    }
-    // scale, mask keys beyond the sequence, online softmax
-    const int t4 = (lane & 3) * 2;
-    float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = k0 + i * 8 + t4;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = (key + (e & 1)) < len;
-        s[i][e] = ok ? s[i][e] * scale_log2 : -INFINITY;
-      }
-      bm0 = fmaxf(bm0, fmaxf(s[i][0], s[i][1]));
-      bm1 = fmaxf(bm1, fmaxf(s[i][2], s[i][3]));
-    }
-    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);   // finite: every block has >=1 valid key
-    const float c0 = exp2f(m0 - nm0), c1 = exp2f(m1 - nm1);
-    m0 = nm0; m1 = nm1;
-    float rs0 = 0.f, rs1 = 0.f;
-    uint32_t pf[4][4];    // P as A fragments: 4 k-steps of 16 keys
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float p0 = exp2f(s[i][0] - nm0), p1 = exp2f(s[i][1] - nm0);
-      const float p2 = exp2f(s[i][2] - nm1), p3 = exp2f(s[i][3] - nm1);
-      rs0 += p0 + p1; rs1 += p2 + p3;
-      pf[i >> 1][(i & 1) * 2 + 0] = pack_bf16(p0, p1);
-      pf[i >> 1][(i & 1) * 2 + 1] = pack_bf16(p2, p3);
-    }
-    l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-    // O += P V
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {         // 16 keys per step
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {       // pairs of 8-wide d tiles
-        const int mid = lane >> 3;
-        const int key = ks * 16 + (mid & 1) * 8 + (lane & 7);
-        const int d = dp * 16 + (mid >> 1) * 8;
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(&sV[key * ATT_PITCH + d]), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * dp], pf[ks], b0, b1);
-        mma_bf16_16816(o[2 * dp + 1], pf[ks], b2, b3);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  const int g = lane >> 2, t4 = (lane & 3) * 2;
-  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int col = head * ATT_D + i * 8 + t4;
-    if (r0 < len)
-      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(tok0 + r0) * hidden + col) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
-    if (r1 < len)
-      *reinterpret_cast<uint32_t*>(ctx + static_cast<size_t>(tok0 + r1) * hidden + col) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
   }
 }
 

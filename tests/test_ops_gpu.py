@@ -157,24 +157,6 @@ def _pad_nhwc4(x_nchw):
     return buf
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 224, 224), (1, 64, 96), (3, 30, 34)])
-def test_stem_conv7x7(h, B, H, W):
-    g = torch.Generator(device="cuda").manual_seed(B + H)
-    x = bf(torch.randn(B, 3, H, W, device="cuda", generator=g)).float()
-    w = bf(torch.randn(64, 3, 7, 7, device="cuda", generator=g) * (147 ** -0.5))
-    bias = torch.randn(64, device="cuda", generator=g)
-    wp = torch.zeros(64, 7, 8, 4, device="cuda", dtype=torch.bfloat16)
-    wp[:, :, :7, :3] = w.permute(0, 2, 3, 1)
-    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    out = torch.full((B, OH, OW, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-    xin = _pad_nhwc4(x)
-    _lib.check(_lib.lib().mmdx_op_stem(h.handle, P(xin), B, H, W, P(wp), P(bias), P(out), S()))
-    torch.cuda.synchronize()
-    ref = F.relu(F.conv2d(x, w.float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1)
-    assert torch.isfinite(out.float()).all()
-    assert rel_err(out, ref) < 1.2e-2
-
-
 def _pack_stem(w):
     out = np.zeros(7 * 4 * 8 * 8 * 8, dtype=np.uint16)
     wf = np.ascontiguousarray(w.float().cpu().numpy())
@@ -242,13 +224,7 @@ def test_preprocess_normalized_bf16(h, B, H, W, Cc):
 
 
 # ---------------------------------------------------------------------------------------- pooling / norms
-def test_maxpool_avgpool(h):
-    x = bf(torch.randn(3, 30, 34, 64, device="cuda"))
-    out = torch.zeros(3, 15, 17, 64, device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().mmdx_op_maxpool(h.handle, P(x), 3, 30, 34, 64, P(out), S()))
-    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
-    torch.cuda.synchronize()
-    assert torch.equal(out.float(), ref)
+def test_avgpool(h):
     y = bf(torch.randn(5, 49, 2048, device="cuda"))
     ob = torch.zeros(5, 2048, device="cuda", dtype=torch.bfloat16)
     of = torch.zeros(5, 2048, device="cuda")
