@@ -182,6 +182,12 @@ struct mmdx_engine {
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
   cudaStream_t copy_stream = nullptr;   // H2D of the image batch overlaps the text branch (mmdx_forward_host)
   cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
+  // The text branch runs on its own stream next to the image branch (they only meet at the fusion head): both are
+  // chains of persistent whole-chip kernels, so they do not share SMs, but each launch's prologue and its last,
+  // partly empty wave are filled by the other branch's CTAs.  MMDX_STREAMS=1 (or profiling mode) serialises them.
+  cudaStream_t text_stream = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  bool two_streams = true;
   DevBuf pre_lut;        // 3 x 256 bf16: ((v / 255) - mean[c]) / std[c], the ToTensor + Normalize arithmetic per byte value
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
@@ -562,6 +568,10 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->copy_ready, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&e->text_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming));
+  if (const char* v = getenv("MMDX_STREAMS")) e->two_streams = atoi(v) != 1;
   {
     std::vector<bf16> lut(3 * 256);
     for (int c = 0; c < 3; ++c)
@@ -584,6 +594,9 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->copy_done) cudaEventDestroy(e->copy_done);
   if (e->copy_ready) cudaEventDestroy(e->copy_ready);
+  if (e->text_stream) cudaStreamDestroy(e->text_stream);
+  if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+  if (e->join_ev) cudaEventDestroy(e->join_ev);
   delete e;
 }
 
@@ -1231,8 +1244,16 @@ extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int 
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
+  const bool fork = e->two_streams && !e->profiling;
+  cudaStream_t ts = fork ? e->text_stream : s;
+  if (fork) {
+    CK(cudaEventRecord(e->fork_ev, s));                 // inputs (and earlier work on `s`) are ready
+    CK(cudaStreamWaitEvent(ts, e->fork_ev, 0));
+  }
+  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, ts));
+  if (fork) CK(cudaEventRecord(e->join_ev, ts));
   TRY(image_encode_locked(e, d_images, B, H, W, C, nullptr, nullptr, s));
-  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, s));
+  if (fork) CK(cudaStreamWaitEvent(s, e->join_ev, 0));
   return head_locked(e, B, d_thr, nullptr, d_logits, d_probs, d_vector, s);
 }
 
@@ -1264,14 +1285,19 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   CK(cudaStreamWaitEvent(e->copy_stream, e->copy_ready, 0));
   CK(cudaMemcpyAsync(d_img, h_images, (size_t)B * H * W * C, cudaMemcpyHostToDevice, e->copy_stream));
   CK(cudaEventRecord(e->copy_done, e->copy_stream));
-  CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  const bool fork = e->two_streams && !e->profiling;
+  cudaStream_t ts = fork ? e->text_stream : s;
+  if (fork) CK(cudaStreamWaitEvent(ts, e->copy_ready, 0));    // earlier work on `s` may still read the token buffers
+  CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
+  CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
+  CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
+  CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ts));
   if (h_thr) CK(cudaMemcpyAsync(d_thr, h_thr, (size_t)e->n_cls * 4, cudaMemcpyHostToDevice, s));
-  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, s));
+  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, ts));
+  if (fork) CK(cudaEventRecord(e->join_ev, ts));
   CK(cudaStreamWaitEvent(s, e->copy_done, 0));
   TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
+  if (fork) CK(cudaStreamWaitEvent(s, e->join_ev, 0));
   TRY(head_locked(e, B, h_thr ? d_thr : nullptr, nullptr, d_logits, d_probs, d_vec, s));
   CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
