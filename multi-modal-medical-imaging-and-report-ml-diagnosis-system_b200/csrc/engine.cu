@@ -13,6 +13,7 @@
 
 #include "../../include/mmdx.h"
 #include "attention_tcgen05.cuh"
+#include "conv3x3_c64_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "stem_tcgen05.cuh"
 #include "kernels.cuh"
@@ -123,7 +124,10 @@ struct DevBuf {
   }
 };
 
-struct GemmLaunch { GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1; };
+struct GemmLaunch {
+  GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1;
+  bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
+};
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
   bf16* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1;
@@ -404,6 +408,44 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
   return 0;
 }
 
+// 3x3 stride-1 64->64 conv through the halo-tile kernel (conv3x3_c64_tcgen05.cuh)
+static bool c64_applicable(int Cin, int Cout, int k, int stride, const void* residual) {
+  static int off = -1;
+  if (off < 0) { const char* v = getenv("MMDX_C64"); off = (v && atoi(v) == 0) ? 1 : 0; }
+  return !off && Cin == 64 && Cout == 64 && k == 3 && stride == 1 && residual == nullptr;
+}
+static int build_c64(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int H, int W, const bf16* w, const float* bias,
+                     bf16* out, int act) {
+  REQUIRE(act == ACT_NONE || act == ACT_RELU, "c64 conv supports no activation or ReLU");
+  g.c64 = true;
+  C64Params& p = g.c;
+  memset(&p, 0, sizeof p);
+  const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+  const uint64_t str[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+  const uint32_t box[4] = {64, C64_HALO_W, C64_HALO_H, 1};
+  TRY(make_tmap(e, &p.tmA, in, 4, dims, str, box, 128));
+  const uint64_t wd[2] = {576, 64};
+  const uint64_t ws[1] = {576 * 2};
+  const uint32_t wb[2] = {64, 64};
+  TRY(make_tmap(e, &p.tmW, w, 2, wd, ws, wb, 128));
+  p.bias = bias; p.out = out; p.NB = NB; p.H = H; p.W = W;
+  p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.num_tiles = NB * p.tiles_w * p.tiles_h;
+  p.relu = act == ACT_RELU;
+  return 0;
+}
+static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(conv3x3_c64_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < e->num_sms ? p.num_tiles : e->num_sms;
+  ProfScope _ps(e);
+  conv3x3_c64_tcgen05_kernel<<<grid, C64_THREADS, C64_SMEM, s>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 template <int BN, int BK, int ST, int CG, int EB>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
@@ -443,6 +485,7 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
+  if (g.c64) return launch_c64(e, g.c, s);
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
@@ -942,9 +985,15 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
     TRY(build_conv(e, gl, x, B, h, w, bk.c1.cin, bk.c1.w, bk.c1.cout, 1, 1));
     TRY(fill_epilogue(e, gl, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0));
     pl->convs.push_back(gl);
-    TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
-    TRY(fill_epilogue(e, gl, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0));
+    gl.c64 = false;
+    if (c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr)) {
+      TRY(build_c64(e, gl, o1, B, h, w, bk.c2.w, bk.c2.bias, o2, ACT_RELU));
+    } else {
+      TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
+      TRY(fill_epilogue(e, gl, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0));
+    }
     pl->convs.push_back(gl);
+    gl.c64 = false;
     const bf16* idt = x;
     if (bk.has_ds) {
       TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
@@ -1327,6 +1376,11 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
   GemmLaunch g;
+  if (c64_applicable(Cin, Cout, k, stride, d_residual) && d_bias != nullptr && (act == ACT_NONE || act == ACT_RELU)) {
+    TRY(build_c64(e, g, static_cast<const bf16*>(d_in), NB, H, W, static_cast<const bf16*>(d_w), d_bias,
+                  static_cast<bf16*>(d_out), act));
+    return launch_gemm(e, g, (cudaStream_t)stream);
+  }
   TRY(build_conv(e, g, static_cast<const bf16*>(d_in), NB, H, W, Cin, static_cast<const bf16*>(d_w), Cout, k, stride));
   TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);

@@ -140,6 +140,8 @@ def _conv_case(h, NB, H, W, Cin, Cout, k, stride, act, res, seed=0):
     (130, 7, 7, 512, 512, 3, 1, 1, False),     # layer4 conv2, (1,1,128)-style tiles
     (1, 7, 7, 512, 2048, 1, 1, 1, True),       # layer4 conv3, batch 1
     (2, 15, 13, 64, 64, 3, 1, 0, False),       # odd sizes
+    (3, 128, 128, 64, 64, 3, 1, 1, False),     # layer1 conv2 at 512x512 input (halo-tile kernel, 8 x 8 tiles per image)
+    (150, 9, 20, 64, 64, 3, 1, 1, False),      # halo-tile kernel, more tiles than SMs, ragged both ways
     (2, 15, 13, 64, 128, 3, 2, 0, False),      # odd sizes, stride 2
     (2, 15, 13, 64, 128, 1, 2, 0, False),
 ])
