@@ -300,15 +300,14 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
 //     S = Q K^T   fp32, columns [0,128)                      tcgen05.mma, A/B K-major from smem
 //     P = softmax numerators, bf16 pairs, columns [0,64)     written in place by tcgen05.st as S is consumed
 //     O = P V     fp32, columns [64,128)                     tcgen05.mma with A = P read from TENSOR MEMORY
-// so the probabilities never touch shared memory.  Roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer
-// (software-pipelined: S of unit i, then P V of unit i-2), warp 2 TMEM allocator, warps 4-19 four softmax groups
+// so the probabilities never touch shared memory.  Roles (640 threads): warp 0 TMA producer, warp 1 issues the S MMAs,
+// warp 3 the P V MMAs (independently, each in unit order), warp 2 TMEM allocator, warps 4-19 four softmax groups
 // (thread = query row).  Warps whose 32 rows are all padding skip the math and only keep the barriers moving;
 // key chunks beyond the sequence are neither exponentiated nor multiplied.
 // =================================================================================================================
 constexpr int ATS_THREADS = 640;
 constexpr int ATS_GROUPS = 4;
 constexpr int ATS_SMEM = ATS_GROUPS * ATC_STAGE_BYTES + ATC_BAR_BYTES + 1024;
-constexpr int ATS_LAG = 2;                         // P V of unit i-2 is issued after S of unit i
 
 struct AttnShortUnit { int tok0, len, head; };
 
@@ -372,39 +371,43 @@ __global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ================= MMA issuer =================
+      // ================= MMA issuer 1: S(i) = Q K^T into region i%4 =================
+      // S and P V are issued by two different warps: a single in-order issuer would sit on the next unit's K/V load
+      // while a finished P waits for its P V (ncu: 39 % of all samples were softmax warps waiting for o_full).
       const int n_mine = blockIdx.x < num_units ? (num_units - 1 - blockIdx.x) / static_cast<int>(gridDim.x) + 1 : 0;
-      for (int i = 0; i < n_mine + ATS_LAG; ++i) {
-        if (i < n_mine) {                             // ---- S(i) = Q K^T into region i%4
-          const int g = i & 3;
-          const uint32_t ph = (i >> 2) & 1;
-          mbar_wait(&kv_full[g], ph);
-          if (i >= ATS_GROUPS) mbar_wait(&o_free[g], ph ^ 1);      // unit i-4's O has been read out of this region
-          tc_fence_after();
-          const uint32_t sQ = smem_u32(smem + g * ATC_STAGE_BYTES);
-          const uint32_t sK = sQ + ATC_BOX;
-          const uint32_t tS = tmem_base + g * 128;
+      for (int i = 0; i < n_mine; ++i) {
+        const int g = i & 3;
+        const uint32_t ph = (i >> 2) & 1;
+        mbar_wait(&kv_full[g], ph);
+        if (i >= ATS_GROUPS) mbar_wait(&o_free[g], ph ^ 1);      // unit i-4's O has been read out of this region
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + g * ATC_STAGE_BYTES);
+        const uint32_t sK = sQ + ATC_BOX;
+        const uint32_t tS = tmem_base + g * 128;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tS, make_sdesc<128>(sQ + k * 32), make_sdesc<128>(sK + k * 32), IDESC_S, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[g]);
-        }
-        const int j = i - ATS_LAG;
-        if (j >= 0) {                                 // ---- O(j) = P V, P from tensor memory
-          const int g = j & 3;
-          const int id = blockIdx.x + j * static_cast<int>(gridDim.x);
-          const AttnShortUnit u = attn_short_unit(p, id);
-          const int nks = (min(u.len, 128) + 15) >> 4;             // 16-key steps that hold any valid key
-          mbar_wait(&p_full[g], (j >> 2) & 1);
-          tc_fence_after();
-          const uint32_t sV = smem_u32(smem + g * ATC_STAGE_BYTES) + 2 * ATC_BOX;
-          const uint32_t tP = tmem_base + g * 128;
-          const uint32_t tO = tP + 64;
-          for (int k = 0; k < nks; ++k)
-            umma_bf16_ts(tO, tP + k * 8, make_sdesc_mn128(sV + k * 2048), IDESC_PV, k != 0 ? 1u : 0u);
-          umma_commit(&o_full[g]);
-          umma_commit(&kv_empty[g]);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS, make_sdesc<128>(sQ + k * 32), make_sdesc<128>(sK + k * 32), IDESC_S, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ================= MMA issuer 2: O(j) = P V, P from tensor memory =================
+      const int n_mine = blockIdx.x < num_units ? (num_units - 1 - blockIdx.x) / static_cast<int>(gridDim.x) + 1 : 0;
+      for (int j = 0; j < n_mine; ++j) {
+        const int g = j & 3;
+        const int id = blockIdx.x + j * static_cast<int>(gridDim.x);
+        const AttnShortUnit u = attn_short_unit(p, id);
+        const int nks = (min(u.len, 128) + 15) >> 4;             // 16-key steps that hold any valid key
+        mbar_wait(&p_full[g], (j >> 2) & 1);
+        tc_fence_after();
+        const uint32_t sV = smem_u32(smem + g * ATC_STAGE_BYTES) + 2 * ATC_BOX;
+        const uint32_t tP = tmem_base + g * 128;
+        const uint32_t tO = tP + 64;
+        for (int k = 0; k < nks; ++k)
+          umma_bf16_ts(tO, tP + k * 8, make_sdesc_mn128(sV + k * 2048), IDESC_PV, k != 0 ? 1u : 0u);
+        umma_commit(&o_full[g]);
+        umma_commit(&kv_empty[g]);                               // S of this unit completed long ago: stage is free
       }
     }
   } else if (warp >= 4) {
