@@ -446,11 +446,11 @@ static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
   return 0;
 }
 
-template <int BN, int BK, int ST, int CG, int EB>
+template <int BN, int BK, int CG, int EB, int RES>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
-  auto* kfn = gemm_tcgen05_kernel<BN, BK, ST, CG, EB>;
-  constexpr int SMEM = GemmSmem<BN, BK, ST, CG, EB>::TOTAL;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES>;
+  constexpr int SMEM = GemmSmem<BN, BK, CG, EB, RES>::TOTAL;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
@@ -475,13 +475,23 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
       CK(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
       REQUIRE(n > 0, "no CTA pair fits on this device");
       max_clusters = n;
-      if (getenv("MMDX_DEBUG")) fprintf(stderr, "mmdx: gemm<%d,%d,%d,%d,%d> max active clusters %d\n", BN, BK, ST, CG, EB, n);
+      if (getenv("MMDX_DEBUG"))
+        fprintf(stderr, "mmdx: gemm<BN %d, CG %d, EB %d, RES %d> %d stages, max active clusters %d\n", BN, CG, EB, RES,
+                GemmSmem<BN, BK, CG, EB, RES>::STAGES, n);
     }
     if (groups > max_clusters) { groups = max_clusters; cfg.gridDim = dim3((unsigned)groups * CG, 1, 1); }
     CK(cudaLaunchKernelEx(&cfg, kfn, g.p));
   }
   CK(cudaGetLastError());
   return 0;
+}
+
+// Instantiations: the residual variants carry the identity block; every variant takes as many ring stages as fit.
+template <int BN, int CG>
+static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s) {
+  const bool res = g.p.res_blocks > 0;
+  if (g.eb == 2) return res ? launch_inst<BN, 64, CG, 2, 1>(g, groups, s) : launch_inst<BN, 64, CG, 2, 0>(g, groups, s);
+  return res ? launch_inst<BN, 64, CG, 1, 1>(g, groups, s) : launch_inst<BN, 64, CG, 1, 0>(g, groups, s);
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
@@ -491,16 +501,16 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   ProfScope _ps(e);
   if (g.cg == 2) {
     switch (g.bn) {
-      case 256: return g.eb == 1 ? launch_inst<256, 64, 6, 2, 1>(g, groups, s) : launch_inst<256, 64, 5, 2, 2>(g, groups, s);
-      case 192: return g.eb == 1 ? launch_inst<192, 64, 7, 2, 1>(g, groups, s) : launch_inst<192, 64, 6, 2, 2>(g, groups, s);
-      case 128: return g.eb == 1 ? launch_inst<128, 64, 8, 2, 1>(g, groups, s) : launch_inst<128, 64, 7, 2, 2>(g, groups, s);
+      case 256: return launch_bn<256, 2>(g, groups, s);
+      case 192: return launch_bn<192, 2>(g, groups, s);
+      case 128: return launch_bn<128, 2>(g, groups, s);
     }
     return fail("mmdx: bad BN for a CTA pair");
   }
   switch (g.bn) {
-    case 256: return launch_inst<256, 64, 4, 1, 1>(g, groups, s);     // 4 x 48 KB ring leaves room for one buffer per group
-    case 128: return launch_inst<128, 64, 5, 1, 2>(g, groups, s);
-    case 64: return launch_inst<64, 64, 7, 1, 2>(g, groups, s);
+    case 256: return launch_bn<256, 1>(g, groups, s);
+    case 128: return launch_bn<128, 1>(g, groups, s);
+    case 64: return launch_bn<64, 1>(g, groups, s);
   }
   return fail("mmdx: bad BN");
 }

@@ -68,18 +68,23 @@ struct alignas(64) GemmParams {
   signed char tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
 };
 
-// EB = staging buffers per epilogue group: with two, the TMA store of chunk c reads its buffer while chunk c+2
-// (same group) is already being converted and written into the other one.
-template <int BN, int BK, int STAGES, int CG, int EB>
+// EB = staging buffers per epilogue group: with two, the TMA store of chunk c reads its buffer while chunk c+2 (same
+// group) is already being converted and written into the other one, and one named barrier per chunk is enough.
+// RES = the GEMM can add a residual on the tensor core (needs the resident identity block).  The ring takes whatever
+// shared memory is left (at most 8 stages).
+template <int BN, int BK, int CG, int EB, int RES>
 struct GemmSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;     // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = kEpiGroups * EB * kEpiBufBytes + (RES ? kIdentBytes : 0);
+  static constexpr int BIAS_BYTES = 2 * BN * 4;          // bias slice of the current tile, double-buffered
+  static constexpr int BAR_BYTES = 512 + BIAS_BYTES;
+  static constexpr int FIXED = STG_BYTES + BAR_BYTES + 1024;                // +1024: manual alignment slack
+  static constexpr int STAGES = (232448 - FIXED) / STAGE_BYTES > 8 ? 8 : (232448 - FIXED) / STAGE_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = kEpiGroups * EB * kEpiBufBytes + kIdentBytes;
-  static constexpr int BAR_BYTES = 512;
-  static constexpr int TOTAL = RING_BYTES + STG_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
-  static_assert(TOTAL <= 232448, "exceeds 227 KB of shared memory");
+  static constexpr int TOTAL = RING_BYTES + FIXED;
+  static_assert(STAGES >= 3 && TOTAL <= 232448, "shared-memory budget");
 };
 
 struct TileCoord { int n_t, w0, h0, n0; };
@@ -98,9 +103,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return t;
 }
 
-template <int BN, int BK, int STAGES, int CG, int EB>
+template <int BN, int BK, int CG, int EB, int RES>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using L = GemmSmem<BN, BK, STAGES, CG, EB>;
+  using L = GemmSmem<BN, BK, CG, EB, RES>;
+  constexpr int STAGES = L::STAGES;
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BN);
   static_assert(CG == 1 || (CG == 2 && BK == 64 && BN >= 128), "CTA pairs: BK 64, BN >= 128");
@@ -118,7 +124,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* ident_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
-  uint8_t* ident = stg + kEpiGroups * EB * kEpiBufBytes;      // 1024-byte aligned
+  float* sbias = reinterpret_cast<float*>(stg + L::STG_BYTES + 512);       // [2][BN]
+  uint8_t* ident = stg + kEpiGroups * EB * kEpiBufBytes;      // 1024-byte aligned (RES only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0;
       // CG = 2: completion is tracked by the LEADER's full barriers (shared::cluster addresses of rank 0)
       const uint32_t full0 = CG == 2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0;
-      if (BK == 64 && p.res_blocks > 0) {               // identity block (this CTA's rows of it): loaded once, stays resident
+      if (RES && BK == 64 && p.res_blocks > 0) {        // identity block (this CTA's rows of it): loaded once, stays resident
         if constexpr (CG == 2) {
           if (rank == 0) mbar_arrive_expect_tx(ident_bar, kIdentBytes);      // both halves
           tma_load_2d_pair(ident, &p.tmI, mapa_rank(smem_u32(ident_bar), 0), 0, rank * 32);
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (++cc == p.kb_per_tap) { cc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (BK == 64) {
+        if constexpr (BK == 64 && RES == 1) {
           for (int j = 0; j < p.res_blocks; ++j) {      // residual tile as extra A blocks + identity B block
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -228,8 +235,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0, soff = 0;              // soff = stage * STAGE_STEP
       int it = 0;
-      if (BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
-      const int nkb = p.num_k_blocks, nres = (BK == 64) ? p.res_blocks : 0;
+      if (RES && BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
+      const int nkb = p.num_k_blocks, nres = (BK == 64 && RES) ? p.res_blocks : 0;
       for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           soff += STAGE_STEP;
           if (++stage == STAGES) { stage = 0; phase ^= 1; soff = 0; }
         }
-        if constexpr (BK == 64) {
+        if constexpr (BK == 64 && RES == 1) {
           constexpr uint32_t IDESC64 = make_idesc_bf16(128 * CG, 64);
           constexpr uint32_t HI128 = sdesc_hi<128>();
           for (int j = 0; j < nres; ++j) {              // D[:, 64j:64j+64] += R_j * I64
@@ -298,6 +305,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
       if (p.epi_mode == EPI_TMA) {
         const int sw = (r >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+        // bias slice of this tile -> shared memory (once per tile, instead of eight dependent global loads per chunk).
+        // The barrier also orders this write after every thread's reads of the same slot two tiles ago.
+        float* sb = sbias + as * BN;
+        {
+          const int et = e * 32 + lane;       // 0..255
+          if (et < BN) sb[et] = p.bias != nullptr ? __ldg(p.bias + t.n_t * BN + et) : 0.0f;
+          named_bar_sync(3, 256);
+        }
 #pragma unroll 1
         for (int c = g; c < NC; c += 2, ++nstore) {
           uint8_t* buf = stg + (g * EB + (EB == 2 ? (nstore & 1) : 0)) * kEpiBufBytes;
@@ -313,12 +328,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+            for (int j = 0; j < 8; ++j) {                   // packed adds: two columns per instruction
+              const float4 b = b4[j];
+              unpack_f32x2(add_f32x2(pack_f32x2(x[4 * j], x[4 * j + 1]), pack_f32x2(b.x, b.y)), x[4 * j], x[4 * j + 1]);
+              unpack_f32x2(add_f32x2(pack_f32x2(x[4 * j + 2], x[4 * j + 3]), pack_f32x2(b.z, b.w)), x[4 * j + 2],
+                           x[4 * j + 3]);
             }
           }
           if (p.act == ACT_RELU) {
@@ -328,8 +345,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 32; j += 2) gelu_erf_x2(x[j], x[j + 1]);
           }
-          if (issuer) tma_store_wait_read<EB - 1>();   // the store that last used `buf` has finished reading it
-          named_bar_sync(1 + g, 128);
+          if constexpr (EB == 1) {
+            if (issuer) tma_store_wait_read<0>();   // the previous store has finished reading `buf`
+            named_bar_sync(1 + g, 128);
+          }
           uint8_t* my_row = buf + r * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -337,6 +356,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
                            pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
           fence_proxy_async();                // make the generic-proxy smem writes visible to the TMA unit
+          if constexpr (EB == 2) {
+            // One barrier per chunk: before it the issuer makes sure the store that last used the OTHER buffer (issued a
+            // whole chunk ago) has finished reading it, so after the barrier everybody may write the next chunk there.
+            if (issuer) tma_store_wait_read<0>();
+          }
           named_bar_sync(1 + g, 128);
           if (issuer) {
             tma_store_4d(&p.tmC, buf, col0, t.w0, t.h0, t.n0);

@@ -301,17 +301,16 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 // max |error| vs the erf form is 3.1e-7 over all x (fp32 evaluation), i.e. < 0.1 bf16 ulp wherever
 // |GELU(x)| > 1e-3 - the same order as fp32 erff itself after the bf16 rounding of the output.
 // 10 ALU ops + 1 MUFU.EX2 per element (erff is ~35 with branches): keeps the FFN1 epilogue under the MMA time.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float t = fabsf(x);
-  const float tc = fminf(t, 6.0f);
-  float q = fmaf(2.9927026844234206e-05f, tc, -0.0007398975430987775f);
-  q = fmaf(q, tc, 0.007977532222867012f);
-  q = fmaf(q, tc, -0.05323828011751175f);
-  q = fmaf(q, tc, -0.4589156210422516f);
-  q = fmaf(q, tc, -1.1511471271514893f);
+__device__ __forceinline__ float gelu_erf(float x) {      // same arithmetic as gelu_erf_x2 below, one value
+  const float s = fmaxf(-fabsf(x), -6.0f);
+  float q = fmaf(2.9927026844234206e-05f, s, 0.0007398975430987775f);
+  q = fmaf(q, s, 0.007977532222867012f);
+  q = fmaf(q, s, 0.05323828011751175f);
+  q = fmaf(q, s, -0.4589156210422516f);
+  q = fmaf(q, s, 1.1511471271514893f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * tc));
-  return fmaf(-0.5f * t, e, fmaxf(x, 0.0f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(q, s, -1.0f)));
+  return fmaf(s, e, fmaxf(x, 0.0f));
 }
 // Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of fp32 math per instruction.
 __device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
@@ -337,25 +336,24 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// gelu_erf (below) on two values at once: the polynomial, the two products and the final FMA run as packed
-// f32x2 instructions - 16 instructions per pair instead of 24.  Same arithmetic, same rounding.
+// gelu_erf (below) on two values at once, 13 instructions per pair.  With s = -min(|x|, 6) (one FMNMX: |.| and the
+// negation are operand modifiers) and Q(s) = -q(-s):  GELU(x) = relu(x) + s * 2^(Q(s)*s - 1), because
+// 2^(Q(s)*s) = erfc(|x|/sqrt2) and the -1 in the exponent is the factor 1/2.  Polynomial, exponent and the final
+// multiply-add run as packed f32x2 instructions.  (Beyond |x| = 6 the clamped s only scales a term < 1e-8.)
 __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
-  const float t0 = fabsf(x0), t1 = fabsf(x1);
-  const uint64_t T = pack_f32x2(fminf(t0, 6.0f), fminf(t1, 6.0f));
-  uint64_t q = fma_f32x2(pack_f32x2(2.9927026844234206e-05f, 2.9927026844234206e-05f), T,
-                         pack_f32x2(-0.0007398975430987775f, -0.0007398975430987775f));
-  q = fma_f32x2(q, T, pack_f32x2(0.007977532222867012f, 0.007977532222867012f));
-  q = fma_f32x2(q, T, pack_f32x2(-0.05323828011751175f, -0.05323828011751175f));
-  q = fma_f32x2(q, T, pack_f32x2(-0.4589156210422516f, -0.4589156210422516f));
-  q = fma_f32x2(q, T, pack_f32x2(-1.1511471271514893f, -1.1511471271514893f));
+  const uint64_t S = pack_f32x2(fmaxf(-fabsf(x0), -6.0f), fmaxf(-fabsf(x1), -6.0f));
+  uint64_t q = fma_f32x2(pack_f32x2(2.9927026844234206e-05f, 2.9927026844234206e-05f), S,
+                         pack_f32x2(0.0007398975430987775f, 0.0007398975430987775f));
+  q = fma_f32x2(q, S, pack_f32x2(0.007977532222867012f, 0.007977532222867012f));
+  q = fma_f32x2(q, S, pack_f32x2(0.05323828011751175f, 0.05323828011751175f));
+  q = fma_f32x2(q, S, pack_f32x2(-0.4589156210422516f, -0.4589156210422516f));
+  q = fma_f32x2(q, S, pack_f32x2(1.1511471271514893f, 1.1511471271514893f));
   float a0, a1;
-  unpack_f32x2(mul_f32x2(q, T), a0, a1);
+  unpack_f32x2(fma_f32x2(q, S, pack_f32x2(-1.0f, -1.0f)), a0, a1);
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  const uint64_t r = fma_f32x2(mul_f32x2(pack_f32x2(t0, t1), pack_f32x2(-0.5f, -0.5f)), pack_f32x2(e0, e1),
-                               pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
-  unpack_f32x2(r, x0, x1);
+  unpack_f32x2(fma_f32x2(S, pack_f32x2(e0, e1), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
 }
 __device__ __forceinline__ float fast_exp2(float x) {     // MUFU.EX2; exp2(-inf) = 0
   float e;

@@ -61,15 +61,19 @@ def bench_attention(h, lib):
 
 def bench_gemm(h, lib):
     M = 32768
-    for name, N, K, act, res in [("qkv", 2304, 768, 0, False), ("attn_out+res", 768, 768, 0, True),
-                                 ("ffn1+gelu", 3072, 768, 2, False), ("ffn2+res", 768, 3072, 0, True)]:
+    cases = [("qkv", 2304, 768, 0, False, 0), ("attn_out+res", 768, 768, 0, True, 0),
+             ("ffn1+gelu", 3072, 768, 2, False, 0), ("ffn1 (no act)", 3072, 768, 0, False, 0),
+             ("ffn2+res", 768, 3072, 0, True, 0), ("ffn2 (no res)", 768, 3072, 0, False, 0)]
+    if os.environ.get("OPBENCH_SWEEP"):        # tile-width sweep on the short-K residual GEMM
+        cases += [(f"attn_out{'+res' if r else ''} bn{bn}", 768, 768, 0, r, bn) for r in (False, True) for bn in (256, 192, 128)]
+    for name, N, K, act, res, bn in cases:
         a = bf(torch.randn(M, K, device="cuda"))
         w = bf(torch.randn(N, K, device="cuda") * K ** -0.5)
         bias = torch.randn(N, device="cuda")
         r = bf(torch.randn(M, N, device="cuda")) if res else None
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        us = timeit(lambda: _lib.check(lib.mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(r), N, P(out), N, M, N, K, act, 0, 0, S())))
-        print(f"gemm {name:14s} M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+        us = timeit(lambda: _lib.check(lib.mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(r), N, P(out), N, M, N, K, act, 0, bn, S())))
+        print(f"gemm {name:18s} M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
 def bench_conv(h, lib):
