@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -353,6 +355,8 @@ __global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(C64_THREADS, 1) conv3x3_c64_tcgen05_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

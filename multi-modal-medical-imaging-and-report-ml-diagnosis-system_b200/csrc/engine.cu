@@ -243,6 +243,39 @@ static int make_tmap(mmdx_engine* e, CUtensorMap* m, const void* base, int rank,
   return 0;
 }
 
+// Every kernel goes through here: programmatic dependent launch (see ptx.cuh pdl_wait / pdl_trigger) so the next
+// kernel's CTAs are scheduled and run their prologue while this one drains; clusters of `cluster` CTAs along x.
+// MMDX_PDL=0 turns the attribute off (plain stream order) for A/B timing.
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("MMDX_PDL"); on = (v && atoi(v) == 0) ? 0 : 1; }
+  return on == 1;
+}
+template <typename... KArgs>
+static cudaError_t launch_typed(const cudaLaunchConfig_t& cfg, void (*kfn)(KArgs...), KArgs... args) {
+  return cudaLaunchKernelEx(&cfg, kfn, args...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return launch_typed<KArgs...>(cfg, kfn, std::forward<Args>(args)...);
+}
+
 ProfScope::ProfScope(mmdx_engine* e_) : e(e_) {
   e->launches++;
   if (!e->profiling) return;
@@ -306,8 +339,9 @@ static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const
   }
   // CTA-pair kernels trade one ring stage for a second staging buffer per epilogue group.  Measured on one box
   // (tools/opbench.py, MMDX_EB=1|2): that pays when the main loop is short and the tile is epilogue/HBM-bound
-  // (layer1/2 conv3: -10 / -4 us) and costs 2-4 us on the long-K text GEMMs.
-  g.eb = (e->epi_bufs == 1 || e->epi_bufs == 2) ? e->epi_bufs : ((p.num_k_blocks + p.res_blocks <= 6) ? 2 : 1);
+  // (layer1/2 conv3: -10 / -4 us) or the epilogue is heavy (erf-GELU of FFN1: -8 us) and costs 2-4 us on the other long-K
+  // text GEMMs.
+  g.eb = (e->epi_bufs == 1 || e->epi_bufs == 2) ? e->epi_bufs : ((p.num_k_blocks + p.res_blocks <= 6 || act == ACT_GELU) ? 2 : 1);
   return 0;
 }
 
@@ -441,7 +475,7 @@ static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
   }
   const int grid = p.num_tiles < e->num_sms ? p.num_tiles : e->num_sms;
   ProfScope _ps(e);
-  conv3x3_c64_tcgen05_kernel<<<grid, C64_THREADS, C64_SMEM, s>>>(p);
+  CK(launch_k(conv3x3_c64_tcgen05_kernel, dim3(grid), dim3(C64_THREADS), C64_SMEM, s, 1, p));
   CK(cudaGetLastError());
   return 0;
 }
@@ -455,22 +489,20 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  if (CG == 1) {
-    kfn<<<groups, kGemmThreads, SMEM, s>>>(g.p);
-  } else {     // CTA pairs: clusters of two along x
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)groups * CG, 1, 1);
-    cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+  if (CG == 2) {     // CTA pairs: clusters of two along x
     // The schedule is static and persistent: every cluster must be resident at once, or the stragglers run as a
     // second wave.  Not every SM can be paired (GPCs with an odd number of enabled SMs), so ask the driver.
     static int max_clusters = 0;
     if (max_clusters == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)groups * CG, 1, 1);
+      cfg.blockDim = dim3(kGemmThreads, 1, 1);
+      cfg.dynamicSmemBytes = SMEM;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
       CK(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
       REQUIRE(n > 0, "no CTA pair fits on this device");
@@ -479,9 +511,9 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
         fprintf(stderr, "mmdx: gemm<BN %d, CG %d, EB %d, RES %d> %d stages, max active clusters %d\n", BN, CG, EB, RES,
                 GemmSmem<BN, BK, CG, EB, RES>::STAGES, n);
     }
-    if (groups > max_clusters) { groups = max_clusters; cfg.gridDim = dim3((unsigned)groups * CG, 1, 1); }
-    CK(cudaLaunchKernelEx(&cfg, kfn, g.p));
+    if (groups > max_clusters) groups = max_clusters;
   }
+  CK(launch_k(kfn, dim3((unsigned)groups * CG), dim3(kGemmThreads), SMEM, s, CG, g.p));
   CK(cudaGetLastError());
   return 0;
 }
@@ -579,7 +611,7 @@ static int launch_stem(mmdx_engine* e, const StemParams& p, cudaStream_t s) {
   }
   const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
   ProfScope _ps(e);
-  stem_pool_tcgen05_kernel<<<grid, STEM_THREADS, smem, s>>>(p);
+  CK(launch_k(stem_pool_tcgen05_kernel, dim3(grid), dim3(STEM_THREADS), smem, s, 1, p));
   CK(cudaGetLastError());
   return 0;
 }
@@ -928,21 +960,21 @@ static int launch_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int
     const size_t total = (size_t)B * H * W * C;
     const bf16* lut = static_cast<const bf16*>(e->pre_lut.p);
     if (C == 3)
-      preprocess_tiled_kernel<3><<<grid, block, smem, s>>>(d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
-                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3);
+      CK(launch_k(preprocess_tiled_kernel<3>, dim3(grid), dim3(block), smem, s, 1, d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
+                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3));
     else
-      preprocess_tiled_kernel<1><<<grid, block, smem, s>>>(d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
-                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3);
+      CK(launch_k(preprocess_tiled_kernel<1>, dim3(grid), dim3(block), smem, s, 1, d_images, total, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y,
+                                                          g.left, g.top, st, lut, out, hp, wp, 3, 3));
   } else {                                      // a strip does not fit in shared memory (extreme down-scaling)
     const float3 sc = make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]);
     const float3 sh = make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]);
     dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
     if (C == 3)
-      preprocess_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
-                                                 g.top, out, hp, wp, 3, 3, sc, sh);
+      CK(launch_k(preprocess_kernel<3>, dim3(grid), dim3(block), 0, s, 1, d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                                 g.top, out, hp, wp, 3, 3, sc, sh));
     else
-      preprocess_kernel<1><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
-                                                 g.top, out, hp, wp, 3, 3, sc, sh);
+      CK(launch_k(preprocess_kernel<1>, dim3(grid), dim3(block), 0, s, 1, d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left,
+                                                 g.top, out, hp, wp, 3, 3, sc, sh));
   }
   CK(cudaGetLastError());
   return 0;
@@ -1108,10 +1140,10 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
   const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: layernorm_kernel<256, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 512: layernorm_kernel<512, false, R><<<grid, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 768: layernorm_kernel<768, false, 2, 3><<<(rows + 15) / 16, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
-    case 1024: layernorm_kernel<1024, false, 2><<<(rows + 15) / 16, 256, 0, s>>>(x, rows, g, b, eps, y, 0, 0, 0, 0, 0, 0); break;
+    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1124,10 +1156,10 @@ static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const in
   const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: layernorm_kernel<256, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 512: layernorm_kernel<512, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 768: layernorm_kernel<768, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
-    case 1024: layernorm_kernel<1024, true, R><<<grid, 256, 0, s>>>(nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab); break;
+    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
     default: return fail("mmdx: hidden width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1158,16 +1190,18 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
   if (max_len <= 128 && !e->attn_force_general) {       // one key block per sequence: the 4-deep TMEM-resident variant
     const int units = n_seq * heads;
     const int grid = units < e->num_sms ? units : e->num_sms;
-    attention_short_tcgen05_kernel<<<grid, ATS_THREADS, ATS_SMEM, s>>>(p);
+    CK(launch_k(attention_short_tcgen05_kernel, dim3(grid), dim3(ATS_THREADS), ATS_SMEM, s, 1, p));
   } else {
     const int grid = p.num_units < e->num_sms ? p.num_units : e->num_sms;
-    attention_tcgen05_kernel<<<grid, ATC_THREADS, ATC_SMEM, s>>>(p);
+    CK(launch_k(attention_tcgen05_kernel, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, s, 1, p));
   }
   CK(cudaGetLastError());
   return 0;
 }
 
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, long long ld, int rows, int cols, float* __restrict__ out) {
+  mmdx::pdl_wait();
+  mmdx::pdl_trigger();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
@@ -1176,7 +1210,7 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, long long ld, in
 static int launch_cvt(mmdx_engine* e, const bf16* in, long long ld, int rows, int cols, float* out, cudaStream_t s) {
   const long long n = (long long)rows * cols;
   ProfScope _ps(e);
-  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, ld, rows, cols, out);
+  CK(launch_k(bf16_to_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, 1, in, ld, rows, cols, out));
   CK(cudaGetLastError());
   return 0;
 }
@@ -1204,7 +1238,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   {
     const int n = B * (e->feat_dim / 8);
     ProfScope _ps(e);
-    avgpool_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->last, B, pl->last_hw, e->feat_dim, e->feats_bf, d_feats);
+    CK(launch_k(avgpool_kernel, dim3((n + 255) / 256), dim3(256), 0, s, 1, pl->last, B, pl->last_hw, e->feat_dim, e->feats_bf, d_feats));
     CK(cudaGetLastError());
   }
   e->cur_cls = CLS_HEAD;
@@ -1246,7 +1280,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   e->cur_cls = CLS_POOL;
   {
     ProfScope _ps(e);
-    seq_mean_pool_kernel<<<dim3(B, (H + 63) / 64), 256, 0, s>>>(tb.hid, d_cu, H, e->pooled_bf, H, d_pooled);
+    CK(launch_k(seq_mean_pool_kernel, dim3(dim3(B, (H + 63) / 64)), dim3(256), 0, s, 1, tb.hid, d_cu, H, e->pooled_bf, H, d_pooled));
     CK(cudaGetLastError());
   }
   e->cur_cls = CLS_HEAD;
@@ -1266,10 +1300,10 @@ static int head_locked(mmdx_engine* e, int B, const float* d_thr, float* d_z_fus
   TRY(get_head_plan(e, B, &hp));
   TRY(launch_gemm(e, hp->fuse, s));
   ProfScope _ps(e);
-  head_tail_kernel<<<B, 256, e->d_fuse * sizeof(float), s>>>(e->fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f,
+  CK(launch_k(head_tail_kernel, dim3(B), dim3(256), e->d_fuse * sizeof(float), s, 1, e->fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f,
                                                              e->head_w, e->head_b, e->n_cls,
                                                              d_thr ? d_thr : e->thr_default, d_z_fuse, d_logits, d_probs,
-                                                             d_vector);
+                                                             d_vector));
   CK(cudaGetLastError());
   return 0;
 }
@@ -1438,11 +1472,11 @@ extern "C" int mmdx_op_resample_u8(mmdx_engine* e, const uint8_t* d_images, int 
   dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
   ProfScope _ps(e);
   if (C == 3)
-    resample_u8_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
-                                                                   g.has_y, g.left, g.top, d_out);
+    CK(launch_k(resample_u8_kernel<3>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, 1, d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
+                                                                   g.has_y, g.left, g.top, d_out));
   else if (C == 1)
-    resample_u8_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
-                                                                   g.has_y, g.left, g.top, d_out);
+    CK(launch_k(resample_u8_kernel<1>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, 1, d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x,
+                                                                   g.has_y, g.left, g.top, d_out));
   else
     return fail("mmdx: images must have 1 or 3 channels");
   CK(cudaGetLastError());
@@ -1454,8 +1488,8 @@ extern "C" int mmdx_op_avgpool(mmdx_engine* e, const void* d_in, int B, int HW, 
   REQUIRE(e && C % 8 == 0, "avgpool needs C%8==0");
   const int n = B * (C / 8);
   ProfScope _ps(e);
-  avgpool_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_in), B, HW, C,
-                                                                    static_cast<bf16*>(d_out_bf16), d_out_f32);
+  CK(launch_k(avgpool_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, 1, static_cast<const bf16*>(d_in), B, HW, C,
+                                                                    static_cast<bf16*>(d_out_bf16), d_out_f32));
   CK(cudaGetLastError());
   return 0;
 }
@@ -1488,8 +1522,8 @@ extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int3
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && hidden % 8 == 0, "hidden % 8");
   ProfScope _ps(e);
-  seq_mean_pool_kernel<<<dim3(n_seq, (hidden + 63) / 64), 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(d_h), d_cu, hidden,
-                                                               static_cast<bf16*>(d_out_bf16), hidden, d_out_f32);
+  CK(launch_k(seq_mean_pool_kernel, dim3(dim3(n_seq, (hidden + 63) / 64)), dim3(256), 0, (cudaStream_t)stream, 1, static_cast<const bf16*>(d_h), d_cu, hidden,
+                                                               static_cast<bf16*>(d_out_bf16), hidden, d_out_f32));
   CK(cudaGetLastError());
   return 0;
 }
@@ -1500,8 +1534,8 @@ extern "C" int mmdx_op_head_tail(mmdx_engine* e, const float* d_hidden, int B, i
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
   REQUIRE(e && D <= 8192, "head width");
   ProfScope _ps(e);
-  head_tail_kernel<<<B, 256, D * sizeof(float), (cudaStream_t)stream>>>(d_hidden, D, d_ln_g, d_ln_b, eps, d_w, d_b, n_cls,
-                                                                        d_thr, d_z_fuse, d_logits, d_probs, d_vector);
+  CK(launch_k(head_tail_kernel, dim3(B), dim3(256), D * sizeof(float), (cudaStream_t)stream, 1, d_hidden, D, d_ln_g, d_ln_b, eps, d_w, d_b, n_cls,
+                                                                        d_thr, d_z_fuse, d_logits, d_probs, d_vector));
   CK(cudaGetLastError());
   return 0;
 }

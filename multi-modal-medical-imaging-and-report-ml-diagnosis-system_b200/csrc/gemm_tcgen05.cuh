@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // the kernel that produced A / the residual has completed (everything above overlapped it)
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

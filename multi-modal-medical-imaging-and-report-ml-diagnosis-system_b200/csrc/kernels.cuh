@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
                                                          int has_x, int has_y, int off_x, int off_y,
                                                          __nv_bfloat16* __restrict__ out, int out_hp, int out_wp,
                                                          int pad_top, int pad_left, float3 scale, float3 shift) {
+  pdl_wait();
+  pdl_trigger();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   const int b = blockIdx.z;
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(256) preprocess_tiled_kernel(const uint8_t* __
                                                                PreStrip st, const __nv_bfloat16* __restrict__ lut,
                                                                __nv_bfloat16* __restrict__ out, int out_hp, int out_wp,
                                                                int pad_top, int pad_left) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* s_in = sm;                                              // [max_rows_in][in_pitch]
   uint8_t* s_h = s_in + st.max_rows_in * st.in_pitch;              // [max_rows_in][h_pitch]
@@ -267,6 +271,8 @@ __global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restr
                                                           ResampleTable tx, ResampleTable ty, int crop_h, int crop_w,
                                                           int has_x, int has_y, int off_x, int off_y,
                                                           uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   const int oy = blockIdx.y;
   const int b = blockIdx.z;
@@ -316,6 +322,8 @@ __global__ void __launch_bounds__(256) resample_u8_kernel(const uint8_t* __restr
 // Global average pool NHWC [B,HW,C] -> bf16 [B,C] (+ optional fp32 copy); 8 channels per thread.
 __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int HW, int C,
                                                       __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_trigger();
   const int cv = C / 8;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * cv) return;
@@ -356,6 +364,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
                                                         const __nv_bfloat16* __restrict__ word,
                                                         const __nv_bfloat16* __restrict__ ptab,
                                                         const __nv_bfloat16* __restrict__ ttab) {
+  pdl_wait();
+  pdl_trigger();
   // R rows per warp: all their 16-byte loads are issued before the first reduction (R * N / 256 loads in flight
   // per lane), which is what an HBM/L2-bound row kernel needs.
   constexpr int CH = N / 256;   // 16-byte chunks per lane and row
@@ -461,6 +471,8 @@ __global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16*
                                                             const int* __restrict__ cu_seqlens, int hidden,
                                                             __nv_bfloat16* __restrict__ out, long long ldo,
                                                             float* __restrict__ out_f32) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float part[32][64 + 1];
   const int seq = blockIdx.x;
   const int c8 = threadIdx.x & 7, tl = threadIdx.x >> 3;
@@ -505,6 +517,8 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict_
                                                         const float* __restrict__ thresholds,
                                                         float* __restrict__ z_fuse, float* __restrict__ logits,
                                                         float* __restrict__ probs, uint8_t* __restrict__ vec) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sz[];        // D floats
   __shared__ float red[8];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -107,6 +107,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be
+// scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel of
+// the stream is still draining.  pdl_wait() blocks until that kernel has completed and its writes are visible - it
+// must precede the first access to any activation buffer; pdl_trigger() lets the NEXT kernel's CTAs be scheduled as
+// soon as every CTA of this grid has passed it (or exited).  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- thread-block clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_pool_tcgen05_kernel(cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -35,6 +35,7 @@ def timeit(fn, reps=7):
     for _ in range(reps):
         _flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400000)     # ~0.2 ms of GPU spin: hides fn()'s host-side work (tensor-map encode, launch)
         a.record()
         fn()
         b.record()
@@ -66,7 +67,10 @@ def bench_gemm(h, lib):
              ("ffn2+res", 768, 3072, 0, True, 0), ("ffn2 (no res)", 768, 3072, 0, False, 0)]
     if os.environ.get("OPBENCH_SWEEP"):        # tile-width sweep on the short-K residual GEMM
         cases += [(f"attn_out{'+res' if r else ''} bn{bn}", 768, 768, 0, r, bn) for r in (False, True) for bn in (256, 192, 128)]
+    only = os.environ.get("OPBENCH_ONLY")
     for name, N, K, act, res, bn in cases:
+        if only and name != only:
+            continue
         a = bf(torch.randn(M, K, device="cuda"))
         w = bf(torch.randn(N, K, device="cuda") * K ** -0.5)
         bias = torch.randn(N, device="cuda")
