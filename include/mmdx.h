@@ -90,6 +90,12 @@ int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_cl
 int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
                  const void* d_residual, int64_t ldr, void* d_out, int64_t ldc, int M, int N, int K, int act,
                  int out_f32, int bn, void* stream);
+/* BertSelfOutput / BertOutput in one launch (HF modeling_bert.py:287-298, 345-356): pre = A * Wt^T + bias + residual
+ * (bf16, [M, ldc]), out = LayerNorm(pre) * gamma + beta ([M, ldo]; may alias pre).  N = 768, M >= 256: each CTA pair computes
+ * the three 256-wide tiles of its rows back to back and then normalises the rows it has just stored. */
+int mmdx_op_gemm_ln(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
+                    const void* d_residual, int64_t ldr, void* d_pre, int64_t ldc, const float* d_gamma,
+                    const float* d_beta, float eps, void* d_out, int64_t ldo, int M, int N, int K, void* stream);
 /* NHWC conv k in {1,3}, stride in {1,2}, pad k/2; weights packed [Cout][k*k][Cin] bf16 (BN folded). */
 int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,
                  const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride, int act,

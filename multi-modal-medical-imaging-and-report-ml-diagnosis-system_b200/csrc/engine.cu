@@ -126,6 +126,7 @@ struct DevBuf {
 
 struct GemmLaunch {
   GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1;
+  int ln = 0;                         // > 0: row LayerNorm fused behind the last N tile of every m-item (row width ln * 256)
   bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
 };
 
@@ -158,6 +159,7 @@ struct ImagePlan {
 };
 struct TextPlan {
   int T = 0, B = 0;
+  bool ln_fused = false;           // ao / ff2 normalise their own rows (no separate LayerNorm launches)
   std::vector<GemmLaunch> gemms;   // per layer: qkv, ao, ff1, ff2
 };
 struct HeadPlan { int B = 0; GemmLaunch proj_img, proj_txt, fuse; };
@@ -345,6 +347,31 @@ static int fill_epilogue(mmdx_engine* e, GemmLaunch& g, const float* bias, const
   return 0;
 }
 
+// Row LayerNorm fused behind a plain GEMM whose N tiles cover whole rows (see GemmParams::item_major).  Legal for
+// N = 768 with 256-wide CTA-pair tiles, tensor-core residual and the TMA epilogue.  OFF by default: measured on B200 at
+// M = 32768 (tools/opbench.py gemm_ln) the fused launch is slower than GEMM + layernorm_kernel under programmatic
+// dependent launch (K = 768: 71.7 vs 66.6 us, K = 3072: 153.6 vs 130.0 us) - 128 items on 74 CTA pairs quantise to
+// 6 tile times instead of 5.25 (7 waves of 192-wide tiles), and the eight epilogue warps re-reading their rows through
+// an L2 that is busy feeding the operand ring take ~25 us per 128 rows, which stalls the MMA warp two tiles later.
+// MMDX_LNFUSE=1 turns it on wherever the shape allows (parity-tested in tests/test_ops_gpu.py).
+static bool ln_fusable(const mmdx_engine* e, int M, int N) {
+  (void)e;
+  if (N != 768 || M < 256) return false;
+  static int mode = -2;
+  if (mode == -2) { const char* v = getenv("MMDX_LNFUSE"); mode = v ? atoi(v) : 0; }
+  return mode == 1;
+}
+static int fuse_ln(GemmLaunch& g, const float* gamma, const float* beta, float eps, bf16* ln_out, long long ld_ln) {
+  GemmParams& p = g.p;
+  REQUIRE(!g.c64 && g.bn == 256 && g.cg == 2 && g.bk == 64 && p.n_tiles == 3 && p.epi_mode == EPI_TMA && p.res_blocks > 0 &&
+              p.Wb == 128 && p.Hb == 1 && p.Nb == 1,
+          "fused LayerNorm needs a plain 768-wide CTA-pair GEMM with residual");
+  REQUIRE(ld_ln % 8 == 0 && p.ldc % 8 == 0, "fused LayerNorm needs 16-byte aligned rows");
+  g.ln = 3; g.eb = 1;
+  p.item_major = 1; p.ln_eps = eps; p.ln_gamma = gamma; p.ln_beta = beta; p.ln_out = ln_out; p.ld_ln = ld_ln;
+  return 0;
+}
+
 // C[M,N] = A[M,K] * W[N,K]^T
 static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long lda, const bf16* Wt, int M, int N, int K,
                       int bn_req) {
@@ -352,6 +379,7 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   REQUIRE(lda % 8 == 0, "gemm lda must be a multiple of 8 elements");
   GemmParams& p = g.p;
   memset(&p, 0, sizeof p);
+  g.ln = 0; g.c64 = false;
   const long long m_tiles = (M + 127) / 128;
   pick_tile_shape(e, m_tiles, N, bn_req, &g.bn, &g.cg);
   REQUIRE(g.bn != 0, "no BN tile divides N");
@@ -480,10 +508,10 @@ static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
   return 0;
 }
 
-template <int BN, int BK, int CG, int EB, int RES>
+template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
-  auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES>;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES, LN>;
   constexpr int SMEM = GemmSmem<BN, BK, CG, EB, RES>::TOTAL;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -532,6 +560,7 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
   if (g.cg == 2) {
+    if (g.ln == 3) return launch_inst<256, 64, 2, 1, 1, 3>(g, groups, s);
     switch (g.bn) {
       case 256: return launch_bn<256, 2>(g, groups, s);
       case 192: return launch_bn<192, 2>(g, groups, s);
@@ -1112,20 +1141,24 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
   if (e->txt_plans.size() > 64) e->txt_plans.clear();
   std::unique_ptr<TextPlan> pl(new TextPlan());
   pl->T = T; pl->B = B;
+  pl->ln_fused = ln_fusable(e, T, H);
+  const int bn_ln = pl->ln_fused ? 256 : 0;
   for (int l = 0; l < e->n_layers; ++l) {
     const BertLayerW& L = e->layers[l];
     GemmLaunch g;
     TRY(build_gemm(e, g, tb->hid, H, L.qkv.w, T, 3 * H, H, 0));
     TRY(fill_epilogue(e, g, L.qkv.bias, nullptr, 0, tb->qkv, 3 * H, ACT_NONE, 0));
     pl->gemms.push_back(g);
-    TRY(build_gemm(e, g, tb->ctx, H, L.ao.w, T, H, H, 0));
+    TRY(build_gemm(e, g, tb->ctx, H, L.ao.w, T, H, H, bn_ln));
     TRY(fill_epilogue(e, g, L.ao.bias, tb->hid, H, tb->pre, H, ACT_NONE, 0));      // + residual (pre-LN)
+    if (pl->ln_fused) TRY(fuse_ln(g, L.ln1.g, L.ln1.b, 1e-12f, tb->hid2, H));
     pl->gemms.push_back(g);
     TRY(build_gemm(e, g, tb->hid2, H, L.ff1.w, T, e->ffn, H, 0));
     TRY(fill_epilogue(e, g, L.ff1.bias, nullptr, 0, tb->ffn, e->ffn, ACT_GELU, 0));
     pl->gemms.push_back(g);
-    TRY(build_gemm(e, g, tb->ffn, e->ffn, L.ff2.w, T, H, e->ffn, 0));
+    TRY(build_gemm(e, g, tb->ffn, e->ffn, L.ff2.w, T, H, e->ffn, bn_ln));
     TRY(fill_epilogue(e, g, L.ff2.bias, tb->hid2, H, tb->pre, H, ACT_NONE, 0));    // + residual (pre-LN)
+    if (pl->ln_fused) TRY(fuse_ln(g, L.ln2.g, L.ln2.b, 1e-12f, tb->hid, H));
     pl->gemms.push_back(g);
   }
   *out = pl.get();
@@ -1270,12 +1303,12 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
     e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 1], s));                                         // out-proj + residual
     e->cur_cls = CLS_LN;
-    TRY(launch_ln(e, tb.pre, T, H, L.ln1.g, L.ln1.b, 1e-12f, tb.hid2, s));
+    if (!pl->ln_fused) TRY(launch_ln(e, tb.pre, T, H, L.ln1.g, L.ln1.b, 1e-12f, tb.hid2, s));
     e->cur_cls = CLS_GEMM_TEXT;
     TRY(launch_gemm(e, pl->gemms[4 * l + 2], s));                                         // FFN1 + GELU
     TRY(launch_gemm(e, pl->gemms[4 * l + 3], s));                                         // FFN2 + residual
     e->cur_cls = CLS_LN;
-    TRY(launch_ln(e, tb.pre, T, H, L.ln2.g, L.ln2.b, 1e-12f, tb.hid, s));
+    if (!pl->ln_fused) TRY(launch_ln(e, tb.pre, T, H, L.ln2.g, L.ln2.b, 1e-12f, tb.hid, s));
   }
   e->cur_cls = CLS_POOL;
   {
@@ -1410,6 +1443,20 @@ extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const 
   GemmLaunch g;
   TRY(build_gemm(e, g, static_cast<const bf16*>(d_a), lda, static_cast<const bf16*>(d_w), M, N, K, bn));
   TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), ldr, d_out, ldc, act, out_f32));
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_gemm_ln(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,
+                               const void* d_residual, int64_t ldr, void* d_pre, int64_t ldc, const float* d_gamma,
+                               const float* d_beta, float eps, void* d_out, int64_t ldo, int M, int N, int K, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
+  REQUIRE(e, "null engine");
+  REQUIRE(N == 768 && M >= 256 && d_residual && d_gamma && d_beta && d_out, "gemm_ln: N = 768, M >= 256, residual required");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  GemmLaunch g;
+  TRY(build_gemm(e, g, static_cast<const bf16*>(d_a), lda, static_cast<const bf16*>(d_w), M, N, K, 256));
+  TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), ldr, d_pre, ldc, ACT_NONE, 0));
+  TRY(fuse_ln(g, d_gamma, d_beta, eps, static_cast<bf16*>(d_out), ldo));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin, const void* d_w,

@@ -66,7 +66,106 @@ struct alignas(64) GemmParams {
   const __nv_bfloat16* residual;   // [M, ldr] or null
   void* out;                   // [M, ldc]
   signed char tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
+  // Fused row LayerNorm (template LN > 0; plain GEMMs whose N tiles cover the whole row): the schedule turns
+  // item-major - one CTA group computes all n_tiles tiles of its 256 (128) rows back to back - and after the last of
+  // them the epilogue warps normalise the rows this CTA has just stored (L2-hot) into ln_out.
+  int item_major;              // 1: tiles of one m-item are consecutive work items of the same CTA group
+  float ln_eps;
+  const float* ln_gamma;       // [N]
+  const float* ln_beta;        // [N]
+  __nv_bfloat16* ln_out;       // [M, ld_ln]; may alias `out` (in place)
+  long long ld_ln;
 };
+
+// Persistent schedule.  Default: tile = group + i * num_groups.  Item-major: group g owns items g, g + num_groups, ...
+// and walks each item's n_tiles tiles consecutively (tile = item * n_tiles + n).
+__device__ __forceinline__ int first_tile(const GemmParams& p, int group) {
+  return p.item_major ? group * p.n_tiles : group;
+}
+__device__ __forceinline__ int next_tile(const GemmParams& p, int tile, int num_groups) {
+  if (!p.item_major) return tile + num_groups;
+  return ((tile + 1) % p.n_tiles != 0) ? tile + 1 : tile + 1 + (num_groups - 1) * p.n_tiles;
+}
+
+// LayerNorm of 2 rows of LNC * 256 columns by one warp, fp32 two-pass statistics in registers (same arithmetic as
+// layernorm_kernel).  Plain coherent loads: the rows were written by this CTA's TMA stores a moment ago.
+__device__ __forceinline__ uint4 ld_global_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+template <int LNC>
+__device__ __forceinline__ void ln_two_rows(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* y, long long ldy, int row0,
+                                            int rows, const float* gamma, const float* beta, float eps, int lane) {
+  constexpr int N = LNC * 256;
+  float v[2][LNC][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = min(row0 + r, rows - 1);
+    const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx);
+    uint4 raw[LNC];
+#pragma unroll
+    for (int c = 0; c < LNC; ++c) raw[c] = ld_global_v4(src + c * 32 + lane);
+#pragma unroll
+    for (int c = 0; c < LNC; ++c) {
+      const uint32_t* u = &raw[c].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(u[j]);
+        v[r][c][2 * j] = f.x; v[r][c][2 * j + 1] = f.y;
+      }
+    }
+  }
+  float mean[2], rstd[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNC; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[r][c][j];
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mean[r] *= (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNC; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[r][c][j] - mean[r]; q += d * d; }
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) rstd[r] = rsqrtf(rstd[r] * (1.0f / N) + eps);
+#pragma unroll
+  for (int c = 0; c < LNC; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (row0 + r >= rows) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[r][c][j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+      reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * ldy)[c * 32 + lane] =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
 
 // EB = staging buffers per epilogue group: with two, the TMA store of chunk c reads its buffer while chunk c+2 (same
 // group) is already being converted and written into the other one, and one named barrier per chunk is enough.
@@ -103,7 +202,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return t;
 }
 
-template <int BN, int BK, int CG, int EB, int RES>
+template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using L = GemmSmem<BN, BK, CG, EB, RES>;
   constexpr int STAGES = L::STAGES;
@@ -177,7 +276,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           tma_load_2d(ident, &p.tmI, ident_bar, 0, 0);
         }
       }
-      for (int tile = group; tile < p.num_tiles; tile += num_groups) {
+      for (int tile = first_tile(p, group); tile < p.num_tiles; tile = next_tile(p, tile, num_groups)) {
         const TileCoord t = decode_tile(p, tile, rank);
         int tap = 0, cc = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -239,7 +338,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int it = 0;
       if (RES && BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
       const int nkb = p.num_k_blocks, nres = (BK == 64 && RES) ? p.res_blocks : 0;
-      for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
+      for (int tile = first_tile(p, group); tile < p.num_tiles; tile = next_tile(p, tile, num_groups), ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);     // the epilogue (of both CTAs) has drained this accumulator
@@ -297,7 +396,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     };
     int it = 0;
     uint32_t nstore = 0;                    // TMA stores issued by this group so far (selects the staging buffer)
-    for (int tile = group; tile < p.num_tiles; tile += num_groups, ++it) {
+    for (int tile = first_tile(p, group); tile < p.num_tiles; tile = next_tile(p, tile, num_groups), ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const TileCoord t = decode_tile(p, tile, rank);
@@ -367,6 +466,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (issuer) {
             tma_store_4d(&p.tmC, buf, col0, t.w0, t.h0, t.n0);
             tma_store_commit();
+          }
+        }
+        if constexpr (LN > 0) {
+          if (t.n_t == p.n_tiles - 1) {
+            // Row LayerNorm of the 128 rows this CTA has just completed.  The accumulators were released above, so the
+            // MMA warp is already two tiles into the next item while this runs.
+            if (issuer) tma_store_wait_all<0>();      // this group's stores of the item have landed (not just been read)
+            named_bar_sync(3, 256);
+            const int rows = p.OW;                    // plain GEMM: OW = M
+            const int m_row0 = ((tile / p.n_tiles) * CG + rank) * 128;   // (not t.w0: a past-the-end m-tile wraps to 0)
+            const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(p.out);
+#pragma unroll 1
+            for (int rr = e * 16; rr < e * 16 + 16; rr += 2) {
+              const int row0 = m_row0 + rr;
+              if (row0 < rows) ln_two_rows<LN>(xin, p.ldc, p.ln_out, p.ld_ln, row0, rows, p.ln_gamma, p.ln_beta, p.ln_eps, lane);
+            }
           }
         }
       } else {

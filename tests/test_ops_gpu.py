@@ -93,6 +93,34 @@ def test_gelu_epilogue_matches_erf_form(h):
     assert torch.equal(ob, out.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("M,K,inplace", [(256, 768, False), (1000, 768, False), (128 * 150 + 77, 768, True), (4096, 3072, True)])
+def test_gemm_fused_layernorm(h, M, K, inplace):
+    """BertSelfOutput / BertOutput as one launch (dense + bias + residual, then LayerNorm eps 1e-12 of the rows the
+    CTA pair has just stored): pre-LN rows equal the plain GEMM's bit for bit, LN output within bf16 rounding of
+    fp32 LayerNorm over those rows.  Ragged M, more items than CTA pairs, in-place output."""
+    N = 768
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = bf(torch.randn(M, K, device="cuda", generator=g))
+    w = bf(torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5))
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = bf(torch.randn(M, N, device="cuda", generator=g))
+    gamma = 1.0 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    pre_ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(res), N, P(pre_ref), N, M, N, K, 0, 0, 256, S()))
+    pre = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = pre if inplace else torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_gemm_ln(h.handle, P(a), K, P(w), P(bias), P(res), N, P(pre), N, P(gamma), P(beta), 1e-12,
+                                          P(out), N, M, N, K, S()))
+    torch.cuda.synchronize()
+    if not inplace:
+        assert torch.equal(pre, pre_ref)
+    ref = F.layer_norm(pre_ref.float(), (N,), gamma, beta, 1e-12)
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).abs().max()) < 0.04          # bf16 rounding of values up to ~5
+    assert rel_err(out, ref) < 4e-3
+
+
 def test_gemm_strided_output_and_no_bias(h):
     M, N, K = 200, 512, 768
     a = bf(torch.randn(M, K, device="cuda"))

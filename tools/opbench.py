@@ -80,6 +80,30 @@ def bench_gemm(h, lib):
         print(f"gemm {name:18s} M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
+def bench_gemm_ln(h, lib):
+    """dense + bias + residual + LayerNorm: one fused launch against GEMM + layernorm_kernel."""
+    M, N = 32768, 768
+    for name, K in [("attn_out+res+LN", 768), ("ffn2+res+LN", 3072)]:
+        a = bf(torch.randn(M, K, device="cuda"))
+        w = bf(torch.randn(N, K, device="cuda") * K ** -0.5)
+        bias = torch.randn(N, device="cuda")
+        r = bf(torch.randn(M, N, device="cuda"))
+        g = torch.ones(N, device="cuda")
+        b = torch.zeros(N, device="cuda")
+        pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+        def two():
+            _lib.check(lib.mmdx_op_gemm(h.handle, P(a), K, P(w), P(bias), P(r), N, P(pre), N, M, N, K, 0, 0, 0, S()))
+            _lib.check(lib.mmdx_op_layernorm(h.handle, P(pre), M, N, P(g), P(b), 1e-12, P(out), S()))
+        us2 = timeit(two)
+        us1 = timeit(lambda: _lib.check(lib.mmdx_op_gemm_ln(h.handle, P(a), K, P(w), P(bias), P(r), N, P(pre), N, P(g), P(b), 1e-12,
+                                                            P(out), N, M, N, K, S())))
+        usi = timeit(lambda: _lib.check(lib.mmdx_op_gemm_ln(h.handle, P(a), K, P(w), P(bias), P(r), N, P(pre), N, P(g), P(b), 1e-12,
+                                                            P(pre), N, M, N, K, S())))
+        print(f"gemm+ln {name:16s} M={M} K={K}: two launches {us2:7.1f} us   fused {us1:7.1f} us   fused in place {usi:7.1f} us", flush=True)
+
+
 def bench_conv(h, lib):
     NB = 256
     cases = [("l1.c1", 56, 256, 64, 1, 1, False), ("l1.c2", 56, 64, 64, 3, 1, False), ("l1.c3+res", 56, 64, 256, 1, 1, True),
@@ -143,7 +167,7 @@ def bench_stem(h, lib):
         print(f"stem pool={pool} B={B} {HW}x{HW}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
 
 
-ALL = {"stem": bench_stem, "attention": bench_attention, "gemm": bench_gemm, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
+ALL = {"stem": bench_stem, "attention": bench_attention, "gemm": bench_gemm, "gemm_ln": bench_gemm_ln, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
