@@ -51,6 +51,43 @@ def flops_per_study(L=SEQ_LEN):
     return gemm_kernel, STEM_FLOPS, attention, head13
 
 
+def gemm_bytes_per_step(B, L, hidden=768, ffn=3072, layers=12, d_img=1024, d_txt=512, d_fuse=1024):
+    """Algorithmic bytes one step moves through gemm_tcgen05_kernel launches (bf16 operands: A read once, weights once,
+    residual once, output written once) - the denominator `roofline.traffic` (ncu DRAM bytes) is compared with."""
+    T = B * L
+    text = layers * (T * hidden * 2 * (1 + 3)            # QKV: A in, 3H out
+                     + T * hidden * 2 * 3                # attention output: A, residual, out
+                     + T * (hidden + ffn) * 2            # FFN1
+                     + T * (ffn + 2 * hidden) * 2        # FFN2: A, residual, out
+                     + (4 * hidden * hidden + 2 * hidden * ffn) * 2)
+    img, cin, hw = 0, 64, 56
+    for mid, cout, blocks, stride in ((64, 256, 3, 1), (128, 512, 4, 2), (256, 1024, 6, 2), (512, 2048, 3, 2)):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            ho = hw // s
+            c2_own_kernel = (mid == 64)                  # layer-1 3x3 convs run in conv3x3_c64_tcgen05_kernel
+            img += B * hw * hw * (cin + mid) * 2 + cin * mid * 2                                    # conv1 1x1
+            if not c2_own_kernel:
+                img += B * (hw * hw + ho * ho) * mid * 2 + 9 * mid * mid * 2                        # conv2 3x3 (stride s)
+            img += B * ho * ho * (mid + 2 * cout) * 2 + mid * cout * 2                              # conv3 1x1 + residual
+            if b == 0:
+                img += B * ho * ho * (cin + cout) * 2 + cin * cout * 2                              # downsample 1x1 (stride s)
+            cin, hw = cout, ho
+    head = B * (2048 + d_img + hidden + d_txt + d_img + d_txt) * 2 + B * d_fuse * 4 \
+        + (2048 * d_img + hidden * d_txt + (d_img + d_txt) * d_fuse) * 2
+    return text + img + head
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)["gemm_tcgen05_kernel"]
+        return t["dram_bytes_per_launch"], t.get("source")
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def class_rooflines(by_class, B, L, peaks, hidden=768, layers=12):
     """Algorithmic FLOPs or bytes per step of every non-GEMM kernel class / its device time, against the measured
     peak that bounds it (DESIGN.md section 4 lists the per-unit figures)."""
@@ -311,13 +348,17 @@ def main():
     f_gemm, f_stem, f_attn, f_head = flops_per_study(L)
     peaks = load_peaks()
     achieved = f_gemm * B / (gemm_ms * 1e-3) / 1e12
+    traffic, traffic_src = measured_traffic() if B == BATCH_PER_GPU else (None, None)
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (52 bottleneck convs + every Linear layer)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16",
-                "traffic": None, "launches_per_step": gemm_launches,
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, B=256)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": gemm_bytes_per_step(B, L) / max(gemm_launches, 1),
+                "launches_per_step": gemm_launches,
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "algorithmic_flops_per_launch": f_gemm * B / max(gemm_launches, 1),
-                "whole_path_frac_of_tensor_roofline": (sum(flops_per_study(L)) * value) / (peaks["bf16_sustained"] * 1e12)}
+                "whole_path_frac_of_tensor_roofline": (sum(flops_per_study(L)) * value / world) / (peaks["bf16_sustained"] * 1e12)}
 
     out = {
         "metric": "studies/sec (image+report) batched inference", "value": value, "unit": "studies/s", "n_gpus": world,
