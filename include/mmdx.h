@@ -51,6 +51,12 @@ void mmdx_destroy(mmdx_engine* e);
 int mmdx_load_tensor(mmdx_engine* e, const char* name, const float* h_data, int ndim, const int64_t* shape);
 /* Fold BatchNorm into conv weights+bias, fuse Q/K/V, cast to bf16, lay out K-major for TMA, upload. */
 int mmdx_finalize_weights(mmdx_engine* e);
+/* Packed weight file (replaces the per-process bundle rebuild of backend/api/views.py:188-258):
+ * mmdx_save_packed writes the finalized arena (BN folded, QKV fused, bf16, kernel-ready layouts) with its table of
+ * dimensions and offsets; mmdx_load_packed on a freshly created engine reads it back with one host-to-device copy
+ * instead of mmdx_load_tensor x N + mmdx_finalize_weights.  Checksummed; a file of another layout version is rejected. */
+int mmdx_save_packed(mmdx_engine* e, const char* path);
+int mmdx_load_packed(mmdx_engine* e, const char* path);
 int mmdx_num_sms(mmdx_engine* e);
 /* dims read from the loaded weights: d_img, d_txt, d_fuse_hidden, n_disease, hidden, n_layers */
 int mmdx_dims(mmdx_engine* e, int32_t out[6]);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "mmdx_destroy": [_p],
     "mmdx_load_tensor": [_p, C.c_char_p, _p, _i, C.POINTER(C.c_int64)],
     "mmdx_finalize_weights": [_p],
+    "mmdx_save_packed": [_p, C.c_char_p],
+    "mmdx_load_packed": [_p, C.c_char_p],
     "mmdx_num_sms": [_p],
     "mmdx_dims": [_p, C.POINTER(C.c_int32)],
     "mmdx_image_encode": [_p, _p, _i, _i, _i, _i, _p, _p, _p],

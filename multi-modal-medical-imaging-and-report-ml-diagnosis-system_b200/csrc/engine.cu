@@ -200,6 +200,7 @@ struct mmdx_engine {
   CUtensorMap tm_ident_half{};   // same identity, box of 32 rows: each CTA of a pair holds half of the B operand
   bool attn_force_general = false;   // MMDX_ATTN=general: use the flash-style kernel for short sequences too (experiments)
   int epi_bufs = 0;      // MMDX_EB=1|2 pins the staging buffers per epilogue group of the CTA-pair kernels; 0 = heuristic
+  int force_bn = 0;      // MMDX_BN=64|128|192|256 pins the tile width wherever it divides N (experiments)
   int force_cg = 0;      // MMDX_CG=1|2 pins the CTA-group size of every eligible GEMM (experiments); 0 = heuristic
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
@@ -299,6 +300,7 @@ static void pick_tile_shape(mmdx_engine* e, long long m_tiles, int N, int bn_req
   struct Cand { int bn, cg; double pen; };
   const Cand cands[] = {{256, 2, 1.00}, {192, 2, 1.03}, {128, 2, 1.15}, {256, 1, 1.35}, {128, 1, 1.35}, {64, 1, 1.60}};
   double best = -1.0; *bn_out = 0; *cg_out = 1;
+  if (bn_req == 0 && e->force_bn != 0 && N % e->force_bn == 0) bn_req = e->force_bn;      // MMDX_BN: tile-shape sweeps
   for (const Cand& c : cands) {
     if (N % c.bn != 0) continue;
     if (bn_req != 0 && c.bn != bn_req) continue;
@@ -695,6 +697,7 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     CK(cudaMemcpy(e->pre_lut.p, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
   }
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
+  if (const char* v = getenv("MMDX_BN")) e->force_bn = atoi(v);
   if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
   if (const char* v = getenv("MMDX_ATTN")) e->attn_force_general = (strcmp(v, "general") == 0);
   *out = e.release();
@@ -896,6 +899,124 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     std::vector<float> thr(e->n_cls, 0.5f);
     TRY(upload(e, thr, &e->thr_default));
   }
+  e->host.clear();
+  e->finalized = true;
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ packed weight file
+// The finalized weight arena (BN folded, QKV fused, bf16, kernel-ready layouts) as one file: a header, the engine's
+// weight table - every dimension and every device pointer as an offset into the arena, in the fixed order of
+// walk_weights - and the arena bytes.  Loading is a file read and ONE host-to-device copy: no torch modules, no
+// state_dict, no re-packing (replaces the bundle rebuild of backend/api/views.py:188-258 and
+// training_pipeline.py:773-796 for serving processes).
+struct PackHeader {
+  char magic[8];            // "MMDXPACK"
+  uint32_t version;         // layout version of walk_weights
+  uint32_t n_words;         // entries of the weight table (int64 each)
+  uint64_t arena_bytes;
+  uint64_t checksum;        // FNV-1a of table + arena
+};
+static const uint32_t kPackVersion = 1;
+
+struct PackWalker {
+  bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
+  void i(int& v) {
+    if (loading) { if (pos < words.size()) v = (int)words[pos++]; else ok = false; }
+    else words.push_back(v);
+  }
+  void b(bool& v) { int t = v ? 1 : 0; i(t); v = t != 0; }
+  template <typename T> void p(T*& ptr) {
+    if (loading) {
+      if (pos >= words.size()) { ok = false; return; }
+      const int64_t off = words[pos++];
+      ptr = off < 0 ? nullptr : reinterpret_cast<T*>(base + off);
+    } else {
+      words.push_back(ptr ? reinterpret_cast<char*>(ptr) - base : -1);
+    }
+  }
+  void conv(ConvW& c) { p(c.w); p(c.bias); i(c.cin); i(c.cout); i(c.k); i(c.stride); }
+  void lin(LinW& l) { p(l.w); p(l.bias); i(l.nin); i(l.nout); }
+  void ln(LnW& l) { p(l.g); p(l.b); }
+};
+// one traversal for both directions: every field mmdx_finalize_weights sets
+static void walk_weights(mmdx_engine* e, PackWalker& w) {
+  w.i(e->d_img); w.i(e->d_txt); w.i(e->d_fuse); w.i(e->n_cls); w.i(e->hidden); w.i(e->n_layers); w.i(e->ffn); w.i(e->feat_dim);
+  w.i(e->cfg.n_heads);
+  w.conv(e->stem); w.p(e->stem_w2);
+  int nb = (int)e->blocks.size();
+  w.i(nb);
+  if (w.loading) e->blocks.assign(nb < 0 || nb > 64 ? 0 : nb, Bottleneck());
+  for (Bottleneck& bk : e->blocks) { w.conv(bk.c1); w.conv(bk.c2); w.conv(bk.c3); w.b(bk.has_ds); w.conv(bk.ds); }
+  w.lin(e->proj_img);
+  w.p(e->word); w.p(e->ptab); w.p(e->ttab); w.ln(e->emb_ln);
+  int nl = (int)e->layers.size();
+  w.i(nl);
+  if (w.loading) e->layers.assign(nl < 0 || nl > 64 ? 0 : nl, BertLayerW());
+  for (BertLayerW& L : e->layers) { w.lin(L.qkv); w.lin(L.ao); w.lin(L.ff1); w.lin(L.ff2); w.ln(L.ln1); w.ln(L.ln2); }
+  w.lin(e->proj_txt); w.lin(e->fuse); w.ln(e->fuse_ln);
+  w.p(e->head_w); w.p(e->head_b); w.p(e->thr_default);
+}
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+extern "C" int mmdx_save_packed(mmdx_engine* e, const char* path) {
+  REQUIRE(e && path, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  REQUIRE(e->finalized, "weights not finalized");
+  CK(cudaSetDevice(e->cfg.device));
+  PackWalker w{false, static_cast<char*>(e->warena.p)};
+  walk_weights(e, w);
+  std::vector<char> arena(e->wused);
+  CK(cudaMemcpy(arena.data(), e->warena.p, e->wused, cudaMemcpyDeviceToHost));
+  PackHeader h;
+  memcpy(h.magic, "MMDXPACK", 8);
+  h.version = kPackVersion; h.n_words = (uint32_t)w.words.size(); h.arena_bytes = e->wused;
+  h.checksum = fnv1a(fnv1a(14695981039346656037ull, w.words.data(), w.words.size() * 8), arena.data(), arena.size());
+  FILE* f = fopen(path, "wb");
+  REQUIRE(f != nullptr, "cannot open the packed weight file for writing");
+  const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(w.words.data(), 8, w.words.size(), f) == w.words.size() &&
+                  fwrite(arena.data(), 1, arena.size(), f) == arena.size();
+  const bool closed = fclose(f) == 0;
+  REQUIRE(ok && closed, "short write to the packed weight file");
+  return 0;
+}
+
+extern "C" int mmdx_load_packed(mmdx_engine* e, const char* path) {
+  REQUIRE(e && path, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  REQUIRE(!e->finalized, "weights already finalized");
+  CK(cudaSetDevice(e->cfg.device));
+  FILE* f = fopen(path, "rb");
+  REQUIRE(f != nullptr, "cannot open the packed weight file");
+  PackHeader h;
+  std::vector<int64_t> words;
+  std::vector<char> arena;
+  bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "MMDXPACK", 8) == 0 && h.version == kPackVersion &&
+            h.n_words < (1u << 20) && h.arena_bytes < (1ull << 36);
+  if (ok) {
+    words.resize(h.n_words); arena.resize(h.arena_bytes);
+    ok = fread(words.data(), 8, words.size(), f) == words.size() && fread(arena.data(), 1, arena.size(), f) == arena.size();
+  }
+  fclose(f);
+  REQUIRE(ok, "not a packed weight file of this layout version (or truncated)");
+  REQUIRE(h.checksum == fnv1a(fnv1a(14695981039346656037ull, words.data(), words.size() * 8), arena.data(), arena.size()),
+          "packed weight file checksum mismatch");
+  for (int64_t v : words) REQUIRE(v < (int64_t)h.arena_bytes, "packed weight table entry out of range");
+  TRY(e->warena.ensure(h.arena_bytes + (1 << 20)));
+  CK(cudaMemcpy(e->warena.p, arena.data(), arena.size(), cudaMemcpyHostToDevice));
+  e->wused = h.arena_bytes;
+  const int heads_cfg = e->cfg.n_heads;
+  PackWalker w{true, static_cast<char*>(e->warena.p), std::move(words)};
+  walk_weights(e, w);
+  REQUIRE(w.ok && w.pos == w.words.size(), "packed weight table does not match this build's layout");
+  REQUIRE(e->n_layers == (int)e->layers.size() && e->n_layers > 0 && !e->blocks.empty(), "packed weight table is inconsistent");
+  REQUIRE(heads_cfg == 0 || heads_cfg == e->cfg.n_heads, "engine was created for a different head count than the file");
+  REQUIRE(e->hidden == e->cfg.n_heads * 64, "head dim must be 64");
   e->host.clear();
   e->finalized = true;
   CK(cudaDeviceSynchronize());

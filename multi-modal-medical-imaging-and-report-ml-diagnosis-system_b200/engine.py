@@ -3,6 +3,7 @@ and thin wrappers over the C ABI (`include/mmdx.h`).  PyTorch is used only for d
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -45,8 +46,8 @@ class Engine:
     """One engine per process/GPU.  `states` = {"image": sd, "text": sd, "fusion": sd} with the reference's
     state_dict key names."""
 
-    def __init__(self, states: dict, device: int | None = None, resize_short: int = 256, crop: int = 224,
-                 n_heads: int = 12):
+    def __init__(self, states: dict | None, device: int | None = None, resize_short: int = 256, crop: int = 224,
+                 n_heads: int = 12, packed: str | None = None):
         if not torch.cuda.is_available():
             raise MmdxError("mmdx needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -54,19 +55,36 @@ class Engine:
                      (C.c_float * 3)(*IMAGENET_STD))
         self._h = C.c_void_p()
         check(lib().mmdx_create(C.byref(cfg), C.byref(self._h)))
-        skip = ("num_batches_tracked", "report_model.", "classifier.", "pooler.", "position_ids", "cond_proj.")
-        for prefix, sd in states.items():
-            for k, v in sd.items():
-                if any(s in k for s in skip):
-                    continue   # dead at inference (I3, T6, T9) or off the named path (T5)
-                t = v.detach().to(dtype=torch.float32, device="cpu").contiguous()
-                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
-                check(lib().mmdx_load_tensor(self._h, f"{prefix}.{k}".encode(), C.c_void_p(t.data_ptr()), t.dim(), shape))
-        check(lib().mmdx_finalize_weights(self._h))
+        if packed is not None:
+            if states is not None:
+                raise ValueError("pass either state dicts or a packed weight file, not both")
+            check(lib().mmdx_load_packed(self._h, os.fsencode(packed)))
+        else:
+            skip = ("num_batches_tracked", "report_model.", "classifier.", "pooler.", "position_ids", "cond_proj.")
+            for prefix, sd in states.items():
+                for k, v in sd.items():
+                    if any(s in k for s in skip):
+                        continue   # dead at inference (I3, T6, T9) or off the named path (T5)
+                    t = v.detach().to(dtype=torch.float32, device="cpu").contiguous()
+                    shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                    check(lib().mmdx_load_tensor(self._h, f"{prefix}.{k}".encode(), C.c_void_p(t.data_ptr()), t.dim(),
+                                                 shape))
+            check(lib().mmdx_finalize_weights(self._h))
         d = (C.c_int32 * 6)()
         check(lib().mmdx_dims(self._h, d))
         self.d_img, self.d_txt, self.d_fuse, self.n_cls, self.hidden, self.n_layers = list(d)
         self.feat_dim = 2048
+
+    @classmethod
+    def from_packed(cls, path: str, device: int | None = None, resize_short: int = 256, crop: int = 224,
+                    n_heads: int = 12) -> "Engine":
+        """Engine from a packed weight file written by save_packed(): one file read + one H2D copy, no torch modules
+        (SURVEY.md section 8f N2 - what a serving process does instead of views.py:188-258)."""
+        return cls(None, device, resize_short, crop, n_heads, packed=path)
+
+    def save_packed(self, path: str) -> None:
+        """Writes the finalized weight arena (BN folded, QKV fused, bf16 kernel layouts) and its table to `path`."""
+        check(lib().mmdx_save_packed(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

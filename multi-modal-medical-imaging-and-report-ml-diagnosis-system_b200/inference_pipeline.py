@@ -65,9 +65,23 @@ def get_engine(model_bundle: dict, device=None) -> Engine:
         if hit is not None and hit[1] is model_bundle:
             return hit[0]
         with torch.cuda.device(idx):
-            eng = Engine(_states_from_bundle(model_bundle), device=idx)
+            if model_bundle.get("packed_weights"):       # serving bundle without torch modules (save_packed_bundle)
+                eng = Engine.from_packed(model_bundle["packed_weights"], device=idx)
+            else:
+                eng = Engine(_states_from_bundle(model_bundle), device=idx)
         _ENGINES[key] = (eng, model_bundle)
         return eng
+
+
+def save_packed_bundle(model_bundle: dict, path: str, device=None) -> dict:
+    """Writes the bundle's weights as one packed file (kernel-ready bf16 arena, Engine.save_packed) and returns the
+    light serving bundle that refers to it: {"packed_weights": path, class_names, thresholds, version, bert_tok,
+    t5_tok}.  `inference()` on that bundle needs no torch modules; `report_text` is "" unless `fusion_model` is kept."""
+    eng = get_engine(model_bundle, "cuda" if device is None else device)
+    eng.save_packed(path)
+    light = {k: model_bundle.get(k) for k in ("class_names", "thresholds", "version", "bert_tok", "t5_tok")}
+    light["packed_weights"] = path
+    return light
 
 
 def clear_engines():

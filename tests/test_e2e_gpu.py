@@ -124,6 +124,37 @@ def test_inference_drop_in_contract(bundle, g1):
     assert ip.get_engine(bundle, "cuda") is ip.get_engine(bundle, torch.device("cuda"))
 
 
+def test_packed_weight_file_round_trip(bundle, eng, g1, tmp_path):
+    """Packed weight file: an engine loaded from the file - no state dicts - reproduces the
+    original engine bit for bit, the light serving bundle drives inference(), and damaged files are rejected."""
+    from PIL import Image
+    from mmdx_b200._lib import MmdxError
+    path = str(tmp_path / "model.mmdx")
+    light = ip.save_packed_bundle(bundle, path, device="cuda")
+    assert light["packed_weights"] == path and "image_encoder" not in light and "image_state" not in light
+    eng2 = engine.Engine.from_packed(path)
+    assert (eng2.d_img, eng2.d_txt, eng2.d_fuse, eng2.n_cls, eng2.hidden, eng2.n_layers) == \
+        (eng.d_img, eng.d_txt, eng.d_fuse, eng.n_cls, eng.hidden, eng.n_layers)
+    imgs = synth.synth_images(8, 224, seed=7)
+    ids, mask = synth.synth_token_ids(8, 128, seed=8, ragged=True)
+    a, b = _run_stages(eng, imgs, ids, mask), _run_stages(eng2, imgs, ids, mask)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    eng2.close()
+    pil = Image.fromarray(np.repeat(g1["gray"][0][..., None], 3, axis=-1))
+    res = ip.inference(light, pil, str(g1["details"][0]), device="cuda", gen_kwargs=False)
+    assert res["disease_vector"] == g1["vector"][0].tolist() and res["report_text"] == ""
+    blob = bytearray(open(path, "rb").read())
+    blob[len(blob) // 2] ^= 0xFF
+    bad = str(tmp_path / "bad.mmdx")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(MmdxError, match="checksum"):
+        engine.Engine.from_packed(bad)
+    open(bad, "wb").write(bytes(blob[:4096]))
+    with pytest.raises(MmdxError):
+        engine.Engine.from_packed(bad)
+
+
 def test_full_size_properties(eng):
     """BASELINE config C2 size (B=256, L=128): size-independent properties instead of the slow oracle:
     a study's result does not depend on its batch neighbours or its position (batch independence), and

@@ -106,10 +106,13 @@ def bench_gemm_ln(h, lib):
 
 def bench_conv(h, lib):
     NB = 256
-    cases = [("l1.c1", 56, 256, 64, 1, 1, False), ("l1.c2", 56, 64, 64, 3, 1, False), ("l1.c3+res", 56, 64, 256, 1, 1, True),
+    cases = [("l1.0.c1", 56, 64, 64, 1, 1, False), ("l1.0.ds", 56, 64, 256, 1, 1, False),
+             ("l1.c1", 56, 256, 64, 1, 1, False), ("l1.c2", 56, 64, 64, 3, 1, False), ("l1.c3+res", 56, 64, 256, 1, 1, True),
+             ("l2.0.c1", 56, 256, 128, 1, 1, False), ("l2.0.c2s2", 56, 128, 128, 3, 2, False), ("l2.0.ds", 56, 256, 512, 1, 2, False),
              ("l2.c1", 28, 512, 128, 1, 1, False), ("l2.c2", 28, 128, 128, 3, 1, False), ("l2.c3+res", 28, 128, 512, 1, 1, True),
-             ("l2.c2s2", 56, 128, 128, 3, 2, False),
+             ("l3.0.c1", 28, 512, 256, 1, 1, False), ("l3.0.c2s2", 28, 256, 256, 3, 2, False), ("l3.0.ds", 28, 512, 1024, 1, 2, False),
              ("l3.c1", 14, 1024, 256, 1, 1, False), ("l3.c2", 14, 256, 256, 3, 1, False), ("l3.c3+res", 14, 256, 1024, 1, 1, True),
+             ("l4.0.c1", 14, 1024, 512, 1, 1, False), ("l4.0.c2s2", 14, 512, 512, 3, 2, False), ("l4.0.ds", 14, 1024, 2048, 1, 2, False),
              ("l4.c1", 7, 2048, 512, 1, 1, False), ("l4.c2", 7, 512, 512, 3, 1, False), ("l4.c3+res", 7, 512, 2048, 1, 1, True)]
     for name, HW, Cin, Cout, k, s, res in cases:
         x = bf(torch.randn(NB, HW, HW, Cin, device="cuda"))
