@@ -13,6 +13,7 @@
 
 #include "../../include/mmdx.h"
 #include "attention_tcgen05.cuh"
+#include "bneck64_tcgen05.cuh"
 #include "conv3x3_c64_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
 #include "stem_tcgen05.cuh"
@@ -128,6 +129,7 @@ struct GemmLaunch {
   GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1;
   int ln = 0;                         // > 0: row LayerNorm fused behind the last N tile of every m-item (row width ln * 256)
   bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
+  int b64 = 0; Bneck64Params b;       // 64 / 128: fused layer-1 bottleneck kernel (conv2 -> conv3+shortcut -> next conv1 of that width)
 };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
@@ -381,7 +383,7 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   REQUIRE(lda % 8 == 0, "gemm lda must be a multiple of 8 elements");
   GemmParams& p = g.p;
   memset(&p, 0, sizeof p);
-  g.ln = 0; g.c64 = false;
+  g.ln = 0; g.c64 = false; g.b64 = 0;
   const long long m_tiles = (M + 127) / 128;
   pick_tile_shape(e, m_tiles, N, bn_req, &g.bn, &g.cg);
   REQUIRE(g.bn != 0, "no BN tile divides N");
@@ -510,6 +512,77 @@ static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
   return 0;
 }
 
+// Fused layer-1 bottleneck (bneck64_tcgen05.cuh): t1 [NB,H,W,64] -> y [NB,H,W,256] and the next block's conv1 output.
+static bool b64_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("MMDX_B64"); on = (v && atoi(v) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* res, bf16* y, bf16* t1n, int NB, int H, int W,
+                     const ConvW& c2, const ConvW& c3, const ConvW& c1n) {
+  REQUIRE(c2.cin == 64 && c2.cout == 64 && c2.k == 3 && c2.stride == 1 && c3.cin == 64 && c3.cout == 256 && c3.k == 1 &&
+              c1n.cin == 256 && c1n.k == 1 && c1n.stride == 1 && (c1n.cout == 64 || c1n.cout == 128),
+          "fused bottleneck: 64 -3x3-> 64 -1x1-> 256 -1x1-> 64|128");
+  g.c64 = false; g.ln = 0; g.b64 = c1n.cout;
+  Bneck64Params& p = g.b;
+  memset(&p, 0, sizeof p);
+  {
+    const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+    const uint32_t box[4] = {64, B64_HALO_W, B64_HALO_H, 1};
+    TRY(make_tmap(e, &p.tmA, t1, 4, dims, str, box, 128));
+  }
+  {
+    const uint64_t d[2] = {576, 64}; const uint64_t st[1] = {576 * 2}; const uint32_t bx[2] = {64, 32};
+    TRY(make_tmap(e, &p.tmW2, c2.w, 2, d, st, bx, 128));
+  }
+  {
+    const uint64_t d[2] = {64, 256}; const uint64_t st[1] = {64 * 2}; const uint32_t bx[2] = {64, 128};
+    TRY(make_tmap(e, &p.tmW3, c3.w, 2, d, st, bx, 128));
+  }
+  {
+    const uint64_t d[2] = {256, (uint64_t)c1n.cout}; const uint64_t st[1] = {256 * 2};
+    const uint32_t bx[2] = {64, (uint32_t)c1n.cout / 2};
+    TRY(make_tmap(e, &p.tmW1, c1n.w, 2, d, st, bx, 128));
+  }
+  {
+    const uint64_t dims[4] = {256, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t str[3] = {512, (uint64_t)W * 512, (uint64_t)H * W * 512};
+    const uint32_t box[4] = {64, 8, 16, 1};
+    TRY(make_tmap(e, &p.tmY, y, 4, dims, str, box, 128));
+  }
+  p.b2 = c2.bias; p.b3 = c3.bias; p.b1 = c1n.bias; p.res = res; p.t1n = t1n;
+  p.NB = NB; p.H = H; p.W = W;
+  p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.num_tiles = NB * p.tiles_w * p.tiles_h;
+  p.num_items = (p.num_tiles + 1) / 2;
+  return 0;
+}
+template <int C1>
+static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t s) {
+  static bool attr_set = false;
+  static int max_clusters = 0;
+  auto* kfn = bneck64_tcgen05_kernel<C1>;
+  constexpr int SMEM = B64Smem<C1>::TOTAL;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 64, 1, 1); cfg.blockDim = dim3(B64_THREADS, 1, 1); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
+    REQUIRE(max_clusters > 0, "no CTA pair fits on this device");
+    attr_set = true;
+  }
+  int pairs = p.num_items < e->num_sms / 2 ? p.num_items : e->num_sms / 2;
+  if (pairs > max_clusters) pairs = max_clusters;
+  ProfScope _ps(e);
+  CK(launch_k(kfn, dim3((unsigned)pairs * 2), dim3(B64_THREADS), SMEM, s, 2, p));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   static bool attr_set = false;
@@ -557,6 +630,8 @@ static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s) {
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
+  if (g.b64 == 64) return launch_b64_inst<64>(e, g.b, s);
+  if (g.b64 == 128) return launch_b64_inst<128>(e, g.b, s);
   if (g.c64) return launch_c64(e, g.c, s);
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
@@ -1595,6 +1670,22 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
   }
   TRY(build_conv(e, g, static_cast<const bf16*>(d_in), NB, H, W, Cin, static_cast<const bf16*>(d_w), Cout, k, stride));
   TRY(fill_epilogue(e, g, d_bias, static_cast<const bf16*>(d_residual), Cout, d_out, Cout, act, 0));
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const void* d_w2, const float* d_b2,
+                               const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n,
+                               void* d_y, void* d_t1n, int NB, int H, int W, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
+  REQUIRE(e && d_t1 && d_res && d_w2 && d_b2 && d_w3 && d_b3 && d_w1n && d_b1n && d_y && d_t1n, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  ConvW c2, c3, c1;
+  c2.w = (bf16*)d_w2; c2.bias = (float*)d_b2; c2.cin = 64; c2.cout = 64; c2.k = 3; c2.stride = 1;
+  c3.w = (bf16*)d_w3; c3.bias = (float*)d_b3; c3.cin = 64; c3.cout = 256; c3.k = 1; c3.stride = 1;
+  c1.w = (bf16*)d_w1n; c1.bias = (float*)d_b1n; c1.cin = 256; c1.cout = c1n; c1.k = 1; c1.stride = 1;
+  GemmLaunch g;
+  TRY(build_b64(e, g, static_cast<const bf16*>(d_t1), static_cast<const bf16*>(d_res), static_cast<bf16*>(d_y),
+                static_cast<bf16*>(d_t1n), NB, H, W, c2, c3, c1));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,
