@@ -108,7 +108,7 @@ int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin
                  void* stream);
 /* One layer-1 bottleneck of ResNet-50 shifted by one conv (torchvision Bottleneck.forward, training_pipeline.py:178-183):
  * t2 = relu(conv3x3(t1, w2) + b2) [64 ch, stays on chip]; y = relu(conv1x1(t2, w3) + b3 + res) [256 ch];
- * t1n = relu(conv1x1(y, w1n) + b1n) [c1n = 64 or 128 ch, the next block's conv1].  NHWC bf16; weights packed
+ * t1n = relu(conv1x1(y, w1n) + b1n) [c1n = 64 ch, the next block's conv1; c1n = 0: not computed].  NHWC bf16; weights packed
  * [Cout][k*k][Cin] bf16 with BN folded, fp32 biases. */
 int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const void* d_w2, const float* d_b2,
                     const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n, void* d_y,

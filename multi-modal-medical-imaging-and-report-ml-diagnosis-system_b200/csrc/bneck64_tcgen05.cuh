@@ -2,7 +2,7 @@
 // shifted by one convolution so that nothing needs a halo recompute:
 //     t2  = relu(conv3x3(t1) + b2)                 64 -> 64, this block's conv2/bn2/relu
 //     y   = relu(conv1x1(t2) + b3 + residual)      64 -> 256, conv3/bn3 + shortcut + relu   -> global (next shortcut)
-//     t1' = relu(conv1x1(y) + b1')                 256 -> C1 (64, or 128 for layer2.0), the NEXT block's conv1/bn1/relu
+//     t1' = relu(conv1x1(y) + b1')                 256 -> 64, the NEXT block's conv1/bn1/relu (C1 = 0: not computed)
 // t2 and the A operand of the third GEMM never leave the SM: the accumulator of one tcgen05 GEMM is read by the epilogue
 // warps (tcgen05.ld), biased / activated / rounded to bf16 and written to shared memory in the 128-byte-swizzled
 // K-major layout that the next tcgen05.mma reads as its A operand (and that the TMA store of y reads as its source).
@@ -14,15 +14,21 @@
 // TMA box, zero-filled outside the image = the padding) is loaded once and the nine taps read it through descriptors
 // shifted by whole pixel rows.  CTA PAIRS (cta_group::2): the pair computes two tiles with M = 256 MMAs issued by the
 // leader; each CTA holds HALF of every weight matrix (its N half), which is what lets all three weight sets stay
-// resident: W2 9 x [32 x 64], W3 [128 x 64], W1' 4 x [C1/2 x 64] = 68-84 KB per CTA instead of 136-168 KB.
+// resident: W2 9 x [32 x 64], W3 [128 x 64], W1' 4 x [32 x 64] = 68 KB per CTA instead of 136 KB.
+// The shortcut tile arrives by TMA, one 64-channel chunk per slot of the four-slot y ring, a tile ahead of its use; the
+// epilogue adds it IN PLACE (reads its row of the slot, writes the activated bf16 result back), after which the same
+// slot is the source of the TMA store of y and the A operand of GEMM1'.  (A first version loaded the shortcut with
+// per-thread global loads one chunk ahead: 35 % of all stall samples sat on those loads and the fused kernel was
+// slower than the three launches it replaces - profiles/r01_bneck64_v1_full.md.)
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issue (leader CTA only), warps 2-9 =
 // epilogue in two groups (column halves) x four TMEM lane quarters; thread = pixel.
 // MMA issue order per tile i:   GEMM3(i), GEMM2(i+1), GEMM1'(i) chunk by chunk as the epilogue delivers y.
 // Epilogue order per tile i:    ep3(i) [y, four 64-channel chunks], ep2(i+1) [t2], ep1'(i) [t1'].
 // Every reuse hazard except the two rings below is ordered by that program order:
-//   halo ring (2): producer waits halo_empty (commit of GEMM2);  y ring (2): epilogue waits y_free (commit of the
-//   GEMM1' chunk that read the slot) and the TMA store that read it (bulk-group wait by the issuing thread).
+//   halo ring (2): producer waits halo_empty (commit of GEMM2);  y ring (4 = the chunks of a tile): the thread that issues
+//   the y stores also issues the shortcut loads, and refills slot j for the next tile once y_free[j] (commit of the
+//   GEMM1' chunk that read it) has flipped and its own store of the slot has been read (bulk-group wait).
 // TMEM (512 columns): D2 2 x 64 | D3 256 | D1' C1.
 #pragma once
 #include "ptx.cuh"
@@ -48,8 +54,8 @@ struct B64Smem {
   static constexpr int OFF_HALO = OFF_W1 + W1_BYTES;
   static constexpr int OFF_T2 = OFF_HALO + 2 * B64_HALO_BYTES;
   static constexpr int OFF_Y = OFF_T2 + B64_T2_BYTES;
-  static constexpr int OFF_BIAS = OFF_Y + 2 * B64_Y_BYTES;         // b3[256] | b1[C1] fp32
-  static constexpr int OFF_BAR = OFF_BIAS + (256 + C1) * 4;
+  static constexpr int OFF_BIAS = OFF_Y + 4 * B64_Y_BYTES;         // b2[64] | b3[256] | b1[C1] fp32
+  static constexpr int OFF_BAR = OFF_BIAS + (64 + 256 + C1) * 4;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;               // + manual 1024-byte alignment slack
   static constexpr int W_BYTES = B64_W2_BYTES + B64_W3_BYTES + W1_BYTES;
   static_assert(TOTAL <= 232448, "shared-memory budget");
@@ -62,10 +68,10 @@ struct Bneck64Params {
   CUtensorMap tmW3;    // W3  [256, 64],  box (64, 128)
   CUtensorMap tmW1;    // W1' [C1, 256],  box (64, C1/2)
   CUtensorMap tmY;     // y   [NB,H,W,256]: dims (256, W, H, NB), box (64, 8, 16, 1), SWIZZLE_128B
+  CUtensorMap tmR;     // shortcut, same geometry as y
   const float* b2;     // [64]
   const float* b3;     // [256]
   const float* b1;     // [C1]
-  const __nv_bfloat16* res;   // [NB,H,W,256]
   __nv_bfloat16* t1n;         // [NB,H,W,C1]
   int NB, H, W, tiles_w, tiles_h, num_tiles, num_items;   // item = two consecutive tiles (one per CTA of the pair)
 };
@@ -73,10 +79,10 @@ struct Bneck64Params {
 template <int C1>
 __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const __grid_constant__ Bneck64Params p) {
   using L = B64Smem<C1>;
-  static_assert(C1 == 64 || C1 == 128, "next conv1 width");
+  static_assert(C1 == 0 || C1 == 64, "next conv1 width (0 = none)");
   constexpr uint32_t IDESC2 = make_idesc_bf16(256, 64);
   constexpr uint32_t IDESC3 = make_idesc_bf16(256, 256);
-  constexpr uint32_t IDESC1 = make_idesc_bf16(256, C1);
+  constexpr uint32_t IDESC1 = make_idesc_bf16(256, C1 > 0 ? C1 : 64);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w2s = smem;
@@ -85,7 +91,8 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint8_t* halo = smem + L::OFF_HALO;
   uint8_t* t2s = smem + L::OFF_T2;
   uint8_t* ys = smem + L::OFF_Y;
-  float* b3s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  float* b2s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  float* b3s = b2s + 64;
   float* b1s = b3s + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* w_bar = bars;                 // leader: weights of both CTAs have landed
@@ -94,10 +101,11 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint64_t* d2_full = bars + 5;           // [2] own
   uint64_t* t2_full = bars + 7;           // leader: 16 epilogue warps (both CTAs) have written their t2 rows
   uint64_t* d3_full = bars + 8;           // own
-  uint64_t* y_full = bars + 9;            // [2] leader: 16 epilogue warps have written the y chunk
-  uint64_t* y_free = bars + 11;           // [2] own: GEMM1' has finished reading the slot
-  uint64_t* d1_full = bars + 13;          // own
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* d1_full = bars + 9;           // own
+  uint64_t* res_full = bars + 10;         // [4] own: the shortcut chunk has landed in slot j
+  uint64_t* y_full = bars + 14;           // [4] leader: 16 epilogue warps have written y chunk j
+  uint64_t* y_free = bars + 18;           // [4] own: GEMM1' has finished reading slot j
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,20 +113,21 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int per_img = p.tiles_w * p.tiles_h;
+  const int n_items = p.num_items > pair ? (p.num_items - pair + num_pairs - 1) / num_pairs : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA); prefetch_tensormap(&p.tmW2); prefetch_tensormap(&p.tmW3);
-    prefetch_tensormap(&p.tmW1); prefetch_tensormap(&p.tmY);
+    if (C1 > 0) prefetch_tensormap(&p.tmW1);
+    prefetch_tensormap(&p.tmY); prefetch_tensormap(&p.tmR);
     mbar_init(w_bar, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); mbar_init(&d2_full[i], 1);
-      mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); mbar_init(&d2_full[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1); }
     mbar_init(t2_full, 16); mbar_init(d3_full, 1); mbar_init(d1_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
-  for (int i = threadIdx.x; i < 256 + C1; i += B64_THREADS) b3s[i] = i < 256 ? __ldg(p.b3 + i) : __ldg(p.b1 + i - 256);
+  for (int i = threadIdx.x; i < 64 + 256 + C1; i += B64_THREADS)
+    b2s[i] = i < 64 ? __ldg(p.b2 + i) : (i < 320 ? __ldg(p.b3 + i - 64) : __ldg(p.b1 + i - 320));
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -133,10 +142,11 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       if (rank == 0) mbar_arrive_expect_tx(w_bar, 2u * L::W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d_pair(w2s + t * B64_W2_TAP_BYTES, &p.tmW2, wb, t * 64, rank * 32);
       tma_load_2d_pair(w3s, &p.tmW3, wb, 0, rank * 128);
-      for (int j = 0; j < 4; ++j) tma_load_2d_pair(w1s + j * L::W1_CHUNK_BYTES, &p.tmW1, wb, j * 64, rank * (C1 / 2));
+      if constexpr (C1 > 0)
+        for (int j = 0; j < 4; ++j) tma_load_2d_pair(w1s + j * L::W1_CHUNK_BYTES, &p.tmW1, wb, j * 64, rank * (C1 / 2));
       const uint32_t hf0 = mapa_rank(smem_u32(&halo_full[0]), 0);
-      int n = 0;
-      for (int item = pair; item < p.num_items; item += num_pairs, ++n) {
+      int item = pair;
+      for (int n = 0; n < n_items; ++n, item += num_pairs) {
         const int tile = 2 * item + rank;               // a past-the-end tile decodes to image NB: zero-filled, clipped
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
@@ -157,7 +167,6 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       const uint32_t t2_lo = sdesc_lo<128>(smem_u32(t2s));
       const uint32_t y_lo = sdesc_lo<128>(smem_u32(ys));
       const uint32_t halo_lo = sdesc_lo<128>(smem_u32(halo));
-      const int n_items = p.num_items > pair ? (p.num_items - pair + num_pairs - 1) / num_pairs : 0;
       auto gemm2 = [&](int n) {           // t2 accumulator of local tile n: nine taps x four K steps, N = 64
         const int buf = n & 1;
         mbar_wait(&halo_full[buf], (n >> 1) & 1);
@@ -195,20 +204,21 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         __syncwarp();
         if (n + 1 < n_items) gemm2(n + 1);
         // ---- GEMM1'(n): D1 += y[:, 64j:64j+64] * W1'[:, 64j:64j+64]^T as the epilogue delivers the chunks
-        for (int j = 0; j < 4; ++j) {
-          const int slot = j & 1;
-          mbar_wait(&y_full[slot], (2 * n + (j >> 1)) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_lo = y_lo + ((slot * B64_Y_BYTES) >> 4);
-            const uint32_t b_lo = w1_lo + ((j * L::W1_CHUNK_BYTES) >> 4);
+        if constexpr (C1 > 0) {
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&y_full[j], n & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = y_lo + ((j * B64_Y_BYTES) >> 4);
+              const uint32_t b_lo = w1_lo + ((j * L::W1_CHUNK_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_words<true>(tmem_base + B64_COL_D1, a_lo + 2 * k, HI, b_lo + 2 * k, HI, IDESC1, (j | k) != 0 ? 1u : 0u);
-            umma_commit_pair(&y_free[slot]);
-            if (j == 3) umma_commit_pair(d1_full);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_words<true>(tmem_base + B64_COL_D1, a_lo + 2 * k, HI, b_lo + 2 * k, HI, IDESC1, (j | k) != 0 ? 1u : 0u);
+              umma_commit_pair(&y_free[j]);
+              if (j == 3) umma_commit_pair(d1_full);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -219,15 +229,23 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;                       // TMEM lane = pixel of the tile: row m >> 3, column m & 7
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool issuer = e == 0 && lane == 0;           // the one thread that issues (and waits for) the y stores
+    const bool issuer = e == 0 && lane == 0;           // issues the shortcut loads and the y stores of this CTA
     const uint32_t t2_full_r = mapa_rank(smem_u32(t2_full), 0);
     const uint32_t y_full_r = mapa_rank(smem_u32(&y_full[0]), 0);
     const int sw = m & 7;                              // 128-byte swizzle: 16-byte chunk index ^= row & 7
-    float bias2[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) bias2[i] = __ldg(p.b2 + g * 32 + i);
-    const int n_items = p.num_items > pair ? (p.num_items - pair + num_pairs - 1) / num_pairs : 0;
 
+    auto tile_coords = [&](int n, int& img, int& th, int& tw) {
+      const int tile = 2 * (pair + n * num_pairs) + rank;
+      img = tile / per_img;
+      const int rem = tile - img * per_img;
+      th = rem / p.tiles_w; tw = rem - th * p.tiles_w;
+    };
+    auto load_res = [&](int n, int j) {                // shortcut chunk j of local tile n -> slot j (issuer only)
+      int img, th, tw;
+      tile_coords(n, img, th, tw);
+      mbar_arrive_expect_tx(&res_full[j], B64_Y_BYTES);
+      tma_load_4d(ys + j * B64_Y_BYTES, &p.tmR, &res_full[j], j * 64, tw * 8, th * 16, img);
+    };
     auto ep2 = [&](int n) {                            // t2 rows of local tile n -> shared memory (A operand of GEMM3)
       const int buf = n & 1;
       mbar_wait(&d2_full[buf], (n >> 1) & 1);
@@ -236,13 +254,14 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       tmem_ld_32x32(lane_base + buf * 64 + g * 32, v);
       tmem_ld_wait();
       uint8_t* row = t2s + m * 128;
+      const float* bb = b2s + g * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = 8 * c + 2 * i;
-          o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bias2[k], 0.f), fmaxf(__uint_as_float(v[k + 1]) + bias2[k + 1], 0.f));
+          o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k], 0.f), fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1], 0.f));
         }
         *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -252,76 +271,79 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       if (lane == 0) mbar_arrive_cluster(t2_full_r);
     };
 
-    if (n_items > 0) ep2(0);
-    int item = pair;
-    for (int n = 0; n < n_items; ++n, item += num_pairs) {
-      const int tile = 2 * item + rank;
-      const int img = tile / per_img, rem = tile - img * per_img;
-      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-      const int oh = th * 16 + (m >> 3), ow = tw * 8 + (m & 7);
-      const bool pix_ok = img < p.NB && oh < p.H && ow < p.W;
-      const size_t pix = (static_cast<size_t>(img) * p.H + oh) * p.W + ow;
-      // ---- ep3(n): y = relu(D3 + b3 + residual), four 64-channel chunks through the two-slot ring
-      const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * 256 + g * 32);
-      uint4 rv[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) rv[c] = pix_ok ? __ldg(rp + c) : make_uint4(0, 0, 0, 0);
+    if (n_items > 0) {
+      if (issuer)
+        for (int j = 0; j < 4; ++j) load_res(0, j);
+      ep2(0);
+    }
+    for (int n = 0; n < n_items; ++n) {
+      int img, th, tw;
+      tile_coords(n, img, th, tw);
+      // ---- ep3(n): y = relu(D3 + b3 + shortcut) in place in the four slots
       mbar_wait(d3_full, n & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
-        const int slot = j & 1;
         uint32_t v[32];
         tmem_ld_32x32(lane_base + B64_COL_D3 + j * 64 + g * 32, v);
-        tmem_ld_wait();
-        uint4 rn[4];                                   // residual of the next chunk, in flight during this one
+        mbar_wait(&res_full[j], n & 1);
+        uint8_t* row = ys + j * B64_Y_BYTES + m * 128;
+        uint4 rv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) rn[c] = (pix_ok && j < 3) ? __ldg(rp + (j + 1) * 8 + c) : make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 4; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 4 + c) ^ sw) << 4));
+        tmem_ld_wait();
         const float* bb = b3s + j * 64 + g * 32;
-        uint32_t o[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t* ru = &rv[c].x;
+          uint32_t o[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int k = 8 * c + 2 * i;
             const float2 r2 = unpack_bf16(ru[i]);
-            o[4 * c + i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k] + r2.x, 0.f),
-                                     fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1] + r2.y, 0.f));
+            o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k] + r2.x, 0.f), fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1] + r2.y, 0.f));
           }
+          *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        mbar_wait(&y_free[slot], ((2 * n + (j >> 1)) & 1) ^ 1);      // GEMM1' of the chunk that used the slot is done
-        uint8_t* row = ys + slot * B64_Y_BYTES + m * 128;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
         fence_proxy_async();
-        if (issuer) tma_store_wait_read<0>();          // the store that read the OTHER slot is done: next chunk may write it
         named_bar_sync(1, 256);
         if (issuer) {
-          tma_store_4d(&p.tmY, ys + slot * B64_Y_BYTES, j * 64, tw * 8, th * 16, img);
+          tma_store_4d(&p.tmY, ys + j * B64_Y_BYTES, j * 64, tw * 8, th * 16, img);
           tma_store_commit();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(y_full_r + slot * 8);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rv[c] = rn[c];
+        if constexpr (C1 > 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(y_full_r + j * 8);
+        }
+        // refill the slot of the PREVIOUS chunk with the next tile's shortcut: its GEMM1' chunk was triggered a chunk
+        // ago and its store is the second most recent bulk group of this thread
+        if (issuer && j > 0 && n + 1 < n_items) {
+          if constexpr (C1 > 0) mbar_wait(&y_free[j - 1], n & 1);
+          tma_store_wait_read<1>();
+          load_res(n + 1, j - 1);
+        }
+      }
+      if (issuer && n + 1 < n_items) {                 // slot 3: after its store (the most recent group) has been read
+        if constexpr (C1 > 0) mbar_wait(&y_free[3], n & 1);
+        tma_store_wait_read<0>();
+        load_res(n + 1, 3);
       }
       // ---- ep2(n+1): the next tile's t2 (its GEMM2 ran under ep3)
       if (n + 1 < n_items) ep2(n + 1);
       // ---- ep1'(n): t1' = relu(D1 + b1') -> global
-      mbar_wait(d1_full, n & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int h2 = 0; h2 < C1 / 64; ++h2) {
-        const int col0 = g * (C1 / 2) + h2 * 32;
+      if constexpr (C1 > 0) {
+        const int oh = th * 16 + (m >> 3), ow = tw * 8 + (m & 7);
+        const bool pix_ok = img < p.NB && oh < p.H && ow < p.W;
+        const size_t pix = (static_cast<size_t>(img) * p.H + oh) * p.W + ow;
+        mbar_wait(d1_full, n & 1);
+        tc_fence_after();
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + B64_COL_D1 + col0, v);
+        tmem_ld_32x32(lane_base + B64_COL_D1 + g * 32, v);
         tmem_ld_wait();
         if (pix_ok) {
-          const float* bb = b1s + col0;
-          uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + col0);
+          const float* bb = b1s + g * 32;
+          uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + g * 32);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t o[4];
@@ -333,8 +355,8 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
             dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
+        tc_fence_before();
       }
-      tc_fence_before();
     }
     if (issuer) tma_store_wait_all<0>();
   }

@@ -129,7 +129,7 @@ struct GemmLaunch {
   GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1;
   int ln = 0;                         // > 0: row LayerNorm fused behind the last N tile of every m-item (row width ln * 256)
   bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
-  int b64 = 0; Bneck64Params b;       // 64 / 128: fused layer-1 bottleneck kernel (conv2 -> conv3+shortcut -> next conv1 of that width)
+  int b64 = 0; Bneck64Params b;       // 1 + C1: fused layer-1 bottleneck kernel (conv2 -> conv3 + shortcut [-> next conv1, C1 = 64])
 };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
@@ -519,11 +519,12 @@ static bool b64_enabled() {
   return on == 1;
 }
 static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* res, bf16* y, bf16* t1n, int NB, int H, int W,
-                     const ConvW& c2, const ConvW& c3, const ConvW& c1n) {
-  REQUIRE(c2.cin == 64 && c2.cout == 64 && c2.k == 3 && c2.stride == 1 && c3.cin == 64 && c3.cout == 256 && c3.k == 1 &&
-              c1n.cin == 256 && c1n.k == 1 && c1n.stride == 1 && (c1n.cout == 64 || c1n.cout == 128),
-          "fused bottleneck: 64 -3x3-> 64 -1x1-> 256 -1x1-> 64|128");
-  g.c64 = false; g.ln = 0; g.b64 = c1n.cout;
+                     const ConvW& c2, const ConvW& c3, const ConvW* c1n) {
+  REQUIRE(c2.cin == 64 && c2.cout == 64 && c2.k == 3 && c2.stride == 1 && c3.cin == 64 && c3.cout == 256 && c3.k == 1,
+          "fused bottleneck: 64 -3x3-> 64 -1x1-> 256");
+  REQUIRE(!c1n || (c1n->cin == 256 && c1n->k == 1 && c1n->stride == 1 && c1n->cout == 64 && t1n),
+          "fused bottleneck: the next conv1 must be 256 -1x1-> 64");
+  g.c64 = false; g.ln = 0; g.b64 = 1 + (c1n ? c1n->cout : 0);
   Bneck64Params& p = g.b;
   memset(&p, 0, sizeof p);
   {
@@ -540,18 +541,20 @@ static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* 
     const uint64_t d[2] = {64, 256}; const uint64_t st[1] = {64 * 2}; const uint32_t bx[2] = {64, 128};
     TRY(make_tmap(e, &p.tmW3, c3.w, 2, d, st, bx, 128));
   }
-  {
-    const uint64_t d[2] = {256, (uint64_t)c1n.cout}; const uint64_t st[1] = {256 * 2};
-    const uint32_t bx[2] = {64, (uint32_t)c1n.cout / 2};
-    TRY(make_tmap(e, &p.tmW1, c1n.w, 2, d, st, bx, 128));
+  p.tmW1 = p.tmW3;
+  if (c1n) {
+    const uint64_t d[2] = {256, (uint64_t)c1n->cout}; const uint64_t st[1] = {256 * 2};
+    const uint32_t bx[2] = {64, (uint32_t)c1n->cout / 2};
+    TRY(make_tmap(e, &p.tmW1, c1n->w, 2, d, st, bx, 128));
   }
   {
     const uint64_t dims[4] = {256, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     const uint64_t str[3] = {512, (uint64_t)W * 512, (uint64_t)H * W * 512};
     const uint32_t box[4] = {64, 8, 16, 1};
     TRY(make_tmap(e, &p.tmY, y, 4, dims, str, box, 128));
+    TRY(make_tmap(e, &p.tmR, res, 4, dims, str, box, 128));
   }
-  p.b2 = c2.bias; p.b3 = c3.bias; p.b1 = c1n.bias; p.res = res; p.t1n = t1n;
+  p.b2 = c2.bias; p.b3 = c3.bias; p.b1 = c1n ? c1n->bias : c3.bias; p.t1n = t1n;
   p.NB = NB; p.H = H; p.W = W;
   p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.num_tiles = NB * p.tiles_w * p.tiles_h;
   p.num_items = (p.num_tiles + 1) / 2;
@@ -630,8 +633,8 @@ static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s) {
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
-  if (g.b64 == 64) return launch_b64_inst<64>(e, g.b, s);
-  if (g.b64 == 128) return launch_b64_inst<128>(e, g.b, s);
+  if (g.b64 == 65) return launch_b64_inst<64>(e, g.b, s);
+  if (g.b64 == 1) return launch_b64_inst<0>(e, g.b, s);
   if (g.c64) return launch_c64(e, g.c, s);
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
@@ -1676,7 +1679,8 @@ extern "C" int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_r
                                const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n,
                                void* d_y, void* d_t1n, int NB, int H, int W, void* stream) {
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
-  REQUIRE(e && d_t1 && d_res && d_w2 && d_b2 && d_w3 && d_b3 && d_w1n && d_b1n && d_y && d_t1n, "null argument");
+  REQUIRE(e && d_t1 && d_res && d_w2 && d_b2 && d_w3 && d_b3 && d_y, "null argument");
+  REQUIRE(c1n == 0 || (c1n == 64 && d_w1n && d_b1n && d_t1n), "bneck64: next conv1 width 0 (none) or 64");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
   ConvW c2, c3, c1;
@@ -1685,7 +1689,7 @@ extern "C" int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_r
   c1.w = (bf16*)d_w1n; c1.bias = (float*)d_b1n; c1.cin = 256; c1.cout = c1n; c1.k = 1; c1.stride = 1;
   GemmLaunch g;
   TRY(build_b64(e, g, static_cast<const bf16*>(d_t1), static_cast<const bf16*>(d_res), static_cast<bf16*>(d_y),
-                static_cast<bf16*>(d_t1n), NB, H, W, c2, c3, c1));
+                static_cast<bf16*>(d_t1n), NB, H, W, c2, c3, c1n ? &c1 : nullptr));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,

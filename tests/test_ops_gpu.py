@@ -121,7 +121,7 @@ def test_gemm_fused_layernorm(h, M, K, inplace):
     assert rel_err(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("NB,H,W,C1", [(3, 16, 8, 64), (2, 56, 56, 64), (1, 20, 24, 128), (3, 56, 56, 128), (40, 56, 56, 64)])
+@pytest.mark.parametrize("NB,H,W,C1", [(3, 16, 8, 64), (2, 56, 56, 64), (1, 20, 24, 0), (3, 56, 56, 0), (40, 56, 56, 64)])
 def test_bneck64_fused_block(h, NB, H, W, C1):
     """Fused layer-1 bottleneck (conv2 3x3 -> conv3 1x1 + shortcut + ReLU -> next conv1 1x1 + ReLU, intermediates
     on chip) against fp32 torch convs with the same bf16 rounding points as the unfused kernels.  Odd tile counts
@@ -132,20 +132,23 @@ def test_bneck64_fused_block(h, NB, H, W, C1):
     res = bf(rn(NB, H, W, 256))
     w2 = bf(rn(64, 64, 3, 3) * (576 ** -0.5)); b2 = rn(64) * 0.5
     w3 = bf(rn(256, 64) * (64 ** -0.5)); b3 = rn(256) * 0.5
-    w1 = bf(rn(C1, 256) * (256 ** -0.5)); b1 = rn(C1) * 0.5
+    CN = max(C1, 64)
+    w1 = bf(rn(CN, 256) * (256 ** -0.5)); b1 = rn(CN) * 0.5
     w2p = w2.permute(0, 2, 3, 1).contiguous()                       # [Cout][kh][kw][Cin]
     y = torch.full((NB, H, W, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
-    t1n = torch.full((NB, H, W, C1), float("nan"), device="cuda", dtype=torch.bfloat16)
+    t1n = torch.full((NB, H, W, CN), float("nan"), device="cuda", dtype=torch.bfloat16)
     _lib.check(_lib.lib().mmdx_op_bneck64(h.handle, P(t1), P(res), P(w2p), P(b2), P(w3), P(b3), P(w1), P(b1), C1, P(y), P(t1n),
                                           NB, H, W, S()))
     torch.cuda.synchronize()
     x = t1.float().permute(0, 3, 1, 2)
     t2 = bf(F.relu(F.conv2d(x, w2.float(), b2, padding=1))).float()
     yr = bf(F.relu(F.conv2d(t2, w3.float()[:, :, None, None], b3) + res.float().permute(0, 3, 1, 2)))
-    tr = F.relu(F.conv2d(yr.float(), w1.float()[:, :, None, None], b1))
-    assert torch.isfinite(y.float()).all() and torch.isfinite(t1n.float()).all()
+    assert torch.isfinite(y.float()).all()
     assert rel_err(y.permute(0, 3, 1, 2), yr.float()) < 1e-2
-    assert rel_err(t1n.permute(0, 3, 1, 2), tr) < 1e-2
+    if C1:
+        tr = F.relu(F.conv2d(yr.float(), w1.float()[:, :, None, None], b1))
+        assert torch.isfinite(t1n.float()).all()
+        assert rel_err(t1n.permute(0, 3, 1, 2), tr) < 1e-2
 
 
 def test_gemm_strided_output_and_no_bias(h):

@@ -127,6 +127,33 @@ def bench_conv(h, lib):
         print(f"conv {name:10s} {HW}x{HW} {Cin}->{Cout} k{k} s{s}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
 
 
+def bench_bneck(h, lib):
+    """Fused layer-1 bottleneck against its three separate launches (conv2 3x3, conv3 + shortcut, next conv1)."""
+    NB, HW = 256, 56
+    for C1 in (64, 0):
+        CN = max(C1, 64)
+        t1 = bf(torch.randn(NB, HW, HW, 64, device="cuda").relu())
+        res = bf(torch.randn(NB, HW, HW, 256, device="cuda"))
+        w2 = bf(torch.randn(64, 9, 64, device="cuda") / 24); b2 = torch.randn(64, device="cuda")
+        w3 = bf(torch.randn(256, 1, 64, device="cuda") / 8); b3 = torch.randn(256, device="cuda")
+        w1 = bf(torch.randn(CN, 1, 256, device="cuda") / 16); b1 = torch.randn(CN, device="cuda")
+        t2 = torch.empty(NB, HW, HW, 64, device="cuda", dtype=torch.bfloat16)
+        y = torch.empty(NB, HW, HW, 256, device="cuda", dtype=torch.bfloat16)
+        t1n = torch.empty(NB, HW, HW, CN, device="cuda", dtype=torch.bfloat16)
+
+        def three():
+            _lib.check(lib.mmdx_op_conv(h.handle, P(t1), NB, HW, HW, 64, P(w2), P(b2), None, P(t2), 64, 3, 1, 1, S()))
+            _lib.check(lib.mmdx_op_conv(h.handle, P(t2), NB, HW, HW, 64, P(w3), P(b3), P(res), P(y), 256, 1, 1, 1, S()))
+            if C1:
+                _lib.check(lib.mmdx_op_conv(h.handle, P(y), NB, HW, HW, 256, P(w1), P(b1), None, P(t1n), C1, 1, 1, 1, S()))
+        us3 = timeit(three)
+        us1 = timeit(lambda: _lib.check(lib.mmdx_op_bneck64(h.handle, P(t1), P(res), P(w2), P(b2), P(w3), P(b3), P(w1), P(b1), C1,
+                                                            P(y), P(t1n), NB, HW, HW, S())))
+        by = 2.0 * NB * HW * HW * (64 + 256 + 256 + C1)
+        print(f"bottleneck 56x56 next conv1 {C1:3d}: separate launches {us3:7.1f} us   fused {us1:7.1f} us  ({by / us1 / 1e3:6.1f} GB/s algorithmic)",
+              flush=True)
+
+
 def bench_ln(h, lib):
     T, N = 32768, 768
     x = bf(torch.randn(T, N, device="cuda"))
@@ -170,7 +197,7 @@ def bench_stem(h, lib):
         print(f"stem pool={pool} B={B} {HW}x{HW}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  {by / us / 1e3:7.1f} GB/s", flush=True)
 
 
-ALL = {"stem": bench_stem, "attention": bench_attention, "gemm": bench_gemm, "gemm_ln": bench_gemm_ln, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
+ALL = {"stem": bench_stem, "attention": bench_attention, "gemm": bench_gemm, "gemm_ln": bench_gemm_ln, "bneck": bench_bneck, "conv": bench_conv, "ln": bench_ln, "pre": bench_pre}
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
