@@ -21,21 +21,23 @@
 // per-thread global loads one chunk ahead: 35 % of all stall samples sat on those loads and the fused kernel was
 // slower than the three launches it replaces - profiles/r01_bneck64_v1_full.md.)
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issue (leader CTA only), warps 2-9 =
-// epilogue in two groups (column halves) x four TMEM lane quarters; thread = pixel.
+// Roles (352 threads): warp 0 = TMA producer (weights, halos), warp 1 = TMEM allocator + MMA issue (leader CTA only),
+// warps 2-9 = epilogue in two groups (column halves) x four TMEM lane quarters, thread = pixel; warp 10 = y ring: stores
+// each finished chunk and refills its slot with the next tile's shortcut, so the epilogue warps never wait for each
+// other or for a TMA instruction (they only arrive on mbarriers).
 // MMA issue order per tile i:   GEMM3(i), GEMM2(i+1), GEMM1'(i) chunk by chunk as the epilogue delivers y.
 // Epilogue order per tile i:    ep3(i) [y, four 64-channel chunks], ep2(i+1) [t2], ep1'(i) [t1'].
 // Every reuse hazard except the two rings below is ordered by that program order:
-//   halo ring (2): producer waits halo_empty (commit of GEMM2);  y ring (4 = the chunks of a tile): the thread that issues
-//   the y stores also issues the shortcut loads, and refills slot j for the next tile once y_free[j] (commit of the
-//   GEMM1' chunk that read it) has flipped and its own store of the slot has been read (bulk-group wait).
+//   halo ring (2): producer waits halo_empty (commit of GEMM2);  y ring (4 = the chunks of a tile): warp 10 stores chunk j
+//   when the eight epilogue warps have arrived on y_ready[j], and refills slot j for the next tile once y_free[j] (commit
+//   of the GEMM1' chunk that read it) has flipped and its own store of the slot has been read (bulk-group wait).
 // TMEM (512 columns): D2 2 x 64 | D3 256 | D1' C1.
 #pragma once
 #include "ptx.cuh"
 
 namespace mmdx {
 
-constexpr int B64_THREADS = 320;
+constexpr int B64_THREADS = 352;
 constexpr int B64_HALO_W = 16, B64_HALO_H = 18;
 constexpr int B64_HALO_BYTES = B64_HALO_W * B64_HALO_H * 128;     // 36 KB
 constexpr int B64_W2_TAP_BYTES = 32 * 128;                         // this CTA's 32 output rows of one tap
@@ -105,7 +107,8 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint64_t* res_full = bars + 10;         // [4] own: the shortcut chunk has landed in slot j
   uint64_t* y_full = bars + 14;           // [4] leader: 16 epilogue warps have written y chunk j
   uint64_t* y_free = bars + 18;           // [4] own: GEMM1' has finished reading slot j
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* y_ready = bars + 22;          // [4] own: the eight epilogue warps of this CTA have written y chunk j
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,7 +124,9 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     prefetch_tensormap(&p.tmY); prefetch_tensormap(&p.tmR);
     mbar_init(w_bar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); mbar_init(&d2_full[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1); mbar_init(&y_ready[i], 8);
+    }
     mbar_init(t2_full, 16); mbar_init(d3_full, 1); mbar_init(d1_full, 1);
     fence_barrier_init();
   }
@@ -222,6 +227,42 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         }
       }
     }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      // ================= y ring: store finished chunks, refill the slots with the next tile's shortcut =================
+      auto load_res = [&](int n, int j) {              // shortcut chunk j of local tile n -> slot j
+        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        mbar_arrive_expect_tx(&res_full[j], B64_Y_BYTES);
+        tma_load_4d(ys + j * B64_Y_BYTES, &p.tmR, &res_full[j], j * 64, tw * 8, th * 16, img);
+      };
+      if (n_items > 0)
+        for (int j = 0; j < 4; ++j) load_res(0, j);
+      for (int n = 0; n < n_items; ++n) {
+        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(&y_ready[j], n & 1);
+          tma_store_4d(&p.tmY, ys + j * B64_Y_BYTES, j * 64, tw * 8, th * 16, img);
+          tma_store_commit();
+          // refill the slot of the PREVIOUS chunk: its GEMM1' was triggered a chunk ago and its store is the second
+          // most recent bulk group of this thread
+          if (j > 0 && n + 1 < n_items) {
+            if constexpr (C1 > 0) mbar_wait(&y_free[j - 1], n & 1);
+            tma_store_wait_read<1>();
+            load_res(n + 1, j - 1);
+          }
+        }
+        if (n + 1 < n_items) {
+          if constexpr (C1 > 0) mbar_wait(&y_free[3], n & 1);
+          tma_store_wait_read<0>();
+          load_res(n + 1, 3);
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else {
     // ================= epilogue warps 2..9: thread = (pixel, column half) =================
     const int e = warp - 2;
@@ -229,22 +270,24 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;                       // TMEM lane = pixel of the tile: row m >> 3, column m & 7
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool issuer = e == 0 && lane == 0;           // issues the shortcut loads and the y stores of this CTA
     const uint32_t t2_full_r = mapa_rank(smem_u32(t2_full), 0);
     const uint32_t y_full_r = mapa_rank(smem_u32(&y_full[0]), 0);
     const int sw = m & 7;                              // 128-byte swizzle: 16-byte chunk index ^= row & 7
 
-    auto tile_coords = [&](int n, int& img, int& th, int& tw) {
-      const int tile = 2 * (pair + n * num_pairs) + rank;
-      img = tile / per_img;
-      const int rem = tile - img * per_img;
-      th = rem / p.tiles_w; tw = rem - th * p.tiles_w;
-    };
-    auto load_res = [&](int n, int j) {                // shortcut chunk j of local tile n -> slot j (issuer only)
-      int img, th, tw;
-      tile_coords(n, img, th, tw);
-      mbar_arrive_expect_tx(&res_full[j], B64_Y_BYTES);
-      tma_load_4d(ys + j * B64_Y_BYTES, &p.tmR, &res_full[j], j * 64, tw * 8, th * 16, img);
+    // 32 accumulator columns + bias -> ReLU -> bf16, 16 bytes (8 channels) at a time into `row` (swizzled chunk g*4+c)
+    auto bias_relu_store = [&](const uint32_t (&v)[32], const float* bias, uint8_t* row) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
+        float x[8];
+        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])), pack_f32x2(ba.x, ba.y)), x[0], x[1]);
+        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])), pack_f32x2(ba.z, ba.w)), x[2], x[3]);
+        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])), pack_f32x2(bb.x, bb.y)), x[4], x[5]);
+        unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])), pack_f32x2(bb.z, bb.w)), x[6], x[7]);
+        *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
+            make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
+      }
     };
     auto ep2 = [&](int n) {                            // t2 rows of local tile n -> shared memory (A operand of GEMM3)
       const int buf = n & 1;
@@ -253,112 +296,82 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       uint32_t v[32];
       tmem_ld_32x32(lane_base + buf * 64 + g * 32, v);
       tmem_ld_wait();
-      uint8_t* row = t2s + m * 128;
-      const float* bb = b2s + g * 32;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = 8 * c + 2 * i;
-          o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k], 0.f), fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1], 0.f));
-        }
-        *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
+      bias_relu_store(v, b2s + g * 32, t2s + m * 128);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(t2_full_r);
     };
 
-    if (n_items > 0) {
-      if (issuer)
-        for (int j = 0; j < 4; ++j) load_res(0, j);
-      ep2(0);
-    }
+    if (n_items > 0) ep2(0);
     for (int n = 0; n < n_items; ++n) {
-      int img, th, tw;
-      tile_coords(n, img, th, tw);
-      // ---- ep3(n): y = relu(D3 + b3 + shortcut) in place in the four slots
+      // ---- ep3(n): y = relu(D3 + b3 + shortcut) in place in the four slots; the next chunk's accumulator load is in
+      //      flight while this one is processed
       mbar_wait(d3_full, n & 1);
       tc_fence_after();
-#pragma unroll 1
+      uint32_t v[2][32];
+      tmem_ld_32x32(lane_base + B64_COL_D3 + g * 32, v[0]);
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + B64_COL_D3 + j * 64 + g * 32, v);
         mbar_wait(&res_full[j], n & 1);
         uint8_t* row = ys + j * B64_Y_BYTES + m * 128;
         uint4 rv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 4 + c) ^ sw) << 4));
         tmem_ld_wait();
-        const float* bb = b3s + j * 64 + g * 32;
+        if (j < 3) tmem_ld_32x32(lane_base + B64_COL_D3 + (j + 1) * 64 + g * 32, v[(j + 1) & 1]);
+        const uint32_t (&a)[32] = v[j & 1];
+        const float4* b4 = reinterpret_cast<const float4*>(b3s + j * 64 + g * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
           const uint32_t* ru = &rv[c].x;
-          uint32_t o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 8 * c + 2 * i;
-            const float2 r2 = unpack_bf16(ru[i]);
-            o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k] + r2.x, 0.f), fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1] + r2.y, 0.f));
-          }
-          *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          float x[8];
+          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_f32x2(ba.x, ba.y)), bf16x2_to_f32x2(ru[0])), x[0], x[1]);
+          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])), pack_f32x2(ba.z, ba.w)), bf16x2_to_f32x2(ru[1])), x[2], x[3]);
+          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_f32x2(bb.x, bb.y)), bf16x2_to_f32x2(ru[2])), x[4], x[5]);
+          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])), pack_f32x2(bb.z, bb.w)), bf16x2_to_f32x2(ru[3])), x[6], x[7]);
+          *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
+              make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
         }
         fence_proxy_async();
-        named_bar_sync(1, 256);
-        if (issuer) {
-          tma_store_4d(&p.tmY, ys + j * B64_Y_BYTES, j * 64, tw * 8, th * 16, img);
-          tma_store_commit();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&y_ready[j]);
+          if constexpr (C1 > 0) mbar_arrive_cluster(y_full_r + j * 8);
         }
-        if constexpr (C1 > 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(y_full_r + j * 8);
-        }
-        // refill the slot of the PREVIOUS chunk with the next tile's shortcut: its GEMM1' chunk was triggered a chunk
-        // ago and its store is the second most recent bulk group of this thread
-        if (issuer && j > 0 && n + 1 < n_items) {
-          if constexpr (C1 > 0) mbar_wait(&y_free[j - 1], n & 1);
-          tma_store_wait_read<1>();
-          load_res(n + 1, j - 1);
-        }
-      }
-      if (issuer && n + 1 < n_items) {                 // slot 3: after its store (the most recent group) has been read
-        if constexpr (C1 > 0) mbar_wait(&y_free[3], n & 1);
-        tma_store_wait_read<0>();
-        load_res(n + 1, 3);
       }
       // ---- ep2(n+1): the next tile's t2 (its GEMM2 ran under ep3)
       if (n + 1 < n_items) ep2(n + 1);
       // ---- ep1'(n): t1' = relu(D1 + b1') -> global
       if constexpr (C1 > 0) {
+        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         const int oh = th * 16 + (m >> 3), ow = tw * 8 + (m & 7);
         const bool pix_ok = img < p.NB && oh < p.H && ow < p.W;
         const size_t pix = (static_cast<size_t>(img) * p.H + oh) * p.W + ow;
         mbar_wait(d1_full, n & 1);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + B64_COL_D1 + g * 32, v);
+        uint32_t v1[32];
+        tmem_ld_32x32(lane_base + B64_COL_D1 + g * 32, v1);
         tmem_ld_wait();
         if (pix_ok) {
-          const float* bb = b1s + g * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(b1s + g * 32);
           uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + g * 32);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 8 * c + 2 * i;
-              o[i] = pack_bf16(fmaxf(__uint_as_float(v[k]) + bb[k], 0.f), fmaxf(__uint_as_float(v[k + 1]) + bb[k + 1], 0.f));
-            }
-            dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+            const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
+            dst[c] = make_uint4(pack_bf16_relu(__uint_as_float(v1[8 * c]) + ba.x, __uint_as_float(v1[8 * c + 1]) + ba.y),
+                                pack_bf16_relu(__uint_as_float(v1[8 * c + 2]) + ba.z, __uint_as_float(v1[8 * c + 3]) + ba.w),
+                                pack_bf16_relu(__uint_as_float(v1[8 * c + 4]) + bb.x, __uint_as_float(v1[8 * c + 5]) + bb.y),
+                                pack_bf16_relu(__uint_as_float(v1[8 * c + 6]) + bb.z, __uint_as_float(v1[8 * c + 7]) + bb.w));
           }
         }
         tc_fence_before();
       }
     }
-    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

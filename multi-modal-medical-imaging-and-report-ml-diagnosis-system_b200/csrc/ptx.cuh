@@ -373,6 +373,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// relu(a), relu(b) -> packed bf16 pair (a in the low half): the ReLU is a modifier of the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// packed bf16 pair -> fp32 pair as one 64-bit register pair (bf16 -> fp32 is a 16-bit shift)
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t u) {
+  return pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
