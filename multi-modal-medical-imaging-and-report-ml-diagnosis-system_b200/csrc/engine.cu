@@ -1249,21 +1249,17 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
   bf16* o2 = bufs[3];
   bf16* ds = bufs[4];
   int h = pl->ph, w = pl->pw;
-  for (const Bottleneck& bk : e->blocks) {
+  bool have_t1 = false;                      // o1 already holds this block's conv1 output (written by the previous fused block)
+  for (size_t bi = 0; bi < e->blocks.size(); ++bi) {
+    const Bottleneck& bk = e->blocks[bi];
     const int s = bk.c2.stride;
     const int oh = (h - 1) / s + 1, ow = (w - 1) / s + 1;
-    TRY(build_conv(e, gl, x, B, h, w, bk.c1.cin, bk.c1.w, bk.c1.cout, 1, 1));
-    TRY(fill_epilogue(e, gl, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0));
-    pl->convs.push_back(gl);
-    gl.c64 = false;
-    if (c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr)) {
-      TRY(build_c64(e, gl, o1, B, h, w, bk.c2.w, bk.c2.bias, o2, ACT_RELU));
-    } else {
-      TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
-      TRY(fill_epilogue(e, gl, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0));
+    if (!have_t1) {
+      TRY(build_conv(e, gl, x, B, h, w, bk.c1.cin, bk.c1.w, bk.c1.cout, 1, 1));
+      TRY(fill_epilogue(e, gl, bk.c1.bias, nullptr, 0, o1, bk.c1.cout, ACT_RELU, 0));
+      pl->convs.push_back(gl);
     }
-    pl->convs.push_back(gl);
-    gl.c64 = false;
+    have_t1 = false;
     const bf16* idt = x;
     if (bk.has_ds) {
       TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
@@ -1271,9 +1267,30 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
       pl->convs.push_back(gl);
       idt = ds;
     }
-    TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
-    TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
-    pl->convs.push_back(gl);
+    // layer-1 shape (64 -3x3-> 64 -1x1-> 256): conv2, conv3 + shortcut and - when the next block starts with a
+    // 256 -> 64 conv1 - that conv1 too run as ONE kernel (bneck64_tcgen05.cuh)
+    if (b64_enabled() && c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr) && bk.c3.cin == 64 && bk.c3.cout == 256 &&
+        bk.c3.k == 1) {
+      const Bottleneck* nx = bi + 1 < e->blocks.size() ? &e->blocks[bi + 1] : nullptr;
+      const bool fuse_next = nx && nx->c1.cin == 256 && nx->c1.cout == 64 && nx->c1.k == 1;
+      TRY(build_b64(e, gl, o1, idt, y, fuse_next ? o2 : nullptr, B, h, w, bk.c2, bk.c3, fuse_next ? &nx->c1 : nullptr));
+      pl->convs.push_back(gl);
+      gl.b64 = 0;
+      if (fuse_next) { bf16* t = o1; o1 = o2; o2 = t; have_t1 = true; }
+    } else {
+      gl.c64 = false;
+      if (c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr)) {
+        TRY(build_c64(e, gl, o1, B, h, w, bk.c2.w, bk.c2.bias, o2, ACT_RELU));
+      } else {
+        TRY(build_conv(e, gl, o1, B, h, w, bk.c2.cin, bk.c2.w, bk.c2.cout, 3, s));
+        TRY(fill_epilogue(e, gl, bk.c2.bias, nullptr, 0, o2, bk.c2.cout, ACT_RELU, 0));
+      }
+      pl->convs.push_back(gl);
+      gl.c64 = false;
+      TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
+      TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
+      pl->convs.push_back(gl);
+    }
     bf16* t = x; x = y; y = t;
     h = oh; w = ow;
   }
