@@ -107,12 +107,14 @@ int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin
                  const float* d_bias, const void* d_residual, void* d_out, int Cout, int k, int stride, int act,
                  void* stream);
 /* One layer-1 bottleneck of ResNet-50 shifted by one conv (torchvision Bottleneck.forward, training_pipeline.py:178-183):
- * t2 = relu(conv3x3(t1, w2) + b2) [64 ch, stays on chip]; y = relu(conv1x1(t2, w3) + b3 + res) [256 ch];
- * t1n = relu(conv1x1(y, w1n) + b1n) [c1n = 64 ch, the next block's conv1; c1n = 0: not computed].  NHWC bf16; weights packed
+ * t2 = relu(conv3x3(t1, w2) + b2) [64 ch, stays on chip]; y = relu(conv1x1(t2, w3) + b3 + shortcut) [256 ch];
+ * t1n = relu(conv1x1(y, w1n) + b1n) [c1n = 64 or 128 ch, the next block's conv1; c1n = 0: not computed].
+ * shortcut = d_res [NB,H,W,256], or - when d_x, d_wd, d_bd are given (layer1.0; needs c1n = 64) - the block's downsample
+ * conv1x1(x, wd) + bd of the 64-channel block input, computed in the kernel.  NHWC bf16; weights packed
  * [Cout][k*k][Cin] bf16 with BN folded, fp32 biases. */
 int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const void* d_w2, const float* d_b2,
-                    const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n, void* d_y,
-                    void* d_t1n, int NB, int H, int W, void* stream);
+                    const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n, const void* d_x,
+                    const void* d_wd, const float* d_bd, void* d_y, void* d_t1n, int NB, int H, int W, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
  * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).

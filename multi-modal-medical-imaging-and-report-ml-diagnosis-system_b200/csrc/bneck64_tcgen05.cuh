@@ -47,21 +47,29 @@ constexpr int B64_T2_BYTES = 128 * 128;
 constexpr int B64_Y_BYTES = 128 * 128;                             // one 64-channel chunk of the y tile
 constexpr int B64_COL_D3 = 128, B64_COL_D1 = 384;
 
-template <int C1>
+// C1 = width of the next block's conv1 (0: not computed); DS = the shortcut is the block's 1x1 downsample conv of the
+// 64-channel block input (layer1.0), computed here as a K extension of GEMM3 instead of being read back from memory;
+// NH = halo buffers (1 where shared memory is short: 2-7 % slower, the next halo then loads under one epilogue phase only).
+template <int C1, bool DS, int NH>
 struct B64Smem {
   static constexpr int W1_CHUNK_BYTES = (C1 / 2) * 128;            // this CTA's C1/2 output rows of one 64-channel K chunk
   static constexpr int W1_BYTES = 4 * W1_CHUNK_BYTES;
+  static constexpr int WD_BYTES = DS ? B64_W3_BYTES : 0;           // this CTA's 128 rows of the downsample weights
+  static constexpr int XS_BYTES = DS ? B64_T2_BYTES : 0;           // the block-input tile (A operand next to t2)
   static constexpr int OFF_W3 = B64_W2_BYTES;
-  static constexpr int OFF_W1 = OFF_W3 + B64_W3_BYTES;
+  static constexpr int OFF_WD = OFF_W3 + B64_W3_BYTES;
+  static constexpr int OFF_W1 = OFF_WD + WD_BYTES;
   static constexpr int OFF_HALO = OFF_W1 + W1_BYTES;
-  static constexpr int OFF_T2 = OFF_HALO + 2 * B64_HALO_BYTES;
-  static constexpr int OFF_Y = OFF_T2 + B64_T2_BYTES;
+  static constexpr int OFF_T2 = OFF_HALO + NH * B64_HALO_BYTES;
+  static constexpr int OFF_XS = OFF_T2 + B64_T2_BYTES;
+  static constexpr int OFF_Y = OFF_XS + XS_BYTES;
   static constexpr int OFF_BIAS = OFF_Y + 4 * B64_Y_BYTES;         // b2[64] | b3[256] | b1[C1] fp32
   static constexpr int OFF_BAR = OFF_BIAS + (64 + 256 + C1) * 4;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;               // + manual 1024-byte alignment slack
-  static constexpr int W_BYTES = B64_W2_BYTES + B64_W3_BYTES + W1_BYTES;
+  static constexpr int W_BYTES = B64_W2_BYTES + B64_W3_BYTES + WD_BYTES + W1_BYTES;
   static_assert(TOTAL <= 232448, "shared-memory budget");
-  static_assert(OFF_HALO % 1024 == 0 && OFF_T2 % 1024 == 0 && OFF_Y % 1024 == 0 && OFF_W1 % 1024 == 0, "swizzle atoms");
+  static_assert(OFF_HALO % 1024 == 0 && OFF_T2 % 1024 == 0 && OFF_Y % 1024 == 0 && OFF_W1 % 1024 == 0 && OFF_XS % 1024 == 0,
+                "swizzle atoms");
 };
 
 struct Bneck64Params {
@@ -70,21 +78,25 @@ struct Bneck64Params {
   CUtensorMap tmW3;    // W3  [256, 64],  box (64, 128)
   CUtensorMap tmW1;    // W1' [C1, 256],  box (64, C1/2)
   CUtensorMap tmY;     // y   [NB,H,W,256]: dims (256, W, H, NB), box (64, 8, 16, 1), SWIZZLE_128B
-  CUtensorMap tmR;     // shortcut, same geometry as y
+  CUtensorMap tmR;     // shortcut, same geometry as y                         (!DS)
+  CUtensorMap tmX;     // block input [NB,H,W,64], box (64, 8, 16, 1)          (DS)
+  CUtensorMap tmWd;    // downsample weights [256, 64], box (64, 128)          (DS)
   const float* b2;     // [64]
   const float* b3;     // [256]
   const float* b1;     // [C1]
+  const float* bd;     // [256] downsample bias (DS), added to b3
   __nv_bfloat16* t1n;         // [NB,H,W,C1]
   int NB, H, W, tiles_w, tiles_h, num_tiles, num_items;   // item = two consecutive tiles (one per CTA of the pair)
 };
 
-template <int C1>
+template <int C1, bool DS, int NH>
 __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const __grid_constant__ Bneck64Params p) {
-  using L = B64Smem<C1>;
-  static_assert(C1 == 0 || C1 == 64, "next conv1 width (0 = none)");
+  using L = B64Smem<C1, DS, NH>;
+  static_assert(C1 == 0 || C1 == 64 || C1 == 128, "next conv1 width (0 = none)");
   constexpr uint32_t IDESC2 = make_idesc_bf16(256, 64);
   constexpr uint32_t IDESC3 = make_idesc_bf16(256, 256);
   constexpr uint32_t IDESC1 = make_idesc_bf16(256, C1 > 0 ? C1 : 64);
+  static_assert(B64_COL_D1 + C1 <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w2s = smem;
@@ -92,6 +104,8 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint8_t* w1s = smem + L::OFF_W1;
   uint8_t* halo = smem + L::OFF_HALO;
   uint8_t* t2s = smem + L::OFF_T2;
+  uint8_t* xss = smem + L::OFF_XS;
+  uint8_t* wds = smem + L::OFF_WD;
   uint8_t* ys = smem + L::OFF_Y;
   float* b2s = reinterpret_cast<float*>(smem + L::OFF_BIAS);
   float* b3s = b2s + 64;
@@ -108,7 +122,9 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint64_t* y_full = bars + 14;           // [4] leader: 16 epilogue warps have written y chunk j
   uint64_t* y_free = bars + 18;           // [4] own: GEMM1' has finished reading slot j
   uint64_t* y_ready = bars + 22;          // [4] own: the eight epilogue warps of this CTA have written y chunk j
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* xs_full = bars + 26;          // leader: both CTAs' block-input tiles have landed (DS)
+  uint64_t* xs_empty = bars + 27;         // own: GEMM3 has finished reading the tile (DS)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,18 +137,21 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&p.tmA); prefetch_tensormap(&p.tmW2); prefetch_tensormap(&p.tmW3);
     if (C1 > 0) prefetch_tensormap(&p.tmW1);
-    prefetch_tensormap(&p.tmY); prefetch_tensormap(&p.tmR);
+    prefetch_tensormap(&p.tmY);
+    if (DS) { prefetch_tensormap(&p.tmX); prefetch_tensormap(&p.tmWd); } else { prefetch_tensormap(&p.tmR); }
     mbar_init(w_bar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); mbar_init(&d2_full[i], 1); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1); mbar_init(&y_ready[i], 8);
     }
     mbar_init(t2_full, 16); mbar_init(d3_full, 1); mbar_init(d1_full, 1);
+    mbar_init(xs_full, 1); mbar_init(xs_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
   for (int i = threadIdx.x; i < 64 + 256 + C1; i += B64_THREADS)
-    b2s[i] = i < 64 ? __ldg(p.b2 + i) : (i < 320 ? __ldg(p.b3 + i - 64) : __ldg(p.b1 + i - 320));
+    b2s[i] = i < 64 ? __ldg(p.b2 + i)
+                    : (i < 320 ? __ldg(p.b3 + i - 64) + (DS ? __ldg(p.bd + i - 64) : 0.f) : __ldg(p.b1 + i - 320));
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -147,18 +166,25 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       if (rank == 0) mbar_arrive_expect_tx(w_bar, 2u * L::W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d_pair(w2s + t * B64_W2_TAP_BYTES, &p.tmW2, wb, t * 64, rank * 32);
       tma_load_2d_pair(w3s, &p.tmW3, wb, 0, rank * 128);
+      if constexpr (DS) tma_load_2d_pair(wds, &p.tmWd, wb, 0, rank * 128);
       if constexpr (C1 > 0)
         for (int j = 0; j < 4; ++j) tma_load_2d_pair(w1s + j * L::W1_CHUNK_BYTES, &p.tmW1, wb, j * 64, rank * (C1 / 2));
       const uint32_t hf0 = mapa_rank(smem_u32(&halo_full[0]), 0);
+      const uint32_t xf = mapa_rank(smem_u32(xs_full), 0);
       int item = pair;
       for (int n = 0; n < n_items; ++n, item += num_pairs) {
         const int tile = 2 * item + rank;               // a past-the-end tile decodes to image NB: zero-filled, clipped
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-        const int buf = n & 1;
-        mbar_wait(&halo_empty[buf], ((n >> 1) & 1) ^ 1);
+        const int buf = n % NH;
+        mbar_wait(&halo_empty[buf], ((n / NH) & 1) ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(&halo_full[buf], 2u * B64_HALO_BYTES);
         tma_load_4d_pair(halo + buf * B64_HALO_BYTES, &p.tmA, hf0 + buf * 8, 0, tw * 8 - 1, th * 16 - 1, img);
+        if constexpr (DS) {                             // the block-input tile, read by GEMM3 next to t2
+          mbar_wait(xs_empty, (n & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(xs_full, 2u * B64_T2_BYTES);
+          tma_load_4d_pair(xss, &p.tmX, xf, 0, tw * 8, th * 16, img);
+        }
       }
     }
   } else if (warp == 1) {
@@ -170,14 +196,16 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       const uint32_t w3_lo = sdesc_lo<128>(smem_u32(w3s));
       const uint32_t w1_lo = sdesc_lo<128>(smem_u32(w1s));
       const uint32_t t2_lo = sdesc_lo<128>(smem_u32(t2s));
+      const uint32_t xs_lo = sdesc_lo<128>(smem_u32(xss));
+      const uint32_t wd_lo = sdesc_lo<128>(smem_u32(wds));
       const uint32_t y_lo = sdesc_lo<128>(smem_u32(ys));
       const uint32_t halo_lo = sdesc_lo<128>(smem_u32(halo));
       auto gemm2 = [&](int n) {           // t2 accumulator of local tile n: nine taps x four K steps, N = 64
-        const int buf = n & 1;
-        mbar_wait(&halo_full[buf], (n >> 1) & 1);
+        const int buf = n % NH, slot = n & 1;
+        mbar_wait(&halo_full[buf], (n / NH) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = tmem_base + buf * 64;
+          const uint32_t d = tmem_base + slot * 64;
           const uint32_t a0 = halo_lo + ((buf * B64_HALO_BYTES) >> 4);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
@@ -189,7 +217,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
               for (int k = 0; k < 4; ++k)
                 umma_bf16_words<true>(d, a_lo + 2 * k, HI_HALO, b_lo + 2 * k, HI, IDESC2, (r | s | k) != 0 ? 1u : 0u);
             }
-          umma_commit_pair(&d2_full[buf]);
+          umma_commit_pair(&d2_full[slot]);
           umma_commit_pair(&halo_empty[buf]);
         }
         __syncwarp();
@@ -197,13 +225,20 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       mbar_wait(w_bar, 0);
       if (n_items > 0) gemm2(0);
       for (int n = 0; n < n_items; ++n) {
-        // ---- GEMM3(n): D3 = t2 * W3^T (K = 64, N = 256)
+        // ---- GEMM3(n): D3 = t2 * W3^T (K = 64, N = 256)  [+ x * Wds^T: the downsample shortcut as 64 more K]
         mbar_wait(t2_full, n & 1);
+        if constexpr (DS) mbar_wait(xs_full, n & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_words<true>(tmem_base + B64_COL_D3, t2_lo + 2 * k, HI, w3_lo + 2 * k, HI, IDESC3, k != 0 ? 1u : 0u);
+          if constexpr (DS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_words<true>(tmem_base + B64_COL_D3, xs_lo + 2 * k, HI, wd_lo + 2 * k, HI, IDESC3, 1u);
+            umma_commit_pair(xs_empty);
+          }
           umma_commit_pair(d3_full);
         }
         __syncwarp();
@@ -234,8 +269,12 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         const int tile = 2 * (pair + n * num_pairs) + rank;
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-        mbar_arrive_expect_tx(&res_full[j], B64_Y_BYTES);
-        tma_load_4d(ys + j * B64_Y_BYTES, &p.tmR, &res_full[j], j * 64, tw * 8, th * 16, img);
+        if constexpr (DS) {
+          mbar_arrive(&res_full[j]);                   // nothing to load: the barrier only says "slot j is free"
+        } else {
+          mbar_arrive_expect_tx(&res_full[j], B64_Y_BYTES);
+          tma_load_4d(ys + j * B64_Y_BYTES, &p.tmR, &res_full[j], j * 64, tw * 8, th * 16, img);
+        }
       };
       if (n_items > 0)
         for (int j = 0; j < 4; ++j) load_res(0, j);
@@ -316,23 +355,29 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         mbar_wait(&res_full[j], n & 1);
         uint8_t* row = ys + j * B64_Y_BYTES + m * 128;
         uint4 rv[4];
+        if constexpr (!DS) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 4 + c) ^ sw) << 4));
+          for (int c = 0; c < 4; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 4 + c) ^ sw) << 4));
+        }
         tmem_ld_wait();
         if (j < 3) tmem_ld_32x32(lane_base + B64_COL_D3 + (j + 1) * 64 + g * 32, v[(j + 1) & 1]);
         const uint32_t (&a)[32] = v[j & 1];
-        const float4* b4 = reinterpret_cast<const float4*>(b3s + j * 64 + g * 32);
+        if constexpr (DS) {
+          bias_relu_store(a, b3s + j * 64 + g * 32, row);
+        } else {
+          const float4* b4 = reinterpret_cast<const float4*>(b3s + j * 64 + g * 32);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
-          const uint32_t* ru = &rv[c].x;
-          float x[8];
-          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_f32x2(ba.x, ba.y)), bf16x2_to_f32x2(ru[0])), x[0], x[1]);
-          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])), pack_f32x2(ba.z, ba.w)), bf16x2_to_f32x2(ru[1])), x[2], x[3]);
-          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_f32x2(bb.x, bb.y)), bf16x2_to_f32x2(ru[2])), x[4], x[5]);
-          unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])), pack_f32x2(bb.z, bb.w)), bf16x2_to_f32x2(ru[3])), x[6], x[7]);
-          *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
-              make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
+          for (int c = 0; c < 4; ++c) {
+            const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
+            const uint32_t* ru = &rv[c].x;
+            float x[8];
+            unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_f32x2(ba.x, ba.y)), bf16x2_to_f32x2(ru[0])), x[0], x[1]);
+            unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])), pack_f32x2(ba.z, ba.w)), bf16x2_to_f32x2(ru[1])), x[2], x[3]);
+            unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_f32x2(bb.x, bb.y)), bf16x2_to_f32x2(ru[2])), x[4], x[5]);
+            unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])), pack_f32x2(bb.z, bb.w)), bf16x2_to_f32x2(ru[3])), x[6], x[7]);
+            *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
+                make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
+          }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -354,19 +399,23 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         const size_t pix = (static_cast<size_t>(img) * p.H + oh) * p.W + ow;
         mbar_wait(d1_full, n & 1);
         tc_fence_after();
-        uint32_t v1[32];
-        tmem_ld_32x32(lane_base + B64_COL_D1 + g * 32, v1);
-        tmem_ld_wait();
-        if (pix_ok) {
-          const float4* b4 = reinterpret_cast<const float4*>(b1s + g * 32);
-          uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + g * 32);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
-            dst[c] = make_uint4(pack_bf16_relu(__uint_as_float(v1[8 * c]) + ba.x, __uint_as_float(v1[8 * c + 1]) + ba.y),
-                                pack_bf16_relu(__uint_as_float(v1[8 * c + 2]) + ba.z, __uint_as_float(v1[8 * c + 3]) + ba.w),
-                                pack_bf16_relu(__uint_as_float(v1[8 * c + 4]) + bb.x, __uint_as_float(v1[8 * c + 5]) + bb.y),
-                                pack_bf16_relu(__uint_as_float(v1[8 * c + 6]) + bb.z, __uint_as_float(v1[8 * c + 7]) + bb.w));
+        for (int h2 = 0; h2 < C1 / 64; ++h2) {
+          const int col0 = g * (C1 / 2) + h2 * 32;
+          uint32_t v1[32];
+          tmem_ld_32x32(lane_base + B64_COL_D1 + col0, v1);
+          tmem_ld_wait();
+          if (pix_ok) {
+            const float4* b4 = reinterpret_cast<const float4*>(b1s + col0);
+            uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + col0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
+              dst[c] = make_uint4(pack_bf16_relu(__uint_as_float(v1[8 * c]) + ba.x, __uint_as_float(v1[8 * c + 1]) + ba.y),
+                                  pack_bf16_relu(__uint_as_float(v1[8 * c + 2]) + ba.z, __uint_as_float(v1[8 * c + 3]) + ba.w),
+                                  pack_bf16_relu(__uint_as_float(v1[8 * c + 4]) + bb.x, __uint_as_float(v1[8 * c + 5]) + bb.y),
+                                  pack_bf16_relu(__uint_as_float(v1[8 * c + 6]) + bb.z, __uint_as_float(v1[8 * c + 7]) + bb.w));
+            }
           }
         }
         tc_fence_before();

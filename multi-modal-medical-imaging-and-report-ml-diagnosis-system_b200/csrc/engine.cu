@@ -129,7 +129,7 @@ struct GemmLaunch {
   GemmParams p; int bn = 128; int bk = 64; int cg = 1; int eb = 1;
   int ln = 0;                         // > 0: row LayerNorm fused behind the last N tile of every m-item (row width ln * 256)
   bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
-  int b64 = 0; Bneck64Params b;       // 1 + C1: fused layer-1 bottleneck kernel (conv2 -> conv3 + shortcut [-> next conv1, C1 = 64])
+  int b64 = 0; Bneck64Params b;       // > 0: fused layer-1 bottleneck kernel, variant code (see build_b64)
 };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
@@ -518,20 +518,25 @@ static bool b64_enabled() {
   if (on < 0) { const char* v = getenv("MMDX_B64"); on = (v && atoi(v) == 0) ? 0 : 1; }
   return on == 1;
 }
+// g.b64 variant codes: 1 = <0,false,2>  2 = <64,false,2>  3 = <128,false,1>  4 = <64,true,1> (shortcut = downsample of x)
 static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* res, bf16* y, bf16* t1n, int NB, int H, int W,
-                     const ConvW& c2, const ConvW& c3, const ConvW* c1n) {
+                     const ConvW& c2, const ConvW& c3, const ConvW* c1n, const ConvW* ds, const bf16* x) {
   REQUIRE(c2.cin == 64 && c2.cout == 64 && c2.k == 3 && c2.stride == 1 && c3.cin == 64 && c3.cout == 256 && c3.k == 1,
           "fused bottleneck: 64 -3x3-> 64 -1x1-> 256");
-  REQUIRE(!c1n || (c1n->cin == 256 && c1n->k == 1 && c1n->stride == 1 && c1n->cout == 64 && t1n),
-          "fused bottleneck: the next conv1 must be 256 -1x1-> 64");
-  g.c64 = false; g.ln = 0; g.b64 = 1 + (c1n ? c1n->cout : 0);
+  REQUIRE(!c1n || (c1n->cin == 256 && c1n->k == 1 && c1n->stride == 1 && (c1n->cout == 64 || c1n->cout == 128) && t1n),
+          "fused bottleneck: the next conv1 must be 256 -1x1-> 64|128");
+  REQUIRE(!ds || (ds->cin == 64 && ds->cout == 256 && ds->k == 1 && ds->stride == 1 && x && c1n && c1n->cout == 64),
+          "fused bottleneck: in-kernel downsample needs 64 -1x1-> 256 and a 64-wide next conv1");
+  REQUIRE(ds || res, "fused bottleneck: shortcut tensor missing");
+  g.c64 = false; g.ln = 0;
+  g.b64 = ds ? 4 : (!c1n ? 1 : (c1n->cout == 64 ? 2 : 3));
   Bneck64Params& p = g.b;
   memset(&p, 0, sizeof p);
+  const uint64_t st64[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+  const uint64_t d64[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
   {
-    const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-    const uint64_t str[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
     const uint32_t box[4] = {64, B64_HALO_W, B64_HALO_H, 1};
-    TRY(make_tmap(e, &p.tmA, t1, 4, dims, str, box, 128));
+    TRY(make_tmap(e, &p.tmA, t1, 4, d64, st64, box, 128));
   }
   {
     const uint64_t d[2] = {576, 64}; const uint64_t st[1] = {576 * 2}; const uint32_t bx[2] = {64, 32};
@@ -540,6 +545,8 @@ static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* 
   {
     const uint64_t d[2] = {64, 256}; const uint64_t st[1] = {64 * 2}; const uint32_t bx[2] = {64, 128};
     TRY(make_tmap(e, &p.tmW3, c3.w, 2, d, st, bx, 128));
+    p.tmWd = p.tmW3;
+    if (ds) TRY(make_tmap(e, &p.tmWd, ds->w, 2, d, st, bx, 128));
   }
   p.tmW1 = p.tmW3;
   if (c1n) {
@@ -552,20 +559,22 @@ static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* 
     const uint64_t str[3] = {512, (uint64_t)W * 512, (uint64_t)H * W * 512};
     const uint32_t box[4] = {64, 8, 16, 1};
     TRY(make_tmap(e, &p.tmY, y, 4, dims, str, box, 128));
-    TRY(make_tmap(e, &p.tmR, res, 4, dims, str, box, 128));
+    p.tmR = p.tmY; p.tmX = p.tmY;
+    if (ds) TRY(make_tmap(e, &p.tmX, x, 4, d64, st64, box, 128));
+    else TRY(make_tmap(e, &p.tmR, res, 4, dims, str, box, 128));
   }
-  p.b2 = c2.bias; p.b3 = c3.bias; p.b1 = c1n ? c1n->bias : c3.bias; p.t1n = t1n;
+  p.b2 = c2.bias; p.b3 = c3.bias; p.b1 = c1n ? c1n->bias : c3.bias; p.bd = ds ? ds->bias : c3.bias; p.t1n = t1n;
   p.NB = NB; p.H = H; p.W = W;
   p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.num_tiles = NB * p.tiles_w * p.tiles_h;
   p.num_items = (p.num_tiles + 1) / 2;
   return 0;
 }
-template <int C1>
+template <int C1, bool DS, int NH>
 static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t s) {
   static bool attr_set = false;
   static int max_clusters = 0;
-  auto* kfn = bneck64_tcgen05_kernel<C1>;
-  constexpr int SMEM = B64Smem<C1>::TOTAL;
+  auto* kfn = bneck64_tcgen05_kernel<C1, DS, NH>;
+  constexpr int SMEM = B64Smem<C1, DS, NH>::TOTAL;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     cudaLaunchConfig_t cfg = {};
@@ -633,8 +642,13 @@ static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s) {
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
-  if (g.b64 == 65) return launch_b64_inst<64>(e, g.b, s);
-  if (g.b64 == 1) return launch_b64_inst<0>(e, g.b, s);
+  switch (g.b64) {
+    case 1: return launch_b64_inst<0, false, 2>(e, g.b, s);
+    case 2: return launch_b64_inst<64, false, 2>(e, g.b, s);
+    case 3: return launch_b64_inst<128, false, 1>(e, g.b, s);
+    case 4: return launch_b64_inst<64, true, 1>(e, g.b, s);
+    default: break;
+  }
   if (g.c64) return launch_c64(e, g.c, s);
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
@@ -1260,20 +1274,25 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
       pl->convs.push_back(gl);
     }
     have_t1 = false;
+    // layer-1 shape (64 -3x3-> 64 -1x1-> 256): conv2, conv3 + shortcut and the next block's conv1 (256 -> 64, or -> 128
+    // for layer2.0) run as ONE kernel (bneck64_tcgen05.cuh); in layer1.0 the downsample conv of the 64-channel block
+    // input joins it as 64 more K of the conv3 GEMM, so its 256-channel output is never written or read back.
+    const bool b64 = b64_enabled() && c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr) && bk.c3.cin == 64 &&
+                     bk.c3.cout == 256 && bk.c3.k == 1;
+    const Bottleneck* nx = bi + 1 < e->blocks.size() ? &e->blocks[bi + 1] : nullptr;
+    const bool fuse_next = b64 && nx && nx->c1.cin == 256 && nx->c1.k == 1 && (nx->c1.cout == 64 || nx->c1.cout == 128);
+    const bool fuse_ds = b64 && bk.has_ds && fuse_next && nx->c1.cout == 64 && bk.ds.cin == 64 && bk.ds.cout == 256 &&
+                         bk.ds.k == 1 && bk.ds.stride == 1;
     const bf16* idt = x;
-    if (bk.has_ds) {
+    if (bk.has_ds && !fuse_ds) {
       TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
       TRY(fill_epilogue(e, gl, bk.ds.bias, nullptr, 0, ds, bk.ds.cout, ACT_NONE, 0));
       pl->convs.push_back(gl);
       idt = ds;
     }
-    // layer-1 shape (64 -3x3-> 64 -1x1-> 256): conv2, conv3 + shortcut and - when the next block starts with a
-    // 256 -> 64 conv1 - that conv1 too run as ONE kernel (bneck64_tcgen05.cuh)
-    if (b64_enabled() && c64_applicable(bk.c2.cin, bk.c2.cout, 3, s, nullptr) && bk.c3.cin == 64 && bk.c3.cout == 256 &&
-        bk.c3.k == 1) {
-      const Bottleneck* nx = bi + 1 < e->blocks.size() ? &e->blocks[bi + 1] : nullptr;
-      const bool fuse_next = nx && nx->c1.cin == 256 && nx->c1.cout == 64 && nx->c1.k == 1;
-      TRY(build_b64(e, gl, o1, idt, y, fuse_next ? o2 : nullptr, B, h, w, bk.c2, bk.c3, fuse_next ? &nx->c1 : nullptr));
+    if (b64) {
+      TRY(build_b64(e, gl, o1, fuse_ds ? nullptr : idt, y, fuse_next ? o2 : nullptr, B, h, w, bk.c2, bk.c3,
+                    fuse_next ? &nx->c1 : nullptr, fuse_ds ? &bk.ds : nullptr, x));
       pl->convs.push_back(gl);
       gl.b64 = 0;
       if (fuse_next) { bf16* t = o1; o1 = o2; o2 = t; have_t1 = true; }
@@ -1694,19 +1713,24 @@ extern "C" int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int
 }
 extern "C" int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const void* d_w2, const float* d_b2,
                                const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n,
-                               void* d_y, void* d_t1n, int NB, int H, int W, void* stream) {
+                               const void* d_x, const void* d_wd, const float* d_bd, void* d_y, void* d_t1n, int NB, int H,
+                               int W, void* stream) {
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
-  REQUIRE(e && d_t1 && d_res && d_w2 && d_b2 && d_w3 && d_b3 && d_y, "null argument");
-  REQUIRE(c1n == 0 || (c1n == 64 && d_w1n && d_b1n && d_t1n), "bneck64: next conv1 width 0 (none) or 64");
+  REQUIRE(e && d_t1 && d_w2 && d_b2 && d_w3 && d_b3 && d_y, "null argument");
+  REQUIRE(c1n == 0 || ((c1n == 64 || c1n == 128) && d_w1n && d_b1n && d_t1n), "bneck64: next conv1 width 0 (none), 64 or 128");
+  REQUIRE((d_x && d_wd && d_bd) || d_res, "bneck64: shortcut tensor, or block input + downsample weights");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
-  ConvW c2, c3, c1;
+  ConvW c2, c3, c1, cd;
   c2.w = (bf16*)d_w2; c2.bias = (float*)d_b2; c2.cin = 64; c2.cout = 64; c2.k = 3; c2.stride = 1;
   c3.w = (bf16*)d_w3; c3.bias = (float*)d_b3; c3.cin = 64; c3.cout = 256; c3.k = 1; c3.stride = 1;
   c1.w = (bf16*)d_w1n; c1.bias = (float*)d_b1n; c1.cin = 256; c1.cout = c1n; c1.k = 1; c1.stride = 1;
+  cd.w = (bf16*)d_wd; cd.bias = (float*)d_bd; cd.cin = 64; cd.cout = 256; cd.k = 1; cd.stride = 1;
+  const bool ds = d_x && d_wd && d_bd;
   GemmLaunch g;
-  TRY(build_b64(e, g, static_cast<const bf16*>(d_t1), static_cast<const bf16*>(d_res), static_cast<bf16*>(d_y),
-                static_cast<bf16*>(d_t1n), NB, H, W, c2, c3, c1n ? &c1 : nullptr));
+  TRY(build_b64(e, g, static_cast<const bf16*>(d_t1), ds ? nullptr : static_cast<const bf16*>(d_res), static_cast<bf16*>(d_y),
+                static_cast<bf16*>(d_t1n), NB, H, W, c2, c3, c1n ? &c1 : nullptr, ds ? &cd : nullptr,
+                static_cast<const bf16*>(d_x)));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,

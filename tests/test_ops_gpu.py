@@ -121,15 +121,20 @@ def test_gemm_fused_layernorm(h, M, K, inplace):
     assert rel_err(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("NB,H,W,C1", [(3, 16, 8, 64), (2, 56, 56, 64), (1, 20, 24, 0), (3, 56, 56, 0), (40, 56, 56, 64)])
-def test_bneck64_fused_block(h, NB, H, W, C1):
+@pytest.mark.parametrize("NB,H,W,C1,DS", [(3, 16, 8, 64, False), (2, 56, 56, 64, False), (1, 20, 24, 0, False),
+                                            (3, 56, 56, 128, False), (40, 56, 56, 64, False), (3, 56, 56, 64, True),
+                                            (33, 24, 40, 64, True), (33, 56, 56, 128, False)])
+def test_bneck64_fused_block(h, NB, H, W, C1, DS):
     """Fused layer-1 bottleneck (conv2 3x3 -> conv3 1x1 + shortcut + ReLU -> next conv1 1x1 + ReLU, intermediates
-    on chip) against fp32 torch convs with the same bf16 rounding points as the unfused kernels.  Odd tile counts
-    (the pair's second CTA runs past the end), partial tiles, several items per CTA pair."""
+    on chip; DS: the shortcut is the downsample conv of the 64-channel block input, computed in the kernel) against
+    fp32 torch convs with the same bf16 rounding points as the unfused kernels.  Odd tile counts (the pair's second
+    CTA runs past the end), partial tiles, several items per CTA pair."""
     g = torch.Generator(device="cuda").manual_seed(NB * 1000 + H + W + C1)
     rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
     t1 = bf(rn(NB, H, W, 64).relu())
     res = bf(rn(NB, H, W, 256))
+    x0 = bf(rn(NB, H, W, 64).relu())
+    wd = bf(rn(256, 64) * (64 ** -0.5)); bd = rn(256) * 0.5
     w2 = bf(rn(64, 64, 3, 3) * (576 ** -0.5)); b2 = rn(64) * 0.5
     w3 = bf(rn(256, 64) * (64 ** -0.5)); b3 = rn(256) * 0.5
     CN = max(C1, 64)
@@ -137,12 +142,17 @@ def test_bneck64_fused_block(h, NB, H, W, C1):
     w2p = w2.permute(0, 2, 3, 1).contiguous()                       # [Cout][kh][kw][Cin]
     y = torch.full((NB, H, W, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
     t1n = torch.full((NB, H, W, CN), float("nan"), device="cuda", dtype=torch.bfloat16)
-    _lib.check(_lib.lib().mmdx_op_bneck64(h.handle, P(t1), P(res), P(w2p), P(b2), P(w3), P(b3), P(w1), P(b1), C1, P(y), P(t1n),
+    _lib.check(_lib.lib().mmdx_op_bneck64(h.handle, P(t1), None if DS else P(res), P(w2p), P(b2), P(w3), P(b3), P(w1), P(b1), C1,
+                                          P(x0) if DS else None, P(wd) if DS else None, P(bd) if DS else None, P(y), P(t1n),
                                           NB, H, W, S()))
     torch.cuda.synchronize()
     x = t1.float().permute(0, 3, 1, 2)
     t2 = bf(F.relu(F.conv2d(x, w2.float(), b2, padding=1))).float()
-    yr = bf(F.relu(F.conv2d(t2, w3.float()[:, :, None, None], b3) + res.float().permute(0, 3, 1, 2)))
+    if DS:      # the unfused path rounds the downsample output to bf16 before the add; here it stays in the fp32 accumulator
+        short = F.conv2d(x0.float().permute(0, 3, 1, 2), wd.float()[:, :, None, None], bd)
+    else:
+        short = res.float().permute(0, 3, 1, 2)
+    yr = bf(F.relu(F.conv2d(t2, w3.float()[:, :, None, None], b3) + short))
     assert torch.isfinite(y.float()).all()
     assert rel_err(y.permute(0, 3, 1, 2), yr.float()) < 1e-2
     if C1:

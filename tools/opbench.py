@@ -130,7 +130,7 @@ def bench_conv(h, lib):
 def bench_bneck(h, lib):
     """Fused layer-1 bottleneck against its three separate launches (conv2 3x3, conv3 + shortcut, next conv1)."""
     NB, HW = 256, 56
-    for C1 in (64, 0):
+    for C1 in (64, 128, 0):
         CN = max(C1, 64)
         t1 = bf(torch.randn(NB, HW, HW, 64, device="cuda").relu())
         res = bf(torch.randn(NB, HW, HW, 256, device="cuda"))
@@ -148,7 +148,7 @@ def bench_bneck(h, lib):
                 _lib.check(lib.mmdx_op_conv(h.handle, P(y), NB, HW, HW, 256, P(w1), P(b1), None, P(t1n), C1, 1, 1, 1, S()))
         us3 = timeit(three)
         us1 = timeit(lambda: _lib.check(lib.mmdx_op_bneck64(h.handle, P(t1), P(res), P(w2), P(b2), P(w3), P(b3), P(w1), P(b1), C1,
-                                                            P(y), P(t1n), NB, HW, HW, S())))
+                                                            None, None, None, P(y), P(t1n), NB, HW, HW, S())))
         by = 2.0 * NB * HW * HW * (64 + 256 + 256 + C1)
         print(f"bottleneck 56x56 next conv1 {C1:3d}: separate launches {us3:7.1f} us   fused {us1:7.1f} us  ({by / us1 / 1e3:6.1f} GB/s algorithmic)",
               flush=True)
