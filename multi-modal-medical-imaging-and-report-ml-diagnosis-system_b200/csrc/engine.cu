@@ -138,7 +138,10 @@ struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp3
 struct LinW { bf16* w = nullptr; float* bias = nullptr; int nin = 0, nout = 0; };
 struct LnW { float* g = nullptr; float* b = nullptr; };
 struct BertLayerW { LinW qkv, ao, ff1, ff2; LnW ln1, ln2; };
-struct Bottleneck { ConvW c1, c2, c3, ds; bool has_ds = false; };
+struct Bottleneck {
+  ConvW c1, c2, c3, ds; bool has_ds = false;
+  ConvW c3ds;      // has_ds: conv3 and the downsample conv as ONE GEMM: weights [Cout][c3.cin + ds.cin], bias b3 + bd
+};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -398,6 +401,8 @@ static int build_gemm(mmdx_engine* e, GemmLaunch& g, const bf16* A, long long ld
   const uint32_t bb[2] = {64, (uint32_t)(g.bn / g.cg)};
   TRY(make_tmap(e, &p.tmB, Wt, 2, bd, bs, bb, 128));
   p.num_k_blocks = K / 64; p.kb_per_tap = K / 64; p.a_box_bytes = 128 * 64 * 2;
+  REQUIRE(K / 64 <= 255, "K too large");
+  p.tap_kb[0] = (unsigned char)(K / 64);
   p.n_tiles = N / g.bn; p.cg = g.cg; p.num_tiles = (int)(((m_tiles + g.cg - 1) / g.cg) * p.n_tiles);
   p.tiles_w = (int)m_tiles; p.tiles_h = 1;
   p.Wb = 128; p.Hb = 1; p.Nb = 1; p.OW = M; p.OH = 1; p.NB = 1;
@@ -468,6 +473,50 @@ static int build_conv(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int
   const uint32_t bb[2] = {64, (uint32_t)(g.bn / g.cg)};
   TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 128));
   p.kb_per_tap = Cin / 64; p.num_k_blocks = k * k * p.kb_per_tap; p.a_box_bytes = Wb * Hb * Nb * 64 * 2;
+  for (int i = 0; i < k * k; ++i) p.tap_kb[i] = (unsigned char)(Cin / 64);
+  p.n_tiles = Cout / g.bn; p.cg = g.cg; p.num_tiles = (int)(((m_tiles + g.cg - 1) / g.cg) * p.n_tiles);
+  p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
+  p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
+  return 0;
+}
+
+// conv3 (1x1, on t2 [NB,OH,OW,Cmid]) + the block's downsample conv (1x1 stride s, on x [NB,H,W,Cin]) as ONE implicit GEMM
+// whose K loop walks two "taps" over two tensors: out = t2 * W3^T + x[::s, ::s] * Wd^T (+ b3 + bd, ReLU in the epilogue).
+// The downsample output (as large as the block output) is never written or read back, and the shortcut add is a
+// longer K loop instead of residual MMAs.  w = [Cout][Cmid + Cin] (Bottleneck::c3ds).
+static int build_c3ds(mmdx_engine* e, GemmLaunch& g, const bf16* t2, int NB, int OH, int OW, int Cmid, const bf16* x, int H,
+                      int W, int Cin, int stride, const bf16* w, int Cout) {
+  REQUIRE(Cmid % 64 == 0 && Cin % 64 == 0 && Cout % 64 == 0 && (stride == 1 || stride == 2), "conv3+downsample shape");
+  REQUIRE(OH == (H - 1) / stride + 1 && OW == (W - 1) / stride + 1, "conv3+downsample geometry");
+  GemmParams& p = g.p;
+  memset(&p, 0, sizeof p);
+  g.ln = 0; g.c64 = false; g.b64 = 0;
+  int Wb, Hb, Nb;
+  pick_tile(OW, OH, NB, Wb, Hb, Nb);
+  const long long m_tiles = (long long)((OW + Wb - 1) / Wb) * ((OH + Hb - 1) / Hb) * ((NB + Nb - 1) / Nb);
+  pick_tile_shape(e, m_tiles, Cout, 0, &g.bn, &g.cg);
+  REQUIRE(g.bn != 0, "no BN tile divides Cout");
+  g.bk = 64;
+  const uint32_t box[4] = {64, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
+  {
+    const uint64_t dims[4] = {(uint64_t)Cmid, (uint64_t)OW, (uint64_t)OH, (uint64_t)NB};
+    const uint64_t str[3] = {(uint64_t)Cmid * 2, (uint64_t)OW * Cmid * 2, (uint64_t)OH * OW * Cmid * 2};
+    TRY(make_tmap(e, &p.tmA[0], t2, 4, dims, str, box, 128));
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)OW, (uint64_t)OH, (uint64_t)NB};
+    const uint64_t str[3] = {(uint64_t)stride * Cin * 2, (uint64_t)stride * W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    TRY(make_tmap(e, &p.tmA[1], x, 4, dims, str, box, 128));
+  }
+  p.tmA[2] = p.tmA[0]; p.tmA[3] = p.tmA[0];
+  p.tap_map[0] = 0; p.tap_map[1] = 1;
+  p.tap_kb[0] = (unsigned char)(Cmid / 64); p.tap_kb[1] = (unsigned char)(Cin / 64);
+  const int K = Cmid + Cin;
+  const uint64_t bd[2] = {(uint64_t)K, (uint64_t)Cout};
+  const uint64_t bs[1] = {(uint64_t)K * 2};
+  const uint32_t bb[2] = {64, (uint32_t)(g.bn / g.cg)};
+  TRY(make_tmap(e, &p.tmB, w, 2, bd, bs, bb, 128));
+  p.kb_per_tap = Cmid / 64; p.num_k_blocks = K / 64; p.a_box_bytes = Wb * Hb * Nb * 64 * 2;
   p.n_tiles = Cout / g.bn; p.cg = g.cg; p.num_tiles = (int)(((m_tiles + g.cg - 1) / g.cg) * p.n_tiles);
   p.tiles_w = (OW + Wb - 1) / Wb; p.tiles_h = (OH + Hb - 1) / Hb;
   p.Wb = Wb; p.Hb = Hb; p.Nb = Nb; p.OW = OW; p.OH = OH; p.NB = NB;
@@ -519,6 +568,11 @@ static bool b64_enabled() {
   return on == 1;
 }
 // g.b64 variant codes: 1 = <0,false,2>  2 = <64,false,2>  3 = <128,false,1>  4 = <64,true,1> (shortcut = downsample of x)
+static bool c3ds_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("MMDX_C3DS"); on = (v && atoi(v) == 0) ? 0 : 1; }
+  return on == 1;
+}
 static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* res, bf16* y, bf16* t1n, int NB, int H, int W,
                      const ConvW& c2, const ConvW& c3, const ConvW* c1n, const ConvW* ds, const bf16* x) {
   REQUIRE(c2.cin == 64 && c2.cout == 64 && c2.k == 3 && c2.stride == 1 && c3.cin == 64 && c3.cout == 256 && c3.k == 1,
@@ -865,6 +919,28 @@ static int pack_conv(mmdx_engine* e, const std::string& wkey, const std::string&
   return 0;
 }
 
+// conv3 | downsample concatenated along K (device to host, once): [Cout][c3.cin + ds.cin] bf16, bias b3 + bd
+static int pack_c3ds(mmdx_engine* e, Bottleneck* bk) {
+  const ConvW& a = bk->c3; const ConvW& d = bk->ds;
+  REQUIRE(a.k == 1 && d.k == 1 && a.cout == d.cout, "conv3 / downsample shapes");
+  std::vector<bf16> wa((size_t)a.cout * a.cin), wd((size_t)d.cout * d.cin), wc((size_t)a.cout * (a.cin + d.cin));
+  std::vector<float> ba(a.cout), bd(d.cout);
+  CK(cudaMemcpy(wa.data(), a.w, wa.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(wd.data(), d.w, wd.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ba.data(), a.bias, ba.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(bd.data(), d.bias, bd.size() * 4, cudaMemcpyDeviceToHost));
+  const int K = a.cin + d.cin;
+  for (int o = 0; o < a.cout; ++o) {
+    memcpy(&wc[(size_t)o * K], &wa[(size_t)o * a.cin], (size_t)a.cin * 2);
+    memcpy(&wc[(size_t)o * K + a.cin], &wd[(size_t)o * d.cin], (size_t)d.cin * 2);
+    ba[o] += bd[o];
+  }
+  bk->c3ds.cin = K; bk->c3ds.cout = a.cout; bk->c3ds.k = 1; bk->c3ds.stride = d.stride;
+  TRY(upload(e, wc, &bk->c3ds.w));
+  TRY(upload(e, ba, &bk->c3ds.bias));
+  return 0;
+}
+
 static int pack_linear(mmdx_engine* e, const std::string& key, LinW* out) {
   GET(w, key + ".weight"); GET(b, key + ".bias");
   REQUIRE(w->shape.size() == 2, "linear weight rank");
@@ -893,7 +969,7 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
   CK(cudaSetDevice(e->cfg.device));
   size_t total = 0;
   for (auto& kv : e->host) total += kv.second.data.size() * 4 + 512;
-  TRY(e->warena.ensure(total + (1 << 20)));
+  TRY(e->warena.ensure(total + (16 << 20)));      // + the conv3|downsample copies (7 MB bf16) and alignment slack
   e->wused = 0;
   // ---- image encoder: stem
   {
@@ -926,6 +1002,7 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
       if (get(e, pfx + ".downsample.0.weight")) {
         bk.has_ds = true;
         TRY(pack_conv(e, pfx + ".downsample.0", pfx + ".downsample.1", s, &bk.ds));
+        TRY(pack_c3ds(e, &bk));
       }
       e->blocks.push_back(bk);
     }
@@ -1010,7 +1087,7 @@ struct PackHeader {
   uint64_t arena_bytes;
   uint64_t checksum;        // FNV-1a of table + arena
 };
-static const uint32_t kPackVersion = 1;
+static const uint32_t kPackVersion = 2;
 
 struct PackWalker {
   bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
@@ -1040,7 +1117,9 @@ static void walk_weights(mmdx_engine* e, PackWalker& w) {
   int nb = (int)e->blocks.size();
   w.i(nb);
   if (w.loading) e->blocks.assign(nb < 0 || nb > 64 ? 0 : nb, Bottleneck());
-  for (Bottleneck& bk : e->blocks) { w.conv(bk.c1); w.conv(bk.c2); w.conv(bk.c3); w.b(bk.has_ds); w.conv(bk.ds); }
+  for (Bottleneck& bk : e->blocks) {
+    w.conv(bk.c1); w.conv(bk.c2); w.conv(bk.c3); w.b(bk.has_ds); w.conv(bk.ds); w.conv(bk.c3ds);
+  }
   w.lin(e->proj_img);
   w.p(e->word); w.p(e->ptab); w.p(e->ttab); w.ln(e->emb_ln);
   int nl = (int)e->layers.size();
@@ -1284,7 +1363,10 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
     const bool fuse_ds = b64 && bk.has_ds && fuse_next && nx->c1.cout == 64 && bk.ds.cin == 64 && bk.ds.cout == 256 &&
                          bk.ds.k == 1 && bk.ds.stride == 1;
     const bf16* idt = x;
-    if (bk.has_ds && !fuse_ds) {
+    // other blocks with a downsample conv: conv3 and the downsample run as one GEMM over [t2 | x] (build_c3ds), unless
+    // the block is a fused layer-1 shape that needs the shortcut as a tensor
+    const bool cat_ds = bk.has_ds && !fuse_ds && !b64 && c3ds_enabled();
+    if (bk.has_ds && !fuse_ds && !cat_ds) {
       TRY(build_conv(e, gl, x, B, h, w, bk.ds.cin, bk.ds.w, bk.ds.cout, 1, s));
       TRY(fill_epilogue(e, gl, bk.ds.bias, nullptr, 0, ds, bk.ds.cout, ACT_NONE, 0));
       pl->convs.push_back(gl);
@@ -1306,8 +1388,13 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
       }
       pl->convs.push_back(gl);
       gl.c64 = false;
-      TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
-      TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
+      if (cat_ds) {
+        TRY(build_c3ds(e, gl, o2, B, oh, ow, bk.c3.cin, x, h, w, bk.ds.cin, s, bk.c3ds.w, bk.c3.cout));
+        TRY(fill_epilogue(e, gl, bk.c3ds.bias, nullptr, 0, y, bk.c3.cout, ACT_RELU, 0));
+      } else {
+        TRY(build_conv(e, gl, o2, B, oh, ow, bk.c3.cin, bk.c3.w, bk.c3.cout, 1, 1));
+        TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
+      }
       pl->convs.push_back(gl);
     }
     bf16* t = x; x = y; y = t;

@@ -66,6 +66,7 @@ struct alignas(64) GemmParams {
   const __nv_bfloat16* residual;   // [M, ldr] or null
   void* out;                   // [M, ldc]
   signed char tap_map[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
+  unsigned char tap_kb[kMaxTaps];   // k-blocks of each tap (all kb_per_tap, except conv3 + downsample: two "taps" over two tensors)
   // Fused row LayerNorm (template LN > 0; plain GEMMs whose N tiles cover the whole row): the schedule turns
   // item-major - one CTA group computes all n_tiles tiles of its 256 (128) rows back to back - and after the last of
   // them the epilogue warps normalise the rows this CTA has just stored (L2-hot) into ln_out.
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         t.h0 + p.tap_dh[tap], t.n0);
             tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, t.n_t * BN);
           }
-          if (++cc == p.kb_per_tap) { cc = 0; ++tap; }
+          if (++cc == p.tap_kb[tap]) { cc = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (BK == 64 && RES == 1) {
