@@ -115,6 +115,11 @@ int mmdx_op_conv(mmdx_engine* e, const void* d_in, int NB, int H, int W, int Cin
 int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const void* d_w2, const float* d_b2,
                     const void* d_w3, const float* d_b3, const void* d_w1n, const float* d_b1n, int c1n, const void* d_x,
                     const void* d_wd, const float* d_bd, void* d_y, void* d_t1n, int NB, int H, int W, void* stream);
+/* Last conv of a bottleneck with a downsample shortcut (layer2-4.0): out = relu(conv1x1(t2, w3) + conv1x1_stride_s(x, wd) + b)
+ * as ONE implicit GEMM over [t2 | x]; d_wcat = [Cout][Cmid + Cin] bf16 (w3 | wd along K, BN folded), d_bias = b3 + bd.
+ * t2 [NB,OH,OW,Cmid], x [NB,H,W,Cin], out [NB,OH,OW,Cout], OH = (H-1)/stride + 1. */
+int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_out,
+                     int NB, int H, int W, int Cin, int Cmid, int Cout, int stride, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
  * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).

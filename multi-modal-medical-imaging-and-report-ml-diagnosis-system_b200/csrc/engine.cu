@@ -1820,6 +1820,19 @@ extern "C" int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_r
                 static_cast<const bf16*>(d_x)));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
+extern "C" int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias,
+                                void* d_out, int NB, int H, int W, int Cin, int Cmid, int Cout, int stride, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
+  REQUIRE(e && d_t2 && d_x && d_wcat && d_bias && d_out, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+  GemmLaunch g;
+  TRY(build_c3ds(e, g, static_cast<const bf16*>(d_t2), NB, OH, OW, Cmid, static_cast<const bf16*>(d_x), H, W, Cin, stride,
+                 static_cast<const bf16*>(d_wcat), Cout));
+  TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, Cout, ACT_RELU, 0));
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,
                                  const float* d_bias, void* d_out, int pool, void* stream) {
   if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }

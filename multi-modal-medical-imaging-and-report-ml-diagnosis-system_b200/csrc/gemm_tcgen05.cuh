@@ -415,21 +415,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (et < BN) sb[et] = p.bias != nullptr ? __ldg(p.bias + t.n_t * BN + et) : 0.0f;
           named_bar_sync(3, 256);
         }
+        uint32_t v[32];
+        tmem_ld_32x32(tbase + g * kEpiCW, v);
 #pragma unroll 1
         for (int c = g; c < NC; c += 2, ++nstore) {
           uint8_t* buf = stg + (g * EB + (EB == 2 ? (nstore & 1) : 0)) * kEpiBufBytes;
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + c * kEpiCW, v);
           tmem_ld_wait();
-          if (c == NC - 2 + g) {              // this warp's last read of the accumulator: hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc(as);
-          }
           const int col0 = t.n_t * BN + c * kEpiCW;
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (c + 2 < NC) {                   // the next chunk's accumulator load is in flight during this chunk's math
+            tmem_ld_32x32(tbase + (c + 2) * kEpiCW, v);
+          } else {                            // this warp's last read of the accumulator: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(as);
+          }
           {
             const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW);
 #pragma unroll

@@ -161,6 +161,28 @@ def test_bneck64_fused_block(h, NB, H, W, C1, DS):
         assert rel_err(t1n.permute(0, 3, 1, 2), tr) < 1e-2
 
 
+@pytest.mark.parametrize("NB,H,W,Cin,Cmid,Cout,stride", [(4, 56, 56, 256, 128, 512, 2), (5, 15, 13, 64, 64, 256, 2),
+                                                          (3, 14, 14, 1024, 512, 2048, 2), (2, 20, 12, 64, 64, 256, 1)])
+def test_conv3_plus_downsample_as_one_gemm(h, NB, H, W, Cin, Cmid, Cout, stride):
+    """conv3 + the stride-s downsample conv of the block input as one implicit GEMM over two tensors (K-concatenated
+    weights) against fp32 torch convs; odd sizes, stride 1 and 2."""
+    g = torch.Generator(device="cuda").manual_seed(NB + H + W + Cin + Cout)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    t2 = bf(rn(NB, OH, OW, Cmid).relu())
+    x = bf(rn(NB, H, W, Cin).relu())
+    w3 = bf(rn(Cout, Cmid) * (Cmid ** -0.5)); wd = bf(rn(Cout, Cin) * (Cin ** -0.5))
+    b = rn(Cout) * 0.5
+    wcat = torch.cat([w3, wd], dim=1).contiguous()
+    out = torch.full((NB, OH, OW, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().mmdx_op_conv3_ds(h.handle, P(t2), P(x), P(wcat), P(b), P(out), NB, H, W, Cin, Cmid, Cout, stride, S()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(t2.float().permute(0, 3, 1, 2), w3.float()[:, :, None, None], b) +
+                 F.conv2d(x.float().permute(0, 3, 1, 2), wd.float()[:, :, None, None], stride=stride))
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.permute(0, 3, 1, 2), ref) < 1e-2
+
+
 def test_gemm_strided_output_and_no_bias(h):
     M, N, K = 200, 512, 768
     a = bf(torch.randn(M, K, device="cuda"))
