@@ -9,7 +9,7 @@ A "step" is one pass of the hot path over one batch of synthetic studies: BASELI
 
   value     studies/s, device-resident inputs (uint8 images + packed int32 ids already in HBM)
   e2e       studies/s through the public host-buffer call (pinned host -> H2D -> forward -> D2H each step)
-  roofline  the dominant kernel (gemm_tcgen05_kernel: the 52 bottleneck convs and every Linear) against the measured
+  roofline  the dominant kernels (gemm_tcgen05_kernel + the fused layer-1 bottleneck kernel: all convs but conv1, every Linear) against the measured
             bf16 peak; kernel_rooflines = the same arithmetic for every other kernel class (tensor or HBM bound)
   cpu_baseline  the CPU oracle port (oracle/forward_ref.py) on this box's host cores, bounded sample
 
@@ -61,17 +61,27 @@ def gemm_bytes_per_step(B, L, hidden=768, ffn=3072, layers=12, d_img=1024, d_txt
                      + T * (ffn + 2 * hidden) * 2        # FFN2: A, residual, out
                      + (4 * hidden * hidden + 2 * hidden * ffn) * 2)
     img, cin, hw = 0, 64, 56
-    for mid, cout, blocks, stride in ((64, 256, 3, 1), (128, 512, 4, 2), (256, 1024, 6, 2), (512, 2048, 3, 2)):
+    for li, (mid, cout, blocks, stride) in enumerate(((64, 256, 3, 1), (128, 512, 4, 2), (256, 1024, 6, 2), (512, 2048, 3, 2))):
         for b in range(blocks):
             s = stride if b == 0 else 1
             ho = hw // s
-            c2_own_kernel = (mid == 64)                  # layer-1 3x3 convs run in conv3x3_c64_tcgen05_kernel
-            img += B * hw * hw * (cin + mid) * 2 + cin * mid * 2                                    # conv1 1x1
-            if not c2_own_kernel:
+            if li == 0:
+                # layer 1: conv1 of block 0, then one bneck64_tcgen05_kernel per block: t1 in, shortcut in (block 0: the
+                # 64-channel block input - its downsample conv runs in the kernel), y out, the next block's conv1 out
+                nxt = 64 if b + 1 < blocks else 128
+                if b == 0:
+                    img += B * hw * hw * (cin + mid) * 2 + cin * mid * 2
+                img += B * hw * hw * (mid + (cin if b == 0 else cout) + cout + nxt) * 2 + (9 * mid * mid + mid * cout + cout * nxt) * 2
+                if b == 0:
+                    img += cin * cout * 2
+            else:
+                if not (li == 1 and b == 0):                                                        # layer2.0 conv1: done above
+                    img += B * hw * hw * (cin + mid) * 2 + cin * mid * 2                            # conv1 1x1
                 img += B * (hw * hw + ho * ho) * mid * 2 + 9 * mid * mid * 2                        # conv2 3x3 (stride s)
-            img += B * ho * ho * (mid + 2 * cout) * 2 + mid * cout * 2                              # conv3 1x1 + residual
-            if b == 0:
-                img += B * ho * ho * (cin + cout) * 2 + cin * cout * 2                              # downsample 1x1 (stride s)
+                if b == 0:      # conv3 + downsample as one GEMM over [t2 | x strided]
+                    img += B * ho * ho * (mid + cin + cout) * 2 + (mid + cin) * cout * 2
+                else:           # conv3 1x1 + residual
+                    img += B * ho * ho * (mid + 2 * cout) * 2 + mid * cout * 2
             cin, hw = cout, ho
     head = B * (2048 + d_img + hidden + d_txt + d_img + d_txt) * 2 + B * d_fuse * 4 \
         + (2048 * d_img + hidden * d_txt + (d_img + d_txt) * d_fuse) * 2
@@ -82,8 +92,10 @@ def measured_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)["gemm_tcgen05_kernel"]
-        return t["dram_bytes_per_launch"], t.get("source")
+            t = json.load(f)
+        ks = [t[k] for k in ("gemm_tcgen05_kernel", "bneck64_tcgen05_kernel") if k in t]
+        n = sum(k["launches_per_step"] for k in ks)
+        return sum(k["dram_bytes_read"] + k["dram_bytes_write"] for k in ks) / n, t["gemm_tcgen05_kernel"].get("source")
     except (OSError, KeyError, ValueError):
         return None, None
 
@@ -349,7 +361,7 @@ def main():
     peaks = load_peaks()
     achieved = f_gemm * B / (gemm_ms * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic() if B == BATCH_PER_GPU else (None, None)
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (52 bottleneck convs + every Linear layer)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (39 bottleneck convs + every Linear layer) + bneck64_tcgen05_kernel (3 fused layer-1 bottlenecks)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16",
                 "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, B=256)",
