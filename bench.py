@@ -304,15 +304,33 @@ def main():
             dist.all_gather_into_tensor(gathered, logits.to(dev, non_blocking=True))
         return logits
 
+    # secondary e2e figure: the host-buffer call as a two-deep request pipeline (mmdx_forward_host_submit / _wait): every
+    # step still copies its inputs from pinned host memory and its results back; the copy of step i+1 runs under step i
+    host_outs = [tuple(torch.empty_like(t).pin_memory() for t in host_out) for _ in range(2)]
+
+    def step_host_pipelined(i):
+        h = host_sets[i % N_INPUT_SETS]
+        eng.forward_host_submit(i % 2, h[0], h[1], h[2], h[3], h[4], mlen, host_outs[i % 2])
+        if i >= 1:
+            eng.forward_host_wait((i - 1) % 2)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, host_outs[(i - 1) % 2][0].to(dev, non_blocking=True))
+
+    def drain_host_pipeline():
+        eng.forward_host_wait(0)
+        eng.forward_host_wait(1)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, drain=None):
         for i in range(warmup):
             fn(i)
+        if drain:
+            drain()
         barrier()
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
@@ -323,6 +341,8 @@ def main():
         e0.record()
         for i in range(steps):
             fn(i)
+        if drain:
+            drain()                # every request of the timed region has delivered its results to host memory
         e1.record()
         barrier()
         t1 = time.time()
@@ -341,6 +361,7 @@ def main():
 
     ms_dev, launches, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _, _ = timed(step_host, args.steps, 3)
+    ms_e2e_pipe, _, _ = timed(step_host_pipelined, args.steps, 3, drain=drain_host_pipeline)
     value = world * B * args.steps / (ms_dev * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
 
@@ -382,7 +403,11 @@ def main():
                    "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches ({N_INPUT_SETS * h2d / 1e6:.0f} MB > 126 MB L2); "
                          "activations (GBs per step) sweep L2 between steps"},
         "e2e": {"value": e2e, "unit": "studies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "api": "mmdx_forward_host (synchronous: H2D, forward, D2H, wait - one call per step)",
+                "pipelined": {"value": world * B * args.steps / (ms_e2e_pipe * 1e-3), "ms_per_step": ms_e2e_pipe / args.steps,
+                              "api": "mmdx_forward_host_submit/_wait, two requests in flight (H2D of step i+1 under the "
+                                     "kernels of step i); no faster: the step is power-bound, not idle-bound"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

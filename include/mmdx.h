@@ -83,6 +83,15 @@ int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, i
 int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
                       const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu_seqlens, int T, int max_len,
                       const float* h_thresholds, float* h_logits, float* h_probs, uint8_t* h_vector, void* stream);
+/* The same call as a two-deep pipeline for throughput serving: _submit enqueues request `slot` (0 or 1: H2D of its inputs,
+ * forward, D2H of its results) and returns; _wait blocks until that slot's results are in the host buffers.  With two
+ * requests in flight the image batch of request k+1 crosses PCIe under the kernels of request k.  Host buffers must stay
+ * valid (pinned, for real overlap) until _wait; submitting to a busy slot waits for it first. */
+int mmdx_forward_host_submit(mmdx_engine* e, int slot, const uint8_t* h_images_u8, int B, int H, int W, int C,
+                             const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu_seqlens,
+                             int T, int max_len, const float* h_thresholds, float* h_logits, float* h_probs,
+                             uint8_t* h_vector, void* stream);
+int mmdx_forward_host_wait(mmdx_engine* e, int slot);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t mmdx_launch_count(mmdx_engine* e);
 /* Per-kernel-class device time: between begin and end every launch is bracketed by CUDA events on its

@@ -209,6 +209,10 @@ struct mmdx_engine {
   int force_cg = 0;      // MMDX_CG=1|2 pins the CTA-group size of every eligible GEMM (experiments); 0 = heuristic
   // workspaces
   DevBuf img_ws, txt_ws, head_ws, tab_ws, io_ws;
+  // mmdx_forward_host_submit / _wait: two request slots, each with its own device I/O buffers and events
+  DevBuf io_slot[2];
+  cudaEvent_t slot_copy_done[2] = {nullptr, nullptr}, slot_tok_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   std::map<std::string, std::unique_ptr<ImagePlan>> img_plans;
   ImagePlan* img_last = nullptr;   // plan whose zero borders currently sit in img_ws
   std::map<std::string, std::unique_ptr<TextPlan>> txt_plans;
@@ -830,6 +834,11 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->copy_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&e->slot_copy_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot_tok_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
+  }
   CK(cudaStreamCreateWithFlags(&e->text_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming));
@@ -857,6 +866,11 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->copy_done) cudaEventDestroy(e->copy_done);
   if (e->copy_ready) cudaEventDestroy(e->copy_ready);
+  for (int i = 0; i < 2; ++i) {
+    if (e->slot_copy_done[i]) cudaEventDestroy(e->slot_copy_done[i]);
+    if (e->slot_tok_done[i]) cudaEventDestroy(e->slot_tok_done[i]);
+    if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
+  }
   if (e->text_stream) cudaStreamDestroy(e->text_stream);
   if (e->fork_ev) cudaEventDestroy(e->fork_ev);
   if (e->join_ev) cudaEventDestroy(e->join_ev);
@@ -1705,19 +1719,20 @@ extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int 
   return head_locked(e, B, d_thr, nullptr, d_logits, d_probs, d_vector, s);
 }
 
-extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C,
-                                 const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu,
-                                 int T, int max_len, const float* h_thr, float* h_logits, float* h_probs,
-                                 uint8_t* h_vector, void* stream) {
-  REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
-  CK(cudaSetDevice(e->cfg.device));
+// Request slot `slot`: H2D of its inputs, the forward, D2H of its results - enqueued, not waited for.  The image batch
+// (the bulk of the bytes) crosses PCIe on the copy stream into the slot's own buffer, so with two slots in flight the
+// copy of request k+1 runs under the kernels of request k; the compute itself stays ordered on `s` / the text stream
+// (the activation workspaces are shared), and the D2H of request k runs under the first kernels of request k+1.
+static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h_images, int B, int H, int W, int C,
+                                      const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu,
+                                      int T, int max_len, const float* h_thr, float* h_logits, float* h_probs,
+                                      uint8_t* h_vector, cudaStream_t s) {
   REQUIRE(e->finalized, "weights not finalized");
-  cudaStream_t s = (cudaStream_t)stream;
+  if (e->slot_busy[slot]) { CK(cudaEventSynchronize(e->slot_done[slot])); e->slot_busy[slot] = false; }
   const size_t img_b = al((size_t)B * H * W * C), tok_b = al((size_t)T * 4), cu_b = al((size_t)(B + 1) * 4);
   const size_t out_f = al((size_t)B * e->n_cls * 4), out_u = al((size_t)B * e->n_cls), thr_b = al((size_t)e->n_cls * 4);
-  TRY(e->io_ws.ensure(img_b + 3 * tok_b + cu_b + 2 * out_f + out_u + thr_b));
-  char* b = static_cast<char*>(e->io_ws.p);
+  TRY(e->io_slot[slot].ensure(img_b + 3 * tok_b + cu_b + 2 * out_f + out_u + thr_b));
+  char* b = static_cast<char*>(e->io_slot[slot].p);
   uint8_t* d_img = reinterpret_cast<uint8_t*>(b); b += img_b;
   int32_t* d_ids = reinterpret_cast<int32_t*>(b); b += tok_b;
   int32_t* d_pos = reinterpret_cast<int32_t*>(b); b += tok_b;
@@ -1727,30 +1742,74 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   float* d_probs = reinterpret_cast<float*>(b); b += out_f;
   uint8_t* d_vec = reinterpret_cast<uint8_t*>(b); b += out_u;
   float* d_thr = reinterpret_cast<float*>(b);
-  // The image batch (the bulk of the input bytes) is copied on the engine's copy stream while the text branch,
-  // whose inputs are a few hundred KB, already runs on `s`; the image branch waits for the copy event.
-  CK(cudaEventRecord(e->copy_ready, s));                       // previous work on `s` may still read d_img
-  CK(cudaStreamWaitEvent(e->copy_stream, e->copy_ready, 0));
+  // the slot's previous request has been waited for (above), so nothing on the device still reads these buffers
+  // All inputs go over the copy stream at submit time - the token arrays (a few hundred KB) FIRST, then the image batch:
+  // one DMA engine serves every host-to-device copy in the order they become ready, and token copies queued behind the
+  // 38 MB image copy would hold the text branch (and with it the whole GPU) back for the 0.75 ms the images take.
+  CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  if (h_thr) CK(cudaMemcpyAsync(d_thr, h_thr, (size_t)e->n_cls * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(e->slot_tok_done[slot], e->copy_stream));
   CK(cudaMemcpyAsync(d_img, h_images, (size_t)B * H * W * C, cudaMemcpyHostToDevice, e->copy_stream));
-  CK(cudaEventRecord(e->copy_done, e->copy_stream));
+  CK(cudaEventRecord(e->slot_copy_done[slot], e->copy_stream));
   const bool fork = e->two_streams && !e->profiling;
   cudaStream_t ts = fork ? e->text_stream : s;
-  if (fork) CK(cudaStreamWaitEvent(ts, e->copy_ready, 0));    // earlier work on `s` may still read the token buffers
-  CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
-  CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
-  CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, ts));
-  CK(cudaMemcpyAsync(d_cu, h_cu, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ts));
-  if (h_thr) CK(cudaMemcpyAsync(d_thr, h_thr, (size_t)e->n_cls * 4, cudaMemcpyHostToDevice, s));
+  if (fork) {                                                  // the previous request on `s` still uses the shared workspaces
+    CK(cudaEventRecord(e->copy_ready, s));
+    CK(cudaStreamWaitEvent(ts, e->copy_ready, 0));
+  }
+  CK(cudaStreamWaitEvent(ts, e->slot_tok_done[slot], 0));
+  if (h_thr && fork) CK(cudaStreamWaitEvent(s, e->slot_tok_done[slot], 0));
   TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, ts));
   if (fork) CK(cudaEventRecord(e->join_ev, ts));
-  CK(cudaStreamWaitEvent(s, e->copy_done, 0));
+  CK(cudaStreamWaitEvent(s, e->slot_copy_done[slot], 0));
   TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
   if (fork) CK(cudaStreamWaitEvent(s, e->join_ev, 0));
   TRY(head_locked(e, B, h_thr ? d_thr : nullptr, nullptr, d_logits, d_probs, d_vec, s));
   CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_vector, d_vec, (size_t)B * e->n_cls, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(e->slot_done[slot], s));
+  e->slot_busy[slot] = true;
+  return 0;
+}
+
+extern "C" int mmdx_forward_host_submit(mmdx_engine* e, int slot, const uint8_t* h_images, int B, int H, int W, int C,
+                                        const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt,
+                                        const int32_t* h_cu, int T, int max_len, const float* h_thr, float* h_logits,
+                                        float* h_probs, uint8_t* h_vector, void* stream) {
+  REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
+  REQUIRE(slot == 0 || slot == 1, "request slot must be 0 or 1");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  return forward_host_submit_locked(e, slot, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits,
+                                    h_probs, h_vector, (cudaStream_t)stream);
+}
+
+extern "C" int mmdx_forward_host_wait(mmdx_engine* e, int slot) {
+  REQUIRE(e, "null engine");
+  REQUIRE(slot == 0 || slot == 1, "request slot must be 0 or 1");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  if (!e->slot_busy[slot]) return 0;
+  CK(cudaEventSynchronize(e->slot_done[slot]));
+  e->slot_busy[slot] = false;
+  return 0;
+}
+
+extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C,
+                                 const int32_t* h_ids, const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu,
+                                 int T, int max_len, const float* h_thr, float* h_logits, float* h_probs,
+                                 uint8_t* h_vector, void* stream) {
+  REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  TRY(forward_host_submit_locked(e, 0, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits, h_probs,
+                                 h_vector, (cudaStream_t)stream));
+  CK(cudaEventSynchronize(e->slot_done[0]));
+  e->slot_busy[0] = false;
   return 0;
 }
 

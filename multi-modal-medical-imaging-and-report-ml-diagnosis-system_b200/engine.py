@@ -161,6 +161,19 @@ class Engine:
                                       _stream()))
         return logits, probs, vec
 
+    def forward_host_submit(self, slot, images_u8, ids, pos, tt, cu, max_len, out, thresholds=None):
+        """Pipelined form of forward_host for throughput serving: enqueue request `slot` (0/1) and return at once;
+        `out` = (logits, probs, vector) pinned host tensors that forward_host_wait(slot) fills.  With two slots in
+        flight the H2D copy of one request runs under the kernels of the other."""
+        B, H, W, Cc = images_u8.shape
+        logits, probs, vec = out
+        check(lib().mmdx_forward_host_submit(self._h, int(slot), _ptr(images_u8), B, H, W, Cc, _ptr(ids), _ptr(pos), _ptr(tt),
+                                             _ptr(cu), ids.numel(), int(max_len), _ptr(thresholds), _ptr(logits), _ptr(probs),
+                                             _ptr(vec), _stream()))
+
+    def forward_host_wait(self, slot):
+        check(lib().mmdx_forward_host_wait(self._h, int(slot)))
+
 
 class RawHandle:
     """An engine handle without weights: enough for the single-kernel entry points (`mmdx_op_*`)."""

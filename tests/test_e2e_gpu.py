@@ -107,6 +107,32 @@ def test_batch_vs_oracle_high_res_and_mixed_sizes(bundle, eng):
         assert np.array_equal(np.array(r["disease_vector"])[decided], ref["vector"][i].numpy()[decided])
 
 
+def test_pipelined_host_requests_match_synchronous_call(eng):
+    """mmdx_forward_host_submit / _wait with two requests in flight (different batches, sizes and lengths, slots
+    reused) return exactly what the synchronous mmdx_forward_host returns for each request."""
+    reqs = []
+    for k, (B, L) in enumerate([(16, 128), (5, 96), (16, 128), (9, 64), (3, 128)]):
+        imgs = synth.synth_images(B, 224, seed=300 + k)
+        ids, mask = synth.synth_token_ids(B, L, seed=400 + k, ragged=True)
+        pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+        host = [torch.from_numpy(x).pin_memory() for x in (np.ascontiguousarray(imgs), pi, pp, pt, cu)]
+        ref = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen)
+        out = (torch.full((B, eng.n_cls), float("nan")).pin_memory(), torch.full((B, eng.n_cls), float("nan")).pin_memory(),
+               torch.zeros(B, eng.n_cls, dtype=torch.uint8).pin_memory())
+        reqs.append((host, mlen, [r.clone() for r in ref], out))
+    for k, (host, mlen, ref, out) in enumerate(reqs):           # submit k while k-1 is still running
+        eng.forward_host_submit(k % 2, host[0], host[1], host[2], host[3], host[4], mlen, out)
+        if k >= 1:
+            eng.forward_host_wait((k - 1) % 2)
+            _, _, pref, pout = reqs[k - 1]
+            for a, b in zip(pref, pout):
+                assert torch.equal(a, b)
+    eng.forward_host_wait((len(reqs) - 1) % 2)
+    for a, b in zip(reqs[-1][2], reqs[-1][3]):
+        assert torch.equal(a, b)
+    eng.forward_host_wait(0); eng.forward_host_wait(1)           # waiting on an idle slot is a no-op
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image
