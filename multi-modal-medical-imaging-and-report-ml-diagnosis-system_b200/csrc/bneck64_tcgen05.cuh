@@ -21,8 +21,10 @@
 // per-thread global loads one chunk ahead: 35 % of all stall samples sat on those loads and the fused kernel was
 // slower than the three launches it replaces - profiles/r01_bneck64_v1_full.md.)
 //
-// Roles (352 threads): warp 0 = TMA producer (weights, halos), warp 1 = TMEM allocator + MMA issue (leader CTA only),
-// warps 2-9 = epilogue in two groups (column halves) x four TMEM lane quarters, thread = pixel; warp 10 = y ring: stores
+// Roles (608 threads): warp 0 = TMA producer (weights, halos), warp 1 = TMEM allocator + MMA issue (leader CTA only),
+// warps 2-17 = epilogue in four groups (16-column quarters of every 64-column chunk) x four TMEM lane quarters, thread =
+// pixel - four epilogue warps per SM sub-partition, because a tile's epilogue work is a chain of latencies (tcgen05.ld,
+// shared-memory round trips, proxy fences) rather than issue-bound; warp 18 = y ring: stores
 // each finished chunk and refills its slot with the next tile's shortcut, so the epilogue warps never wait for each
 // other or for a TMA instruction (they only arrive on mbarriers).
 // MMA issue order per tile i:   GEMM3(i), GEMM2(i+1), GEMM1'(i) chunk by chunk as the epilogue delivers y.
@@ -37,7 +39,9 @@
 
 namespace mmdx {
 
-constexpr int B64_THREADS = 352;
+constexpr int B64_EW = 16;                                         // epilogue warps: 4 column groups x 4 TMEM lane quarters
+constexpr int B64_CW = 64 / (B64_EW / 4);                          // columns of a 64-column chunk per thread
+constexpr int B64_THREADS = 64 + 32 * B64_EW + 32;
 constexpr int B64_HALO_W = 16, B64_HALO_H = 18;
 constexpr int B64_HALO_BYTES = B64_HALO_W * B64_HALO_H * 128;     // 36 KB
 constexpr int B64_W2_TAP_BYTES = 32 * 128;                         // this CTA's 32 output rows of one tap
@@ -115,13 +119,13 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
   uint64_t* halo_full = bars + 1;         // [2] leader: both CTAs' halo bytes
   uint64_t* halo_empty = bars + 3;        // [2] own: GEMM2 has finished reading the buffer (multicast commit)
   uint64_t* d2_full = bars + 5;           // [2] own
-  uint64_t* t2_full = bars + 7;           // leader: 16 epilogue warps (both CTAs) have written their t2 rows
+  uint64_t* t2_full = bars + 7;           // leader: the epilogue warps of both CTAs have written their t2 rows
   uint64_t* d3_full = bars + 8;           // own
   uint64_t* d1_full = bars + 9;           // own
   uint64_t* res_full = bars + 10;         // [4] own: the shortcut chunk has landed in slot j
-  uint64_t* y_full = bars + 14;           // [4] leader: 16 epilogue warps have written y chunk j
+  uint64_t* y_full = bars + 14;           // [4] leader: the epilogue warps of both CTAs have written y chunk j
   uint64_t* y_free = bars + 18;           // [4] own: GEMM1' has finished reading slot j
-  uint64_t* y_ready = bars + 22;          // [4] own: the eight epilogue warps of this CTA have written y chunk j
+  uint64_t* y_ready = bars + 22;          // [4] own: the epilogue warps of this CTA have written y chunk j
   uint64_t* xs_full = bars + 26;          // leader: both CTAs' block-input tiles have landed (DS)
   uint64_t* xs_empty = bars + 27;         // own: GEMM3 has finished reading the tile (DS)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     mbar_init(w_bar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); mbar_init(&d2_full[i], 1); }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 16); mbar_init(&y_free[i], 1); mbar_init(&y_ready[i], 8);
+      mbar_init(&res_full[i], 1); mbar_init(&y_full[i], 2 * B64_EW); mbar_init(&y_free[i], 1); mbar_init(&y_ready[i], B64_EW);
     }
-    mbar_init(t2_full, 16); mbar_init(d3_full, 1); mbar_init(d1_full, 1);
+    mbar_init(t2_full, 2 * B64_EW); mbar_init(d3_full, 1); mbar_init(d1_full, 1);
     mbar_init(xs_full, 1); mbar_init(xs_empty, 1);
     fence_barrier_init();
   }
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2 + B64_EW) {
     if (lane == 0) {
       // ================= y ring: store finished chunks, refill the slots with the next tile's shortcut =================
       auto load_res = [&](int n, int j) {              // shortcut chunk j of local tile n -> slot j
@@ -303,9 +307,10 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       tma_store_wait_all<0>();
     }
   } else {
-    // ================= epilogue warps 2..9: thread = (pixel, column half) =================
+    // ================= epilogue warps: thread = (pixel, 16-column group) =================
+    constexpr int CW = B64_CW;                         // 16 columns = two 16-byte chunks of a 128-byte row
     const int e = warp - 2;
-    const int g = e >> 2;                              // column half
+    const int g = e >> 2;                              // column group
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;                       // TMEM lane = pixel of the tile: row m >> 3, column m & 7
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -313,18 +318,18 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     const uint32_t y_full_r = mapa_rank(smem_u32(&y_full[0]), 0);
     const int sw = m & 7;                              // 128-byte swizzle: 16-byte chunk index ^= row & 7
 
-    // 32 accumulator columns + bias -> ReLU -> bf16, 16 bytes (8 channels) at a time into `row` (swizzled chunk g*4+c)
-    auto bias_relu_store = [&](const uint32_t (&v)[32], const float* bias, uint8_t* row) {
+    // 16 accumulator columns + bias -> ReLU -> bf16, 16 bytes (8 channels) at a time into `row` (swizzled chunks g*2, g*2+1)
+    auto bias_relu_store = [&](const uint32_t (&v)[16], const float* bias, uint8_t* row) {
       const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
         float x[8];
         unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])), pack_f32x2(ba.x, ba.y)), x[0], x[1]);
         unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])), pack_f32x2(ba.z, ba.w)), x[2], x[3]);
         unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])), pack_f32x2(bb.x, bb.y)), x[4], x[5]);
         unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])), pack_f32x2(bb.z, bb.w)), x[6], x[7]);
-        *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
+        *reinterpret_cast<uint4*>(row + (((g * 2 + c) ^ sw) << 4)) =
             make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
       }
     };
@@ -332,10 +337,10 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       const int buf = n & 1;
       mbar_wait(&d2_full[buf], (n >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(lane_base + buf * 64 + g * 32, v);
+      uint32_t v[16];
+      tmem_ld_32x16(lane_base + buf * 64 + g * CW, v);
       tmem_ld_wait();
-      bias_relu_store(v, b2s + g * 32, t2s + m * 128);
+      bias_relu_store(v, b2s + g * CW, t2s + m * 128);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -348,26 +353,26 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       //      flight while this one is processed
       mbar_wait(d3_full, n & 1);
       tc_fence_after();
-      uint32_t v[2][32];
-      tmem_ld_32x32(lane_base + B64_COL_D3 + g * 32, v[0]);
+      uint32_t v[2][16];
+      tmem_ld_32x16(lane_base + B64_COL_D3 + g * CW, v[0]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         mbar_wait(&res_full[j], n & 1);
         uint8_t* row = ys + j * B64_Y_BYTES + m * 128;
-        uint4 rv[4];
+        uint4 rv[2];
         if constexpr (!DS) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 4 + c) ^ sw) << 4));
+          for (int c = 0; c < 2; ++c) rv[c] = *reinterpret_cast<const uint4*>(row + (((g * 2 + c) ^ sw) << 4));
         }
         tmem_ld_wait();
-        if (j < 3) tmem_ld_32x32(lane_base + B64_COL_D3 + (j + 1) * 64 + g * 32, v[(j + 1) & 1]);
-        const uint32_t (&a)[32] = v[j & 1];
+        if (j < 3) tmem_ld_32x16(lane_base + B64_COL_D3 + (j + 1) * 64 + g * CW, v[(j + 1) & 1]);
+        const uint32_t (&a)[16] = v[j & 1];
         if constexpr (DS) {
-          bias_relu_store(a, b3s + j * 64 + g * 32, row);
+          bias_relu_store(a, b3s + j * 64 + g * CW, row);
         } else {
-          const float4* b4 = reinterpret_cast<const float4*>(b3s + j * 64 + g * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(b3s + j * 64 + g * CW);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
             const uint32_t* ru = &rv[c].x;
             float x[8];
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
             unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])), pack_f32x2(ba.z, ba.w)), bf16x2_to_f32x2(ru[1])), x[2], x[3]);
             unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_f32x2(bb.x, bb.y)), bf16x2_to_f32x2(ru[2])), x[4], x[5]);
             unpack_f32x2(add_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])), pack_f32x2(bb.z, bb.w)), bf16x2_to_f32x2(ru[3])), x[6], x[7]);
-            *reinterpret_cast<uint4*>(row + (((g * 4 + c) ^ sw) << 4)) =
+            *reinterpret_cast<uint4*>(row + (((g * 2 + c) ^ sw) << 4)) =
                 make_uint4(pack_bf16_relu(x[0], x[1]), pack_bf16_relu(x[2], x[3]), pack_bf16_relu(x[4], x[5]), pack_bf16_relu(x[6], x[7]));
           }
         }
@@ -401,15 +406,15 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
         tc_fence_after();
 #pragma unroll
         for (int h2 = 0; h2 < C1 / 64; ++h2) {
-          const int col0 = g * (C1 / 2) + h2 * 32;
-          uint32_t v1[32];
-          tmem_ld_32x32(lane_base + B64_COL_D1 + col0, v1);
+          const int col0 = g * (C1 / 4) + h2 * CW;
+          uint32_t v1[16];
+          tmem_ld_32x16(lane_base + B64_COL_D1 + col0, v1);
           tmem_ld_wait();
           if (pix_ok) {
             const float4* b4 = reinterpret_cast<const float4*>(b1s + col0);
             uint4* dst = reinterpret_cast<uint4*>(p.t1n + pix * C1 + col0);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
               const float4 ba = b4[2 * c], bb = b4[2 * c + 1];
               dst[c] = make_uint4(pack_bf16_relu(__uint_as_float(v1[8 * c]) + ba.x, __uint_as_float(v1[8 * c + 1]) + ba.y),
                                   pack_bf16_relu(__uint_as_float(v1[8 * c + 2]) + ba.z, __uint_as_float(v1[8 * c + 3]) + ba.w),
