@@ -41,6 +41,7 @@ namespace mmdx {
 
 constexpr int B64_EW = 16;                                         // epilogue warps: 4 column groups x 4 TMEM lane quarters
 constexpr int B64_CW = 64 / (B64_EW / 4);                          // columns of a 64-column chunk per thread
+static_assert(B64_CW == 16, "the epilogue is written for 16 columns per thread (tcgen05.ld 32x32b.x16)");
 constexpr int B64_THREADS = 64 + 32 * B64_EW + 32;
 constexpr int B64_HALO_W = 16, B64_HALO_H = 18;
 constexpr int B64_HALO_BYTES = B64_HALO_W * B64_HALO_H * 128;     // 36 KB
