@@ -185,6 +185,7 @@ struct mmdx_engine {
   bool finalized = false;
   // dims
   int d_img = 0, d_txt = 0, d_fuse = 0, n_cls = 0, hidden = 0, n_layers = 0, ffn = 0, feat_dim = 2048;
+  int vocab = 0, max_pos = 0;     // rows of the word / position embedding tables
   // weights (one arena)
   DevBuf warena; size_t wused = 0;
   ConvW stem; bf16* stem_w2 = nullptr;   // stem weights in the stem kernel's resident layout
@@ -1031,6 +1032,8 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     TRY(pack_table(e, eb + "token_type_embeddings.weight", &e->ttab));
     TRY(pack_ln(e, eb + "LayerNorm", &e->emb_ln));
     e->hidden = (int)get(e, eb + "word_embeddings.weight")->shape[1];
+    e->vocab = (int)get(e, eb + "word_embeddings.weight")->shape[0];
+    e->max_pos = (int)get(e, eb + "position_embeddings.weight")->shape[0];
     e->layers.clear();
     for (int l = 0;; ++l) {
       const std::string p = "text.encoder.encoder.layer." + std::to_string(l) + ".";
@@ -1101,7 +1104,7 @@ struct PackHeader {
   uint64_t arena_bytes;
   uint64_t checksum;        // FNV-1a of table + arena
 };
-static const uint32_t kPackVersion = 2;
+static const uint32_t kPackVersion = 3;
 
 struct PackWalker {
   bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
@@ -1126,7 +1129,7 @@ struct PackWalker {
 // one traversal for both directions: every field mmdx_finalize_weights sets
 static void walk_weights(mmdx_engine* e, PackWalker& w) {
   w.i(e->d_img); w.i(e->d_txt); w.i(e->d_fuse); w.i(e->n_cls); w.i(e->hidden); w.i(e->n_layers); w.i(e->ffn); w.i(e->feat_dim);
-  w.i(e->cfg.n_heads);
+  w.i(e->cfg.n_heads); w.i(e->vocab); w.i(e->max_pos);
   w.conv(e->stem); w.p(e->stem_w2);
   int nb = (int)e->blocks.size();
   w.i(nb);
@@ -1623,6 +1626,8 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
                               cudaStream_t s) {
   REQUIRE(e->finalized, "weights not finalized");
   REQUIRE(B > 0 && T > 0 && max_len > 0, "bad token batch");
+  REQUIRE(max_len <= e->max_pos, "sequence longer than the position embedding table (BERT: 512)");
+  REQUIRE((long long)T <= (long long)B * max_len, "more packed tokens than B * max_len");
   TRY(ensure_head_buffers(e, B));
   TextPlan* pl;
   TextBufs tb;

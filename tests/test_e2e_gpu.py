@@ -133,6 +133,44 @@ def test_pipelined_host_requests_match_synchronous_call(eng):
     eng.forward_host_wait(0); eng.forward_host_wait(1)           # waiting on an idle slot is a no-op
 
 
+def test_edge_cases_and_error_behaviour(bundle, eng):
+    """Boundaries of the C ABI: one study, one-token reports, the longest sequence BERT has positions for (512),
+    grayscale input, a small non-square image; over-long sequences and empty batches fail with a clean error (no
+    crash, engine still usable afterwards)."""
+    from mmdx_b200._lib import MmdxError
+    # B = 1, report of a single [CLS] token next to a full-length one (L = 512: the flash attention variant)
+    imgs = synth.synth_images(2, 224, seed=5)
+    ids, mask = synth.synth_token_ids(2, 512, seed=6, ragged=False)
+    mask[0, 1:] = 0
+    out = _run_stages(eng, imgs, ids, mask)
+    ref = R.inference_batch(bundle, list(imgs), torch.from_numpy(ids), torch.from_numpy(mask))
+    assert np.abs(out["probs"] - ref["probs"].numpy()).max() < PROB_TOL
+    one = _run_stages(eng, imgs[:1], ids[:1], mask[:1])
+    assert np.abs(one["probs"] - out["probs"][:1]).max() < 2e-3          # batch independence down to B = 1
+    # grayscale (1-channel) input == the same image replicated to RGB (T.Lambda, training_pipeline.py:116)
+    gray = imgs[:, :, :, :1].copy()
+    rgb = np.repeat(gray, 3, axis=-1)
+    a = _run_stages(eng, gray, ids[:, :64], mask[:, :64])
+    b = _run_stages(eng, rgb, ids[:, :64], mask[:, :64])
+    assert np.array_equal(a["probs"], b["probs"])
+    # errors
+    # a small, non-square image is up-sampled like any other (Resize(256) + CenterCrop(224)): compare with the oracle
+    small = synth.synth_images(1, 100, seed=9)[:, :90]
+    so = _run_stages(eng, small, ids[:1, :64], mask[:1, :64])
+    sr = R.inference_batch(bundle, list(small), torch.from_numpy(ids[:1, :64]), torch.from_numpy(mask[:1, :64]))
+    assert np.abs(so["probs"] - sr["probs"].numpy()).max() < PROB_TOL
+    pi, pp, pt, cu, _ = engine.pack_tokens(np.ones((1, 600), np.int64), np.ones((1, 600), np.int64))
+    t = [torch.from_numpy(x).cuda() for x in (pi, pp, pt, cu)]
+    with pytest.raises(MmdxError):
+        eng.text_encode(t[0], t[1], t[2], t[3], 600)
+    with pytest.raises((MmdxError, ValueError, AssertionError, RuntimeError)):
+        eng.image_encode(torch.zeros((0, 224, 224, 3), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        ip.inference_batch(bundle, [imgs[0]], ["a", "b"], device="cuda")
+    again = _run_stages(eng, imgs[:1], ids[:1], mask[:1])              # the engine survived the failed calls
+    assert np.array_equal(again["probs"], one["probs"])
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image
