@@ -58,8 +58,9 @@ int mmdx_finalize_weights(mmdx_engine* e);
 int mmdx_save_packed(mmdx_engine* e, const char* path);
 int mmdx_load_packed(mmdx_engine* e, const char* path);
 int mmdx_num_sms(mmdx_engine* e);
-/* dims read from the loaded weights: d_img, d_txt, d_fuse_hidden, n_disease, hidden, n_layers */
-int mmdx_dims(mmdx_engine* e, int32_t out[6]);
+/* dims read from the loaded weights: d_img, d_txt, d_fuse_hidden, n_disease, hidden, n_layers, width of cond_proj
+ * (n_cond * h_dec; 0 if the bundle has none), rows of the position table (longest sequence) */
+int mmdx_dims(mmdx_engine* e, int32_t out[8]);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* image_transfom_into_tensor (training_pipeline.py:112-119) + ImageEncoderCNN.forward (:306-311).
@@ -83,6 +84,11 @@ int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, i
 int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
                       const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu_seqlens, int T, int max_len,
                       const float* h_thresholds, float* h_logits, float* h_probs, uint8_t* h_vector, void* stream);
+/* Report-generation conditioning (first step): cond = GELU(z_fuse * Wc^T + bc), fp32
+ * [B, n_cond * h_dec], for the batch mmdx_head (or mmdx_forward*) has just processed - FusionTransformerModel.
+ * _make_encoder_outputs (training_pipeline.py:574-578), i.e. the "encoder output" the T5 decoder cross-attends to.
+ * Fails if the bundle carried no fusion.cond_proj.0 weights. */
+int mmdx_cond_tokens(mmdx_engine* e, int B, float* d_cond, void* stream);
 /* The same call as a two-deep pipeline for throughput serving: _submit enqueues request `slot` (0 or 1: H2D of its inputs,
  * forward, D2H of its results) and returns; _wait blocks until that slot's results are in the host buffers.  With two
  * requests in flight the image batch of request k+1 crosses PCIe under the kernels of request k.  Host buffers must stay

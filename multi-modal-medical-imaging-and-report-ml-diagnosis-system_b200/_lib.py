@@ -53,6 +53,7 @@ SIGNATURES = {
     "mmdx_image_encode": [_p, _p, _i, _i, _i, _i, _p, _p, _p],
     "mmdx_text_encode": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p],
     "mmdx_head": [_p, _i, _p, _p, _p, _p, _p, _p],
+    "mmdx_cond_tokens": [_p, _i, _p, _p],
     "mmdx_forward": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host_submit": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],

@@ -192,6 +192,7 @@ struct mmdx_engine {
   std::vector<Bottleneck> blocks;
   bf16 *word = nullptr, *ptab = nullptr, *ttab = nullptr; LnW emb_ln; std::vector<BertLayerW> layers;
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
+  LinW cond;             // optional: fusion.cond_proj.0 (z_fuse -> the T5 decoder's conditioning tokens)
   cudaStream_t copy_stream = nullptr;   // H2D of the image batch overlaps the text branch (mmdx_forward_host)
   cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
   // The text branch runs on its own stream next to the image branch (they only meet at the fusion head): both are
@@ -221,6 +222,7 @@ struct mmdx_engine {
   // head-side persistent buffers (capacity B)
   int head_cap = 0;
   bf16* feats_bf = nullptr; bf16* pooled_bf = nullptr; bf16* zcat = nullptr; float* fuse_h = nullptr;
+  bf16* zfuse_bf = nullptr;   // bf16 copy of z_fuse (A operand of cond_proj)
   float* thr_default = nullptr;
   // attention: tensor map over the packed qkv buffer, rebuilt when (pointer, T, hidden) changes
   const void* attn_qkv = nullptr; int attn_T = 0, attn_hidden = 0; CUtensorMap attn_tm{};
@@ -1077,6 +1079,10 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
   TRY(pack_ln(e, "fusion.fusion_mlp.3", &e->fuse_ln));
   e->d_fuse = e->fuse.nout;
   REQUIRE(e->fuse.nin == e->d_img + e->d_txt, "fusion_mlp.0 input width != d_img + d_txt");
+  if (get(e, "fusion.cond_proj.0.weight")) {     // optional: report-generation conditioning (training_pipeline.py:553-558)
+    TRY(pack_linear(e, "fusion.cond_proj.0", &e->cond));
+    REQUIRE(e->cond.nin == e->d_fuse && e->cond.nout % 64 == 0, "cond_proj.0 shape");
+  }
   {
     GET(w, "fusion.disease_head.weight"); GET(b, "fusion.disease_head.bias");
     e->n_cls = (int)w->shape[0];
@@ -1104,7 +1110,7 @@ struct PackHeader {
   uint64_t arena_bytes;
   uint64_t checksum;        // FNV-1a of table + arena
 };
-static const uint32_t kPackVersion = 3;
+static const uint32_t kPackVersion = 4;
 
 struct PackWalker {
   bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
@@ -1143,7 +1149,7 @@ static void walk_weights(mmdx_engine* e, PackWalker& w) {
   w.i(nl);
   if (w.loading) e->layers.assign(nl < 0 || nl > 64 ? 0 : nl, BertLayerW());
   for (BertLayerW& L : e->layers) { w.lin(L.qkv); w.lin(L.ao); w.lin(L.ff1); w.lin(L.ff2); w.ln(L.ln1); w.ln(L.ln2); }
-  w.lin(e->proj_txt); w.lin(e->fuse); w.ln(e->fuse_ln);
+  w.lin(e->proj_txt); w.lin(e->fuse); w.ln(e->fuse_ln); w.lin(e->cond);
   w.p(e->head_w); w.p(e->head_b); w.p(e->thr_default);
 }
 static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -1211,9 +1217,10 @@ extern "C" int mmdx_load_packed(mmdx_engine* e, const char* path) {
   return 0;
 }
 
-extern "C" int mmdx_dims(mmdx_engine* e, int32_t out[6]) {
+extern "C" int mmdx_dims(mmdx_engine* e, int32_t out[8]) {
   REQUIRE(e && e->finalized, "weights not finalized");
   out[0] = e->d_img; out[1] = e->d_txt; out[2] = e->d_fuse; out[3] = e->n_cls; out[4] = e->hidden; out[5] = e->n_layers;
+  out[6] = e->cond.w ? e->cond.nout : 0; out[7] = e->max_pos;
   return 0;
 }
 
@@ -1426,13 +1433,15 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
 static int ensure_head_buffers(mmdx_engine* e, int B) {
   if (B <= e->head_cap) return 0;
   const size_t f = al((size_t)B * e->feat_dim * 2), p = al((size_t)B * e->hidden * 2),
-               z = al((size_t)B * (e->d_img + e->d_txt) * 2), h = al((size_t)B * e->d_fuse * 4);
-  TRY(e->head_ws.ensure(f + p + z + h));
+               z = al((size_t)B * (e->d_img + e->d_txt) * 2), h = al((size_t)B * e->d_fuse * 4),
+               zb = al((size_t)B * e->d_fuse * 2);
+  TRY(e->head_ws.ensure(f + p + z + h + zb));
   char* b = static_cast<char*>(e->head_ws.p);
   e->feats_bf = reinterpret_cast<bf16*>(b);
   e->pooled_bf = reinterpret_cast<bf16*>(b + f);
   e->zcat = reinterpret_cast<bf16*>(b + f + p);
   e->fuse_h = reinterpret_cast<float*>(b + f + p + z);
+  e->zfuse_bf = reinterpret_cast<bf16*>(b + f + p + z + h);
   e->head_cap = B;
   e->head_plans.clear();
   return 0;
@@ -1677,7 +1686,7 @@ static int head_locked(mmdx_engine* e, int B, const float* d_thr, float* d_z_fus
   CK(launch_k(head_tail_kernel, dim3(B), dim3(256), e->d_fuse * sizeof(float), s, 1, e->fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f,
                                                              e->head_w, e->head_b, e->n_cls,
                                                              d_thr ? d_thr : e->thr_default, d_z_fuse, d_logits, d_probs,
-                                                             d_vector));
+                                                             d_vector, e->cond.w ? e->zfuse_bf : nullptr));
   CK(cudaGetLastError());
   return 0;
 }
@@ -1703,6 +1712,20 @@ extern "C" int mmdx_head(mmdx_engine* e, int B, const float* d_thr, float* d_z_f
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
   return head_locked(e, B, d_thr, d_z_fuse, d_logits, d_probs, d_vector, (cudaStream_t)stream);
+}
+// FusionTransformerModel._make_encoder_outputs (training_pipeline.py:574-578) for the batch mmdx_head has just processed:
+// cond = GELU(z_fuse * Wc^T + bc), fp32 [B, n_cond * h_dec] - the "encoder output" the T5 decoder is conditioned on.
+extern "C" int mmdx_cond_tokens(mmdx_engine* e, int B, float* d_cond, void* stream) {
+  REQUIRE(e && d_cond, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  REQUIRE(e->finalized && e->cond.w, "the bundle has no cond_proj weights");
+  REQUIRE(B > 0 && B <= e->head_cap, "cond_tokens called before mmdx_head");
+  e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_HEAD;
+  GemmLaunch g;
+  TRY(build_gemm(e, g, e->zfuse_bf, e->d_fuse, e->cond.w, B, e->cond.nout, e->d_fuse, 0));
+  TRY(fill_epilogue(e, g, e->cond.bias, nullptr, 0, d_cond, e->cond.nout, ACT_GELU, 1));
+  return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
                             const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu, int T, int max_len,
@@ -2003,7 +2026,7 @@ extern "C" int mmdx_op_head_tail(mmdx_engine* e, const float* d_hidden, int B, i
   REQUIRE(e && D <= 8192, "head width");
   ProfScope _ps(e);
   CK(launch_k(head_tail_kernel, dim3(B), dim3(256), D * sizeof(float), (cudaStream_t)stream, 1, d_hidden, D, d_ln_g, d_ln_b, eps, d_w, d_b, n_cls,
-                                                                        d_thr, d_z_fuse, d_logits, d_probs, d_vector));
+                                                                        d_thr, d_z_fuse, d_logits, d_probs, d_vector, nullptr));
   CK(cudaGetLastError());
   return 0;
 }

@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict_
                                                         const float* __restrict__ b_head, int n_cls,
                                                         const float* __restrict__ thresholds,
                                                         float* __restrict__ z_fuse, float* __restrict__ logits,
-                                                        float* __restrict__ probs, uint8_t* __restrict__ vec) {
+                                                        float* __restrict__ probs, uint8_t* __restrict__ vec,
+                                                        __nv_bfloat16* __restrict__ z_fuse_bf) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sz[];        // D floats
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict_
     const float z = (sz[i] - mean) * rstd * ln_g[i] + ln_b[i];
     sz[i] = z;
     if (z_fuse != nullptr) z_fuse[static_cast<size_t>(b) * D + i] = z;
+    if (z_fuse_bf != nullptr) z_fuse_bf[static_cast<size_t>(b) * D + i] = __float2bfloat16(z);   // A operand of cond_proj
   }
   __syncthreads();
   for (int c = warp; c < n_cls; c += 8) {

@@ -60,7 +60,7 @@ class Engine:
                 raise ValueError("pass either state dicts or a packed weight file, not both")
             check(lib().mmdx_load_packed(self._h, os.fsencode(packed)))
         else:
-            skip = ("num_batches_tracked", "report_model.", "classifier.", "pooler.", "position_ids", "cond_proj.")
+            skip = ("num_batches_tracked", "report_model.", "classifier.", "pooler.", "position_ids")
             for prefix, sd in states.items():
                 for k, v in sd.items():
                     if any(s in k for s in skip):
@@ -70,9 +70,9 @@ class Engine:
                     check(lib().mmdx_load_tensor(self._h, f"{prefix}.{k}".encode(), C.c_void_p(t.data_ptr()), t.dim(),
                                                  shape))
             check(lib().mmdx_finalize_weights(self._h))
-        d = (C.c_int32 * 6)()
+        d = (C.c_int32 * 8)()
         check(lib().mmdx_dims(self._h, d))
-        self.d_img, self.d_txt, self.d_fuse, self.n_cls, self.hidden, self.n_layers = list(d)
+        self.d_img, self.d_txt, self.d_fuse, self.n_cls, self.hidden, self.n_layers, self.cond_width, self.max_pos = list(d)
         self.feat_dim = 2048
 
     @classmethod
@@ -135,6 +135,16 @@ class Engine:
         vec = torch.empty(B, self.n_cls, dtype=torch.uint8, device=dev)
         check(lib().mmdx_head(self._h, B, _ptr(thresholds), _ptr(z_fuse), _ptr(logits), _ptr(probs), _ptr(vec), _stream()))
         return z_fuse, logits, probs, vec
+
+    def cond_tokens(self, B, n_cond: int | None = None):
+        """GELU(cond_proj(z_fuse)) for the batch head() has just processed: fp32 [B, n_cond*h_dec], or
+        [B, n_cond, h_dec] when n_cond is given - the conditioning tokens of the report decoder
+        (training_pipeline.py:574-578)."""
+        if not self.cond_width:
+            raise MmdxError("the bundle has no cond_proj weights")
+        out = torch.empty(B, self.cond_width, dtype=torch.float32, device=self._dev())
+        check(lib().mmdx_cond_tokens(self._h, B, _ptr(out), _stream()))
+        return out if n_cond is None else out.view(B, n_cond, -1)
 
     def forward(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None):
         """Whole path, device in / device out: (logits, probs, vector)."""

@@ -144,6 +144,10 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
         groups.setdefault(a.shape, []).append(i)
     want_report = gen_kwargs is not False and model_bundle.get("fusion_model") is not None \
         and model_bundle.get("t5_tok") is not None
+    fusion_mod = model_bundle.get("fusion_model")
+    use_cond = bool(want_report and eng.cond_width and hasattr(fusion_mod, "report_model")
+                    and getattr(fusion_mod, "n_cond", 0) * getattr(fusion_mod, "h_dec", 0) == eng.cond_width)
+    cond_out = np.zeros((B, eng.cond_width), np.float32) if use_cond else None
     with torch.cuda.device(dev):
         thr_d = thr.to(dev)
         for shape, idxs in groups.items():
@@ -156,8 +160,11 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
             probs_out[idxs] = probs.cpu().numpy()
             vec_out[idxs] = vec.cpu().numpy()
             if want_report:
-                z_img_out[idxs] = z_img.cpu().numpy()
-                z_txt_out[idxs] = z_txt.cpu().numpy()
+                if use_cond:     # cond_proj on the engine: the decoder only needs these tokens
+                    cond_out[idxs] = eng.cond_tokens(len(idxs)).cpu().numpy()
+                else:
+                    z_img_out[idxs] = z_img.cpu().numpy()
+                    z_txt_out[idxs] = z_txt.cpu().numpy()
 
     reports = [""] * B
     if want_report:
@@ -169,7 +176,16 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
                               pad_token_id=t5_tok.pad_token_id)
         if gen_kwargs:
             gen_attributes.update(gen_kwargs)
-        gen_ids = fusion.generate(torch.from_numpy(z_img_out).to(dev), torch.from_numpy(z_txt_out).to(dev), **gen_attributes)
+        if use_cond:
+            # FusionTransformerModel.generate (training_pipeline.py:613-618) minus the two steps the engine has already
+            # done (fusion_mlp, cond_proj): the T5 decoder is driven with the conditioning tokens directly
+            from transformers.modeling_outputs import BaseModelOutput
+            cond = torch.from_numpy(cond_out).to(dev).view(B, fusion.n_cond, fusion.h_dec)
+            cond = cond.to(next(fusion.report_model.parameters()).dtype)
+            gen_ids = fusion.report_model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **gen_attributes)
+        else:
+            gen_ids = fusion.generate(torch.from_numpy(z_img_out).to(dev), torch.from_numpy(z_txt_out).to(dev),
+                                      **gen_attributes)
         reports = t5_tok.batch_decode(gen_ids, skip_special_tokens=True)
 
     return [{

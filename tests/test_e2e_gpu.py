@@ -171,6 +171,66 @@ def test_edge_cases_and_error_behaviour(bundle, eng):
     assert np.array_equal(again["probs"], one["probs"])
 
 
+def test_report_conditioning_tokens_and_generation(bundle, eng, g1):
+    """SURVEY.md 8f N1, first step: cond_proj runs on the engine (GELU(z_fuse Wc^T + bc), conditioning tokens of the T5
+    decoder, training_pipeline.py:574-578) and inference() drives the bundle's own T5 with them on the GPU.  Stand-in
+    fusion module: the reference class cannot be imported on the GPU box; same attributes, T5-small from its config."""
+    from PIL import Image
+    from transformers import T5Config, T5ForConditionalGeneration
+    assert eng.cond_width == 4 * 512
+    imgs = synth.synth_images(6, 224, seed=21)
+    ids, mask = synth.synth_token_ids(6, 96, seed=22, ragged=True)
+    out = _run_stages(eng, imgs, ids, mask)
+    cond = eng.cond_tokens(6).cpu()
+    fs = bundle["fusion_state"]
+    w, b = fs["cond_proj.0.weight"].float(), fs["cond_proj.0.bias"].float()
+    ref = torch.nn.functional.gelu(torch.from_numpy(out["z_fuse"]) @ w.t() + b)
+    assert float((cond - ref).abs().max()) < 3e-2 * float(ref.abs().max())
+
+    class Fusion(torch.nn.Module):                      # attributes inference_batch relies on
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.n_cond, self.h_dec = 4, 512
+            self.report_model = T5ForConditionalGeneration(T5Config(decoder_start_token_id=0)).eval()
+            self.calls = 0
+
+        def state_dict(self, *a, **k):                  # the real module's state_dict minus report_model.* (skipped anyway)
+            return fs
+
+        def generate(self, z_img, z_txt, **kw):         # the reference's own path: must NOT be taken when cond tokens exist
+            self.calls += 1
+            raise AssertionError("fusion.generate called although the engine provides the conditioning tokens")
+
+    class Tok:
+        eos_token_id, pad_token_id = 1, 0
+
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return [" ".join(str(int(t)) for t in row) for row in ids]
+
+    b2 = dict(bundle)
+    b2["fusion_model"], b2["t5_tok"] = Fusion(), Tok()
+    pil = Image.fromarray(np.repeat(g1["gray"][0][..., None], 3, axis=-1))
+    gen = dict(max_new_tokens=6, min_new_tokens=6, num_beams=2)
+    res = ip.inference(b2, pil, str(g1["details"][0]), device="cuda", gen_kwargs=gen)
+    assert res["disease_vector"] == g1["vector"][0].tolist()
+    toks = res["report_text"].split()
+    assert len(toks) >= 6 and all(t.isdigit() for t in toks)
+    # the same decoder driven from fp32 torch conditioning tokens gives the same token ids for this study
+    fm = b2["fusion_model"].report_model
+    z = torch.from_numpy(_run_stages(ip.get_engine(b2, "cuda"), np.array(pil)[None], *_tok(b2, g1))["z_fuse"])
+    from transformers.modeling_outputs import BaseModelOutput
+    c_ref = torch.nn.functional.gelu(z @ w.t() + b).view(1, 4, 512).cuda()
+    ids_ref = fm.generate(encoder_outputs=BaseModelOutput(last_hidden_state=c_ref), eos_token_id=1, pad_token_id=0,
+                          no_repeat_ngram_size=3, length_penalty=1.1, early_stopping=True, **gen)
+    assert res["report_text"] == " ".join(str(int(t)) for t in ids_ref[0].cpu())
+
+
+def _tok(b, g1):
+    t = ip.tokenize(b, [str(g1["details"][0])], 96)
+    return np.asarray(t["input_ids"]), np.asarray(t["attention_mask"])
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image
