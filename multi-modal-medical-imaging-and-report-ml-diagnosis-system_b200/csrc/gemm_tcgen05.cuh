@@ -6,9 +6,9 @@
 //     Stride-2 convs read one of four "parity" views of the input (even/odd rows x even/odd cols).
 //   (The 7x7/2 stem has its own kernel, stem_tcgen05.cuh.)
 //
-// Roles (384 threads): warp 0 = TMA producer (A/B ring), warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 4..11 = epilogue in two groups of four (group g owns the 32-column chunks with
-// index = g mod 2; each warp reads its TMEM lane quarter).
+// Roles (640 threads): warp 0 = TMA producer (A/B ring), warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 4..19 = epilogue in two groups of eight (group g owns the 32-column chunks with
+// index = g mod 2; inside a group four warps - one per TMEM lane quarter - own each 16-column half).
 // Residual add (bottleneck shortcut, BERT skip connections) rides the MMA pipeline: after the main K loop
 // the producer streams the residual tile through the same smem ring as extra A blocks (128 rows x 64
 // columns) next to a 64x64 identity B block, and the issuer accumulates D[:, 64j:64j+64] += R_j * I
@@ -40,7 +40,8 @@ constexpr int kEpiCW = 32;                    // epilogue chunk width (columns):
 constexpr int kEpiGroups = 2;                 // epilogue groups (four warps each)
 constexpr int kIdentBytes = 64 * 64 * 2;      // resident 64x64 identity (B operand of the residual MMAs)
 constexpr int kEpiBufBytes = 128 * kEpiCW * 2;
-constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 16;                 // epilogue warps (two groups of eight)
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[4];
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8 * CG);        // epilogue warps of every CTA of the group
+      mbar_init(&tempty_bar[s], kEpiWarps * CG);        // epilogue warps of every CTA of the group
     }
     mbar_init(ident_bar, 1);
     fence_barrier_init();
@@ -384,12 +385,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue warps 4..11 =================
+    // ================= epilogue warps 4..19 =================
+    // Two groups of eight warps; group g owns the 32-column chunks with (c & 1) == g and, inside the group, each set
+    // of four warps (one per TMEM lane quarter) owns one 16-column half of the chunk.  Four epilogue warps per SM
+    // sub-partition: a chunk is a chain of latencies (tcgen05.ld, MUFU, shared-memory round trip, proxy fence), and with
+    // two warps per sub-partition the erf-GELU epilogue of FFN1 did not fit under the MMAs of the next tile.
+    constexpr int TW = kEpiCW / 2;          // columns per thread
     const int e = warp - 4;
-    const int g = e >> 2;                   // group: chunks c with (c & 1) == g
+    const int g = e >> 3;                   // group: chunks c with (c & 1) == g
+    const int hh = (e >> 2) & 1;            // column half of the chunk
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;            // row inside the 128-row tile
-    const bool issuer = (e & 3) == 0 && lane == 0;
+    const bool issuer = (e & 7) == 0 && lane == 0;
     // accumulator-empty barriers live in the leader CTA (its MMA thread waits on them)
     const uint32_t tempty0 = CG == 2 ? mapa_rank(smem_u32(&tempty_bar[0]), 0) : 0;
     auto release_acc = [&](int as) {
@@ -403,39 +410,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const TileCoord t = decode_tile(p, tile, rank);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * TW;
 
       if (p.epi_mode == EPI_TMA) {
         const int sw = (r >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-        // bias slice of this tile -> shared memory (once per tile, instead of eight dependent global loads per chunk).
+        // bias slice of this tile -> shared memory (once per tile, instead of dependent global loads per chunk).
         // The barrier also orders this write after every thread's reads of the same slot two tiles ago.
         float* sb = sbias + as * BN;
         {
-          const int et = e * 32 + lane;       // 0..255
+          const int et = e * 32 + lane;       // 0..511
           if (et < BN) sb[et] = p.bias != nullptr ? __ldg(p.bias + t.n_t * BN + et) : 0.0f;
-          named_bar_sync(3, 256);
+          named_bar_sync(3, 32 * kEpiWarps);
         }
-        uint32_t v[32];
-        tmem_ld_32x32(tbase + g * kEpiCW, v);
+        uint32_t v[TW];
+        tmem_ld_32x16(tbase + g * kEpiCW, v);
 #pragma unroll 1
         for (int c = g; c < NC; c += 2, ++nstore) {
           uint8_t* buf = stg + (g * EB + (EB == 2 ? (nstore & 1) : 0)) * kEpiBufBytes;
           tmem_ld_wait();
           const int col0 = t.n_t * BN + c * kEpiCW;
-          float x[32];
+          float x[TW];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < TW; ++j) x[j] = __uint_as_float(v[j]);
           if (c + 2 < NC) {                   // the next chunk's accumulator load is in flight during this chunk's math
-            tmem_ld_32x32(tbase + (c + 2) * kEpiCW, v);
+            tmem_ld_32x16(tbase + (c + 2) * kEpiCW, v);
           } else {                            // this warp's last read of the accumulator: hand it back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) release_acc(as);
           }
           {
-            const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW);
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW + hh * TW);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {                   // packed adds: two columns per instruction
+            for (int j = 0; j < TW / 4; ++j) {              // packed adds: two columns per instruction
               const float4 b = b4[j];
               unpack_f32x2(add_f32x2(pack_f32x2(x[4 * j], x[4 * j + 1]), pack_f32x2(b.x, b.y)), x[4 * j], x[4 * j + 1]);
               unpack_f32x2(add_f32x2(pack_f32x2(x[4 * j + 2], x[4 * j + 3]), pack_f32x2(b.z, b.w)), x[4 * j + 2],
@@ -444,19 +451,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           }
           if (p.act == ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+            for (int j = 0; j < TW; ++j) x[j] = fmaxf(x[j], 0.0f);
           } else if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf_x2(x[j], x[j + 1]);
+            for (int j = 0; j < TW; j += 2) gelu_erf_x2(x[j], x[j + 1]);
           }
           if constexpr (EB == 1) {
             if (issuer) tma_store_wait_read<0>();   // the previous store has finished reading `buf`
-            named_bar_sync(1 + g, 128);
+            named_bar_sync(1 + g, 16 * kEpiWarps);
           }
           uint8_t* my_row = buf + r * 64;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+          for (int j = 0; j < TW / 8; ++j)
+            *reinterpret_cast<uint4*>(my_row + (((hh * (TW / 8) + j) ^ sw) << 4)) =
                 make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
                            pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
           fence_proxy_async();                // make the generic-proxy smem writes visible to the TMA unit
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             // whole chunk ago) has finished reading it, so after the barrier everybody may write the next chunk there.
             if (issuer) tma_store_wait_read<0>();
           }
-          named_bar_sync(1 + g, 128);
+          named_bar_sync(1 + g, 16 * kEpiWarps);
           if (issuer) {
             tma_store_4d(&p.tmC, buf, col0, t.w0, t.h0, t.n0);
             tma_store_commit();
@@ -476,12 +483,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             // Row LayerNorm of the 128 rows this CTA has just completed.  The accumulators were released above, so the
             // MMA warp is already two tiles into the next item while this runs.
             if (issuer) tma_store_wait_all<0>();      // this group's stores of the item have landed (not just been read)
-            named_bar_sync(3, 256);
+            named_bar_sync(3, 32 * kEpiWarps);
             const int rows = p.OW;                    // plain GEMM: OW = M
             const int m_row0 = ((tile / p.n_tiles) * CG + rank) * 128;   // (not t.w0: a past-the-end m-tile wraps to 0)
             const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(p.out);
+            constexpr int RW = 128 / kEpiWarps;       // rows per warp
 #pragma unroll 1
-            for (int rr = e * 16; rr < e * 16 + 16; rr += 2) {
+            for (int rr = e * RW; rr < e * RW + RW; rr += 2) {
               const int row0 = m_row0 + rr;
               if (row0 < rows) ln_two_rows<LN>(xin, p.ldc, p.ln_out, p.ld_ln, row0, rows, p.ln_gamma, p.ln_beta, p.ln_eps, lane);
             }
@@ -498,8 +506,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         const long long orow = (static_cast<long long>(n) * p.OH + h) * p.OW + w;
 #pragma unroll 1
         for (int c = g; c < NC; c += 2) {
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + c * kEpiCW, v);
+          uint32_t v[TW];
+          tmem_ld_32x16(tbase + c * kEpiCW, v);
           tmem_ld_wait();
           if (c == NC - 2 + g) {
             tc_fence_before();
@@ -507,14 +515,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (lane == 0) release_acc(as);
           }
           if (valid) {
-            const int col0 = t.n_t * BN + c * kEpiCW;
-            float x[32];
+            const int col0 = t.n_t * BN + c * kEpiCW + hh * TW;
+            float x[TW];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < TW; ++j) x[j] = __uint_as_float(v[j]);
             if (p.bias != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < TW / 4; ++j) {
                 const float4 b = __ldg(b4 + j);
                 x[4 * j + 0] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
               }
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (res_direct) {
               const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + orow * p.ldr + col0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < TW / 8; ++j) {
                 const uint4 u = __ldg(r4 + j);
                 float2 f;
                 f = unpack_bf16(u.x); x[8 * j + 0] += f.x; x[8 * j + 1] += f.y;
@@ -533,19 +541,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             }
             if (p.act == ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+              for (int j = 0; j < TW; ++j) x[j] = fmaxf(x[j], 0.0f);
             } else if (p.act == ACT_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+              for (int j = 0; j < TW; ++j) x[j] = gelu_erf(x[j]);
             }
             if (p.out_f32) {
               float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow * p.ldc + col0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+              for (int j = 0; j < TW / 4; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
             } else {
               uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col0);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
+              for (int j = 0; j < TW / 8; ++j)
                 o4[j] = make_uint4(pack_bf16(x[8 * j], x[8 * j + 1]), pack_bf16(x[8 * j + 2], x[8 * j + 3]),
                                    pack_bf16(x[8 * j + 4], x[8 * j + 5]), pack_bf16(x[8 * j + 6], x[8 * j + 7]));
             }
