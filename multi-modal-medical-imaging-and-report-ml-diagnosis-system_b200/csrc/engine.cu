@@ -258,6 +258,14 @@ static int make_tmap(mmdx_engine* e, CUtensorMap* m, const void* base, int rank,
   return 0;
 }
 
+// cudaFuncSetAttribute and cluster occupancy are per DEVICE: one process may drive several GPUs (inference(device="cuda:1")
+// after "cuda:0"), so the "done once" flags of the launch helpers are indexed by the current device.
+static int cur_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+
 // Every kernel goes through here: programmatic dependent launch (see ptx.cuh pdl_wait / pdl_trigger) so the next
 // kernel's CTAs are scheduled and run their prologue while this one drains; clusters of `cluster` CTAs along x.
 // MMDX_PDL=0 turns the attribute off (plain stream order) for A/B timing.
@@ -556,7 +564,8 @@ static int build_c64(mmdx_engine* e, GemmLaunch& g, const bf16* in, int NB, int 
   return 0;
 }
 static int launch_c64(mmdx_engine* e, const C64Params& p, cudaStream_t s) {
-  static bool attr_set = false;
+  static bool attr_set_[64] = {};
+  bool& attr_set = attr_set_[cur_dev()];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(conv3x3_c64_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C64_SMEM));
     attr_set = true;
@@ -632,8 +641,10 @@ static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* 
 }
 template <int C1, bool DS, int NH>
 static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t s) {
-  static bool attr_set = false;
-  static int max_clusters = 0;
+  static bool attr_set_[64] = {};
+  static int max_clusters_[64] = {};
+  bool& attr_set = attr_set_[cur_dev()];
+  int& max_clusters = max_clusters_[cur_dev()];
   auto* kfn = bneck64_tcgen05_kernel<C1, DS, NH>;
   constexpr int SMEM = B64Smem<C1, DS, NH>::TOTAL;
   if (!attr_set) {
@@ -658,7 +669,8 @@ static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t 
 
 template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
-  static bool attr_set = false;
+  static bool attr_set_[64] = {};
+  bool& attr_set = attr_set_[cur_dev()];
   auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES, LN>;
   constexpr int SMEM = GemmSmem<BN, BK, CG, EB, RES>::TOTAL;
   if (!attr_set) {
@@ -668,7 +680,8 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
   if (CG == 2) {     // CTA pairs: clusters of two along x
     // The schedule is static and persistent: every cluster must be resident at once, or the stragglers run as a
     // second wave.  Not every SM can be paired (GPCs with an odd number of enabled SMs), so ask the driver.
-    static int max_clusters = 0;
+    static int max_clusters_[64] = {};
+    int& max_clusters = max_clusters_[cur_dev()];
     if (max_clusters == 0) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)groups * CG, 1, 1);
@@ -788,7 +801,8 @@ static int plan_stem(mmdx_engine* e, StemParams& p, const bf16* in_pad, int B, i
 static int launch_stem(mmdx_engine* e, const StemParams& p, cudaStream_t s) {
   const int smem = 1024 + STEM_W_BYTES + STEM_ROWBUF_BYTES + 2 * p.in_buf_bytes + 512;
   REQUIRE(smem <= 232448, "stem strip does not fit in shared memory");
-  static int attr_smem = 0;
+  static int attr_smem_[64] = {};
+  int& attr_smem = attr_smem_[cur_dev()];
   if (smem > attr_smem) {
     CK(cudaFuncSetAttribute(stem_pool_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_smem = 232448;
@@ -1295,7 +1309,8 @@ static int launch_preprocess(mmdx_engine* e, const uint8_t* d_images, int B, int
   ProfScope _ps(e);
   if (st.rows_per_block > 0) {                  // strip-tiled two-pass kernel
     const size_t smem = (size_t)st.max_rows_in * (st.in_pitch + st.h_pitch) + 256 * 3 * 2 + 64;
-    static bool attr_set = false;
+    static bool attr_set_[64] = {};
+    bool& attr_set = attr_set_[cur_dev()];
     if (!attr_set) {
       CK(cudaFuncSetAttribute(preprocess_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 2048));
       CK(cudaFuncSetAttribute(preprocess_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 2048));
@@ -1550,7 +1565,8 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
                             int hidden, bf16* ctx, cudaStream_t s) {
   REQUIRE(hidden == heads * 64, "attention head dim must be 64");
   REQUIRE(n_seq > 0 && T > 0 && max_len > 0, "bad attention batch");
-  static bool attr_set = false;
+  static bool attr_set_[64] = {};
+  bool& attr_set = attr_set_[cur_dev()];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     CK(cudaFuncSetAttribute(attention_short_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM));

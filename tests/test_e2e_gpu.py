@@ -231,6 +231,22 @@ def _tok(b, g1):
     return np.asarray(t["input_ids"]), np.asarray(t["attention_mask"])
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(bundle, g1):
+    """The drop-in contract lets a caller pick the device per call (inference_pipeline.py:152-159): a second engine on
+    cuda:1 in the same process (kernel attributes and cluster occupancy are per device) gives the same result."""
+    from PIL import Image
+    pil = Image.fromarray(np.repeat(g1["gray"][0][..., None], 3, axis=-1))
+    r0 = ip.inference(bundle, pil, str(g1["details"][0]), device="cuda:0", gen_kwargs=False)
+    r1 = ip.inference(bundle, pil, str(g1["details"][0]), device="cuda:1", gen_kwargs=False)
+    assert r0 == r1
+    imgs = synth.synth_images(40, 224, seed=31)
+    ids, mask = synth.synth_token_ids(40, 128, seed=32, ragged=True)
+    a = ip.inference_batch(bundle, list(imgs), tokens={"input_ids": ids, "attention_mask": mask}, device="cuda:0")
+    b = ip.inference_batch(bundle, list(imgs), tokens={"input_ids": ids, "attention_mask": mask}, device="cuda:1")
+    assert a == b
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image
