@@ -36,6 +36,7 @@ struct AttnParams {
   __nv_bfloat16* ctx;      // [T, HID]
   int n_seq, heads, hidden, nqb, num_units;   // nqb = query blocks per sequence at max_len
   float scale_log2;        // 1/sqrt(64) * log2(e)
+  int reverse;             // 1: walk the units from the last to the first (see mmdx_engine::zigzag)
 };
 
 // B operand in MN-major form (rows = K index, 128-byte rows of 64 consecutive N elements, SWIZZLE_128B):
@@ -49,6 +50,7 @@ __device__ __forceinline__ uint64_t make_sdesc_mn128(uint32_t saddr) {
 struct AttnUnit { int seq, head, qb, tok0, len; };
 
 __device__ __forceinline__ bool attn_unit(const AttnParams& p, int id, AttnUnit& u) {
+  if (p.reverse) id = p.num_units - 1 - id;
   const int per_seq = p.heads * p.nqb;
   u.seq = id / per_seq;
   const int rem = id - u.seq * per_seq;
@@ -315,6 +317,7 @@ struct AttnShortUnit { int tok0, len, head; };
 
 __device__ __forceinline__ AttnShortUnit attn_short_unit(const AttnParams& p, int id) {
   AttnShortUnit u;
+  if (p.reverse) id = p.n_seq * p.heads - 1 - id;
   const int seq = id / p.heads;
   u.head = id - seq * p.heads;
   u.tok0 = __ldg(p.cu_seqlens + seq);

@@ -92,6 +92,7 @@ struct Bneck64Params {
   const float* bd;     // [256] downsample bias (DS), added to b3
   __nv_bfloat16* t1n;         // [NB,H,W,C1]
   int NB, H, W, tiles_w, tiles_h, num_tiles, num_items;   // item = two consecutive tiles (one per CTA of the pair)
+  int reverse;         // 1: walk the items from the last to the first (see mmdx_engine::zigzag)
 };
 
 template <int C1, bool DS, int NH>
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       const uint32_t xf = mapa_rank(smem_u32(xs_full), 0);
       int item = pair;
       for (int n = 0; n < n_items; ++n, item += num_pairs) {
-        const int tile = 2 * item + rank;               // a past-the-end tile decodes to image NB: zero-filled, clipped
+        const int tile = 2 * (p.reverse ? p.num_items - 1 - item : item) + rank;               // a past-the-end tile decodes to image NB: zero-filled, clipped
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         const int buf = n % NH;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
     if (lane == 0) {
       // ================= y ring: store finished chunks, refill the slots with the next tile's shortcut =================
       auto load_res = [&](int n, int j) {              // shortcut chunk j of local tile n -> slot j
-        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int tile = 2 * (p.reverse ? p.num_items - 1 - (pair + n * num_pairs) : pair + n * num_pairs) + rank;
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         if constexpr (DS) {
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       if (n_items > 0)
         for (int j = 0; j < 4; ++j) load_res(0, j);
       for (int n = 0; n < n_items; ++n) {
-        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int tile = 2 * (p.reverse ? p.num_items - 1 - (pair + n * num_pairs) : pair + n * num_pairs) + rank;
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         for (int j = 0; j < 4; ++j) {
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(B64_THREADS, 1) bneck64_tcgen05_kernel(const _
       if (n + 1 < n_items) ep2(n + 1);
       // ---- ep1'(n): t1' = relu(D1 + b1') -> global
       if constexpr (C1 > 0) {
-        const int tile = 2 * (pair + n * num_pairs) + rank;
+        const int tile = 2 * (p.reverse ? p.num_items - 1 - (pair + n * num_pairs) : pair + n * num_pairs) + rank;
         const int img = tile / per_img, rem = tile - img * per_img;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         const int oh = th * 16 + (m >> 3), ow = tw * 8 + (m & 7);

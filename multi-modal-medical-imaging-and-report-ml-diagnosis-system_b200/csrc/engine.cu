@@ -201,6 +201,11 @@ struct mmdx_engine {
   cudaStream_t text_stream = nullptr;
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   bool two_streams = true;
+  // Zigzag traversal: consecutive kernels of a branch walk their tiles / rows / units in opposite directions, so a
+  // consumer starts with what its producer wrote LAST - the part of a streamed tensor that is still in the 126 MB L2
+  // (read in the producer's order, an LRU cache smaller than the tensor gives no hits at all).  MMDX_ZIGZAG=0 turns it off.
+  bool zigzag = true;
+  int zz_txt = 1, zz_img = 1;   // direction of the next launch on the text / image branch
   DevBuf pre_lut;        // 3 x 256 bf16: ((v / 255) - mean[c]) / std[c], the ToTensor + Normalize arithmetic per byte value
   DevBuf ident;          // 64x64 bf16 identity: B operand of the residual-add MMAs
   CUtensorMap tm_ident{};
@@ -640,7 +645,7 @@ static int build_b64(mmdx_engine* e, GemmLaunch& g, const bf16* t1, const bf16* 
   return 0;
 }
 template <int C1, bool DS, int NH>
-static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t s) {
+static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t s, int reverse) {
   static bool attr_set_[64] = {};
   static int max_clusters_[64] = {};
   bool& attr_set = attr_set_[cur_dev()];
@@ -662,13 +667,24 @@ static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t 
   int pairs = p.num_items < e->num_sms / 2 ? p.num_items : e->num_sms / 2;
   if (pairs > max_clusters) pairs = max_clusters;
   ProfScope _ps(e);
-  CK(launch_k(kfn, dim3((unsigned)pairs * 2), dim3(B64_THREADS), SMEM, s, 2, p));
+  Bneck64Params prm = p;
+  prm.reverse = reverse;
+  CK(launch_k(kfn, dim3((unsigned)pairs * 2), dim3(B64_THREADS), SMEM, s, 2, prm));
   CK(cudaGetLastError());
   return 0;
 }
 
+// direction of this launch on its branch (and flip it for the next one)
+static int next_direction(mmdx_engine* e, cudaStream_t s) {
+  if (!e->zigzag) return 0;
+  int& z = (s == e->text_stream || e->cur_cls == CLS_GEMM_TEXT || e->cur_cls == CLS_ATTN || e->cur_cls == CLS_LN) ? e->zz_txt : e->zz_img;
+  const int d = z;
+  z ^= 1;
+  return d;
+}
+
 template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
-static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
+static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s, int reverse) {
   static bool attr_set_[64] = {};
   bool& attr_set = attr_set_[cur_dev()];
   auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES, LN>;
@@ -702,25 +718,28 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s) {
     }
     if (groups > max_clusters) groups = max_clusters;
   }
-  CK(launch_k(kfn, dim3((unsigned)groups * CG), dim3(kGemmThreads), SMEM, s, CG, g.p));
+  GemmParams prm = g.p;
+  prm.reverse = reverse;
+  CK(launch_k(kfn, dim3((unsigned)groups * CG), dim3(kGemmThreads), SMEM, s, CG, prm));
   CK(cudaGetLastError());
   return 0;
 }
 
 // Instantiations: the residual variants carry the identity block; every variant takes as many ring stages as fit.
 template <int BN, int CG>
-static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s) {
+static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s, int rv) {
   const bool res = g.p.res_blocks > 0;
-  if (g.eb == 2) return res ? launch_inst<BN, 64, CG, 2, 1>(g, groups, s) : launch_inst<BN, 64, CG, 2, 0>(g, groups, s);
-  return res ? launch_inst<BN, 64, CG, 1, 1>(g, groups, s) : launch_inst<BN, 64, CG, 1, 0>(g, groups, s);
+  if (g.eb == 2) return res ? launch_inst<BN, 64, CG, 2, 1>(g, groups, s, rv) : launch_inst<BN, 64, CG, 2, 0>(g, groups, s, rv);
+  return res ? launch_inst<BN, 64, CG, 1, 1>(g, groups, s, rv) : launch_inst<BN, 64, CG, 1, 0>(g, groups, s, rv);
 }
 
 static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
+  const int rv = next_direction(e, s);
   switch (g.b64) {
-    case 1: return launch_b64_inst<0, false, 2>(e, g.b, s);
-    case 2: return launch_b64_inst<64, false, 2>(e, g.b, s);
-    case 3: return launch_b64_inst<128, false, 1>(e, g.b, s);
-    case 4: return launch_b64_inst<64, true, 1>(e, g.b, s);
+    case 1: return launch_b64_inst<0, false, 2>(e, g.b, s, rv);
+    case 2: return launch_b64_inst<64, false, 2>(e, g.b, s, rv);
+    case 3: return launch_b64_inst<128, false, 1>(e, g.b, s, rv);
+    case 4: return launch_b64_inst<64, true, 1>(e, g.b, s, rv);
     default: break;
   }
   if (g.c64) return launch_c64(e, g.c, s);
@@ -728,18 +747,18 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
   if (g.cg == 2) {
-    if (g.ln == 3) return launch_inst<256, 64, 2, 1, 1, 3>(g, groups, s);
+    if (g.ln == 3) return launch_inst<256, 64, 2, 1, 1, 3>(g, groups, s, rv);
     switch (g.bn) {
-      case 256: return launch_bn<256, 2>(g, groups, s);
-      case 192: return launch_bn<192, 2>(g, groups, s);
-      case 128: return launch_bn<128, 2>(g, groups, s);
+      case 256: return launch_bn<256, 2>(g, groups, s, rv);
+      case 192: return launch_bn<192, 2>(g, groups, s, rv);
+      case 128: return launch_bn<128, 2>(g, groups, s, rv);
     }
     return fail("mmdx: bad BN for a CTA pair");
   }
   switch (g.bn) {
-    case 256: return launch_bn<256, 1>(g, groups, s);
-    case 128: return launch_bn<128, 1>(g, groups, s);
-    case 64: return launch_bn<64, 1>(g, groups, s);
+    case 256: return launch_bn<256, 1>(g, groups, s, rv);
+    case 128: return launch_bn<128, 1>(g, groups, s, rv);
+    case 64: return launch_bn<64, 1>(g, groups, s, rv);
   }
   return fail("mmdx: bad BN");
 }
@@ -868,6 +887,7 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     TRY(e->pre_lut.ensure(lut.size() * 2));
     CK(cudaMemcpy(e->pre_lut.p, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
   }
+  if (const char* v = getenv("MMDX_ZIGZAG")) e->zigzag = atoi(v) != 0;
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
   if (const char* v = getenv("MMDX_BN")) e->force_bn = atoi(v);
   if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
@@ -1534,12 +1554,13 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
                      cudaStream_t s) {
   constexpr int R = 4;                          // rows per warp
   const int grid = (rows + 8 * R - 1) / (8 * R);
+  const int rv = next_direction(e, s);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1552,10 +1573,10 @@ static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const in
   const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
     default: return fail("mmdx: hidden width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1583,6 +1604,7 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
   p.tm = e->attn_tm; p.cu_seqlens = cu; p.ctx = ctx; p.n_seq = n_seq; p.heads = heads; p.hidden = hidden;
   p.nqb = (max_len + 127) / 128; p.num_units = n_seq * heads * p.nqb;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.reverse = next_direction(e, s);
   ProfScope _ps(e);
   if (max_len <= 128 && !e->attn_force_general) {       // one key block per sequence: the 4-deep TMEM-resident variant
     const int units = n_seq * heads;
@@ -1622,6 +1644,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   TRY(get_image_plan(e, B, H, W, C, &pl));
   PreGeom g{0, 0, pl->off_y, pl->off_x, pl->crop_h, pl->crop_w, pl->has_x, pl->has_y};
   e->cur_stream = s; e->cur_cls = CLS_PRE;
+  e->zz_img = 1;                                   // preprocess / stem write forward: the first conv walks backwards
   if (e->img_last != pl) {   // another geometry used the arena: restore the zero border + zero 4th channel
     CK(cudaMemsetAsync(pl->in_pad, 0, pl->in_pad_bytes, s));
     e->img_last = pl;
@@ -1659,6 +1682,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   TRY(get_text_plan(e, T, B, &pl, &tb));
   const int H = e->hidden;
   e->cur_stream = s; e->cur_cls = CLS_LN;
+  e->zz_txt = 1;                                   // the embedding kernel writes forward: the first consumer walks backwards
   TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s));
   for (int l = 0; l < e->n_layers; ++l) {
     const BertLayerW& L = e->layers[l];

@@ -71,6 +71,7 @@ struct alignas(64) GemmParams {
   // Fused row LayerNorm (template LN > 0; plain GEMMs whose N tiles cover the whole row): the schedule turns
   // item-major - one CTA group computes all n_tiles tiles of its 256 (128) rows back to back - and after the last of
   // them the epilogue warps normalise the rows this CTA has just stored (L2-hot) into ln_out.
+  int reverse;                 // 1: walk the tiles from the last to the first (see mmdx_engine::zigzag)
   int item_major;              // 1: tiles of one m-item are consecutive work items of the same CTA group
   float ln_eps;
   const float* ln_gamma;       // [N]
@@ -192,6 +193,7 @@ struct TileCoord { int n_t, w0, h0, n0; };
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int rank) {
   TileCoord t;
+  if (p.reverse) tile = p.num_tiles - 1 - tile;
   t.n_t = tile % p.n_tiles;
   const int m_t = (tile / p.n_tiles) * p.cg + rank;   // past-the-end m-tiles of an odd pair land out of bounds:
                                                       // TMA zero-fills the loads and clips the stores
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (issuer) tma_store_wait_all<0>();      // this group's stores of the item have landed (not just been read)
             named_bar_sync(3, 32 * kEpiWarps);
             const int rows = p.OW;                    // plain GEMM: OW = M
-            const int m_row0 = ((tile / p.n_tiles) * CG + rank) * 128;   // (not t.w0: a past-the-end m-tile wraps to 0)
+            const int m_row0 = (((p.reverse ? p.num_tiles - 1 - tile : tile) / p.n_tiles) * CG + rank) * 128;   // (not t.w0: a past-the-end m-tile wraps to 0)
             const __nv_bfloat16* xin = static_cast<const __nv_bfloat16*>(p.out);
             constexpr int RW = 128 / kEpiWarps;       // rows per warp
 #pragma unroll 1

@@ -363,13 +363,14 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
                                                         const int* __restrict__ tts,
                                                         const __nv_bfloat16* __restrict__ word,
                                                         const __nv_bfloat16* __restrict__ ptab,
-                                                        const __nv_bfloat16* __restrict__ ttab) {
+                                                        const __nv_bfloat16* __restrict__ ttab, int reverse) {
   pdl_wait();
   pdl_trigger();
   // R rows per warp: all their 16-byte loads are issued before the first reduction (R * N / 256 loads in flight
   // per lane), which is what an HBM/L2-bound row kernel needs.
   constexpr int CH = N / 256;   // 16-byte chunks per lane and row
-  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  const int blk = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;   // zigzag: start with the rows the producer wrote last
+  const int row0 = (blk * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   const int lane = threadIdx.x & 31;
   if (row0 >= rows) return;
   float v[R][CH][8];
