@@ -220,6 +220,18 @@ struct mmdx_engine {
   DevBuf io_slot[2];
   cudaEvent_t slot_copy_done[2] = {nullptr, nullptr}, slot_tok_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
+  // Small host requests (B <= graph_max_b) replay a captured CUDA graph of the whole call: at B = 1 the 135 launches
+  // of a step cost more host time than GPU time.  One graph per request shape; inputs / outputs go through engine-owned
+  // pinned staging buffers so that every pointer inside the graph is fixed.  MMDX_GRAPH_MAX_B=0 turns it off.
+  struct HostGraph {
+    cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0;
+    void* h_in = nullptr; void* h_out = nullptr; size_t in_bytes = 0, out_bytes = 0;
+  };
+  std::map<std::string, HostGraph> host_graphs;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_fork = nullptr;
+  int graph_max_b = 8;
+  bool capturing = false;
   std::map<std::string, std::unique_ptr<ImagePlan>> img_plans;
   ImagePlan* img_last = nullptr;   // plan whose zero borders currently sit in img_ws
   std::map<std::string, std::unique_ptr<TextPlan>> txt_plans;
@@ -888,6 +900,9 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
     CK(cudaMemcpy(e->pre_lut.p, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice));
   }
   if (const char* v = getenv("MMDX_ZIGZAG")) e->zigzag = atoi(v) != 0;
+  if (const char* v = getenv("MMDX_GRAPH_MAX_B")) e->graph_max_b = atoi(v);
+  CK(cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->graph_fork, cudaEventDisableTiming));
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
   if (const char* v = getenv("MMDX_BN")) e->force_bn = atoi(v);
   if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
@@ -908,6 +923,13 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
     if (e->slot_tok_done[i]) cudaEventDestroy(e->slot_tok_done[i]);
     if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
   }
+  for (auto& kv : e->host_graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.h_in) cudaFreeHost(kv.second.h_in);
+    if (kv.second.h_out) cudaFreeHost(kv.second.h_out);
+  }
+  if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
+  if (e->graph_fork) cudaEventDestroy(e->graph_fork);
   if (e->text_stream) cudaStreamDestroy(e->text_stream);
   if (e->fork_ev) cudaEventDestroy(e->fork_ev);
   if (e->join_ev) cudaEventDestroy(e->join_ev);
@@ -1796,7 +1818,7 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
                                       int T, int max_len, const float* h_thr, float* h_logits, float* h_probs,
                                       uint8_t* h_vector, cudaStream_t s) {
   REQUIRE(e->finalized, "weights not finalized");
-  if (e->slot_busy[slot]) { CK(cudaEventSynchronize(e->slot_done[slot])); e->slot_busy[slot] = false; }
+  if (e->slot_busy[slot] && !e->capturing) { CK(cudaEventSynchronize(e->slot_done[slot])); e->slot_busy[slot] = false; }
   const size_t img_b = al((size_t)B * H * W * C), tok_b = al((size_t)T * 4), cu_b = al((size_t)(B + 1) * 4);
   const size_t out_f = al((size_t)B * e->n_cls * 4), out_u = al((size_t)B * e->n_cls), thr_b = al((size_t)e->n_cls * 4);
   TRY(e->io_slot[slot].ensure(img_b + 3 * tok_b + cu_b + 2 * out_f + out_u + thr_b));
@@ -1814,6 +1836,10 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
   // All inputs go over the copy stream at submit time - the token arrays (a few hundred KB) FIRST, then the image batch:
   // one DMA engine serves every host-to-device copy in the order they become ready, and token copies queued behind the
   // 38 MB image copy would hold the text branch (and with it the whole GPU) back for the 0.75 ms the images take.
+  if (e->capturing) {                                          // the copy stream has to join the capture of `s`
+    CK(cudaEventRecord(e->graph_fork, s));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->graph_fork, 0));
+  }
   CK(cudaMemcpyAsync(d_ids, h_ids, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
   CK(cudaMemcpyAsync(d_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
   CK(cudaMemcpyAsync(d_tt, h_tt, (size_t)T * 4, cudaMemcpyHostToDevice, e->copy_stream));
@@ -1839,8 +1865,84 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
   CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_vector, d_vec, (size_t)B * e->n_cls, cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(e->slot_done[slot], s));
-  e->slot_busy[slot] = true;
+  if (!e->capturing) {
+    CK(cudaEventRecord(e->slot_done[slot], s));
+    e->slot_busy[slot] = true;
+  }
+  return 0;
+}
+
+// mmdx_forward_host for a small request: host copy into the staging buffer, one cudaGraphLaunch, host copy out.
+// The first call of a shape runs the ordinary path (it creates plans and workspaces), the second captures the graph.
+static int forward_host_graphed(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
+                                const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu, int T, int max_len,
+                                const float* h_thr, float* h_logits, float* h_probs, uint8_t* h_vector, cudaStream_t s,
+                                bool* done) {
+  *done = false;
+  char key[96];
+  snprintf(key, sizeof key, "%d_%d_%d_%d_%d_%d_%d", B, H, W, C, T, max_len, h_thr ? 1 : 0);
+  if (e->host_graphs.size() > 32 && e->host_graphs.find(key) == e->host_graphs.end()) return 0;   // bounded
+  mmdx_engine::HostGraph& hg = e->host_graphs[key];
+  if (hg.seen < 0) return 0;                                   // capture failed once for this shape: ordinary path
+  if (hg.seen++ == 0) return 0;                                // first call of this shape: ordinary path (warm-up)
+  const size_t img_b = al((size_t)B * H * W * C), tok_b = al((size_t)T * 4), cu_b = al((size_t)(B + 1) * 4);
+  const size_t thr_b = al((size_t)e->n_cls * 4), of = al((size_t)B * e->n_cls * 4), ou = al((size_t)B * e->n_cls);
+  if (!hg.exec) {
+    hg.in_bytes = img_b + 3 * tok_b + cu_b + thr_b; hg.out_bytes = 2 * of + ou;
+    CK(cudaMallocHost(&hg.h_in, hg.in_bytes));
+    CK(cudaMallocHost(&hg.h_out, hg.out_bytes));
+  }
+  char* hi = static_cast<char*>(hg.h_in);
+  uint8_t* s_img = reinterpret_cast<uint8_t*>(hi);
+  int32_t* s_ids = reinterpret_cast<int32_t*>(hi + img_b);
+  int32_t* s_pos = reinterpret_cast<int32_t*>(hi + img_b + tok_b);
+  int32_t* s_tt = reinterpret_cast<int32_t*>(hi + img_b + 2 * tok_b);
+  int32_t* s_cu = reinterpret_cast<int32_t*>(hi + img_b + 3 * tok_b);
+  float* s_thr = reinterpret_cast<float*>(hi + img_b + 3 * tok_b + cu_b);
+  char* ho = static_cast<char*>(hg.h_out);
+  float* s_logits = reinterpret_cast<float*>(ho);
+  float* s_probs = reinterpret_cast<float*>(ho + of);
+  uint8_t* s_vec = reinterpret_cast<uint8_t*>(ho + 2 * of);
+  if (!hg.exec) {
+    // slot 0 must be idle and its buffers allocated (the warm-up call did both); capture on the engine's own stream
+    // (the caller's may be the legacy default stream, which cannot be captured)
+    if (e->slot_busy[0]) { CK(cudaEventSynchronize(e->slot_done[0])); e->slot_busy[0] = false; }
+    const int64_t n0 = e->launches;
+    const int zt = e->zz_txt, zi = e->zz_img;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(e->graph_stream, cudaStreamCaptureModeRelaxed));
+    e->capturing = true;
+    const int rc = forward_host_submit_locked(e, 0, s_img, B, H, W, C, s_ids, s_pos, s_tt, s_cu, T, max_len,
+                                              h_thr ? s_thr : nullptr, s_logits, s_probs, s_vec, e->graph_stream);
+    e->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(e->graph_stream, &graph);
+    e->zz_txt = zt; e->zz_img = zi;
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      hg.seen = -1000000;                                      // do not try again for this shape
+      return rc != 0 ? rc : 0;
+    }
+    hg.launches = e->launches - n0;
+    e->launches = n0;
+    const cudaError_t ie = cudaGraphInstantiate(&hg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); hg.exec = nullptr; hg.seen = -1000000; return 0; }
+  }
+  if (hg.seen < 0) return 0;
+  memcpy(s_img, h_images, (size_t)B * H * W * C);
+  memcpy(s_ids, h_ids, (size_t)T * 4); memcpy(s_pos, h_pos, (size_t)T * 4); memcpy(s_tt, h_tt, (size_t)T * 4);
+  memcpy(s_cu, h_cu, (size_t)(B + 1) * 4);
+  if (h_thr) memcpy(s_thr, h_thr, (size_t)e->n_cls * 4);
+  CK(cudaEventRecord(e->graph_fork, s));                       // order behind whatever the caller queued on `s`
+  CK(cudaStreamWaitEvent(e->graph_stream, e->graph_fork, 0));
+  CK(cudaGraphLaunch(hg.exec, e->graph_stream));
+  CK(cudaStreamSynchronize(e->graph_stream));
+  e->launches += hg.launches;
+  memcpy(h_logits, s_logits, (size_t)B * e->n_cls * 4);
+  memcpy(h_probs, s_probs, (size_t)B * e->n_cls * 4);
+  memcpy(h_vector, s_vec, (size_t)B * e->n_cls);
+  *done = true;
   return 0;
 }
 
@@ -1874,6 +1976,12 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
+  if (B <= e->graph_max_b && !e->profiling) {
+    bool done = false;
+    TRY(forward_host_graphed(e, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits, h_probs, h_vector,
+                             (cudaStream_t)stream, &done));
+    if (done) return 0;
+  }
   TRY(forward_host_submit_locked(e, 0, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits, h_probs,
                                  h_vector, (cudaStream_t)stream));
   CK(cudaEventSynchronize(e->slot_done[0]));

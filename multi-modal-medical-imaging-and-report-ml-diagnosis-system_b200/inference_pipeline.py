@@ -151,20 +151,25 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
     with torch.cuda.device(dev):
         thr_d = thr.to(dev)
         for shape, idxs in groups.items():
-            batch = torch.from_numpy(np.stack([imgs[i] for i in idxs])).pin_memory().to(dev, non_blocking=True)
             ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs])
+            if not want_report or use_cond:
+                # one C call per shape group: H2D, forward, D2H (small groups replay a captured CUDA graph)
+                host = [torch.from_numpy(x).pin_memory() for x in (np.stack([imgs[i] for i in idxs]), ids, pos, tt, cu)]
+                _, probs, vec = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen, thresholds=thr)
+                probs_out[idxs] = probs.numpy()
+                vec_out[idxs] = vec.numpy()
+                if want_report:  # cond_proj on the engine: the decoder only needs these tokens
+                    cond_out[idxs] = eng.cond_tokens(len(idxs)).cpu().numpy()
+                continue
+            batch = torch.from_numpy(np.stack([imgs[i] for i in idxs])).pin_memory().to(dev, non_blocking=True)
             t = [torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (ids, pos, tt, cu)]
             _, z_img = eng.image_encode(batch, want_feats=False)
             _, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen, want_pooled=False)
             _, _, probs, vec = eng.head(len(idxs), thr_d, want_z_fuse=False)
             probs_out[idxs] = probs.cpu().numpy()
             vec_out[idxs] = vec.cpu().numpy()
-            if want_report:
-                if use_cond:     # cond_proj on the engine: the decoder only needs these tokens
-                    cond_out[idxs] = eng.cond_tokens(len(idxs)).cpu().numpy()
-                else:
-                    z_img_out[idxs] = z_img.cpu().numpy()
-                    z_txt_out[idxs] = z_txt.cpu().numpy()
+            z_img_out[idxs] = z_img.cpu().numpy()
+            z_txt_out[idxs] = z_txt.cpu().numpy()
 
     reports = [""] * B
     if want_report:

@@ -107,6 +107,29 @@ def test_batch_vs_oracle_high_res_and_mixed_sizes(bundle, eng):
         assert np.array_equal(np.array(r["disease_vector"])[decided], ref["vector"][i].numpy()[decided])
 
 
+def test_small_requests_replay_a_cuda_graph(eng):
+    """mmdx_forward_host on small batches: the first call of a shape runs the ordinary path, the second captures a CUDA
+    graph of the whole call, later ones replay it.  Every call must equal the device-buffer path bit for bit, for
+    changing inputs, with and without thresholds, and the launch counter keeps counting kernels."""
+    for B, L in [(1, 96), (3, 128)]:
+        for k in range(4):
+            imgs = synth.synth_images(B, 224, seed=500 + 10 * B + k)
+            ids, mask = synth.synth_token_ids(B, L, seed=600 + 10 * B + k, ragged=False)      # same T -> same graph key
+            pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+            host = [torch.from_numpy(x).pin_memory() for x in (np.ascontiguousarray(imgs), pi, pp, pt, cu)]
+            thr = torch.full((eng.n_cls,), 0.4 + 0.05 * k) if k % 2 else None
+            n0 = eng.launch_count
+            lg, pr, vec = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen, thresholds=thr)
+            n_host = eng.launch_count - n0
+            dev = [x.cuda() for x in host]
+            n0 = eng.launch_count
+            lg2, pr2, vec2 = eng.forward(dev[0], dev[1], dev[2], dev[3], dev[4], mlen,
+                                         thresholds=None if thr is None else thr.cuda())
+            torch.cuda.synchronize()
+            assert n_host == eng.launch_count - n0 > 100
+            assert torch.equal(lg, lg2.cpu()) and torch.equal(pr, pr2.cpu()) and torch.equal(vec, vec2.cpu()), (B, k)
+
+
 def test_pipelined_host_requests_match_synchronous_call(eng):
     """mmdx_forward_host_submit / _wait with two requests in flight (different batches, sizes and lengths, slots
     reused) return exactly what the synchronous mmdx_forward_host returns for each request."""
