@@ -114,7 +114,10 @@ def bench_conv(h, lib):
              ("l3.c1", 14, 1024, 256, 1, 1, False), ("l3.c2", 14, 256, 256, 3, 1, False), ("l3.c3+res", 14, 256, 1024, 1, 1, True),
              ("l4.0.c1", 14, 1024, 512, 1, 1, False), ("l4.0.c2s2", 14, 512, 512, 3, 2, False), ("l4.0.ds", 14, 1024, 2048, 1, 2, False),
              ("l4.c1", 7, 2048, 512, 1, 1, False), ("l4.c2", 7, 512, 512, 3, 1, False), ("l4.c3+res", 7, 512, 2048, 1, 1, True)]
+    only = os.environ.get("OPBENCH_ONLY")
     for name, HW, Cin, Cout, k, s, res in cases:
+        if only and name != only:
+            continue
         x = bf(torch.randn(NB, HW, HW, Cin, device="cuda"))
         w = bf(torch.randn(Cout, k * k, Cin, device="cuda") * (k * k * Cin) ** -0.5)
         bias = torch.randn(Cout, device="cuda")
