@@ -98,6 +98,14 @@ int mmdx_forward_host_submit(mmdx_engine* e, int slot, const uint8_t* h_images_u
                              int T, int max_len, const float* h_thresholds, float* h_logits, float* h_probs,
                              uint8_t* h_vector, void* stream);
 int mmdx_forward_host_wait(mmdx_engine* e, int slot);
+/* Optional GPU JPEG decode (api/views.py:70 decodes with Pillow on the host, which sustains 6.8 k
+ * images/s on 16 cores against 29 k studies/s of the GPU path): n baseline JPEGs of one size H x W (host pointers) ->
+ * uint8 HWC RGB [n,H,W,3] on the device = the image input of mmdx_forward.  nvJPEG is loaded with dlopen on first use
+ * (no link dependency); NOT bit-identical to libjpeg-turbo (~2 % of the bytes differ by one), so the drop-in inference()
+ * keeps Pillow and this path has its own tolerance test.  mmdx_jpeg_backend: nvjpegBackend_t in use (-1 before first use). */
+int mmdx_decode_jpeg_batch(mmdx_engine* e, const uint8_t* const* h_blobs, const size_t* h_sizes, int n, int H, int W,
+                           uint8_t* d_out_rgb, void* stream);
+int mmdx_jpeg_backend(mmdx_engine* e);
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int64_t mmdx_launch_count(mmdx_engine* e);
 /* Per-kernel-class device time: between begin and end every launch is bracketed by CUDA events on its

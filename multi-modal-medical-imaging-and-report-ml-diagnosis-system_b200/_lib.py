@@ -58,6 +58,8 @@ SIGNATURES = {
     "mmdx_forward_host": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host_submit": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host_wait": [_p, _i],
+    "mmdx_decode_jpeg_batch": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "mmdx_jpeg_backend": [_p],
     "mmdx_launch_count": [_p],
     "mmdx_profile_begin": [_p],
     "mmdx_profile_end": [_p, _p, _p, _i],

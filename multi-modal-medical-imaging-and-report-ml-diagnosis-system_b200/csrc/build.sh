@@ -12,6 +12,6 @@ if [ "$stale" = "0" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "libmmdx.so up to date"; exit 0
 fi
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr \
-  -Xptxas -v -shared -Xcompiler -fPIC,-O2 -o "$OUT" engine.cu 2> build.log || { cat build.log; exit 1; }
+  -Xptxas -v -shared -Xcompiler -fPIC,-O2 -o "$OUT" engine.cu -ldl 2> build.log || { cat build.log; exit 1; }
 grep -E "error|warning" build.log | grep -v "Wno" | head -20 || true
 echo "built $OUT"

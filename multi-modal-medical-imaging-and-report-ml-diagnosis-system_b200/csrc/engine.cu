@@ -2,6 +2,8 @@
 // launch plans (tensor maps + workspace), and the forward: K_pre -> stem/maxpool/16 bottlenecks/avgpool
 // -> BERT-base over packed tokens -> fused head.  All compute is in hand-written sm_100a kernels.
 #include <cmath>
+#include <dlfcn.h>
+#include <nvjpeg.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -228,6 +230,15 @@ struct mmdx_engine {
     void* h_in = nullptr; void* h_out = nullptr; size_t in_bytes = 0, out_bytes = 0;
   };
   std::map<std::string, HostGraph> host_graphs;
+  // optional GPU JPEG decode: nvJPEG, loaded with dlopen on first use so that libmmdx.so has no hard
+  // dependency on it
+  struct Jpeg {
+    void* lib = nullptr; nvjpegHandle_t h = nullptr; nvjpegJpegState_t st = nullptr; int batch = 0; int backend = -1;
+    decltype(&nvjpegCreateEx) create_ex = nullptr; decltype(&nvjpegCreateSimple) create_simple = nullptr;
+    decltype(&nvjpegDestroy) destroy = nullptr; decltype(&nvjpegJpegStateCreate) state_create = nullptr;
+    decltype(&nvjpegJpegStateDestroy) state_destroy = nullptr; decltype(&nvjpegGetImageInfo) image_info = nullptr;
+    decltype(&nvjpegDecodeBatchedInitialize) batched_init = nullptr; decltype(&nvjpegDecodeBatched) batched = nullptr;
+  } jpeg;
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t graph_fork = nullptr;
   int graph_max_b = 8;
@@ -923,6 +934,9 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
     if (e->slot_tok_done[i]) cudaEventDestroy(e->slot_tok_done[i]);
     if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
   }
+  if (e->jpeg.st) e->jpeg.state_destroy(e->jpeg.st);
+  if (e->jpeg.h) e->jpeg.destroy(e->jpeg.h);
+  if (e->jpeg.lib) dlclose(e->jpeg.lib);
   for (auto& kv : e->host_graphs) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (kv.second.h_in) cudaFreeHost(kv.second.h_in);
@@ -1988,6 +2002,84 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   e->slot_busy[0] = false;
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------ GPU JPEG decode (N3)
+// A batch of baseline JPEGs of one size -> uint8 HWC RGB on the device (the input layout of mmdx_forward), decoded by
+// nvJPEG (hardware JPEG engine where the backend is available, GPU-hybrid otherwise).  NOT bit-identical to Pillow /
+// libjpeg-turbo (different IDCT and chroma up-sampling rounding: ~2 % of the bytes differ by one), which is why the
+// drop-in inference() keeps Pillow and this is an opt-in entry point with its own tolerance test.
+static int jpeg_init(mmdx_engine* e) {
+  mmdx_engine::Jpeg& j = e->jpeg;
+  if (j.h) return 0;
+  if (!j.lib) {
+    for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) {
+      j.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (j.lib) break;
+    }
+    REQUIRE(j.lib != nullptr, "libnvjpeg is not available on this machine (GPU JPEG decode is optional; use Pillow)");
+    j.create_ex = reinterpret_cast<decltype(j.create_ex)>(dlsym(j.lib, "nvjpegCreateEx"));
+    j.create_simple = reinterpret_cast<decltype(j.create_simple)>(dlsym(j.lib, "nvjpegCreateSimple"));
+    j.destroy = reinterpret_cast<decltype(j.destroy)>(dlsym(j.lib, "nvjpegDestroy"));
+    j.state_create = reinterpret_cast<decltype(j.state_create)>(dlsym(j.lib, "nvjpegJpegStateCreate"));
+    j.state_destroy = reinterpret_cast<decltype(j.state_destroy)>(dlsym(j.lib, "nvjpegJpegStateDestroy"));
+    j.image_info = reinterpret_cast<decltype(j.image_info)>(dlsym(j.lib, "nvjpegGetImageInfo"));
+    j.batched_init = reinterpret_cast<decltype(j.batched_init)>(dlsym(j.lib, "nvjpegDecodeBatchedInitialize"));
+    j.batched = reinterpret_cast<decltype(j.batched)>(dlsym(j.lib, "nvjpegDecodeBatched"));
+    REQUIRE(j.create_ex && j.create_simple && j.destroy && j.state_create && j.state_destroy && j.image_info &&
+                j.batched_init && j.batched, "libnvjpeg lacks the batched decode API");
+  }
+  const char* want = getenv("MMDX_NVJPEG_BACKEND");          // "hardware" | "hybrid" | unset: hardware, then default
+  nvjpegStatus_t st = NVJPEG_STATUS_NOT_INITIALIZED;
+  if (!want || strcmp(want, "hardware") == 0) {
+    st = j.create_ex(NVJPEG_BACKEND_HARDWARE, nullptr, nullptr, 0, &j.h);
+    if (st == NVJPEG_STATUS_SUCCESS) j.backend = (int)NVJPEG_BACKEND_HARDWARE;
+  }
+  if (st != NVJPEG_STATUS_SUCCESS && (!want || strcmp(want, "hybrid") == 0)) {
+    st = j.create_ex(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, 0, &j.h);
+    if (st == NVJPEG_STATUS_SUCCESS) j.backend = (int)NVJPEG_BACKEND_GPU_HYBRID;
+  }
+  if (st != NVJPEG_STATUS_SUCCESS) {
+    st = j.create_simple(&j.h);
+    if (st == NVJPEG_STATUS_SUCCESS) j.backend = (int)NVJPEG_BACKEND_DEFAULT;
+  }
+  REQUIRE(st == NVJPEG_STATUS_SUCCESS, "nvjpegCreate failed");
+  REQUIRE(j.state_create(j.h, &j.st) == NVJPEG_STATUS_SUCCESS, "nvjpegJpegStateCreate failed");
+  j.batch = 0;
+  return 0;
+}
+
+extern "C" int mmdx_decode_jpeg_batch(mmdx_engine* e, const uint8_t* const* h_blobs, const size_t* h_sizes, int n, int H, int W,
+                                      uint8_t* d_out_rgb, void* stream) {
+  REQUIRE(e && h_blobs && h_sizes && d_out_rgb && n > 0 && H > 0 && W > 0, "bad argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  TRY(jpeg_init(e));
+  mmdx_engine::Jpeg& j = e->jpeg;
+  for (int i = 0; i < n; ++i) {                                // every image must have the batch's size
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t ss;
+    REQUIRE(j.image_info(j.h, h_blobs[i], h_sizes[i], &nc, &ss, ws, hs) == NVJPEG_STATUS_SUCCESS, "not a decodable JPEG");
+    REQUIRE(ws[0] == W && hs[0] == H, "every JPEG of a batch must be H x W");
+  }
+  if (j.batch != n) {
+    REQUIRE(j.batched_init(j.h, j.st, n, 1, NVJPEG_OUTPUT_RGBI) == NVJPEG_STATUS_SUCCESS, "nvjpegDecodeBatchedInitialize failed");
+    j.batch = n;
+  }
+  std::vector<nvjpegImage_t> out(n);
+  for (int i = 0; i < n; ++i) {
+    memset(&out[i], 0, sizeof(nvjpegImage_t));
+    out[i].channel[0] = d_out_rgb + (size_t)i * H * W * 3;
+    out[i].pitch[0] = (size_t)W * 3;
+  }
+  const nvjpegStatus_t st = j.batched(j.h, j.st, h_blobs, h_sizes, out.data(), (cudaStream_t)stream);
+  if (st != NVJPEG_STATUS_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "nvjpegDecodeBatched failed (status %d, backend %d)", (int)st, j.backend);
+    return fail(buf);
+  }
+  return 0;
+}
+extern "C" int mmdx_jpeg_backend(mmdx_engine* e) { return e ? e->jpeg.backend : -1; }
 
 // ------------------------------------------------------------------------------------------ single-op entry points
 extern "C" int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,

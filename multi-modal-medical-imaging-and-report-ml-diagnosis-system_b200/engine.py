@@ -146,6 +146,17 @@ class Engine:
         check(lib().mmdx_cond_tokens(self._h, B, _ptr(out), _stream()))
         return out if n_cond is None else out.view(B, n_cond, -1)
 
+    def decode_jpeg_batch(self, blobs, H, W):
+        """Baseline JPEGs of one size (list of bytes) -> uint8 [n,H,W,3] on the device, decoded by nvJPEG (optional path,
+        SURVEY.md 8f N3; ~2 % of the bytes differ by one from Pillow / libjpeg-turbo)."""
+        n = len(blobs)
+        bufs = [(C.c_ubyte * len(b)).from_buffer_copy(b) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        sizes = (C.c_size_t * n)(*[len(b) for b in blobs])
+        out = torch.empty(n, H, W, 3, dtype=torch.uint8, device=self._dev())
+        check(lib().mmdx_decode_jpeg_batch(self._h, ptrs, sizes, n, int(H), int(W), _ptr(out), _stream()))
+        return out
+
     def forward(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None):
         """Whole path, device in / device out: (logits, probs, vector)."""
         B, H, W, Cc = images_u8.shape

@@ -202,6 +202,50 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
 
 
 @torch.no_grad()
+def inference_batch_jpeg(model_bundle, jpeg_blobs, details=None, device=None, max_len=96, tokens=None):
+    """Batched inference straight from JPEG bytes (what api/views.py:67-70 receives): the images are decoded on the GPU
+    by nvJPEG and never exist on the host.  Classification only (report_text ""), same result dicts as
+    inference_batch.  nvJPEG is not bit-identical to Pillow (about 2 % of the bytes differ by one), so probabilities
+    move in the 4th decimal; use inference_batch with PIL images where bit parity with the reference matters."""
+    import io
+    from PIL import Image
+    dev = _parse_device(device)
+    eng = get_engine(model_bundle, dev)
+    class_names = model_bundle["class_names"]
+    B = len(jpeg_blobs)
+    if tokens is None:
+        if details is None or len(details) != B:
+            raise ValueError("need one patient_details string per image")
+        tokens = tokenize(model_bundle, details, max_len)
+    ids_all = np.asarray(tokens["input_ids"])
+    mask_all = np.asarray(tokens["attention_mask"])
+    tt_all = np.asarray(tokens["token_type_ids"]) if tokens.get("token_type_ids") is not None else np.zeros_like(ids_all)
+    if ids_all.shape[0] != B:
+        raise ValueError("tokens and images disagree on the batch size")
+    groups: dict = {}
+    for i, b in enumerate(jpeg_blobs):
+        w, h = Image.open(io.BytesIO(b)).size                    # header only
+        groups.setdefault((h, w), []).append(i)
+    probs_out = np.zeros((B, eng.n_cls), np.float32)
+    vec_out = np.zeros((B, eng.n_cls), np.uint8)
+    with torch.cuda.device(dev):
+        thr_d = torch.tensor(model_bundle["thresholds"], dtype=torch.float32).to(dev)
+        for (h, w), idxs in groups.items():
+            imgs = eng.decode_jpeg_batch([jpeg_blobs[i] for i in idxs], h, w)
+            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs])
+            t = [torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (ids, pos, tt, cu)]
+            _, probs, vec = eng.forward(imgs, t[0], t[1], t[2], t[3], mlen, thresholds=thr_d)
+            probs_out[idxs] = probs.cpu().numpy()
+            vec_out[idxs] = vec.cpu().numpy()
+    return [{
+        "report_text": "",
+        "disease_probs": {class_names[j]: float(probs_out[i, j]) for j in range(len(class_names))},
+        "disease_vector": [int(v) for v in vec_out[i]],
+        "model_version": model_bundle["version"],
+    } for i in range(B)]
+
+
+@torch.no_grad()
 def inference(model_bundle, image_pil, patient_details, device=None, gen_kwargs=None):
     """Same contract as the reference's inference() (inference_pipeline.py:150-206):
     returns {report_text, disease_probs{class: float}, disease_vector[0/1], model_version}."""

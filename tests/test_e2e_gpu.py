@@ -270,6 +270,42 @@ def test_two_devices_in_one_process(bundle, g1):
     assert a == b
 
 
+def test_gpu_jpeg_decode_path(bundle, eng):
+    """JPEG bytes -> nvJPEG on the GPU -> forward.  Not bit-identical to Pillow by construction: the
+    decoded bytes may differ by a few counts on a small fraction of positions; labels and probabilities must agree with
+    the Pillow-decoded path within the bf16 tolerance, and malformed / mixed-size batches fail cleanly."""
+    import io
+    from PIL import Image
+    from mmdx_b200._lib import MmdxError
+    raw = synth.synth_images(6, 512, seed=41)
+    blobs = []
+    for a in raw:
+        buf = io.BytesIO()
+        Image.fromarray(a).save(buf, format="JPEG", quality=90)
+        blobs.append(buf.getvalue())
+    try:
+        dec = eng.decode_jpeg_batch(blobs, 512, 512).cpu().numpy()
+    except MmdxError as ex:
+        if "not available" in str(ex):
+            pytest.skip("libnvjpeg is not installed on this machine")
+        raise
+    pil = np.stack([np.asarray(Image.open(io.BytesIO(b)).convert("RGB")) for b in blobs])
+    d = np.abs(dec.astype(int) - pil.astype(int))
+    assert d.max() <= 3 and (d > 0).mean() < 0.10, (d.max(), (d > 0).mean())
+    details = ["patient age 54 male cough fever"] * 6
+    a = ip.inference_batch_jpeg(bundle, blobs, details, device="cuda")
+    b = ip.inference_batch(bundle, list(pil), details, device="cuda")
+    for ra, rb in zip(a, b):
+        pa, pb = np.array(list(ra["disease_probs"].values())), np.array(list(rb["disease_probs"].values()))
+        assert np.abs(pa - pb).max() < PROB_TOL
+        decided = np.abs(pb - 0.5) > 5e-3
+        assert np.array_equal(np.array(ra["disease_vector"])[decided], np.array(rb["disease_vector"])[decided])
+    with pytest.raises(MmdxError):
+        eng.decode_jpeg_batch([b"not a jpeg"], 512, 512)
+    with pytest.raises(MmdxError):
+        eng.decode_jpeg_batch(blobs[:2], 256, 256)              # wrong size for the batch
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image

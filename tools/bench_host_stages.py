@@ -78,6 +78,24 @@ def main():
     except Exception as e:                                      # noqa: BLE001 - report, do not hide
         res["nvjpeg_error"] = repr(e)[:200]
 
+    try:                                                        # the engine's own batched nvJPEG entry point
+        import torch
+        from mmdx_b200 import synth as _synth
+        from mmdx_b200 import inference_pipeline as ip
+        from mmdx_b200._lib import lib
+        eng = ip.get_engine(_synth.make_state_bundle(seed=0), "cuda")
+        for nb in (64, 256):
+            eng.decode_jpeg_batch(blobs[:nb], 512, 512)
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(4):
+                eng.decode_jpeg_batch(blobs[:nb], 512, 512)
+            torch.cuda.synchronize()
+            res[f"mmdx_nvjpeg_batch{nb}_img_s"] = 4 * nb / (time.perf_counter() - t)
+        res["mmdx_nvjpeg_backend"] = int(lib().mmdx_jpeg_backend(eng.handle))
+    except Exception as e:                                      # noqa: BLE001
+        res["mmdx_nvjpeg_error"] = repr(e)[:200]
+
     from mmdx_b200 import synth
     tok = synth.make_bert_tokenizer()
     rng = np.random.default_rng(0)
