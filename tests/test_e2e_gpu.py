@@ -306,6 +306,33 @@ def test_gpu_jpeg_decode_path(bundle, eng):
         eng.decode_jpeg_batch(blobs[:2], 256, 256)              # wrong size for the batch
 
 
+def test_concurrent_callers(bundle, g1):
+    """Django's dev server may enter inference() from several threads at once (only bundle loading is
+    lock-protected in the reference): every engine entry point takes the engine's mutex, so concurrent callers get the
+    results a single caller gets."""
+    import threading
+    from PIL import Image
+    pils = [Image.fromarray(np.repeat(g1["gray"][i][..., None], 3, axis=-1)) for i in range(2)]
+    want = [ip.inference(bundle, pils[i], str(g1["details"][i]), device="cuda", gen_kwargs=False) for i in range(2)]
+    got, errs = {}, []
+
+    def worker(k):
+        try:
+            for r in range(6):
+                i = (k + r) % 2
+                got[(k, r)] = (i, ip.inference(bundle, pils[i], str(g1["details"][i]), device="cuda", gen_kwargs=False))
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert len(got) == 24 and all(res == want[i] for i, res in got.values())
+
+
 def test_inference_drop_in_contract(bundle, g1):
     """Signature, result dict and error behaviour of inference() (inference_pipeline.py:150-206)."""
     from PIL import Image
