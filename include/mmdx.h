@@ -61,6 +61,11 @@ int mmdx_num_sms(mmdx_engine* e);
 /* dims read from the loaded weights: d_img, d_txt, d_fuse_hidden, n_disease, hidden, n_layers, width of cond_proj
  * (n_cond * h_dec; 0 if the bundle has none), rows of the position table (longest sequence) */
 int mmdx_dims(mmdx_engine* e, int32_t out[8]);
+/* rows of the word / position / token-type embedding tables.  nn.Embedding raises IndexError on an index outside its
+ * table (training_pipeline.py:470-473 -> HF BertEmbeddings): the HOST entry points (mmdx_forward_host*) check every id
+ * against these sizes and fail; the device-pointer entry points cannot see the ids, so the kernel clamps them (memory
+ * safety) and the Python wrappers validate at token-packing time. */
+int mmdx_table_sizes(mmdx_engine* e, int32_t out[3]);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* image_transfom_into_tensor (training_pipeline.py:112-119) + ImageEncoderCNN.forward (:306-311).

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mmdx_load_packed": [_p, C.c_char_p],
     "mmdx_num_sms": [_p],
     "mmdx_dims": [_p, C.POINTER(C.c_int32)],
+    "mmdx_table_sizes": [_p, C.POINTER(C.c_int32)],
     "mmdx_image_encode": [_p, _p, _i, _i, _i, _i, _p, _p, _p],
     "mmdx_text_encode": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p],
     "mmdx_head": [_p, _i, _p, _p, _p, _p, _p, _p],

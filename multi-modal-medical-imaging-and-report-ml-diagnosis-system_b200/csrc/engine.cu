@@ -116,9 +116,11 @@ struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
 
 struct DevBuf {
   void* p = nullptr; size_t bytes = 0;
+  int64_t* gen = nullptr;     // bumped when the buffer moves: captured CUDA graphs that point into it are stale
   ~DevBuf() { if (p) cudaFree(p); }
   int ensure(size_t n) {
     if (n <= bytes) return 0;
+    if (gen) ++*gen;
     if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) return fail(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
@@ -187,7 +189,7 @@ struct mmdx_engine {
   bool finalized = false;
   // dims
   int d_img = 0, d_txt = 0, d_fuse = 0, n_cls = 0, hidden = 0, n_layers = 0, ffn = 0, feat_dim = 2048;
-  int vocab = 0, max_pos = 0;     // rows of the word / position embedding tables
+  int vocab = 0, max_pos = 0, type_vocab = 2;     // rows of the word / position / token-type embedding tables
   // weights (one arena)
   DevBuf warena; size_t wused = 0;
   ConvW stem; bf16* stem_w2 = nullptr;   // stem weights in the stem kernel's resident layout
@@ -227,9 +229,16 @@ struct mmdx_engine {
   // pinned staging buffers so that every pointer inside the graph is fixed.  MMDX_GRAPH_MAX_B=0 turns it off.
   struct HostGraph {
     cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0;
+    int64_t gen = -1;          // ws_gen the plans / workspaces of this shape were last laid out under
     void* h_in = nullptr; void* h_out = nullptr; size_t in_bytes = 0, out_bytes = 0;
   };
   std::map<std::string, HostGraph> host_graphs;
+  // Workspace generation: every reallocation of an arena a captured graph points into (img_ws, txt_ws, head_ws, the
+  // request slots) bumps it; a graph captured under another generation holds dangling pointers and is dropped.
+  int64_t ws_gen = 0;
+  // Cross-call ordering: the activation / head workspaces are shared by every call, so a call on another stream than
+  // the previous one waits for the previous call's last kernel (calls on one stream are ordered anyway).
+  cudaEvent_t last_done = nullptr; cudaStream_t last_stream = nullptr; bool have_last = false;
   // optional GPU JPEG decode: nvJPEG, loaded with dlopen on first use so that libmmdx.so has no hard
   // dependency on it
   struct Jpeg {
@@ -914,6 +923,8 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   if (const char* v = getenv("MMDX_GRAPH_MAX_B")) e->graph_max_b = atoi(v);
   CK(cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->graph_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
+  e->img_ws.gen = e->txt_ws.gen = e->head_ws.gen = e->io_slot[0].gen = e->io_slot[1].gen = &e->ws_gen;
   if (const char* v = getenv("MMDX_CG")) e->force_cg = atoi(v);
   if (const char* v = getenv("MMDX_BN")) e->force_bn = atoi(v);
   if (const char* v = getenv("MMDX_EB")) e->epi_bufs = atoi(v);
@@ -944,6 +955,7 @@ extern "C" void mmdx_destroy(mmdx_engine* e) {
   }
   if (e->graph_stream) cudaStreamDestroy(e->graph_stream);
   if (e->graph_fork) cudaEventDestroy(e->graph_fork);
+  if (e->last_done) cudaEventDestroy(e->last_done);
   if (e->text_stream) cudaStreamDestroy(e->text_stream);
   if (e->fork_ev) cudaEventDestroy(e->fork_ev);
   if (e->join_ev) cudaEventDestroy(e->join_ev);
@@ -1106,6 +1118,7 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     e->hidden = (int)get(e, eb + "word_embeddings.weight")->shape[1];
     e->vocab = (int)get(e, eb + "word_embeddings.weight")->shape[0];
     e->max_pos = (int)get(e, eb + "position_embeddings.weight")->shape[0];
+    e->type_vocab = (int)get(e, eb + "token_type_embeddings.weight")->shape[0];
     e->layers.clear();
     for (int l = 0;; ++l) {
       const std::string p = "text.encoder.encoder.layer." + std::to_string(l) + ".";
@@ -1180,7 +1193,7 @@ struct PackHeader {
   uint64_t arena_bytes;
   uint64_t checksum;        // FNV-1a of table + arena
 };
-static const uint32_t kPackVersion = 4;
+static const uint32_t kPackVersion = 5;
 
 struct PackWalker {
   bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
@@ -1205,7 +1218,7 @@ struct PackWalker {
 // one traversal for both directions: every field mmdx_finalize_weights sets
 static void walk_weights(mmdx_engine* e, PackWalker& w) {
   w.i(e->d_img); w.i(e->d_txt); w.i(e->d_fuse); w.i(e->n_cls); w.i(e->hidden); w.i(e->n_layers); w.i(e->ffn); w.i(e->feat_dim);
-  w.i(e->cfg.n_heads); w.i(e->vocab); w.i(e->max_pos);
+  w.i(e->cfg.n_heads); w.i(e->vocab); w.i(e->max_pos); w.i(e->type_vocab);
   w.conv(e->stem); w.p(e->stem_w2);
   int nb = (int)e->blocks.size();
   w.i(nb);
@@ -1291,6 +1304,12 @@ extern "C" int mmdx_dims(mmdx_engine* e, int32_t out[8]) {
   REQUIRE(e && e->finalized, "weights not finalized");
   out[0] = e->d_img; out[1] = e->d_txt; out[2] = e->d_fuse; out[3] = e->n_cls; out[4] = e->hidden; out[5] = e->n_layers;
   out[6] = e->cond.w ? e->cond.nout : 0; out[7] = e->max_pos;
+  return 0;
+}
+
+extern "C" int mmdx_table_sizes(mmdx_engine* e, int32_t out[3]) {
+  REQUIRE(e && e->finalized && out, "weights not finalized");
+  out[0] = e->vocab; out[1] = e->max_pos; out[2] = e->type_vocab;
   return 0;
 }
 
@@ -1593,10 +1612,10 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
   const int rv = next_direction(e, s);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1604,15 +1623,15 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
 }
 static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const int* tt, int rows, int N, const bf16* word,
                         const bf16* ptab, const bf16* ttab, const float* g, const float* b, float eps, bf16* y,
-                        cudaStream_t s) {
+                        cudaStream_t s, int n_word = 0x7fffffff, int n_pos = 0x7fffffff, int n_type = 0x7fffffff) {
   constexpr int R = 2;
   const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
     default: return fail("mmdx: hidden width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1671,6 +1690,20 @@ static int launch_cvt(mmdx_engine* e, const bf16* in, long long ld, int rows, in
 }
 
 // ------------------------------------------------------------------------------------------ hot path
+// Calls share the activation workspaces.  Work of one call is ordered on its stream(s); a call that arrives on a
+// DIFFERENT stream than the previous one (torch per-thread streams) first waits for the previous call's last kernel.
+static int order_begin(mmdx_engine* e, cudaStream_t s) {
+  if (e->capturing) return 0;
+  if (e->have_last && e->last_stream != s) CK(cudaStreamWaitEvent(s, e->last_done, 0));
+  return 0;
+}
+static int order_end(mmdx_engine* e, cudaStream_t s) {
+  if (e->capturing) return 0;
+  CK(cudaEventRecord(e->last_done, s));
+  e->last_stream = s; e->have_last = true;
+  return 0;
+}
+
 static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, float* d_feats,
                                float* d_z_img, cudaStream_t s) {
   REQUIRE(e->finalized, "weights not finalized");
@@ -1681,9 +1714,12 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   PreGeom g{0, 0, pl->off_y, pl->off_x, pl->crop_h, pl->crop_w, pl->has_x, pl->has_y};
   e->cur_stream = s; e->cur_cls = CLS_PRE;
   e->zz_img = 1;                                   // preprocess / stem write forward: the first conv walks backwards
-  if (e->img_last != pl) {   // another geometry used the arena: restore the zero border + zero 4th channel
+  // Another geometry may have used the arena since this plan last ran: restore the zero border + zero 4th channel.
+  // A captured graph cannot know what ran before each of its replays, so it always carries the memset (and a replay
+  // resets img_last, see forward_host_graphed).
+  if (e->capturing || e->img_last != pl) {
     CK(cudaMemsetAsync(pl->in_pad, 0, pl->in_pad_bytes, s));
-    e->img_last = pl;
+    if (!e->capturing) e->img_last = pl;
   }
   TRY(launch_preprocess(e, d_images, B, H, W, C, g, pl->tx, pl->ty, pl->strip, pl->in_pad, pl->hp, pl->wp, s));
   e->cur_cls = CLS_STEM;
@@ -1719,7 +1755,8 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   const int H = e->hidden;
   e->cur_stream = s; e->cur_cls = CLS_LN;
   e->zz_txt = 1;                                   // the embedding kernel writes forward: the first consumer walks backwards
-  TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s));
+  TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s,
+                   e->vocab, e->max_pos, e->type_vocab));
   for (int l = 0; l < e->n_layers; ++l) {
     const BertLayerW& L = e->layers[l];
     e->cur_cls = CLS_GEMM_TEXT;
@@ -1772,7 +1809,9 @@ extern "C" int mmdx_image_encode(mmdx_engine* e, const uint8_t* d_images, int B,
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
-  return image_encode_locked(e, d_images, B, H, W, C, d_feats, d_z_img, (cudaStream_t)stream);
+  TRY(order_begin(e, (cudaStream_t)stream));
+  TRY(image_encode_locked(e, d_images, B, H, W, C, d_feats, d_z_img, (cudaStream_t)stream));
+  return order_end(e, (cudaStream_t)stream);
 }
 extern "C" int mmdx_text_encode(mmdx_engine* e, const int32_t* d_ids, const int32_t* d_pos, const int32_t* d_tt,
                                 const int32_t* d_cu, int B, int T, int max_len, float* d_pooled, float* d_z_txt,
@@ -1780,14 +1819,18 @@ extern "C" int mmdx_text_encode(mmdx_engine* e, const int32_t* d_ids, const int3
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
-  return text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, d_pooled, d_z_txt, (cudaStream_t)stream);
+  TRY(order_begin(e, (cudaStream_t)stream));
+  TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, d_pooled, d_z_txt, (cudaStream_t)stream));
+  return order_end(e, (cudaStream_t)stream);
 }
 extern "C" int mmdx_head(mmdx_engine* e, int B, const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs,
                          uint8_t* d_vector, void* stream) {
   REQUIRE(e, "null engine");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
-  return head_locked(e, B, d_thr, d_z_fuse, d_logits, d_probs, d_vector, (cudaStream_t)stream);
+  TRY(order_begin(e, (cudaStream_t)stream));
+  TRY(head_locked(e, B, d_thr, d_z_fuse, d_logits, d_probs, d_vector, (cudaStream_t)stream));
+  return order_end(e, (cudaStream_t)stream);
 }
 // FusionTransformerModel._make_encoder_outputs (training_pipeline.py:574-578) for the batch mmdx_head has just processed:
 // cond = GELU(z_fuse * Wc^T + bc), fp32 [B, n_cond * h_dec] - the "encoder output" the T5 decoder is conditioned on.
@@ -1801,7 +1844,9 @@ extern "C" int mmdx_cond_tokens(mmdx_engine* e, int B, float* d_cond, void* stre
   GemmLaunch g;
   TRY(build_gemm(e, g, e->zfuse_bf, e->d_fuse, e->cond.w, B, e->cond.nout, e->d_fuse, 0));
   TRY(fill_epilogue(e, g, e->cond.bias, nullptr, 0, d_cond, e->cond.nout, ACT_GELU, 1));
-  return launch_gemm(e, g, (cudaStream_t)stream);
+  TRY(order_begin(e, (cudaStream_t)stream));
+  TRY(launch_gemm(e, g, (cudaStream_t)stream));
+  return order_end(e, (cudaStream_t)stream);
 }
 extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
                             const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu, int T, int max_len,
@@ -1812,6 +1857,7 @@ extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int 
   cudaStream_t s = (cudaStream_t)stream;
   const bool fork = e->two_streams && !e->profiling;
   cudaStream_t ts = fork ? e->text_stream : s;
+  TRY(order_begin(e, s));
   if (fork) {
     CK(cudaEventRecord(e->fork_ev, s));                 // inputs (and earlier work on `s`) are ready
     CK(cudaStreamWaitEvent(ts, e->fork_ev, 0));
@@ -1820,7 +1866,8 @@ extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int 
   if (fork) CK(cudaEventRecord(e->join_ev, ts));
   TRY(image_encode_locked(e, d_images, B, H, W, C, nullptr, nullptr, s));
   if (fork) CK(cudaStreamWaitEvent(s, e->join_ev, 0));
-  return head_locked(e, B, d_thr, nullptr, d_logits, d_probs, d_vector, s);
+  TRY(head_locked(e, B, d_thr, nullptr, d_logits, d_probs, d_vector, s));
+  return order_end(e, s);
 }
 
 // Request slot `slot`: H2D of its inputs, the forward, D2H of its results - enqueued, not waited for.  The image batch
@@ -1864,6 +1911,7 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
   CK(cudaEventRecord(e->slot_copy_done[slot], e->copy_stream));
   const bool fork = e->two_streams && !e->profiling;
   cudaStream_t ts = fork ? e->text_stream : s;
+  TRY(order_begin(e, s));
   if (fork) {                                                  // the previous request on `s` still uses the shared workspaces
     CK(cudaEventRecord(e->copy_ready, s));
     CK(cudaStreamWaitEvent(ts, e->copy_ready, 0));
@@ -1876,6 +1924,7 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
   TRY(image_encode_locked(e, d_img, B, H, W, C, nullptr, nullptr, s));
   if (fork) CK(cudaStreamWaitEvent(s, e->join_ev, 0));
   TRY(head_locked(e, B, h_thr ? d_thr : nullptr, nullptr, d_logits, d_probs, d_vec, s));
+  TRY(order_end(e, s));
   CK(cudaMemcpyAsync(h_logits, d_logits, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * e->n_cls * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(h_vector, d_vec, (size_t)B * e->n_cls, cudaMemcpyDeviceToHost, s));
@@ -1891,17 +1940,29 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
 static int forward_host_graphed(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
                                 const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu, int T, int max_len,
                                 const float* h_thr, float* h_logits, float* h_probs, uint8_t* h_vector, cudaStream_t s,
-                                bool* done) {
-  *done = false;
+                                bool* done, mmdx_engine::HostGraph** warm) {
+  *done = false; *warm = nullptr;
   char key[96];
   snprintf(key, sizeof key, "%d_%d_%d_%d_%d_%d_%d", B, H, W, C, T, max_len, h_thr ? 1 : 0);
   if (e->host_graphs.size() > 32 && e->host_graphs.find(key) == e->host_graphs.end()) return 0;   // bounded
   mmdx_engine::HostGraph& hg = e->host_graphs[key];
   if (hg.seen < 0) return 0;                                   // capture failed once for this shape: ordinary path
-  if (hg.seen++ == 0) return 0;                                // first call of this shape: ordinary path (warm-up)
+  if (hg.exec && hg.gen != e->ws_gen) {
+    // A workspace moved since the capture (cudaFree + cudaMalloc in DevBuf::ensure: a longer report, a larger image or a
+    // bigger batch came by): every pointer and tensor map inside the graph is stale.  Drop it and start over.
+    cudaGraphExecDestroy(hg.exec);
+    hg.exec = nullptr; hg.seen = 0;
+  }
+  if (hg.seen == 0 || hg.gen != e->ws_gen) {
+    // first call of this shape (or first after a move): the ordinary path creates the plans and sizes the workspaces;
+    // the caller stamps hg.gen when it has run
+    hg.seen = 1; *warm = &hg;
+    return 0;
+  }
+  ++hg.seen;
   const size_t img_b = al((size_t)B * H * W * C), tok_b = al((size_t)T * 4), cu_b = al((size_t)(B + 1) * 4);
   const size_t thr_b = al((size_t)e->n_cls * 4), of = al((size_t)B * e->n_cls * 4), ou = al((size_t)B * e->n_cls);
-  if (!hg.exec) {
+  if (!hg.h_in) {
     hg.in_bytes = img_b + 3 * tok_b + cu_b + thr_b; hg.out_bytes = 2 * of + ou;
     CK(cudaMallocHost(&hg.h_in, hg.in_bytes));
     CK(cudaMallocHost(&hg.h_out, hg.out_bytes));
@@ -1921,7 +1982,7 @@ static int forward_host_graphed(mmdx_engine* e, const uint8_t* h_images, int B, 
     // slot 0 must be idle and its buffers allocated (the warm-up call did both); capture on the engine's own stream
     // (the caller's may be the legacy default stream, which cannot be captured)
     if (e->slot_busy[0]) { CK(cudaEventSynchronize(e->slot_done[0])); e->slot_busy[0] = false; }
-    const int64_t n0 = e->launches;
+    const int64_t n0 = e->launches, gen0 = e->ws_gen;
     const int zt = e->zz_txt, zi = e->zz_img;
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(e->graph_stream, cudaStreamCaptureModeRelaxed));
@@ -1939,9 +2000,15 @@ static int forward_host_graphed(mmdx_engine* e, const uint8_t* h_images, int B, 
     }
     hg.launches = e->launches - n0;
     e->launches = n0;
+    if (e->ws_gen != gen0) {                                   // a buffer moved while capturing: the graph is unusable
+      cudaGraphDestroy(graph);
+      hg.seen = 0;
+      return 0;
+    }
     const cudaError_t ie = cudaGraphInstantiate(&hg.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) { cudaGetLastError(); hg.exec = nullptr; hg.seen = -1000000; return 0; }
+    hg.gen = e->ws_gen;
   }
   if (hg.seen < 0) return 0;
   memcpy(s_img, h_images, (size_t)B * H * W * C);
@@ -1950,13 +2017,30 @@ static int forward_host_graphed(mmdx_engine* e, const uint8_t* h_images, int B, 
   if (h_thr) memcpy(s_thr, h_thr, (size_t)e->n_cls * 4);
   CK(cudaEventRecord(e->graph_fork, s));                       // order behind whatever the caller queued on `s`
   CK(cudaStreamWaitEvent(e->graph_stream, e->graph_fork, 0));
+  TRY(order_begin(e, e->graph_stream));                        // ... and behind the previous call, whatever its stream
   CK(cudaGraphLaunch(hg.exec, e->graph_stream));
   CK(cudaStreamSynchronize(e->graph_stream));
+  e->have_last = false;                                        // everything has completed
+  e->img_last = nullptr;           // the replay laid its own plan's tensors over the image arena (and zeroed only its own in_pad)
   e->launches += hg.launches;
   memcpy(h_logits, s_logits, (size_t)B * e->n_cls * 4);
   memcpy(h_probs, s_probs, (size_t)B * e->n_cls * 4);
   memcpy(h_vector, s_vec, (size_t)B * e->n_cls);
   *done = true;
+  return 0;
+}
+
+// nn.Embedding raises IndexError on an out-of-range index (a tokenizer / vocabulary mismatch, caller-made tokens); the
+// host entry points see the ids and reject them before anything is launched.
+static int validate_tokens(mmdx_engine* e, const int32_t* ids, const int32_t* pos, const int32_t* tt, const int32_t* cu,
+                           int B, int T, int max_len) {
+  REQUIRE(B > 0 && T > 0 && cu[0] == 0 && cu[B] == T, "cu_seqlens must run from 0 to T");
+  for (int b = 0; b < B; ++b) REQUIRE(cu[b + 1] > cu[b] && cu[b + 1] - cu[b] <= max_len, "sequence lengths must be in 1..max_len");
+  unsigned bad = 0;
+  for (int i = 0; i < T; ++i)
+    bad |= (unsigned)((unsigned)ids[i] >= (unsigned)e->vocab) | (unsigned)((unsigned)pos[i] >= (unsigned)e->max_pos) |
+           (unsigned)((unsigned)tt[i] >= (unsigned)e->type_vocab);
+  REQUIRE(bad == 0, "token id / position / token type outside the embedding tables (index out of range)");
   return 0;
 }
 
@@ -1968,6 +2052,8 @@ extern "C" int mmdx_forward_host_submit(mmdx_engine* e, int slot, const uint8_t*
   REQUIRE(slot == 0 || slot == 1, "request slot must be 0 or 1");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
+  REQUIRE(e->finalized, "weights not finalized");
+  TRY(validate_tokens(e, h_ids, h_pos, h_tt, h_cu, B, T, max_len));
   return forward_host_submit_locked(e, slot, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits,
                                     h_probs, h_vector, (cudaStream_t)stream);
 }
@@ -1990,16 +2076,20 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   REQUIRE(e && h_images && h_ids && h_pos && h_tt && h_cu && h_logits && h_probs && h_vector, "null argument");
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->cfg.device));
+  REQUIRE(e->finalized, "weights not finalized");
+  TRY(validate_tokens(e, h_ids, h_pos, h_tt, h_cu, B, T, max_len));
+  mmdx_engine::HostGraph* warm = nullptr;
   if (B <= e->graph_max_b && !e->profiling) {
     bool done = false;
     TRY(forward_host_graphed(e, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits, h_probs, h_vector,
-                             (cudaStream_t)stream, &done));
+                             (cudaStream_t)stream, &done, &warm));
     if (done) return 0;
   }
   TRY(forward_host_submit_locked(e, 0, h_images, B, H, W, C, h_ids, h_pos, h_tt, h_cu, T, max_len, h_thr, h_logits, h_probs,
                                  h_vector, (cudaStream_t)stream));
   CK(cudaEventSynchronize(e->slot_done[0]));
   e->slot_busy[0] = false;
+  if (warm) warm->gen = e->ws_gen;      // plans and workspaces of this shape exist under this generation: capture next time
   return 0;
 }
 

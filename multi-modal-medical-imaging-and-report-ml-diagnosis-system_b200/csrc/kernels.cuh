@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
                                                         const int* __restrict__ tts,
                                                         const __nv_bfloat16* __restrict__ word,
                                                         const __nv_bfloat16* __restrict__ ptab,
-                                                        const __nv_bfloat16* __restrict__ ttab, int reverse) {
+                                                        const __nv_bfloat16* __restrict__ ttab, int reverse,
+                                                        int n_word, int n_pos, int n_type) {
   pdl_wait();
   pdl_trigger();
   // R rows per warp: all their 16-byte loads are issued before the first reduction (R * N / 256 loads in flight
@@ -378,9 +379,14 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int row = min(row0 + r, rows - 1);        // clamped duplicates are computed but not stored
-      const uint4* w = reinterpret_cast<const uint4*>(word + static_cast<size_t>(__ldg(ids + row)) * N);
-      const uint4* pp = reinterpret_cast<const uint4*>(ptab + static_cast<size_t>(__ldg(pos + row)) * N);
-      const uint4* tt = reinterpret_cast<const uint4*>(ttab + static_cast<size_t>(__ldg(tts + row)) * N);
+      // Indices are clamped to the tables (memory safety only: the host entry points reject out-of-range ids the way
+      // nn.Embedding raises IndexError; device-resident ids cannot be checked without a round trip).
+      const int iw = min(max(__ldg(ids + row), 0), n_word - 1);
+      const int ip = min(max(__ldg(pos + row), 0), n_pos - 1);
+      const int it = min(max(__ldg(tts + row), 0), n_type - 1);
+      const uint4* w = reinterpret_cast<const uint4*>(word + static_cast<size_t>(iw) * N);
+      const uint4* pp = reinterpret_cast<const uint4*>(ptab + static_cast<size_t>(ip) * N);
+      const uint4* tt = reinterpret_cast<const uint4*>(ttab + static_cast<size_t>(it) * N);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const uint4 a = __ldg(w + c * 32 + lane), b = __ldg(pp + c * 32 + lane), d = __ldg(tt + c * 32 + lane);

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -23,15 +24,25 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def pack_tokens(input_ids, attention_mask, token_type_ids=None):
+def pack_tokens(input_ids, attention_mask, token_type_ids=None, table_sizes=None):
     """Host-side unpadding: keep the tokens with attention_mask==1 (padded keys are masked to -inf and
     padded query rows are dropped by the masked mean in the reference, training_pipeline.py:452-459, so
     computing only valid tokens is results-identical).  Returns int32 numpy arrays
-    (ids[T], pos[T], tt[T], cu_seqlens[B+1]) and max_len."""
+    (ids[T], pos[T], tt[T], cu_seqlens[B+1]) and max_len.
+    `table_sizes` = (vocab, max_positions, type_vocab) of the engine (Engine.table_sizes): ids outside the
+    embedding tables raise IndexError, like nn.Embedding in the reference."""
     ids = np.asarray(input_ids)
     mask = np.asarray(attention_mask).astype(bool)
     B, L = ids.shape
     tt = np.zeros_like(ids) if token_type_ids is None else np.asarray(token_type_ids)
+    if table_sizes is not None:
+        vocab, max_pos, type_vocab = table_sizes
+        if ids[mask].size and (ids[mask].min() < 0 or ids[mask].max() >= vocab):
+            raise IndexError(f"token id out of range for the word embedding table ({vocab} rows)")
+        if tt[mask].size and (tt[mask].min() < 0 or tt[mask].max() >= type_vocab):
+            raise IndexError(f"token_type_id out of range for the token-type embedding table ({type_vocab} rows)")
+        if L > max_pos and mask[:, max_pos:].any():
+            raise IndexError(f"sequence longer than the position embedding table ({max_pos} rows)")
     lens = mask.sum(1)
     if (lens == 0).any():
         raise ValueError("every study needs at least one unmasked token")
@@ -74,6 +85,18 @@ class Engine:
         check(lib().mmdx_dims(self._h, d))
         self.d_img, self.d_txt, self.d_fuse, self.n_cls, self.hidden, self.n_layers, self.cond_width, self.max_pos = list(d)
         self.feat_dim = 2048
+        t = (C.c_int32 * 3)()
+        check(lib().mmdx_table_sizes(self._h, t))
+        self.vocab, _, self.type_vocab = list(t)
+        # A request is often several C calls (forward, then cond_tokens; or image_encode / text_encode / head) that
+        # hand results to each other through engine-owned buffers: callers that may run concurrently (Django's threaded
+        # dev server) hold this lock around the whole sequence.  Each C call also takes the engine's
+        # own mutex, so single calls are safe without it.
+        self.lock = threading.RLock()
+
+    @property
+    def table_sizes(self):
+        return self.vocab, self.max_pos, self.type_vocab
 
     @classmethod
     def from_packed(cls, path: str, device: int | None = None, resize_short: int = 256, crop: int = 224,

@@ -134,6 +134,8 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
     if ids_all.shape[0] != B:
         raise ValueError("tokens and images disagree on the batch size")
     thr = torch.tensor(model_bundle["thresholds"], dtype=torch.float32)
+    if thr.numel() != eng.n_cls or len(class_names) != eng.n_cls:
+        raise ValueError(f"bundle has {thr.numel()} thresholds / {len(class_names)} class names for {eng.n_cls} classes")
 
     probs_out = np.zeros((B, eng.n_cls), np.float32)
     vec_out = np.zeros((B, eng.n_cls), np.uint8)
@@ -151,25 +153,27 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
     with torch.cuda.device(dev):
         thr_d = thr.to(dev)
         for shape, idxs in groups.items():
-            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs])
+            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs], eng.table_sizes)
             if not want_report or use_cond:
                 # one C call per shape group: H2D, forward, D2H (small groups replay a captured CUDA graph)
                 host = [torch.from_numpy(x).pin_memory() for x in (np.stack([imgs[i] for i in idxs]), ids, pos, tt, cu)]
-                _, probs, vec = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen, thresholds=thr)
+                with eng.lock:   # forward + cond_tokens hand z_fuse over inside the engine: one request at a time
+                    _, probs, vec = eng.forward_host(host[0], host[1], host[2], host[3], host[4], mlen, thresholds=thr)
+                    if want_report:  # cond_proj on the engine: the decoder only needs these tokens
+                        cond_out[idxs] = eng.cond_tokens(len(idxs)).cpu().numpy()
                 probs_out[idxs] = probs.numpy()
                 vec_out[idxs] = vec.numpy()
-                if want_report:  # cond_proj on the engine: the decoder only needs these tokens
-                    cond_out[idxs] = eng.cond_tokens(len(idxs)).cpu().numpy()
                 continue
             batch = torch.from_numpy(np.stack([imgs[i] for i in idxs])).pin_memory().to(dev, non_blocking=True)
             t = [torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (ids, pos, tt, cu)]
-            _, z_img = eng.image_encode(batch, want_feats=False)
-            _, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen, want_pooled=False)
-            _, _, probs, vec = eng.head(len(idxs), thr_d, want_z_fuse=False)
-            probs_out[idxs] = probs.cpu().numpy()
-            vec_out[idxs] = vec.cpu().numpy()
-            z_img_out[idxs] = z_img.cpu().numpy()
-            z_txt_out[idxs] = z_txt.cpu().numpy()
+            with eng.lock:       # the three staged calls meet in the engine's shared head buffers
+                _, z_img = eng.image_encode(batch, want_feats=False)
+                _, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen, want_pooled=False)
+                _, _, probs, vec = eng.head(len(idxs), thr_d, want_z_fuse=False)
+                probs_out[idxs] = probs.cpu().numpy()
+                vec_out[idxs] = vec.cpu().numpy()
+                z_img_out[idxs] = z_img.cpu().numpy()
+                z_txt_out[idxs] = z_txt.cpu().numpy()
 
     reports = [""] * B
     if want_report:
@@ -232,7 +236,7 @@ def inference_batch_jpeg(model_bundle, jpeg_blobs, details=None, device=None, ma
         thr_d = torch.tensor(model_bundle["thresholds"], dtype=torch.float32).to(dev)
         for (h, w), idxs in groups.items():
             imgs = eng.decode_jpeg_batch([jpeg_blobs[i] for i in idxs], h, w)
-            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs])
+            ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs], eng.table_sizes)
             t = [torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (ids, pos, tt, cu)]
             _, probs, vec = eng.forward(imgs, t[0], t[1], t[2], t[3], mlen, thresholds=thr_d)
             probs_out[idxs] = probs.cpu().numpy()

@@ -232,6 +232,13 @@ def fusion_head(z_img, z_txt, sd: dict):
     return z_fuse, F.linear(z_fuse, sd["disease_head.weight"], sd["disease_head.bias"])
 
 
+def cond_tokens(z_fuse, sd: dict, n_cond: int = 4):
+    """FusionTransformerModel._make_encoder_outputs (training_pipeline.py:553-558, 574-578): Linear -> GELU(erf),
+    viewed as [B, n_cond, h_dec] - the "encoder output" the T5 decoder cross-attends to."""
+    c = F.gelu(F.linear(z_fuse, sd["cond_proj.0.weight"], sd["cond_proj.0.bias"]))
+    return c.view(z_fuse.size(0), n_cond, -1)
+
+
 @torch.no_grad()
 def forward_batch(bundle: dict, x_img: torch.Tensor, input_ids, attention_mask, token_type_ids=None) -> dict:
     """The named path on preprocessed fp32 images and token ids; every intermediate kept."""
@@ -241,8 +248,11 @@ def forward_batch(bundle: dict, x_img: torch.Tensor, input_ids, attention_mask, 
     probs = torch.sigmoid(logits)
     thr = torch.tensor(bundle["thresholds"], dtype=torch.float32)
     vector = (probs >= thr).int()          # inference_pipeline.py:186 (>=)
-    return {"feats": feats, "z_img": z_img, "pooled": pooled, "z_txt": z_txt, "z_fuse": z_fuse,
-            "logits": logits, "probs": probs, "vector": vector}
+    out = {"feats": feats, "z_img": z_img, "pooled": pooled, "z_txt": z_txt, "z_fuse": z_fuse,
+           "logits": logits, "probs": probs, "vector": vector}
+    if "cond_proj.0.weight" in bundle["fusion_state"]:
+        out["cond"] = cond_tokens(z_fuse, bundle["fusion_state"])
+    return out
 
 
 @torch.no_grad()

@@ -3,7 +3,9 @@
 Generates tests/golden/*.npz by running the REFERENCE's own modules
 (/root/reference/backend, imported through oracle/ref_import.py) on
   G1: backend/sample_images/e{1,2}.jpg + backend/sample_details/patient_details.json,
-      B=1 each, L=96 (inference_pipeline.py:174-186), seed-0 weights;
+      B=1 each, L=96 (inference_pipeline.py:174-186), seed-0 weights; each study also goes through the
+      reference's real entry point `inference()` (inference_pipeline.py:150-206, T5 beam search stubbed: off the
+      named path) and its `disease_probs` / `disease_vector` are stored as inf_probs / inf_vector;
   G2: seeded synthetic studies, B=8, L in {96,128}, full and ragged valid lengths;
   G3: Pillow/torchvision Resize(256)+CenterCrop(224) uint8 known answers for
       512x512, 224x224, 300x400 and 1024x768 inputs (crc32 of the cropped bytes).
@@ -40,10 +42,35 @@ def run_reference(tp, rb, pil_images, tok):
     probs = torch.sigmoid(logits)
     vector = (probs >= torch.tensor(rb["thresholds"])).int()
     pre_u8 = np.stack([np.asarray(T_crop(tp, p)) for p in pil_images])
+    # conditioning tokens of the report decoder from the reference's own helper (training_pipeline.py:574-578)
+    cond = fm._make_encoder_outputs(out["z_fuse"]).last_hidden_state
     return {"pre_u8": pre_u8, "x_checksum": np.float64(x.double().sum().item()),
             "feats": feats.numpy(), "z_img": z_img.numpy(), "pooled": pooled.numpy(), "z_txt": z_txt.numpy(),
             "z_fuse": out["z_fuse"].numpy(), "logits": logits.numpy(), "probs": probs.numpy(),
-            "vector": vector.numpy().astype(np.uint8)}
+            "vector": vector.numpy().astype(np.uint8), "cond": cond.numpy()}
+
+
+class _StubT5Tok:
+    """`inference()` only reads eos/pad ids from the T5 tokenizer and decodes what `generate` returned."""
+    eos_token_id, pad_token_id = 1, 0
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return ["" for _ in ids]
+
+
+def run_reference_entry_point(ip, rb, pil, details):
+    """The reference's real `inference()` (inference_pipeline.py:150-206) on one study.  Report generation (T5 beam
+    search, :190-196) is off the named path: `fusion_model.generate` is replaced by a stub for the duration of the call;
+    everything else - device ladder, transform, tokenizer call, the three modules, sigmoid, `[0]`, the threshold tensor,
+    `>=`, the result dict - is the reference's own code."""
+    fm = rb["fusion_model"]
+    b = dict(rb)
+    b["t5_tok"] = _StubT5Tok()
+    fm.generate = lambda z_img, z_txt, **kw: torch.zeros(1, 1, dtype=torch.long)
+    try:
+        return ip.inference(b, pil, details)
+    finally:
+        del fm.generate
 
 
 def T_crop(tp, pil):
@@ -70,8 +97,14 @@ def main():
         grays.append(a[..., 0].copy())
         tok = tp.tokenize_patient_details([det[n]], max_len=96)             # inference_pipeline.py:175
         r = run_reference(tp, rb, [pil], tok)
-        # cross-check with the reference's real entry point (report generation stubbed out: off-path)
-        r.update(input_ids=tok["input_ids"].numpy(), attention_mask=tok["attention_mask"].numpy())
+        res = run_reference_entry_point(ip, rb, pil, det[n])
+        assert list(res["disease_probs"]) == list(rb["class_names"]) and res["model_version"] == rb["version"]
+        inf_probs = np.array([[res["disease_probs"][c] for c in rb["class_names"]]], np.float32)
+        inf_vector = np.array([res["disease_vector"]], np.uint8)
+        # the staged run above (which also yields the intermediates) and the entry point must agree exactly
+        assert np.array_equal(inf_probs, r["probs"]) and np.array_equal(inf_vector, r["vector"]), n
+        r.update(input_ids=tok["input_ids"].numpy(), attention_mask=tok["attention_mask"].numpy(),
+                 inf_probs=inf_probs, inf_vector=inf_vector)
         rows.append(r)
         texts.append(det[n])
     g1 = {k: np.concatenate([r[k] for r in rows]) if rows[0][k].ndim else np.array([r[k] for r in rows])
