@@ -40,6 +40,7 @@ CLASSES = ["preprocess", "stem_conv", "pooling", "bottleneck_convs", "text_gemms
            "head", "other"]
 
 
+HEAD_NON_GEMM_LAUNCHES = 1       # launches of the "head" class that are not GEMMs (head_tail_kernel)
 STEM_FLOPS = 2 * 64 * 3 * 49 * 112 * 112          # conv1 7x7/2 @224: 236,027,904 FLOP per study (stem_pool_tcgen05_kernel)
 
 
@@ -150,7 +151,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -201,7 +202,7 @@ def cpu_forward_sample(n_studies, passes, threads):
     best = float("inf")
     for i in range(passes + 1):
         t = time.perf_counter()
-        R.inference_batch(bundle, list(imgs), ids_t, mask_t)
+        R.inference_batch(bundle, list(imgs), ids_t, mask_t, pillow=True)
         dt = time.perf_counter() - t
         if i > 0:
             best = min(best, dt)
@@ -209,11 +210,13 @@ def cpu_forward_sample(n_studies, passes, threads):
 
 
 def run_reference(args, rank):
-    """Reference arm: the reference's own CPU algorithm (oracle port) on all host threads."""
+    """Reference arm: the reference's own CPU algorithm (oracle port) on all host threads, on the SAME config as our
+    arm (C2, batch 256 per step unless --batch says otherwise) with steps / warm-ups bounded so that the run ends
+    within a few minutes (36 studies/s on 16 cores = 7 s per 256-study step)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = 16
+    n = args.batch
     from mmdx_b200 import synth
     from oracle import forward_ref as R
     torch.set_num_threads(threads)
@@ -221,25 +224,42 @@ def run_reference(args, rank):
     imgs = synth.synth_images(n, IMG, seed=1234)
     ids, mask = synth.synth_token_ids(n, SEQ_LEN, seed=1235, ragged=False)
     ids_t, mask_t = torch.from_numpy(ids), torch.from_numpy(mask)
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
+    chunk = 32                       # the CPU's best batch; the step is still all n studies
+    def one_step():
+        for lo in range(0, n, chunk):
+            R.inference_batch(bundle, list(imgs[lo:lo + chunk]), ids_t[lo:lo + chunk], mask_t[lo:lo + chunk], pillow=True)
+    budget = max(1, int(1500 // max(n, 1)))          # ~1500 studies of CPU work in total
+    steps = max(1, min(args.steps, budget))
+    warm = 1 if n >= 64 else max(1, min(args.warmup, 2))
     for _ in range(warm):
-        R.inference_batch(bundle, list(imgs), ids_t, mask_t)
+        one_step()
     t = time.perf_counter()
     for _ in range(steps):
-        R.inference_batch(bundle, list(imgs), ids_t, mask_t)
+        one_step()
     dt = time.perf_counter() - t
     v = n * steps / dt
-    sample = f"{n} studies/step of the C2 workload (224x224 + {SEQ_LEN} tokens), fp32, torch CPU, {steps} steps"
+    sample = (f"{n} studies/step of the C2 workload (224x224 + {SEQ_LEN} tokens) in chunks of {chunk}, fp32, torch CPU, "
+              f"{steps} steps (requested {args.steps})")
     print(json.dumps({
         "impl": "reference", "metric": "studies/sec (image+report) batched inference", "value": v, "unit": "studies/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: synthetic 224x224 chest X-ray + {SEQ_LEN}-token report, bounded sample of {n} studies per step",
-                   "note": "reference algorithm on host CPU (oracle port of backend/ml inference forward; random-init weights)"},
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "steps_requested": args.steps, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n, SEQ_LEN, 1),
+        "note": "reference algorithm on host CPU (oracle port of backend/ml inference forward; random-init weights); "
+                "the CPU arm does not scale with --gpus",
         "cpu_baseline": {"value": v, "unit": "studies/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "studies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def workload_config(B, L, world):
+    """The `config` object - identical for both arms so that the driver can compare them."""
+    return {"workload": f"C2: synthetic {IMG}x{IMG} chest X-ray + {L}-token report, batch {B} per GPU, "
+                        "random-init ResNet-50 + BERT-base + fusion head",
+            "global_batch": world * B, "seq_len": L}
+
+
+MIN_TIMED_S = 2.0       # the timed region is extended to at least this long (power / clocks settle; >= 20 clock samples)
 
 
 def main():
@@ -250,6 +270,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--exact-steps", action="store_true", help="time exactly --steps steps (no extension to 2 s)")
     ap.add_argument("--profile-only", action="store_true", help="one warm pass + few steps, for ncu")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -274,15 +296,19 @@ def main():
     bundle = synth.make_state_bundle(seed=0)
     eng = ip.get_engine(bundle, dev)
 
-    # ---- synthetic inputs: N_INPUT_SETS distinct batches per rank, host-pinned and device-resident copies
-    host_sets, dev_sets = [], []
-    for s in range(N_INPUT_SETS):
-        imgs = synth.synth_images(B, IMG, seed=1234 + 1000 * s + 17 * rank)
-        ids, mask = synth.synth_token_ids(B, L, seed=1235 + 1000 * s + 17 * rank, ragged=False)
-        pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
-        hs = [torch.from_numpy(x).pin_memory() for x in (imgs, pi, pp, pt, cu)]
-        host_sets.append(hs)
-        dev_sets.append([x.to(dev) for x in hs])
+    def make_sets(b, n_sets, seed_off=0):
+        """n_sets distinct batches of b studies for this rank: host-pinned and device-resident copies."""
+        hs_all, ds_all, ml = [], [], L
+        for s in range(n_sets):
+            imgs = synth.synth_images(b, IMG, seed=1234 + 1000 * s + 17 * rank + seed_off)
+            ids, mask = synth.synth_token_ids(b, L, seed=1235 + 1000 * s + 17 * rank + seed_off, ragged=False)
+            pi, pp, pt, cu, ml = engine.pack_tokens(ids, mask, None, eng.table_sizes)
+            hs = [torch.from_numpy(x).pin_memory() for x in (imgs, pi, pp, pt, cu)]
+            hs_all.append(hs)
+            ds_all.append([x.to(dev) for x in hs])
+        return hs_all, ds_all, ml
+
+    host_sets, dev_sets, mlen = make_sets(B, N_INPUT_SETS)
     h2d = sum(x.numel() * x.element_size() for x in host_sets[0])
     d2h = B * eng.n_cls * (4 + 4 + 1)
     host_out = (torch.empty(B, eng.n_cls, dtype=torch.float32).pin_memory(),
@@ -326,12 +352,35 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def agree_steps(est_ms, requested):
+        """Steps of a timed region: the driver's --steps is the minimum; extended so that the region lasts >= 2 s
+        (all ranks agree on the largest count)."""
+        k = requested
+        if not args.exact_steps and est_ms > 0:
+            k = max(requested, int(np.ceil(MIN_TIMED_S * 1e3 / est_ms)))
+        if world > 1:
+            t = torch.tensor([k], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            k = int(t.item())
+        return k
+
     def timed(fn, steps, warmup, sample_clocks=False, drain=None):
+        """warm-up, a short untimed estimate (sizes the timed region), then the timed region: barrier + sync on both
+        sides, CUDA events on the launch stream, max over ranks."""
         for i in range(warmup):
             fn(i)
         if drain:
             drain()
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(3):
+            fn(i)
+        if drain:
+            drain()
+        e1.record()
+        barrier()
+        steps = agree_steps(e0.elapsed_time(e1) / 3, steps)
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             time.sleep(0.25)
@@ -353,19 +402,56 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, launches, clocks
+        return ms, launches, clocks, steps
 
     if args.profile_only:
+        args.exact_steps = True
         timed(step_device, args.steps, args.warmup)
         return
 
-    ms_dev, launches, clocks = timed(step_device, args.steps, args.warmup, sample_clocks=True)
-    ms_e2e, _, _ = timed(step_host, args.steps, 3)
-    ms_e2e_pipe, _, _ = timed(step_host_pipelined, args.steps, 3, drain=drain_host_pipeline)
-    value = world * B * args.steps / (ms_dev * 1e-3)
-    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    ms_dev, launches, clocks, K = timed(step_device, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _, _, K_e2e = timed(step_host, args.steps, 3)
+    ms_e2e_pipe, _, _, K_pipe = timed(step_host_pipelined, args.steps, 3, drain=drain_host_pipeline)
+    value = world * B * K / (ms_dev * 1e-3)
+    e2e = world * B * K_e2e / (ms_e2e * 1e-3)
+    step_ms = ms_dev / K
 
-    # ---- per-kernel-class device time (CUDA events around every launch) for the roofline of the dominant kernel
+    # ---- N > 1: the gathered logits are checked on every rank (each rank's block must be what that rank computed)
+    gather_check = None
+    if world > 1:
+        mine = step_device(0).clone()
+        torch.cuda.synchronize()
+        ok = torch.equal(gathered[rank * B:(rank + 1) * B], mine)
+        chk = gathered.double().sum().reshape(1)
+        allchk = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)                              # every rank holds the same gathered tensor
+        ok = ok and all(float(c) == float(allchk[0]) for c in allchk) and bool(torch.isfinite(gathered).all())
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_check = bool(t.item())
+        assert gather_check, "gathered logits differ from the per-rank results"
+
+    # ---- strong scaling: the SAME global batch (256 studies) split over the ranks (BASELINE configs[2])
+    strong = None
+    if world > 1 and BATCH_PER_GPU % world == 0:
+        bs = BATCH_PER_GPU // world
+        _, dsets_s, mlen_s = make_sets(bs, N_INPUT_SETS, seed_off=5)
+        gathered_s = torch.empty(world * bs, eng.n_cls, dtype=torch.float32, device=dev)
+
+        def step_strong(i):
+            d = dsets_s[i % N_INPUT_SETS]
+            logits, _, _ = eng.forward(d[0], d[1], d[2], d[3], d[4], mlen_s)
+            dist.all_gather_into_tensor(gathered_s, logits)
+
+        ms_s, _, _, K_s = timed(step_strong, args.steps, args.warmup)
+        strong = {"global_batch": BATCH_PER_GPU, "per_gpu_batch": bs, "value": BATCH_PER_GPU * K_s / (ms_s * 1e-3),
+                  "unit": "studies/s", "ms_per_step": ms_s / K_s, "steps": K_s,
+                  "note": "fixed global batch of 256 studies split over the ranks (strong scaling); `value` above is weak"}
+
+    # ---- per-kernel-class device time.  Profiling mode brackets every launch with CUDA events, which serialises the two
+    # branches and defeats programmatic dependent launch, so its absolute times overstate the step.  What it gives reliably
+    # is each class's SHARE of the kernel time; the per-class time inside the real (concurrent) step is share x ms_per_step,
+    # so the classes sum to the step and every roofline below follows from the timed region.
     prof_steps = 3
     step_device(0); torch.cuda.synchronize()
     lib().mmdx_profile_begin(eng.handle)
@@ -373,16 +459,21 @@ def main():
         step_device(i)
     ms_cls = (C.c_float * 16)(); n_cls = (C.c_int64 * 16)()
     lib().mmdx_profile_end(eng.handle, ms_cls, n_cls, 16)
-    by_class = {CLASSES[i]: {"ms_per_step": ms_cls[i] / prof_steps, "launches_per_step": n_cls[i] // prof_steps}
-                for i in range(len(CLASSES)) if n_cls[i]}
+    serial_total = sum(ms_cls[i] for i in range(len(CLASSES))) / prof_steps
+    by_class = {}
+    for i in range(len(CLASSES)):
+        if n_cls[i]:
+            ser = ms_cls[i] / prof_steps
+            by_class[CLASSES[i]] = {"ms_per_step": step_ms * ser / serial_total, "share": ser / serial_total,
+                                    "ms_serialised": ser, "launches_per_step": n_cls[i] // prof_steps}
     gemm_classes = ("bottleneck_convs", "text_gemms", "head")
     gemm_ms = sum(by_class[c]["ms_per_step"] for c in gemm_classes if c in by_class)
-    gemm_launches = sum(by_class[c]["launches_per_step"] for c in gemm_classes if c in by_class) - 1   # head_tail is not a GEMM
+    gemm_launches = sum(by_class[c]["launches_per_step"] for c in gemm_classes if c in by_class) - HEAD_NON_GEMM_LAUNCHES
     f_gemm, f_stem, f_attn, f_head = flops_per_study(L)
     peaks = load_peaks()
     achieved = f_gemm * B / (gemm_ms * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic() if B == BATCH_PER_GPU else (None, None)
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (39 bottleneck convs + every Linear layer) + bneck64_tcgen05_kernel (3 fused layer-1 bottlenecks)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (bottleneck convs + every Linear layer) + the fused bottleneck kernels",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16",
                 "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, B=256)",
@@ -391,29 +482,66 @@ def main():
                 "launches_per_step": gemm_launches,
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                 "algorithmic_flops_per_launch": f_gemm * B / max(gemm_launches, 1),
+                "time_basis": "class share (event-bracketed profile pass) x ms_per_step of the timed region",
+                "serialised_profile_ms_per_step": serial_total,
                 "whole_path_frac_of_tensor_roofline": (sum(flops_per_study(L)) * value / world) / (peaks["bf16_sustained"] * 1e12)}
+
+    # ---- latency of the reference's real call shape (inference(): B = 1, one 512x512 image, a ~27-token report)
+    lat = None
+    if rank == 0:
+        im1 = synth.synth_images(1, 512, seed=77)
+        ids1, mask1 = synth.synth_token_ids(1, 96, seed=78, ragged=True)
+        p1 = engine.pack_tokens(ids1, mask1, None, eng.table_sizes)
+        h1 = [torch.from_numpy(x).pin_memory() for x in (im1, p1[0], p1[1], p1[2], p1[3])]
+        for _ in range(10):
+            eng.forward_host(h1[0], h1[1], h1[2], h1[3], h1[4], p1[4])
+        n0 = eng.launch_count
+        ts = []
+        for _ in range(200):
+            t = time.perf_counter()
+            eng.forward_host(h1[0], h1[1], h1[2], h1[3], h1[4], p1[4])
+            ts.append(time.perf_counter() - t)
+        lat = {"ms_median": 1e3 * float(np.median(ts)), "ms_p99": 1e3 * float(np.percentile(ts, 99)),
+               "launches": int((eng.launch_count - n0) // 200),
+               "shape": f"B=1, 512x512 image, {int(p1[0].numel())} tokens, host buffers in / host results out (CUDA graph replay)"}
 
     out = {
         "metric": "studies/sec (image+report) batched inference", "value": value, "unit": "studies/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "steps": K, "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"C2: synthetic {IMG}x{IMG} chest X-ray + {L}-token report, batch {B} per GPU, bf16, "
-                               "random-init ResNet-50 + BERT-base + fusion head",
-                   "global_batch": world * B, "seq_len": L, "parallelism": f"dp{world} (batch-sharded, NCCL all_gather of logits)",
-                   "l2": f"inputs rotate over {N_INPUT_SETS} distinct batches ({N_INPUT_SETS * h2d / 1e6:.0f} MB > 126 MB L2); "
-                         "activations (GBs per step) sweep L2 between steps"},
+        "config": dict(workload_config(B, L, world),
+                       parallelism=f"dp{world} (batch-sharded, NCCL all_gather of logits)",
+                       timed_region=f">= {MIN_TIMED_S} s: --steps is the minimum, extended until the region lasts that long",
+                       l2=f"inputs rotate over {N_INPUT_SETS} distinct batches ({N_INPUT_SETS * h2d / 1e6:.0f} MB > 126 MB L2); "
+                          "activations (GBs per step) sweep L2 between steps"),
         "e2e": {"value": e2e, "unit": "studies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
+                "ms_per_step": ms_e2e / K_e2e, "steps": K_e2e,
                 "api": "mmdx_forward_host (synchronous: H2D, forward, D2H, wait - one call per step)",
-                "pipelined": {"value": world * B * args.steps / (ms_e2e_pipe * 1e-3), "ms_per_step": ms_e2e_pipe / args.steps,
+                "pipelined": {"value": world * B * K_pipe / (ms_e2e_pipe * 1e-3), "ms_per_step": ms_e2e_pipe / K_pipe,
                               "api": "mmdx_forward_host_submit/_wait, two requests in flight (H2D of step i+1 under the "
-                                     "kernels of step i); no faster: the step is power-bound, not idle-bound"}},
+                                     "kernels of step i)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "kernel_classes": by_class,
         "kernel_rooflines": class_rooflines(by_class, B, L, peaks),
     }
+    if gather_check is not None:
+        out["gather_check"] = gather_check
+    if strong is not None:
+        out["strong"] = strong
+    if lat is not None:
+        out["latency_b1_ms"] = lat["ms_median"]
+        out["latency_b1"] = lat
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_stock_gpu
+            lb = bench_stock_gpu.run(batch=B, seq=L, steps=40, warmup=5, device=f"cuda:{local_rank}")
+            out["gpu_library_baseline"] = dict(lb, value=lb["studies_per_s"], unit="studies/s",
+                                               speedup_of_this_repo=value / lb["studies_per_s"])
+        except Exception as ex:      # noqa: BLE001 - the library arm must never take the bench line down
+            out["gpu_library_baseline"] = {"unavailable": repr(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n = 32

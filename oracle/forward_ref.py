@@ -106,12 +106,18 @@ def center_crop_offsets(h: int, w: int, size: int = 224):
 
 
 def preprocess_u8(img: np.ndarray, resize: int = 256, crop: int = 224) -> np.ndarray:
-    """Resize(256) + CenterCrop(224) on an HWC uint8 image -> uint8 [crop,crop,C]."""
-    h, w = img.shape[:2]
-    oh, ow = resize_output_size(h, w, resize)
-    r = pil_resize_bilinear_u8(img, oh, ow)
-    top, left = center_crop_offsets(oh, ow, crop)
-    return np.ascontiguousarray(r[top:top + crop, left:left + crop])
+    """Resize(256) + CenterCrop(224) on an HWC uint8 image -> uint8 [crop,crop,C].
+    resize=0 / crop=0 skip that stage (BASELINE config C4(i): the CNN at the image's own resolution, which the
+    reference's modules allow - adaptive avgpool, training_pipeline.py:183 - with ToTensor + Normalize only)."""
+    r = img
+    if resize:
+        h, w = img.shape[:2]
+        oh, ow = resize_output_size(h, w, resize)
+        r = pil_resize_bilinear_u8(img, oh, ow)
+    if crop:
+        top, left = center_crop_offsets(r.shape[0], r.shape[1], crop)
+        r = r[top:top + crop, left:left + crop]
+    return np.ascontiguousarray(r)
 
 
 def preprocess_f32(img: np.ndarray, resize: int = 256, crop: int = 224) -> torch.Tensor:
@@ -123,6 +129,20 @@ def preprocess_f32(img: np.ndarray, resize: int = 256, crop: int = 224) -> torch
     mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
     return (x - mean) / std
+
+
+def preprocess_f32_pillow(img: np.ndarray) -> torch.Tensor:
+    """The same transform through the libraries the reference itself calls (training_pipeline.py:112-119: torchvision
+    Resize/CenterCrop/ToTensor/Normalize over Pillow's C resampler) - used by the timed CPU baseline so that the
+    reference arm is not slowed down by this file's numpy restatement of Pillow.  Bit-identical to preprocess_f32
+    (tests/test_oracle.py)."""
+    import torchvision.transforms as T
+    from PIL import Image
+    t = T.Compose([T.Resize(256, antialias=True), T.CenterCrop(224), T.ToTensor(),
+                   T.Lambda(lambda x: x.repeat(3, 1, 1) if x.size(0) == 1 else x),
+                   T.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
+    a = img[..., 0] if img.ndim == 3 and img.shape[2] == 1 else img
+    return t(Image.fromarray(a))
 
 
 # ---------------------------------------------------------------------------
@@ -256,7 +276,13 @@ def forward_batch(bundle: dict, x_img: torch.Tensor, input_ids, attention_mask, 
 
 
 @torch.no_grad()
-def inference_batch(bundle: dict, images_u8: list, input_ids, attention_mask, token_type_ids=None) -> dict:
-    """images_u8: list of HWC uint8 arrays (already decoded, as after `.convert("RGB")`)."""
-    x = torch.stack([preprocess_f32(im) for im in images_u8])
+def inference_batch(bundle: dict, images_u8: list, input_ids, attention_mask, token_type_ids=None,
+                    resize: int = 256, crop: int = 224, pillow: bool = False) -> dict:
+    """images_u8: list of HWC uint8 arrays (already decoded, as after `.convert("RGB")`).
+    pillow=True: preprocessing through Pillow / torchvision themselves (the timed CPU baseline)."""
+    if pillow:
+        assert resize == 256 and crop == 224
+        x = torch.stack([preprocess_f32_pillow(im) for im in images_u8])
+    else:
+        x = torch.stack([preprocess_f32(im, resize, crop) for im in images_u8])
     return forward_batch(bundle, x, input_ids, attention_mask, token_type_ids)

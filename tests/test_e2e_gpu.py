@@ -46,12 +46,28 @@ def _run_stages(eng, imgs_u8, ids, mask):
                                                 logits=logits, probs=probs, vector=vec).items()}
 
 
+def label_accounting(vec, ref_probs, ref_vec, margin=2e-3, thr=0.5):
+    """bf16 label parity, accounted for instead of hidden: how many labels sit within `margin` of the threshold in the
+    reference (bf16 noise on the probability is ~2e-3), how many of THOSE differ, and how many labels
+    outside the margin differ (must be 0).  The fp32 mode (test_fp32_gpu.py) asserts every label with no margin."""
+    vec, ref_probs, ref_vec = np.asarray(vec), np.asarray(ref_probs), np.asarray(ref_vec)
+    near = np.abs(ref_probs - thr) <= margin
+    diff = vec.astype(np.int64) != ref_vec.astype(np.int64)
+    return {"labels": int(vec.size), "near_threshold": int(near.sum()), "flips_near_threshold": int((diff & near).sum()),
+            "flips_decided": int((diff & ~near).sum())}
+
+
 def _check(out, ref, safe_margin=0.0):
     for k in ("feats", "z_img", "pooled", "z_txt", "z_fuse"):
         assert _rel(out[k], ref[k]) < REL_TOL, (k, _rel(out[k], ref[k]))
     assert np.abs(out["probs"] - ref["probs"]).max() < PROB_TOL
-    decided = np.abs(ref["probs"] - 0.5) > safe_margin
-    assert np.array_equal(out["vector"][decided], ref["vector"][decided])
+    acc = label_accounting(out["vector"], ref["probs"], ref["vector"], safe_margin)
+    print("label accounting:", acc)
+    assert acc["flips_decided"] == 0, acc
+    # a label may differ from the reference's only where OUR probability is on the other side of the threshold by
+    # less than the probability error itself (labels are a pure function of the probabilities)
+    diff = out["vector"].astype(np.int64) != np.asarray(ref["vector"]).astype(np.int64)
+    assert (np.abs(np.asarray(ref["probs"])[diff] - 0.5) <= np.abs(out["probs"] - ref["probs"])[diff] + 1e-7).all()
 
 
 def test_samples_match_reference_goldens(eng, g1):
@@ -398,3 +414,251 @@ def test_full_size_properties(eng):
     assert np.abs(shuf["probs"] - big["probs"][perm]).max() < 4e-3
     g = load_golden("g2_B8_L128_full")       # first 8 studies are the golden batch
     assert np.abs(big["probs"][:8] - g["probs"]).max() < PROB_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the parity holes VERDICT r01 lists
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _ref_np(ref):
+    return {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in ref.items()}
+
+
+def test_c2_full_batch_stratified_sample_vs_oracle(bundle, eng):
+    """BASELINE configs[1] at its full size (B=256, L=128): 64 studies spread over the whole batch (every 4th, so
+    every CTA pair / tile position of the batch is represented) are recomputed by the CPU oracle and compared -
+    probabilities within 1e-2, intermediates within REL_TOL, labels accounted for."""
+    B, L = 256, 128
+    imgs = synth.synth_images(B, 224, seed=1234)
+    ids, mask = synth.synth_token_ids(B, L, seed=1235, ragged=False)
+    big = _run_stages(eng, imgs, ids, mask)
+    sel = np.arange(3, B, 4)
+    assert len(sel) == 64
+    ref = _ref_np(R.inference_batch(bundle, list(imgs[sel]), torch.from_numpy(ids[sel]), torch.from_numpy(mask[sel])))
+    _check({k: v[sel] for k, v in big.items()}, ref, safe_margin=2e-3)
+
+
+def test_c4_faithful_resize_512_L512_vs_oracle(bundle, eng):
+    """BASELINE configs[3], variant (ii): 512x512 images through the reference's own transform (Resize 256 + crop 224)
+    with 512-token reports (the flash attention variant), B=8, against the CPU oracle."""
+    B, L = 8, 512
+    imgs = synth.synth_images(B, 512, seed=71)
+    ids, mask = synth.synth_token_ids(B, L, seed=72, ragged=False)
+    mask[1, 300:] = 0; ids[1, 299] = 102; ids[1, 300:] = 0         # one shorter report in the batch
+    out = _run_stages(eng, imgs, ids, mask)
+    ref = _ref_np(R.inference_batch(bundle, list(imgs), torch.from_numpy(ids), torch.from_numpy(mask)))
+    _check(out, ref, safe_margin=2e-3)
+
+
+def test_c4_cnn_at_512_L512_vs_oracle(bundle):
+    """BASELINE configs[3], variant (i): the CNN at 512x512 (engine with resize_short=0, crop=0: ToTensor + Normalize
+    only; legal for the reference's modules - adaptive avgpool, training_pipeline.py:183) + 512-token reports, B=4,
+    against the CPU oracle fed the normalised 512x512 tensor."""
+    eng512 = engine.Engine(ip._states_from_bundle(bundle), resize_short=0, crop=0)
+    try:
+        B, L = 4, 512
+        imgs = synth.synth_images(B, 512, seed=81)
+        ids, mask = synth.synth_token_ids(B, L, seed=82, ragged=False)
+        out = _run_stages(eng512, imgs, ids, mask)
+        ref = _ref_np(R.inference_batch(bundle, list(imgs), torch.from_numpy(ids), torch.from_numpy(mask), resize=0, crop=0))
+        _check(out, ref, safe_margin=2e-3)
+        # non-square, odd-sized input at native resolution (stem / pooling edge handling)
+        odd = synth.synth_images(2, 300, seed=83)[:, :251, :277]
+        out = _run_stages(eng512, np.ascontiguousarray(odd), ids[:2, :64], mask[:2, :64])
+        ref = _ref_np(R.inference_batch(bundle, list(odd), torch.from_numpy(ids[:2, :64]), torch.from_numpy(mask[:2, :64]),
+                                        resize=0, crop=0))
+        _check(out, ref, safe_margin=2e-3)
+    finally:
+        eng512.close()
+
+
+def test_cond_tokens_match_reference_golden(eng, g1):
+    """the conditioning tokens against the REFERENCE's FusionTransformerModel._make_encoder_outputs
+    (tests/golden `cond`, written by oracle/make_golden.py from the reference module) - not against the engine's own
+    z_fuse."""
+    for i in range(2):
+        rgb = np.repeat(g1["gray"][i][None, ..., None], 3, axis=-1)
+        _run_stages(eng, rgb, g1["input_ids"][i:i + 1], g1["attention_mask"][i:i + 1])
+        cond = eng.cond_tokens(1, n_cond=4).cpu().numpy()
+        assert cond.shape == g1["cond"][i:i + 1].shape
+        assert _rel(cond, g1["cond"][i:i + 1]) < REL_TOL
+    g = load_golden("g2_B8_L128_ragged")
+    imgs = synth.synth_images(8, 224, seed=1234)
+    ids, mask = synth.synth_token_ids(8, 128, seed=1235, ragged=True)
+    _run_stages(eng, imgs, ids, mask)
+    assert _rel(eng.cond_tokens(8, n_cond=4).cpu().numpy(), g["cond"]) < REL_TOL
+
+
+def test_entry_point_matches_reference_entry_point(bundle, g1):
+    """inference() against what the reference's own inference() returned for e1/e2 (golden inf_probs / inf_vector)."""
+    from PIL import Image
+    for i in range(2):
+        pil = Image.fromarray(np.repeat(g1["gray"][i][..., None], 3, axis=-1))
+        res = ip.inference(bundle, pil, str(g1["details"][i]), device="cuda", gen_kwargs=False)
+        p = np.array([res["disease_probs"][c] for c in bundle["class_names"]])
+        assert np.abs(p - g1["inf_probs"][i]).max() < PROB_TOL
+        assert res["disease_vector"] == g1["inf_vector"][i].tolist()
+
+
+def _host_inputs(B, L, size, seed, ragged=True):
+    imgs = synth.synth_images(B, size, seed=seed)
+    ids, mask = synth.synth_token_ids(B, L, seed=seed + 1, ragged=ragged)
+    pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+    return [torch.from_numpy(x).pin_memory() for x in (np.ascontiguousarray(imgs), pi, pp, pt, cu)], mlen
+
+
+def test_captured_graph_survives_workspace_growth(bundle):
+    """a fresh serving process captures a graph for a small request, then a longer report / larger
+    image / bigger batch reallocates the arenas (cudaFree + cudaMalloc).  The stale graph must be dropped, not replayed."""
+    e2 = engine.Engine(ip._states_from_bundle(bundle))
+    try:
+        small, mlen_s = _host_inputs(1, 32, 224, seed=900, ragged=False)
+        want = [t.clone() for t in e2.forward_host(*small, mlen_s)]           # ordinary path (plans created)
+        got = e2.forward_host(*small, mlen_s)                                 # captured + replayed
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
+        n_graph = e2.launch_count
+        big, mlen_b = _host_inputs(12, 128, 320, seed=910, ragged=False)      # grows img_ws, txt_ws, head_ws, io_slot
+        e2.forward_host(*big, mlen_b)
+        for _ in range(3):       # ordinary path (new generation), re-capture, replay
+            got = e2.forward_host(*small, mlen_s)
+            assert all(torch.equal(a, b) for a, b in zip(want, got))
+        assert e2.launch_count > n_graph
+        torch.cuda.synchronize()
+    finally:
+        e2.close()
+
+
+def test_graph_replay_restores_image_border_after_another_plan(bundle):
+    """all image plans lay their tensors over the same arena.  B=8 (graph captured), then a B=1
+    call whose activations overwrite the padded-input borders of images 1..7, then the B=8 graph again - and the other
+    way round (a non-graph call right after a replay of another plan)."""
+    e2 = engine.Engine(ip._states_from_bundle(bundle))
+    try:
+        h8, m8 = _host_inputs(8, 64, 224, seed=920)
+        h1, m1 = _host_inputs(1, 64, 224, seed=930)
+        h9, m9 = _host_inputs(9, 64, 224, seed=940)       # B=9 > graph_max_b: always the ordinary path
+        d8 = [x.cuda() for x in h8]; d1 = [x.cuda() for x in h1]; d9 = [x.cuda() for x in h9]
+        w8 = [t.clone().cpu() for t in e2.forward(*d8, m8)]
+        w1 = [t.clone().cpu() for t in e2.forward(*d1, m1)]
+        w9 = [t.clone().cpu() for t in e2.forward(*d9, m9)]
+        for _ in range(2):
+            assert all(torch.equal(a, b) for a, b in zip(w8, e2.forward_host(*h8, m8)))
+        for _ in range(2):
+            assert all(torch.equal(a, b) for a, b in zip(w1, e2.forward_host(*h1, m1)))
+        assert all(torch.equal(a, b) for a, b in zip(w8, e2.forward_host(*h8, m8)))      # B=8 replay after B=1 replays
+        assert all(torch.equal(a, b) for a, b in zip(w9, e2.forward_host(*h9, m9)))      # ordinary call after a replay
+        assert all(torch.equal(a, b) for a, b in zip(w1, e2.forward_host(*h1, m1)))
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(e2.forward(*d8, m8), w8))
+    finally:
+        e2.close()
+
+
+def test_out_of_range_token_ids_are_rejected(bundle, eng):
+    """nn.Embedding raises IndexError on an id outside its table; the host entry points reject such
+    ids before anything is launched, the Python packer raises IndexError, and the engine stays usable."""
+    from mmdx_b200._lib import MmdxError
+    assert eng.table_sizes == (30522, 512, 2)
+    h, mlen = _host_inputs(2, 32, 224, seed=950, ragged=False)
+    good = [t.clone() for t in eng.forward_host(*h, mlen)]
+    bad = [x.clone() for x in h]
+    bad[1][5] = 30522
+    with pytest.raises(MmdxError, match="out of range"):
+        eng.forward_host(*bad, mlen)
+    bad = [x.clone() for x in h]
+    bad[3][0] = 2                                            # token type outside the 2-row table
+    with pytest.raises(MmdxError, match="out of range"):
+        eng.forward_host(*bad, mlen)
+    ids, mask = synth.synth_token_ids(2, 32, seed=951)
+    ids[0, 3] = 40000
+    with pytest.raises(IndexError):
+        engine.pack_tokens(ids, mask, None, eng.table_sizes)
+    with pytest.raises(IndexError):
+        ip.inference_batch(bundle, list(synth.synth_images(2, 224, seed=1)), tokens={"input_ids": ids, "attention_mask": mask},
+                           device="cuda")
+    b2 = dict(bundle); b2["thresholds"] = [0.5] * 12
+    with pytest.raises(ValueError):
+        ip.inference_batch(b2, list(synth.synth_images(1, 224, seed=1)), ["x"], device="cuda")
+    assert all(torch.equal(a, b) for a, b in zip(good, eng.forward_host(*h, mlen)))
+
+
+def test_weight_import_errors_and_reference_dim_quirk(bundle):
+    """mmdx_load_tensor / mmdx_finalize_weights error paths: a missing tensor and a fusion width that does not match the
+    encoders fail with a clean message; a bundle whose text projection is 1024 wide (the Hopsworks loader's default,
+    inference_pipeline.py:74, vs 512 in views.py:209) works because dimensions are read from the weights."""
+    from mmdx_b200._lib import MmdxError
+    st = ip._states_from_bundle(bundle)
+    broken = {k: dict(v) for k, v in st.items()}
+    del broken["image"]["backbone.5.2.conv2.weight"]
+    with pytest.raises(MmdxError, match="missing weight tensor image.backbone.5.2.conv2.weight"):
+        engine.Engine(broken)
+    broken = {k: dict(v) for k, v in st.items()}
+    broken["text"]["proj.weight"] = torch.zeros(1024, 768)
+    broken["text"]["proj.bias"] = torch.zeros(1024)
+    with pytest.raises(MmdxError, match="d_img \\+ d_txt"):
+        engine.Engine(broken)
+    wide = synth.make_state_bundle(seed=3, d_txt=1024)
+    e3 = engine.Engine(ip._states_from_bundle(wide))
+    try:
+        assert e3.d_txt == 1024
+        imgs = synth.synth_images(2, 224, seed=11)
+        ids, mask = synth.synth_token_ids(2, 64, seed=12, ragged=True)
+        out = _run_stages(e3, imgs, ids, mask)
+        ref = _ref_np(R.inference_batch(wide, list(imgs), torch.from_numpy(ids), torch.from_numpy(mask)))
+        _check(out, ref, safe_margin=2e-3)
+    finally:
+        e3.close()
+
+
+def test_concurrent_callers_default_report_path(bundle, g1):
+    """the default path (gen_kwargs=None, as api/views.py:85 calls it) is forward + cond_tokens -
+    two C calls that hand z_fuse over inside the engine.  Four threads on two different studies: every report must be
+    the one generated from ITS study's conditioning tokens."""
+    import threading
+    from PIL import Image
+
+    class Report(torch.nn.Module):                      # stands in for T5: "generates" a fingerprint of its conditioning
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def generate(self, encoder_outputs=None, **kw):
+            c = encoder_outputs.last_hidden_state.float()
+            return (c.flatten(1)[:, :8] * 1e4).round().long()
+
+    class Fusion(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.n_cond, self.h_dec = 4, 512
+            self.report_model = Report()
+
+        def state_dict(self, *a, **k):
+            return bundle["fusion_state"]
+
+    class Tok:
+        eos_token_id, pad_token_id = 1, 0
+
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return [" ".join(str(int(t)) for t in row) for row in ids]
+
+    b2 = dict(bundle)
+    b2["fusion_model"], b2["t5_tok"] = Fusion(), Tok()
+    pils = [Image.fromarray(np.repeat(g1["gray"][i][..., None], 3, axis=-1)) for i in range(2)]
+    want = [ip.inference(b2, pils[i], str(g1["details"][i]), device="cuda") for i in range(2)]
+    assert want[0]["report_text"] != want[1]["report_text"] and want[0]["report_text"]
+    got, errs = {}, []
+
+    def worker(k):
+        try:
+            for r in range(8):
+                i = (k + r) % 2
+                got[(k, r)] = (i, ip.inference(b2, pils[i], str(g1["details"][i]), device="cuda"))
+        except Exception as ex:          # noqa: BLE001
+            errs.append(ex)
+
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    assert len(got) == 32 and all(res == want[i] for i, res in got.values())

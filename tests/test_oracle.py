@@ -50,6 +50,14 @@ def test_preprocess_samples_bit_exact(g1):
         assert abs(float(x.double().sum()) - float(g1["x_checksum"][i])) < 1e-6 * 3 * 224 * 224
 
 
+def test_pillow_backed_preprocess_equals_the_restatement():
+    """The CPU baseline's preprocessing (Pillow / torchvision called directly) and the numpy restatement agree bit for bit."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    for shape in ((512, 512, 3), (300, 400, 3), (260, 300, 1)):
+        a = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        assert torch.equal(R.preprocess_f32_pillow(a), R.preprocess_f32(a))
+
+
 def test_forward_matches_reference_on_samples(state_bundle, g1):
     """Config C1: backend/sample_images + sample_details, B=1, L=96, fp32 CPU."""
     for i in range(2):
