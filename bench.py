@@ -503,7 +503,7 @@ def main():
             ts.append(time.perf_counter() - t)
         lat = {"ms_median": 1e3 * float(np.median(ts)), "ms_p99": 1e3 * float(np.percentile(ts, 99)),
                "launches": int((eng.launch_count - n0) // 200),
-               "shape": f"B=1, 512x512 image, {int(p1[0].numel())} tokens, host buffers in / host results out (CUDA graph replay)"}
+               "shape": f"B=1, 512x512 image, {int(p1[0].size)} tokens, host buffers in / host results out (CUDA graph replay)"}
 
     out = {
         "metric": "studies/sec (image+report) batched inference", "value": value, "unit": "studies/s", "n_gpus": world,

@@ -15,6 +15,7 @@
  */
 #ifndef MMDX_H
 #define MMDX_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -118,6 +119,23 @@ int64_t mmdx_launch_count(mmdx_engine* e);
  * 6 layernorm/embedding, 7 head, 8 other.  mmdx_profile_end returns the number of classes (9) on success, 1 on error. */
 int mmdx_profile_begin(mmdx_engine* e);
 int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_class, int n_classes);
+
+/* ---- native WordPiece tokenizer (host only, no GPU needed) ---------------------------------
+ * Replaces the per-call HF tokenizer of tokenize_patient_details (training_pipeline.py:323,335-342) for 7-bit ASCII text
+ * with bit-identical ids: BertNormalizer (clean text, lower-case) -> BertPreTokenizer (whitespace + punctuation) ->
+ * WordPiece ("##" continuation, 100-character words, [UNK]) -> [CLS] pieces[:max_len-2] [SEP] -> [PAD] to max_len.
+ * vocab_txt: the bytes of a BERT vocab.txt (one token per line, id = line number).
+ * mmdx_tokenize_batch: string i is text[offsets[i] : offsets[i+1]] (UTF-8 bytes, no terminator).  Writes ids [n, max_len]
+ * and lens [n] (valid tokens including [CLS]/[SEP]; attention_mask = position < len, token_type_ids = 0).
+ * fallback[i] = 1 marks a string this code does not handle (a byte >= 0x80, or the literal text of a special token such as
+ * "[SEP]"): its ids row is undefined and the caller must tokenise exactly that string with the bundle's HF tokenizer.
+ * n_threads <= 0: one per hardware thread (never more than one per 64 strings). */
+typedef struct mmdx_tokenizer mmdx_tokenizer;
+int mmdx_tokenizer_create(const char* vocab_txt, size_t vocab_bytes, int lower_case, mmdx_tokenizer** out);
+void mmdx_tokenizer_destroy(mmdx_tokenizer* t);
+int mmdx_tokenize_batch(mmdx_tokenizer* t, const char* text, const int64_t* offsets, int n, int max_len, int n_threads,
+                        int32_t* ids, int32_t* lens, uint8_t* fallback);
+const char* mmdx_tokenizer_last_error(void);
 
 /* ---- single-kernel entry points (parity tests call the hot kernels one at a time) ---------- */
 /* out[M,N] = act(A[M,K] * Wt[N,K]^T + bias (+ residual)); bf16 A/Wt/residual, bf16 or fp32 out. */

@@ -64,6 +64,10 @@ SIGNATURES = {
     "mmdx_launch_count": [_p],
     "mmdx_profile_begin": [_p],
     "mmdx_profile_end": [_p, _p, _p, _i],
+    "mmdx_tokenizer_create": [C.c_char_p, C.c_size_t, _i, C.POINTER(_p)],
+    "mmdx_tokenizer_destroy": [_p],
+    "mmdx_tokenize_batch": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "mmdx_tokenizer_last_error": [],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_gemm_ln": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _f, _p, _i64, _i, _i, _i, _p],
     "mmdx_op_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -81,6 +85,7 @@ SIGNATURES = {
     "mmdx_op_head_tail": [_p, _p, _i, _i, _p, _p, _f, _p, _p, _i, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPE = {"mmdx_last_error": C.c_char_p, "mmdx_version": C.c_char_p, "mmdx_destroy": None,
+            "mmdx_tokenizer_last_error": C.c_char_p, "mmdx_tokenizer_destroy": None,
             "mmdx_launch_count": C.c_int64}
 
 _lib = None

@@ -106,11 +106,37 @@ def _to_u8(img) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
+_TOKENIZERS: dict = {}
+
+
+def native_tokenizer(model_bundle):
+    """The C++ WordPiece tokenizer for the bundle's BERT tokenizer (built once per tokenizer object), or None when that
+    tokenizer is not a plain tokenizers-backed BERT WordPiece tokenizer (then HF is used as is)."""
+    tok = model_bundle.get("bert_tok")
+    if tok is None:
+        return None
+    with _LOCK:
+        hit = _TOKENIZERS.get(id(tok))
+        if hit is not None and hit[1] is tok:
+            return hit[0]
+        try:
+            from .tokenizer import NativeBertTokenizer
+            nt = NativeBertTokenizer(tok)
+        except Exception:      # noqa: BLE001 - unsupported tokenizer type: not an error, HF does the work
+            nt = None
+        _TOKENIZERS[id(tok)] = (nt, tok)
+        return nt
+
+
 def tokenize(model_bundle, text_list, max_len=96):
-    """tokenize_patient_details (training_pipeline.py:335-342) with the bundle's BERT tokenizer."""
+    """tokenize_patient_details (training_pipeline.py:335-342) with the bundle's BERT tokenizer - through the native
+    WordPiece tokenizer (csrc/tokenizer.cpp, bit-identical ids) when the tokenizer is a plain BERT one."""
     tok = model_bundle.get("bert_tok")
     if tok is None:
         raise ValueError("Bundle missing 'bert_tok'")
+    nt = native_tokenizer(model_bundle)
+    if nt is not None:
+        return nt(list(text_list), max_length=max_len)
     return tok(list(text_list), padding="max_length", truncation=True, return_tensors="np", max_length=max_len)
 
 

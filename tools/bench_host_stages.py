@@ -106,8 +106,22 @@ def main():
     for _ in range(8):
         tok(texts, padding="max_length", truncation=True, return_tensors="np", max_length=128)
     dt = time.perf_counter() - t
-    res["tokenizer_class"] = type(tok).__name__
+    res["tokenizer_class"] = type(tok).__name__ + (" (tokenizers-backed)" if getattr(tok, "is_fast", False) else " (python)")
     res["tokenize_batch256_studies_s"] = 8 * 256 / dt
+    # the native WordPiece tokenizer of libmmdx.so (csrc/tokenizer.cpp), same strings, same ids
+    from mmdx_b200.tokenizer import NativeBertTokenizer
+    nt = NativeBertTokenizer(tok)
+    a = tok(texts, padding="max_length", truncation=True, return_tensors="np", max_length=128)
+    b = nt(texts, max_length=128)
+    res["native_tokenizer_ids_identical"] = bool(all((a[k] == b[k]).all() for k in a))
+    details = synth.synth_details(4096, seed=2)
+    for name, tx in (("batch256", texts), ("batch4096_details", details)):
+        nt(tx, max_length=128)
+        t = time.perf_counter()
+        reps = 50 if len(tx) <= 256 else 10
+        for _ in range(reps):
+            nt(tx, max_length=128)
+        res[f"native_tokenize_{name}_studies_s"] = reps * len(tx) / (time.perf_counter() - t)
     print(json.dumps(res))
 
 
