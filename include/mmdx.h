@@ -31,6 +31,7 @@ typedef struct mmdx_config {
   int32_t n_heads;        /* BERT attention heads (12) */
   float   mean[3];        /* T.Normalize mean   training_pipeline.py:117 */
   float   std[3];         /* T.Normalize std */
+  int32_t keep_fp32;      /* != 0: mmdx_finalize_weights also keeps an fp32 copy of every weight (+452 MB) for mmdx_forward_f32 */
 } mmdx_config;
 
 const char* mmdx_last_error(void);
@@ -86,6 +87,15 @@ int mmdx_head(mmdx_engine* e, int B, const float* d_thresholds, float* d_z_fuse,
 int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
                  const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu_seqlens, int T, int max_len,
                  const float* d_thresholds, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream);
+/* The same path in fp32 (the reference's own precision, inference_pipeline.py:156-157): weights, activations and
+ * arithmetic in fp32 on the CUDA cores, held to 1e-5 on the probabilities and to EXACT labels against the reference (BASELINE
+ * north_star "1e-5 if run in fp32").  A parity mode - an order of magnitude slower than mmdx_forward.  Needs an engine
+ * created with keep_fp32 != 0 and weights loaded by mmdx_load_tensor.  Every fp32 intermediate output is nullable:
+ * d_feats [B,2048], d_z_img [B,d_img], d_pooled [B,hidden], d_z_txt [B,d_txt], d_z_fuse [B,d_fuse]. */
+int mmdx_forward_f32(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
+                     const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu_seqlens, int T, int max_len,
+                     const float* d_thresholds, float* d_feats, float* d_z_img, float* d_pooled, float* d_z_txt,
+                     float* d_z_fuse, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream);
 /* Same with HOST buffers (pinned recommended): H2D copies, forward, D2H copies, stream sync. */
 int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B, int H, int W, int C, const int32_t* h_ids,
                       const int32_t* h_pos, const int32_t* h_tt, const int32_t* h_cu_seqlens, int T, int max_len,

@@ -18,7 +18,7 @@ class MmdxError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("resize_short", C.c_int32), ("crop", C.c_int32), ("n_heads", C.c_int32),
-                ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+                ("mean", C.c_float * 3), ("std", C.c_float * 3), ("keep_fp32", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -56,6 +56,7 @@ SIGNATURES = {
     "mmdx_head": [_p, _i, _p, _p, _p, _p, _p, _p],
     "mmdx_cond_tokens": [_p, _i, _p, _p],
     "mmdx_forward": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
+    "mmdx_forward_f32": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "mmdx_forward_host": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host_submit": [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p],
     "mmdx_forward_host_wait": [_p, _i],

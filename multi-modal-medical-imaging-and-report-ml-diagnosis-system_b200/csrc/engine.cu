@@ -20,6 +20,7 @@
 #include "gemm_tcgen05.cuh"
 #include "stem_tcgen05.cuh"
 #include "kernels.cuh"
+#include "fp32_kernels.cuh"
 
 using namespace mmdx;
 typedef __nv_bfloat16 bf16;
@@ -140,7 +141,12 @@ struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp3
   bf16* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1;
 };
 struct LinW { bf16* w = nullptr; float* bias = nullptr; int nin = 0, nout = 0; };
+// fp32 mode (fp32_kernels.cuh): the same tensors kept in fp32 in a second arena (BN folded in fp32, QKV concatenated)
+struct Conv32 { float* w = nullptr; float* bias = nullptr; int cin = 0, cout = 0, k = 1, stride = 1; };
+struct Lin32 { float* w = nullptr; float* bias = nullptr; int nin = 0, nout = 0; };
+struct Block32 { Conv32 c1, c2, c3, ds; bool has_ds = false; };
 struct LnW { float* g = nullptr; float* b = nullptr; };
+struct Bert32 { Lin32 qkv, ao, ff1, ff2; LnW ln1, ln2; };
 struct BertLayerW { LinW qkv, ao, ff1, ff2; LnW ln1, ln2; };
 struct Bottleneck {
   ConvW c1, c2, c3, ds; bool has_ds = false;
@@ -196,6 +202,12 @@ struct mmdx_engine {
   std::vector<Bottleneck> blocks;
   bf16 *word = nullptr, *ptab = nullptr, *ttab = nullptr; LnW emb_ln; std::vector<BertLayerW> layers;
   LinW proj_img, proj_txt, fuse; LnW fuse_ln; float* head_w = nullptr; float* head_b = nullptr;
+  // fp32 mode: filled by mmdx_finalize_weights when cfg.keep_fp32 != 0
+  bool has_f32 = false;
+  DevBuf w32; size_t w32_used = 0;
+  Conv32 stem32; std::vector<Block32> blocks32; Lin32 proj_img32, proj_txt32, fuse32;
+  float *word32 = nullptr, *ptab32 = nullptr, *ttab32 = nullptr; std::vector<Bert32> layers32;
+  DevBuf f32_ws;
   LinW cond;             // optional: fusion.cond_proj.0 (z_fuse -> the T5 decoder's conditioning tokens)
   cudaStream_t copy_stream = nullptr;   // H2D of the image batch overlaps the text branch (mmdx_forward_host)
   cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
@@ -881,6 +893,7 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   std::unique_ptr<mmdx_engine> e(new mmdx_engine());
   e->cfg = *cfg;
   if (e->cfg.n_heads <= 0) e->cfg.n_heads = 12;
+  if (const char* v = getenv("MMDX_KEEP_FP32")) e->cfg.keep_fp32 = atoi(v);
   e->num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1063,6 +1076,92 @@ static int pack_table(mmdx_engine* e, const std::string& key, bf16** out) {
   return upload(e, pw, out);
 }
 
+// ---- fp32 arena (fp32 mode)
+static int upload32(mmdx_engine* e, const std::vector<float>& v, float** out) {
+  const size_t bytes = (v.size() * 4 + 255) & ~size_t(255);
+  REQUIRE(e->w32_used + bytes <= e->w32.bytes, "fp32 weight arena overflow");
+  float* p = reinterpret_cast<float*>(static_cast<char*>(e->w32.p) + e->w32_used);
+  CK(cudaMemcpy(p, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  e->w32_used += bytes;
+  *out = p;
+  return 0;
+}
+static int pack_conv32(mmdx_engine* e, const std::string& wkey, const std::string& bnkey, int stride, Conv32* out) {
+  GET(w, wkey + ".weight"); GET(g, bnkey + ".weight"); GET(b, bnkey + ".bias");
+  GET(m, bnkey + ".running_mean"); GET(v, bnkey + ".running_var");
+  const int cout = (int)w->shape[0], cin = (int)w->shape[1], k = (int)w->shape[2];
+  std::vector<float> pw((size_t)cout * k * k * cin), bias(cout);
+  for (int o = 0; o < cout; ++o) {
+    // y = (conv - mean) / sqrt(var + eps) * gamma + beta, folded in double and rounded once
+    const double sc = (double)g->data[o] / std::sqrt((double)v->data[o] + 1e-5);
+    bias[o] = (float)((double)b->data[o] - (double)m->data[o] * sc);
+    for (int c = 0; c < cin; ++c)
+      for (int r = 0; r < k; ++r)
+        for (int s = 0; s < k; ++s)
+          pw[((size_t)o * k * k + r * k + s) * cin + c] = (float)((double)w->data[(((size_t)o * cin + c) * k + r) * k + s] * sc);
+  }
+  out->cin = cin; out->cout = cout; out->k = k; out->stride = stride;
+  TRY(upload32(e, pw, &out->w));
+  return upload32(e, bias, &out->bias);
+}
+static int pack_linear32(mmdx_engine* e, const std::string& key, Lin32* out) {
+  GET(w, key + ".weight"); GET(b, key + ".bias");
+  out->nout = (int)w->shape[0]; out->nin = (int)w->shape[1];
+  TRY(upload32(e, w->data, &out->w));
+  return upload32(e, b->data, &out->bias);
+}
+static int finalize_f32(mmdx_engine* e) {
+  size_t total = 0;
+  for (auto& kv : e->host) total += kv.second.data.size() * 4 + 512;
+  TRY(e->w32.ensure(total + (4 << 20)));
+  e->w32_used = 0;
+  TRY(pack_conv32(e, "image.backbone.0", "image.backbone.1", 2, &e->stem32));
+  const int nblocks[4] = {3, 4, 6, 3};
+  e->blocks32.clear();
+  for (int li = 0; li < 4; ++li)
+    for (int bi = 0; bi < nblocks[li]; ++bi) {
+      const std::string pfx = "image.backbone." + std::to_string(4 + li) + "." + std::to_string(bi);
+      Block32 bk;
+      const int s = (bi == 0 && li > 0) ? 2 : 1;
+      TRY(pack_conv32(e, pfx + ".conv1", pfx + ".bn1", 1, &bk.c1));
+      TRY(pack_conv32(e, pfx + ".conv2", pfx + ".bn2", s, &bk.c2));
+      TRY(pack_conv32(e, pfx + ".conv3", pfx + ".bn3", 1, &bk.c3));
+      if (get(e, pfx + ".downsample.0.weight")) {
+        bk.has_ds = true;
+        TRY(pack_conv32(e, pfx + ".downsample.0", pfx + ".downsample.1", s, &bk.ds));
+      }
+      e->blocks32.push_back(bk);
+    }
+  TRY(pack_linear32(e, "image.proj", &e->proj_img32));
+  const std::string eb = "text.encoder.embeddings.";
+  { GET(t, eb + "word_embeddings.weight"); TRY(upload32(e, t->data, &e->word32)); }
+  { GET(t, eb + "position_embeddings.weight"); TRY(upload32(e, t->data, &e->ptab32)); }
+  { GET(t, eb + "token_type_embeddings.weight"); TRY(upload32(e, t->data, &e->ttab32)); }
+  e->layers32.clear();
+  for (int l = 0;; ++l) {
+    const std::string p = "text.encoder.encoder.layer." + std::to_string(l) + ".";
+    if (!get(e, p + "attention.self.query.weight")) break;
+    Bert32 L;
+    GET(q, p + "attention.self.query.weight"); GET(k, p + "attention.self.key.weight");
+    GET(v, p + "attention.self.value.weight"); GET(qb, p + "attention.self.query.bias");
+    GET(kb, p + "attention.self.key.bias"); GET(vb, p + "attention.self.value.bias");
+    std::vector<float> w3, b3;
+    for (const HostTensor* t : {q, k, v}) w3.insert(w3.end(), t->data.begin(), t->data.end());
+    for (const HostTensor* t : {qb, kb, vb}) b3.insert(b3.end(), t->data.begin(), t->data.end());
+    L.qkv.nin = (int)q->shape[1]; L.qkv.nout = 3 * (int)q->shape[0];
+    TRY(upload32(e, w3, &L.qkv.w));
+    TRY(upload32(e, b3, &L.qkv.bias));
+    TRY(pack_linear32(e, p + "attention.output.dense", &L.ao));
+    TRY(pack_linear32(e, p + "intermediate.dense", &L.ff1));
+    TRY(pack_linear32(e, p + "output.dense", &L.ff2));
+    e->layers32.push_back(L);
+  }
+  TRY(pack_linear32(e, "text.proj", &e->proj_txt32));
+  TRY(pack_linear32(e, "fusion.fusion_mlp.0", &e->fuse32));
+  e->has_f32 = true;
+  return 0;
+}
+
 extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
   REQUIRE(e && !e->finalized, "bad engine state");
   CK(cudaSetDevice(e->cfg.device));
@@ -1173,6 +1272,10 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
     TRY(upload(e, b->data, &e->head_b));
     std::vector<float> thr(e->n_cls, 0.5f);
     TRY(upload(e, thr, &e->thr_default));
+  }
+  if (e->cfg.keep_fp32) {
+    TRY(finalize_f32(e));
+    for (size_t l = 0; l < e->layers32.size(); ++l) { e->layers32[l].ln1 = e->layers[l].ln1; e->layers32[l].ln2 = e->layers[l].ln2; }
   }
   e->host.clear();
   e->finalized = true;
@@ -2091,6 +2194,153 @@ extern "C" int mmdx_forward_host(mmdx_engine* e, const uint8_t* h_images, int B,
   e->slot_busy[0] = false;
   if (warm) warm->gen = e->ws_gen;      // plans and workspaces of this shape exist under this generation: capture next time
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ fp32 mode
+// The whole path in fp32 on the CUDA cores (fp32_kernels.cuh), one kernel per reference op, for the north_star's
+// "1e-5 if run in fp32" bar: labels equal the reference's with no margin.  Plain launches (no programmatic dependent
+// launch: these kernels do not carry the griddepcontrol handshake), one stream.
+static int f32_conv(mmdx_engine* e, const float* in, int NB, int H, int W, const Conv32& c, const float* res, float* out,
+                    int act, cudaStream_t s, long long ld_out = 0) {
+  F32ConvParams p;
+  p.in = in; p.w = c.w; p.bias = c.bias; p.res = res; p.out = out;
+  p.NB = NB; p.H = H; p.W = W; p.Cin = c.cin; p.Cout = c.cout; p.k = c.k; p.stride = c.stride; p.pad = c.k / 2;
+  p.OH = (H + 2 * p.pad - c.k) / c.stride + 1; p.OW = (W + 2 * p.pad - c.k) / c.stride + 1; p.act = act;
+  p.ld_out = ld_out ? ld_out : c.cout;
+  const long long M = (long long)NB * p.OH * p.OW;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((c.cout + 63) / 64));
+  e->launches++;
+  f32_conv_kernel<<<grid, 256, 0, s>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+static int f32_linear(mmdx_engine* e, const float* in, int M, const Lin32& l, const float* res, float* out, int act,
+                      cudaStream_t s, long long ld_out = 0) {
+  Conv32 c; c.w = l.w; c.bias = l.bias; c.cin = l.nin; c.cout = l.nout; c.k = 1; c.stride = 1;
+  return f32_conv(e, in, M, 1, 1, c, res, out, act, s, ld_out);
+}
+
+extern "C" int mmdx_forward_f32(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, const int32_t* d_ids,
+                                const int32_t* d_pos, const int32_t* d_tt, const int32_t* d_cu, int T, int max_len,
+                                const float* d_thr, float* d_feats, float* d_z_img, float* d_pooled, float* d_z_txt,
+                                float* d_z_fuse, float* d_logits, float* d_probs, uint8_t* d_vector, void* stream) {
+  REQUIRE(e && d_images && d_ids && d_pos && d_tt && d_cu && d_logits && d_probs && d_vector, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  REQUIRE(e->finalized && e->has_f32, "fp32 weights were not kept: create the engine with mmdx_config.keep_fp32 = 1 "
+                                      "(not available for engines loaded from a packed bf16 file)");
+  REQUIRE(B > 0 && T > 0 && max_len > 0 && max_len <= e->max_pos && max_len <= F32_ATT_MAXL, "bad batch");
+  REQUIRE(C == 1 || C == 3, "images must have 1 or 3 channels");
+  cudaStream_t s = (cudaStream_t)stream;
+  TRY(order_begin(e, s));
+  PreGeom g;
+  TRY(pre_geometry(e, H, W, &g));
+  const int IH = g.crop_h, IW = g.crop_w;
+  const int sh = (IH - 1) / 2 + 1, sw = (IW - 1) / 2 + 1, ph = (sh - 1) / 2 + 1, pw = (sw - 1) / 2 + 1;
+  const int Hd = e->hidden, dz = e->d_img + e->d_txt;
+  // workspace: u8 crop | x | stem | 4 activation buffers | text buffers | head buffers
+  const size_t u8_b = al((size_t)B * IH * IW * C), x_b = al((size_t)B * IH * IW * 3 * 4), stem_b = al((size_t)B * sh * sw * 64 * 4);
+  const size_t act_b = al((size_t)B * ph * pw * 256 * 4);
+  const size_t hid_b = al((size_t)T * Hd * 4), qkv_b = al((size_t)T * 3 * Hd * 4), ffn_b = al((size_t)T * e->ffn * 4);
+  const size_t head_b = al((size_t)B * (e->feat_dim + Hd + dz + e->d_fuse) * 4);
+  TRY(e->f32_ws.ensure(u8_b + x_b + stem_b + 4 * act_b + 4 * hid_b + qkv_b + ffn_b + head_b));
+  char* b = static_cast<char*>(e->f32_ws.p);
+  uint8_t* u8 = reinterpret_cast<uint8_t*>(b); b += u8_b;
+  float* x = reinterpret_cast<float*>(b); b += x_b;
+  float* stem = reinterpret_cast<float*>(b); b += stem_b;
+  float* act[4];
+  for (int i = 0; i < 4; ++i) { act[i] = reinterpret_cast<float*>(b); b += act_b; }
+  float* hid = reinterpret_cast<float*>(b); b += hid_b;
+  float* hid2 = reinterpret_cast<float*>(b); b += hid_b;
+  float* ctx = reinterpret_cast<float*>(b); b += hid_b;
+  float* pre = reinterpret_cast<float*>(b); b += hid_b;
+  float* qkv = reinterpret_cast<float*>(b); b += qkv_b;
+  float* ffn = reinterpret_cast<float*>(b); b += ffn_b;
+  float* feats = reinterpret_cast<float*>(b);
+  float* pooled = feats + (size_t)B * e->feat_dim;
+  float* zcat = pooled + (size_t)B * Hd;
+  float* fuse_h = zcat + (size_t)B * dz;
+  // ---- image branch: integer resample (bit-exact), ToTensor + Normalize, ResNet-50
+  const uint8_t* crop = d_images;
+  if (g.has_x || g.has_y || g.crop_h != H || g.crop_w != W) {
+    ResampleTable tx, ty;
+    PreStrip strip;
+    TRY(build_tables(e, e->tab_ws, H, W, C, g, &tx, &ty, &strip));
+    dim3 grid((g.crop_w + 255) / 256, g.crop_h, B), block(256);
+    e->launches++;
+    if (C == 3) resample_u8_kernel<3><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left, g.top, u8);
+    else resample_u8_kernel<1><<<grid, block, 0, s>>>(d_images, B, H, W, tx, ty, g.crop_h, g.crop_w, g.has_x, g.has_y, g.left, g.top, u8);
+    CK(cudaGetLastError());
+    crop = u8;
+  }
+  {
+    const long long npix = (long long)B * IH * IW;
+    e->launches++;
+    f32_normalize_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(
+        crop, npix, C, make_float3(e->cfg.mean[0], e->cfg.mean[1], e->cfg.mean[2]),
+        make_float3(e->cfg.std[0], e->cfg.std[1], e->cfg.std[2]), x);
+    CK(cudaGetLastError());
+  }
+  TRY(f32_conv(e, x, B, IH, IW, e->stem32, nullptr, stem, F32_ACT_RELU, s));
+  {
+    const long long n = (long long)B * ph * pw * 64;
+    e->launches++;
+    f32_maxpool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(stem, B, sh, sw, 64, ph, pw, act[0]);
+    CK(cudaGetLastError());
+  }
+  float *cur = act[0], *nxt = act[1], *t1 = act[2], *t2 = act[3];
+  int h = ph, w = pw;
+  for (const Block32& bk : e->blocks32) {
+    const int st = bk.c2.stride, oh = (h - 1) / st + 1, ow = (w - 1) / st + 1;
+    TRY(f32_conv(e, cur, B, h, w, bk.c1, nullptr, t1, F32_ACT_RELU, s));
+    TRY(f32_conv(e, t1, B, h, w, bk.c2, nullptr, t2, F32_ACT_RELU, s));
+    const float* idt = cur;
+    if (bk.has_ds) { TRY(f32_conv(e, cur, B, h, w, bk.ds, nullptr, t1, F32_ACT_NONE, s)); idt = t1; }
+    TRY(f32_conv(e, t2, B, oh, ow, bk.c3, idt, nxt, F32_ACT_RELU, s));
+    float* t = cur; cur = nxt; nxt = t;
+    h = oh; w = ow;
+  }
+  e->launches++;
+  f32_avgpool_kernel<<<(B * e->feat_dim + 255) / 256, 256, 0, s>>>(cur, B, h * w, e->feat_dim, feats);
+  CK(cudaGetLastError());
+  TRY(f32_linear(e, feats, B, e->proj_img32, nullptr, zcat, F32_ACT_NONE, s, dz));
+  // ---- text branch: BERT over packed tokens
+  e->launches++;
+  f32_layernorm_kernel<true><<<(T + 7) / 8, 256, 0, s>>>(nullptr, T, Hd, e->emb_ln.g, e->emb_ln.b, 1e-12f, hid, d_ids, d_pos, d_tt,
+                                                          e->word32, e->ptab32, e->ttab32, e->vocab, e->max_pos, e->type_vocab);
+  CK(cudaGetLastError());
+  for (const Bert32& L : e->layers32) {
+    TRY(f32_linear(e, hid, T, L.qkv, nullptr, qkv, F32_ACT_NONE, s));
+    e->launches++;
+    f32_attention_kernel<<<dim3((max_len + 3) / 4, e->cfg.n_heads, B), 128, 0, s>>>(qkv, d_cu, e->cfg.n_heads, Hd, 0.125f, ctx);
+    CK(cudaGetLastError());
+    TRY(f32_linear(e, ctx, T, L.ao, hid, pre, F32_ACT_NONE, s));
+    e->launches++;
+    f32_layernorm_kernel<false><<<(T + 7) / 8, 256, 0, s>>>(pre, T, Hd, L.ln1.g, L.ln1.b, 1e-12f, hid2, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr, nullptr, 0, 0, 0);
+    TRY(f32_linear(e, hid2, T, L.ff1, nullptr, ffn, F32_ACT_GELU, s));
+    TRY(f32_linear(e, ffn, T, L.ff2, hid2, pre, F32_ACT_NONE, s));
+    e->launches++;
+    f32_layernorm_kernel<false><<<(T + 7) / 8, 256, 0, s>>>(pre, T, Hd, L.ln2.g, L.ln2.b, 1e-12f, hid, nullptr, nullptr, nullptr,
+                                                             nullptr, nullptr, nullptr, 0, 0, 0);
+    CK(cudaGetLastError());
+  }
+  e->launches++;
+  f32_seq_mean_pool_kernel<<<B, 256, 0, s>>>(hid, d_cu, Hd, pooled);
+  CK(cudaGetLastError());
+  TRY(f32_linear(e, pooled, B, e->proj_txt32, nullptr, zcat + e->d_img, F32_ACT_NONE, s, dz));
+  // ---- fusion head: Linear + GELU (fp32), then LayerNorm + disease head + sigmoid + threshold (head_tail_kernel is fp32)
+  TRY(f32_linear(e, zcat, B, e->fuse32, nullptr, fuse_h, F32_ACT_GELU, s));
+  e->launches++;
+  head_tail_kernel<<<B, 256, e->d_fuse * sizeof(float), s>>>(fuse_h, e->d_fuse, e->fuse_ln.g, e->fuse_ln.b, 1e-5f, e->head_w, e->head_b,
+                                                            e->n_cls, d_thr ? d_thr : e->thr_default, d_z_fuse, d_logits, d_probs,
+                                                            d_vector, nullptr);
+  CK(cudaGetLastError());
+  if (d_feats) CK(cudaMemcpyAsync(d_feats, feats, (size_t)B * e->feat_dim * 4, cudaMemcpyDeviceToDevice, s));
+  if (d_pooled) CK(cudaMemcpyAsync(d_pooled, pooled, (size_t)B * Hd * 4, cudaMemcpyDeviceToDevice, s));
+  if (d_z_img) CK(cudaMemcpy2DAsync(d_z_img, (size_t)e->d_img * 4, zcat, (size_t)dz * 4, (size_t)e->d_img * 4, B, cudaMemcpyDeviceToDevice, s));
+  if (d_z_txt) CK(cudaMemcpy2DAsync(d_z_txt, (size_t)e->d_txt * 4, zcat + e->d_img, (size_t)dz * 4, (size_t)e->d_txt * 4, B, cudaMemcpyDeviceToDevice, s));
+  return order_end(e, s);
 }
 
 // ------------------------------------------------------------------------------------------ GPU JPEG decode (N3)

@@ -58,12 +58,14 @@ class Engine:
     state_dict key names."""
 
     def __init__(self, states: dict | None, device: int | None = None, resize_short: int = 256, crop: int = 224,
-                 n_heads: int = 12, packed: str | None = None):
+                 n_heads: int = 12, packed: str | None = None, fp32: bool = False):
+        """fp32=True also keeps an fp32 copy of the weights (+452 MB) for `forward_f32`, the parity mode held to 1e-5."""
         if not torch.cuda.is_available():
             raise MmdxError("mmdx needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.cuda.current_device() if device is None else int(device)
+        self.has_fp32 = bool(fp32) and packed is None
         cfg = Config(self.device, resize_short, crop, n_heads, (C.c_float * 3)(*IMAGENET_MEAN),
-                     (C.c_float * 3)(*IMAGENET_STD))
+                     (C.c_float * 3)(*IMAGENET_STD), 1 if self.has_fp32 else 0)
         self._h = C.c_void_p()
         check(lib().mmdx_create(C.byref(cfg), C.byref(self._h)))
         if packed is not None:
@@ -191,6 +193,23 @@ class Engine:
                                  ids.numel(), int(max_len), _ptr(thresholds), _ptr(logits), _ptr(probs), _ptr(vec),
                                  _stream()))
         return logits, probs, vec
+
+    def forward_f32(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None):
+        """The whole path in fp32 (parity mode, engine created with fp32=True): device tensors in, dict of device
+        tensors out - every intermediate the goldens hold plus logits / probs / vector."""
+        if not self.has_fp32:
+            raise MmdxError("engine was created without fp32 weights (Engine(..., fp32=True))")
+        B, H, W, Cc = images_u8.shape
+        dev = self._dev()
+        f = lambda n: torch.empty(B, n, dtype=torch.float32, device=dev)      # noqa: E731
+        o = {"feats": f(self.feat_dim), "z_img": f(self.d_img), "pooled": f(self.hidden), "z_txt": f(self.d_txt),
+             "z_fuse": f(self.d_fuse), "logits": f(self.n_cls), "probs": f(self.n_cls),
+             "vector": torch.empty(B, self.n_cls, dtype=torch.uint8, device=dev)}
+        check(lib().mmdx_forward_f32(self._h, _ptr(images_u8), B, H, W, Cc, _ptr(ids), _ptr(pos), _ptr(tt), _ptr(cu),
+                                     ids.numel(), int(max_len), _ptr(thresholds), _ptr(o["feats"]), _ptr(o["z_img"]),
+                                     _ptr(o["pooled"]), _ptr(o["z_txt"]), _ptr(o["z_fuse"]), _ptr(o["logits"]),
+                                     _ptr(o["probs"]), _ptr(o["vector"]), _stream()))
+        return o
 
     def forward_host(self, images_u8, ids, pos, tt, cu, max_len, thresholds=None, out=None):
         """Whole path with HOST tensors (pinned recommended): H2D, forward, D2H, sync inside the C call."""

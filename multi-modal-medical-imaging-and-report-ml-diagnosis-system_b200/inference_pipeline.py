@@ -55,11 +55,19 @@ def _states_from_bundle(model_bundle: dict) -> dict:
     return out
 
 
-def get_engine(model_bundle: dict, device=None) -> Engine:
-    """Weights are packed to the device once per bundle identity and device, never per call."""
+def _precision(model_bundle: dict, precision=None) -> str:
+    p = precision or model_bundle.get("precision") or "bf16"
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' (tcgen05 path) or 'fp32' (parity mode)")
+    return p
+
+
+def get_engine(model_bundle: dict, device=None, precision=None) -> Engine:
+    """Weights are packed to the device once per bundle identity, device and precision, never per call."""
     dev = _parse_device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    key = (id(model_bundle), idx)
+    fp32 = _precision(model_bundle, precision) == "fp32"
+    key = (id(model_bundle), idx, fp32)
     with _LOCK:
         hit = _ENGINES.get(key)
         if hit is not None and hit[1] is model_bundle:
@@ -68,7 +76,7 @@ def get_engine(model_bundle: dict, device=None) -> Engine:
             if model_bundle.get("packed_weights"):       # serving bundle without torch modules (save_packed_bundle)
                 eng = Engine.from_packed(model_bundle["packed_weights"], device=idx)
             else:
-                eng = Engine(_states_from_bundle(model_bundle), device=idx)
+                eng = Engine(_states_from_bundle(model_bundle), device=idx, fp32=fp32)
         _ENGINES[key] = (eng, model_bundle)
         return eng
 
@@ -141,12 +149,16 @@ def tokenize(model_bundle, text_list, max_len=96):
 
 
 @torch.no_grad()
-def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=False, max_len=96, tokens=None):
+def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=False, max_len=96, tokens=None,
+                    precision=None):
     """Batched `inference`: images = list of PIL / uint8 HWC arrays (any sizes), details = list[str]
     (or `tokens` = dict with input_ids / attention_mask / token_type_ids [B,L] already tokenized).
-    Returns a list of result dicts in input order."""
+    Returns a list of result dicts in input order.
+    precision (or model_bundle["precision"]): "bf16" = the tcgen05 path (probabilities within 1e-2 of the reference),
+    "fp32" = the parity mode (within 1e-5, labels exact; ~20x slower; classification only)."""
     dev = _parse_device(device)
-    eng = get_engine(model_bundle, dev)
+    fp32 = _precision(model_bundle, precision) == "fp32"
+    eng = get_engine(model_bundle, dev, precision)
     class_names = model_bundle["class_names"]
     imgs = [_to_u8(im) for im in images]
     B = len(imgs)
@@ -171,7 +183,7 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
     for i, a in enumerate(imgs):
         groups.setdefault(a.shape, []).append(i)
     want_report = gen_kwargs is not False and model_bundle.get("fusion_model") is not None \
-        and model_bundle.get("t5_tok") is not None
+        and model_bundle.get("t5_tok") is not None and not fp32
     fusion_mod = model_bundle.get("fusion_model")
     use_cond = bool(want_report and eng.cond_width and hasattr(fusion_mod, "report_model")
                     and getattr(fusion_mod, "n_cond", 0) * getattr(fusion_mod, "h_dec", 0) == eng.cond_width)
@@ -180,6 +192,12 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
         thr_d = thr.to(dev)
         for shape, idxs in groups.items():
             ids, pos, tt, cu, mlen = pack_tokens(ids_all[idxs], mask_all[idxs], tt_all[idxs], eng.table_sizes)
+            if fp32:
+                t = [torch.from_numpy(x).to(dev) for x in (np.stack([imgs[i] for i in idxs]), ids, pos, tt, cu)]
+                o = eng.forward_f32(t[0], t[1], t[2], t[3], t[4], mlen, thresholds=thr_d)
+                probs_out[idxs] = o["probs"].cpu().numpy()
+                vec_out[idxs] = o["vector"].cpu().numpy()
+                continue
             if not want_report or use_cond:
                 # one C call per shape group: H2D, forward, D2H (small groups replay a captured CUDA graph)
                 host = [torch.from_numpy(x).pin_memory() for x in (np.stack([imgs[i] for i in idxs]), ids, pos, tt, cu)]
@@ -278,7 +296,8 @@ def inference_batch_jpeg(model_bundle, jpeg_blobs, details=None, device=None, ma
 @torch.no_grad()
 def inference(model_bundle, image_pil, patient_details, device=None, gen_kwargs=None):
     """Same contract as the reference's inference() (inference_pipeline.py:150-206):
-    returns {report_text, disease_probs{class: float}, disease_vector[0/1], model_version}."""
+    returns {report_text, disease_probs{class: float}, disease_vector[0/1], model_version}.
+    model_bundle["precision"] = "fp32" selects the parity mode (see inference_batch)."""
     _parse_device(device)   # TypeError before any work, like the reference
     return inference_batch(model_bundle, [image_pil], [patient_details], device=device, gen_kwargs=gen_kwargs,
                            max_len=96)[0]
