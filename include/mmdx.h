@@ -129,6 +129,9 @@ int64_t mmdx_launch_count(mmdx_engine* e);
  * 6 layernorm/embedding, 7 head, 8 other.  mmdx_profile_end returns the number of classes (9) on success, 1 on error. */
 int mmdx_profile_begin(mmdx_engine* e);
 int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_class, int n_classes);
+/* same, per launch: device time (ms) and class of every launch since mmdx_profile_begin, in launch order; returns the
+ * number of launches written (<= cap) or -1 */
+int mmdx_profile_end_list(mmdx_engine* e, float* ms, int32_t* cls, int cap);
 
 /* ---- native WordPiece tokenizer (host only, no GPU needed) ---------------------------------
  * Replaces the per-call HF tokenizer of tokenize_patient_details (training_pipeline.py:323,335-342) for 7-bit ASCII text

@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmdx.so")
+LIB_PATH = os.environ.get("MMDX_LIB") or os.path.join(_HERE, "libmmdx.so")     # MMDX_LIB: A/B builds of the same source
 
 
 class MmdxError(RuntimeError):
@@ -65,6 +65,7 @@ SIGNATURES = {
     "mmdx_launch_count": [_p],
     "mmdx_profile_begin": [_p],
     "mmdx_profile_end": [_p, _p, _p, _i],
+    "mmdx_profile_end_list": [_p, _p, _p, _i],
     "mmdx_tokenizer_create": [C.c_char_p, C.c_size_t, _i, C.POINTER(_p)],
     "mmdx_tokenizer_destroy": [_p],
     "mmdx_tokenize_batch": [_p, _p, _p, _i, _i, _i, _p, _p, _p],

@@ -37,7 +37,20 @@ struct AttnParams {
   int n_seq, heads, hidden, nqb, num_units;   // nqb = query blocks per sequence at max_len
   float scale_log2;        // 1/sqrt(64) * log2(e)
   int reverse;             // 1: walk the units from the last to the first (see mmdx_engine::zigzag)
+  // Folded LayerNorm (gemm_tcgen05.cuh): when set, row t of ctx is written as ctx[t] / rstd[t], rstd from the row sums of
+  // the pre-LayerNorm tensor the NEXT GEMM re-creates its residual from (it multiplies the whole accumulator by rstd).
+  const long long* row_stats;   // [T][2] 2^24 fixed-point (sum x, sum x^2), or null
+  float inv_n, eps;
 };
+
+__device__ __forceinline__ float attn_row_sigma(const AttnParams& p, int tok) {
+  if (p.row_stats == nullptr) return 1.0f;
+  const float s1 = static_cast<float>(static_cast<double>(p.row_stats[2 * static_cast<size_t>(tok)]) * (1.0 / 16777216.0));
+  const float s2 = static_cast<float>(static_cast<double>(p.row_stats[2 * static_cast<size_t>(tok) + 1]) * (1.0 / 16777216.0));
+  const float mu = s1 * p.inv_n;
+  const float var = fmaxf(s2 * p.inv_n - mu * mu, 0.0f);
+  return 1.0f / rsqrtf(var + p.eps);        // exactly the reciprocal of the rstd the consumer's epilogue computes
+}
 
 // B operand in MN-major form (rows = K index, 128-byte rows of 64 consecutive N elements, SWIZZLE_128B):
 // 8-row groups every 1024 B.  N = 64 is a single MN atom, so the MN stride is unused; both stride fields
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) attention_tcgen05_kernel(const
       if (lane == 0) mbar_arrive(&o_free[g]);
       const int row = u.qb * 128 + r;
       if (row < u.len) {
-        const float inv = 1.0f / l;
+        const float inv = attn_row_sigma(p, u.tok0 + row) / l;
         uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<size_t>(u.tok0 + row) * p.hidden + u.head * 64);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel
       mbar_wait(&o_full[g], n & 1);
       tc_fence_after();
       if (active) {
-        const float inv = 1.0f / l;
+        const float inv = (r < len ? attn_row_sigma(p, u.tok0 + r) : 1.0f) / l;
         uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<size_t>(u.tok0 + r) * p.hidden + u.head * 64);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {

@@ -147,7 +147,15 @@ struct Lin32 { float* w = nullptr; float* bias = nullptr; int nin = 0, nout = 0;
 struct Block32 { Conv32 c1, c2, c3, ds; bool has_ds = false; };
 struct LnW { float* g = nullptr; float* b = nullptr; };
 struct Bert32 { Lin32 qkv, ao, ff1, ff2; LnW ln1, ln2; };
-struct BertLayerW { LinW qkv, ao, ff1, ff2; LnW ln1, ln2; };
+// Folded LayerNorm (gemm_tcgen05.cuh): what a GEMM needs to consume LN(x) - or add it as a residual - straight from the
+// pre-LayerNorm tensor x and its row sums.
+struct LnFold {
+  bf16* wf = nullptr;      // consumer GEMM: gamma folded in and the row mean projected out, bf16(gamma[k] W[n][k] - mean_k); null for residual GEMMs
+  float* c1 = nullptr;     // consumer: row sums of gamma o W (unused by the kernel: folded into wf); residual: float(bf16(gamma))
+  float* c2 = nullptr;     // consumer: W beta + b;                residual: b + beta
+  bf16* gdiag = nullptr;   // residual GEMM: [N][64] bf16, row n holds gamma[n] at column n % 64 (diag(gamma) in 64-blocks)
+};
+struct BertLayerW { LinW qkv, ao, ff1, ff2; LnW ln1, ln2; LnFold f_qkv, f_ao, f_ff1, f_ff2; };
 struct Bottleneck {
   ConvW c1, c2, c3, ds; bool has_ds = false;
   ConvW c3ds;      // has_ds: conv3 and the downsample conv as ONE GEMM: weights [Cout][c3.cin + ds.cin], bias b3 + bd
@@ -174,6 +182,7 @@ struct ImagePlan {
 };
 struct TextPlan {
   int T = 0, B = 0;
+  bool folded = false;             // LayerNorm folded into the GEMMs: no LayerNorm launches, 5 launches per layer
   bool ln_fused = false;           // ao / ff2 normalise their own rows (no separate LayerNorm launches)
   std::vector<GemmLaunch> gemms;   // per layer: qkv, ao, ff1, ff2
 };
@@ -727,12 +736,12 @@ static int next_direction(mmdx_engine* e, cudaStream_t s) {
   return d;
 }
 
-template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
+template <int BN, int BK, int CG, int EB, int RES, int LN = 0, int LNF = 0>
 static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s, int reverse) {
   static bool attr_set_[64] = {};
   bool& attr_set = attr_set_[cur_dev()];
-  auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES, LN>;
-  constexpr int SMEM = GemmSmem<BN, BK, CG, EB, RES>::TOTAL;
+  auto* kfn = gemm_tcgen05_kernel<BN, BK, CG, EB, RES, LN, LNF>;
+  constexpr int SMEM = GemmSmem<BN, BK, CG, EB, RES, LNF>::TOTAL;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
@@ -758,7 +767,7 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s, int reve
       max_clusters = n;
       if (getenv("MMDX_DEBUG"))
         fprintf(stderr, "mmdx: gemm<BN %d, CG %d, EB %d, RES %d> %d stages, max active clusters %d\n", BN, CG, EB, RES,
-                GemmSmem<BN, BK, CG, EB, RES>::STAGES, n);
+                GemmSmem<BN, BK, CG, EB, RES, LNF>::STAGES, n);
     }
     if (groups > max_clusters) groups = max_clusters;
   }
@@ -773,6 +782,11 @@ static int launch_inst(const GemmLaunch& g, int groups, cudaStream_t s, int reve
 template <int BN, int CG>
 static int launch_bn(const GemmLaunch& g, int groups, cudaStream_t s, int rv) {
   const bool res = g.p.res_blocks > 0;
+  if (g.p.lnf) {       // folded LayerNorm (text encoder): one variant per role, with the staging buffers that role gets
+    if (g.p.lnf_diag) return launch_inst<BN, 64, CG, 1, 1, 0, 3>(g, groups, s, rv);          // attention output, FFN2
+    if (g.p.lnf_post) return launch_inst<BN, 64, CG, 2, 0, 0, 2>(g, groups, s, rv);          // FFN1 (erf-GELU)
+    return launch_inst<BN, 64, CG, 1, 0, 0, 1>(g, groups, s, rv);                            // QKV
+  }
   if (g.eb == 2) return res ? launch_inst<BN, 64, CG, 2, 1>(g, groups, s, rv) : launch_inst<BN, 64, CG, 2, 0>(g, groups, s, rv);
   return res ? launch_inst<BN, 64, CG, 1, 1>(g, groups, s, rv) : launch_inst<BN, 64, CG, 1, 0>(g, groups, s, rv);
 }
@@ -1076,6 +1090,46 @@ static int pack_table(mmdx_engine* e, const std::string& key, bf16** out) {
   return upload(e, pw, out);
 }
 
+// ---- folded LayerNorm weights.  `lin` = the GEMM's Linear (host fp32), (g, b) = the LayerNorm whose output it consumes
+static int fold_consumer(mmdx_engine* e, const HostTensor* w, const HostTensor* bias, const HostTensor* g, const HostTensor* b,
+                         LnFold* out) {
+  const int n = (int)w->shape[0], k = (int)w->shape[1];
+  REQUIRE((int)g->data.size() == k && (int)b->data.size() == k, "LayerNorm width != Linear input width");
+  std::vector<bf16> wf((size_t)n * k);
+  std::vector<float> c1(n), c2(n);
+  for (int o = 0; o < n; ++o) {
+    // W"[o][i] = gamma[i] W[o][i] - mean_i(gamma[i] W[o][i]): x W"^T = (x - mean(x)) (gamma o W)^T, the mean subtraction of
+    // the LayerNorm is done by the tensor core; the epilogue only scales by rstd and adds c2 = W beta + b
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < k; ++i) {
+      s1 += (double)w->data[(size_t)o * k + i] * (double)g->data[i];
+      s2 += (double)w->data[(size_t)o * k + i] * (double)b->data[i];
+    }
+    const double m = s1 / k;
+    for (int i = 0; i < k; ++i)
+      wf[(size_t)o * k + i] = __float2bfloat16((float)((double)w->data[(size_t)o * k + i] * (double)g->data[i] - m));
+    c1[o] = (float)s1; c2[o] = (float)(s2 + (double)bias->data[o]);
+  }
+  TRY(upload(e, wf, &out->wf));
+  TRY(upload(e, c1, &out->c1));
+  return upload(e, c2, &out->c2);
+}
+static int fold_residual(mmdx_engine* e, const HostTensor* bias, const HostTensor* g, const HostTensor* b, LnFold* out) {
+  const int n = (int)g->data.size();
+  REQUIRE((int)bias->data.size() == n && n % 64 == 0, "LayerNorm width != Linear output width");
+  std::vector<bf16> gd((size_t)n * 64, __float2bfloat16(0.f));
+  std::vector<float> c1(n), c2(n);
+  for (int o = 0; o < n; ++o) {
+    const bf16 q = __float2bfloat16(g->data[o]);
+    gd[(size_t)o * 64 + (o & 63)] = q;
+    c1[o] = __bfloat162float(q);
+    c2[o] = bias->data[o] + b->data[o];
+  }
+  TRY(upload(e, gd, &out->gdiag));
+  TRY(upload(e, c1, &out->c1));
+  return upload(e, c2, &out->c2);
+}
+
 // ---- fp32 arena (fp32 mode)
 static int upload32(mmdx_engine* e, const std::vector<float>& v, float** out) {
   const size_t bytes = (v.size() * 4 + 255) & ~size_t(255);
@@ -1167,7 +1221,10 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
   CK(cudaSetDevice(e->cfg.device));
   size_t total = 0;
   for (auto& kv : e->host) total += kv.second.data.size() * 4 + 512;
-  TRY(e->warena.ensure(total + (16 << 20)));      // + the conv3|downsample copies (7 MB bf16) and alignment slack
+  // + the conv3|downsample copies (7 MB bf16), the gamma-folded QKV / FFN1 weights and diag(gamma) blocks of the text
+  // encoder (~100 MB bf16: already counted above at 4 bytes per fp32 source element, which is twice their bf16 size) and
+  // alignment slack
+  TRY(e->warena.ensure(total + (32 << 20)));
   e->wused = 0;
   // ---- image encoder: stem
   {
@@ -1246,6 +1303,25 @@ extern "C" int mmdx_finalize_weights(mmdx_engine* e) {
       TRY(pack_linear(e, p + "intermediate.dense", &L.ff1));
       TRY(pack_linear(e, p + "output.dense", &L.ff2));
       TRY(pack_ln(e, p + "output.LayerNorm", &L.ln2));
+      {   // folded LayerNorm: the LN in front of this layer (embeddings, or the previous layer's output LN) and ln1
+        const std::string prev = l == 0 ? eb + "LayerNorm" : "text.encoder.encoder.layer." + std::to_string(l - 1) + ".output.LayerNorm";
+        GET(pg, prev + ".weight"); GET(pb, prev + ".bias");
+        GET(g1, p + "attention.output.LayerNorm.weight"); GET(b1, p + "attention.output.LayerNorm.bias");
+        GET(q, p + "attention.self.query.weight"); GET(k, p + "attention.self.key.weight");
+        GET(v, p + "attention.self.value.weight"); GET(qb, p + "attention.self.query.bias");
+        GET(kb, p + "attention.self.key.bias"); GET(vb, p + "attention.self.value.bias");
+        HostTensor w3, b3;
+        for (const HostTensor* t : {q, k, v}) w3.data.insert(w3.data.end(), t->data.begin(), t->data.end());
+        for (const HostTensor* t : {qb, kb, vb}) b3.data.insert(b3.data.end(), t->data.begin(), t->data.end());
+        w3.shape = {3 * q->shape[0], q->shape[1]};
+        TRY(fold_consumer(e, &w3, &b3, pg, pb, &L.f_qkv));
+        GET(aob, p + "attention.output.dense.bias");
+        TRY(fold_residual(e, aob, pg, pb, &L.f_ao));
+        GET(w1, p + "intermediate.dense.weight"); GET(bb1, p + "intermediate.dense.bias");
+        TRY(fold_consumer(e, w1, bb1, g1, b1, &L.f_ff1));
+        GET(b2, p + "output.dense.bias");
+        TRY(fold_residual(e, b2, g1, b1, &L.f_ff2));
+      }
       e->layers.push_back(L);
     }
     e->n_layers = (int)e->layers.size();
@@ -1296,7 +1372,7 @@ struct PackHeader {
   uint64_t arena_bytes;
   uint64_t checksum;        // FNV-1a of table + arena
 };
-static const uint32_t kPackVersion = 5;
+static const uint32_t kPackVersion = 6;
 
 struct PackWalker {
   bool loading; char* base; std::vector<int64_t> words; size_t pos = 0; bool ok = true;
@@ -1317,6 +1393,7 @@ struct PackWalker {
   void conv(ConvW& c) { p(c.w); p(c.bias); i(c.cin); i(c.cout); i(c.k); i(c.stride); }
   void lin(LinW& l) { p(l.w); p(l.bias); i(l.nin); i(l.nout); }
   void ln(LnW& l) { p(l.g); p(l.b); }
+  void fold(LnFold& f) { p(f.wf); p(f.c1); p(f.c2); p(f.gdiag); }
 };
 // one traversal for both directions: every field mmdx_finalize_weights sets
 static void walk_weights(mmdx_engine* e, PackWalker& w) {
@@ -1334,7 +1411,10 @@ static void walk_weights(mmdx_engine* e, PackWalker& w) {
   int nl = (int)e->layers.size();
   w.i(nl);
   if (w.loading) e->layers.assign(nl < 0 || nl > 64 ? 0 : nl, BertLayerW());
-  for (BertLayerW& L : e->layers) { w.lin(L.qkv); w.lin(L.ao); w.lin(L.ff1); w.lin(L.ff2); w.ln(L.ln1); w.ln(L.ln2); }
+  for (BertLayerW& L : e->layers) {
+    w.lin(L.qkv); w.lin(L.ao); w.lin(L.ff1); w.lin(L.ff2); w.ln(L.ln1); w.ln(L.ln2);
+    w.fold(L.f_qkv); w.fold(L.f_ao); w.fold(L.f_ff1); w.fold(L.f_ff2);
+  }
   w.lin(e->proj_txt); w.lin(e->fuse); w.ln(e->fuse_ln); w.lin(e->cond);
   w.p(e->head_w); w.p(e->head_b); w.p(e->thr_default);
 }
@@ -1658,12 +1738,38 @@ static int get_head_plan(mmdx_engine* e, int B, HeadPlan** out) {
   return 0;
 }
 
-struct TextBufs { bf16 *hid, *qkv, *ctx, *pre, *ffn, *hid2; };
+struct TextBufs { bf16 *hid, *qkv, *ctx, *pre, *ffn, *hid2; long long* stats; size_t stats_bytes; };
+
+// LayerNorm folded into the text GEMMs (gemm_tcgen05.cuh, GemmParams::lnf).  MMDX_LNFOLD=0 restores the separate
+// LayerNorm launches (A/B timing; also the path the fused-LN experiment uses).
+static bool lnfold_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("MMDX_LNFOLD"); on = (v && atoi(v) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static int apply_fold(mmdx_engine* e, GemmLaunch& g, const LnFold& f, const long long* stats, long long* stat_out, bool post,
+                      bool diag, int ln_width) {
+  GemmParams& p = g.p;
+  REQUIRE(p.epi_mode == EPI_TMA && p.Wb == 128 && p.Hb == 1 && p.Nb == 1, "folded LayerNorm needs a plain GEMM with the TMA epilogue");
+  p.lnf = 1; p.lnf_post = post ? 1 : 0; p.lnf_diag = diag ? 1 : 0;
+  g.eb = post ? 2 : 1;                                               // the variants launch_bn instantiates
+  p.lnf_inv_n = 1.0f / (float)ln_width; p.ln_eps = 1e-12f;          // BertLayerNorm eps
+  p.lnf_c1 = f.c1; p.lnf_stats = stats; p.stat_out = reinterpret_cast<unsigned long long*>(stat_out);
+  if (diag) {
+    REQUIRE(p.res_blocks > 0 && f.gdiag, "folded residual needs the tensor-core residual path");
+    const uint64_t d[2] = {64, (uint64_t)p.n_tiles * g.bn};
+    const uint64_t st[1] = {128};
+    const uint32_t bx[2] = {64, (uint32_t)(64 / g.cg)};
+    TRY(make_tmap(e, &p.tmI, f.gdiag, 2, d, st, bx, 128));
+  }
+  return 0;
+}
 
 static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs* tb) {
   const int H = e->hidden;
   const size_t hb = al((size_t)T * H * 2), qb = al((size_t)T * 3 * H * 2), fb = al((size_t)T * e->ffn * 2);
-  const size_t total = 4 * hb + qb + fb;
+  const size_t sb = al((size_t)(1 + 2 * e->n_layers) * T * 16);      // row sums per LayerNorm input (folded LN)
+  const size_t total = 4 * hb + qb + fb + sb;
   char* old = static_cast<char*>(e->txt_ws.p);
   TRY(e->txt_ws.ensure(total));
   if (old != e->txt_ws.p) e->txt_plans.clear();
@@ -1675,6 +1781,8 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
   tb->pre = reinterpret_cast<bf16*>(base + 3 * hb);
   tb->qkv = reinterpret_cast<bf16*>(base + 4 * hb);
   tb->ffn = reinterpret_cast<bf16*>(base + 4 * hb + qb);
+  tb->stats = reinterpret_cast<long long*>(base + 4 * hb + qb + fb);
+  tb->stats_bytes = sb;
   char key[48];
   snprintf(key, sizeof key, "%d", T);
   auto it = e->txt_plans.find(key);
@@ -1682,9 +1790,35 @@ static int get_text_plan(mmdx_engine* e, int T, int B, TextPlan** out, TextBufs*
   if (e->txt_plans.size() > 64) e->txt_plans.clear();
   std::unique_ptr<TextPlan> pl(new TextPlan());
   pl->T = T; pl->B = B;
-  pl->ln_fused = ln_fusable(e, T, H);
+  pl->folded = lnfold_enabled() && e->layers[0].f_qkv.wf != nullptr;
+  pl->ln_fused = !pl->folded && ln_fusable(e, T, H);
   const int bn_ln = pl->ln_fused ? 256 : 0;
-  for (int l = 0; l < e->n_layers; ++l) {
+  for (int l = 0; l < e->n_layers && pl->folded; ++l) {
+    // x_a = tb->hid (pre-LN input of the layer), x_b = tb->hid2 (pre-LN attention output); stats[0] = embeddings,
+    // stats[1 + 2l] = x_b of layer l, stats[2 + 2l] = x_a leaving layer l
+    const BertLayerW& L = e->layers[l];
+    long long* s_in = tb->stats + (size_t)(l == 0 ? 0 : 2 * l) * T * 2;
+    long long* s_mid = tb->stats + (size_t)(1 + 2 * l) * T * 2;
+    long long* s_out = tb->stats + (size_t)(2 + 2 * l) * T * 2;
+    GemmLaunch g;
+    TRY(build_gemm(e, g, tb->hid, H, L.f_qkv.wf, T, 3 * H, H, 0));
+    TRY(fill_epilogue(e, g, L.f_qkv.c2, nullptr, 0, tb->qkv, 3 * H, ACT_NONE, 0));
+    TRY(apply_fold(e, g, L.f_qkv, s_in, nullptr, false, false, H));
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->ctx, H, L.ao.w, T, H, H, 0));
+    TRY(fill_epilogue(e, g, L.f_ao.c2, tb->hid, H, tb->hid2, H, ACT_NONE, 0));
+    TRY(apply_fold(e, g, L.f_ao, s_in, s_mid, false, true, H));
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->hid2, H, L.f_ff1.wf, T, e->ffn, H, 0));
+    TRY(fill_epilogue(e, g, L.f_ff1.c2, nullptr, 0, tb->ffn, e->ffn, ACT_GELU, 0));
+    TRY(apply_fold(e, g, L.f_ff1, s_mid, nullptr, true, false, H));
+    pl->gemms.push_back(g);
+    TRY(build_gemm(e, g, tb->ffn, e->ffn, L.ff2.w, T, H, e->ffn, 0));
+    TRY(fill_epilogue(e, g, L.f_ff2.c2, tb->hid2, H, tb->hid, H, ACT_NONE, 0));
+    TRY(apply_fold(e, g, L.f_ff2, s_mid, s_out, false, true, H));
+    pl->gemms.push_back(g);
+  }
+  for (int l = 0; l < e->n_layers && !pl->folded; ++l) {
     const BertLayerW& L = e->layers[l];
     GemmLaunch g;
     TRY(build_gemm(e, g, tb->hid, H, L.qkv.w, T, 3 * H, H, 0));
@@ -1715,10 +1849,10 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
   const int rv = next_direction(e, s);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0, (long long*)nullptr)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, false, R>, dim3(grid), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0, (long long*)nullptr)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, false, 2, 3>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0, (long long*)nullptr)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, false, 2>, dim3((rows + 15) / 16), dim3(256), 0, s, 1, x, rows, g, b, eps, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rv, 0, 0, 0, (long long*)nullptr)); break;
     default: return fail("mmdx: layernorm width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
@@ -1726,22 +1860,23 @@ static int launch_ln(mmdx_engine* e, const bf16* x, int rows, int N, const float
 }
 static int launch_embed(mmdx_engine* e, const int* ids, const int* pos, const int* tt, int rows, int N, const bf16* word,
                         const bf16* ptab, const bf16* ttab, const float* g, const float* b, float eps, bf16* y,
-                        cudaStream_t s, int n_word = 0x7fffffff, int n_pos = 0x7fffffff, int n_type = 0x7fffffff) {
+                        cudaStream_t s, int n_word = 0x7fffffff, int n_pos = 0x7fffffff, int n_type = 0x7fffffff,
+                        long long* stats_out = nullptr) {
   constexpr int R = 2;
   const int grid = (rows + 8 * R - 1) / (8 * R);
   ProfScope _ps(e);
   switch (N) {
-    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
-    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
-    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
-    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type)); break;
+    case 256: CK(launch_k(layernorm_kernel<256, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type, stats_out)); break;
+    case 512: CK(launch_k(layernorm_kernel<512, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type, stats_out)); break;
+    case 768: CK(launch_k(layernorm_kernel<768, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type, stats_out)); break;
+    case 1024: CK(launch_k(layernorm_kernel<1024, true, R>, dim3(grid), dim3(256), 0, s, 1, nullptr, rows, g, b, eps, y, ids, pos, tt, word, ptab, ttab, 0, n_word, n_pos, n_type, stats_out)); break;
     default: return fail("mmdx: hidden width must be 256/512/768/1024");
   }
   CK(cudaGetLastError());
   return 0;
 }
 static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int n_seq, int T, int max_len, int heads,
-                            int hidden, bf16* ctx, cudaStream_t s) {
+                            int hidden, bf16* ctx, cudaStream_t s, const long long* row_stats = nullptr) {
   REQUIRE(hidden == heads * 64, "attention head dim must be 64");
   REQUIRE(n_seq > 0 && T > 0 && max_len > 0, "bad attention batch");
   static bool attr_set_[64] = {};
@@ -1762,6 +1897,7 @@ static int launch_attention(mmdx_engine* e, const bf16* qkv, const int* cu, int 
   p.tm = e->attn_tm; p.cu_seqlens = cu; p.ctx = ctx; p.n_seq = n_seq; p.heads = heads; p.hidden = hidden;
   p.nqb = (max_len + 127) / 128; p.num_units = n_seq * heads * p.nqb;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.row_stats = row_stats; p.inv_n = 1.0f / (float)hidden; p.eps = 1e-12f;
   p.reverse = next_direction(e, s);
   ProfScope _ps(e);
   if (max_len <= 128 && !e->attn_force_general) {       // one key block per sequence: the 4-deep TMEM-resident variant
@@ -1858,6 +1994,39 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   const int H = e->hidden;
   e->cur_stream = s; e->cur_cls = CLS_LN;
   e->zz_txt = 1;                                   // the embedding kernel writes forward: the first consumer walks backwards
+  if (pl->folded) {
+    // LayerNorm folded into the GEMMs: the embedding kernel stores the raw sum + its row sums, every GEMM applies /
+    // re-creates the LayerNorm in its epilogue, AO and FFN2 accumulate the row sums of what they write: 5 launches per layer
+    CK(cudaMemsetAsync(tb.stats + (size_t)T * 2, 0, (size_t)2 * e->n_layers * T * 16, s));
+    TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s,
+                     e->vocab, e->max_pos, e->type_vocab, tb.stats));
+    for (int l = 0; l < e->n_layers; ++l) {
+      const long long* s_in = tb.stats + (size_t)(l == 0 ? 0 : 2 * l) * T * 2;
+      e->cur_cls = CLS_GEMM_TEXT;
+      TRY(launch_gemm(e, pl->gemms[4 * l + 0], s));                                       // QKV of LN(x_a)
+      e->cur_cls = CLS_ATTN;
+      TRY(launch_attention(e, tb.qkv, d_cu, B, T, max_len, e->cfg.n_heads, H, tb.ctx, s, s_in));   // ctx / rstd
+      e->cur_cls = CLS_GEMM_TEXT;
+      TRY(launch_gemm(e, pl->gemms[4 * l + 1], s));                                       // x_b = out-proj + LN(x_a)
+      TRY(launch_gemm(e, pl->gemms[4 * l + 2], s));                                       // GELU(FFN1 of LN(x_b)) / rstd
+      TRY(launch_gemm(e, pl->gemms[4 * l + 3], s));                                       // x_a = FFN2 + LN(x_b)
+    }
+    e->cur_cls = CLS_POOL;
+    {
+      const LnW& ln = e->layers.back().ln2;
+      const long long* s_last = tb.stats + (size_t)(2 * e->n_layers) * T * 2;
+      ProfScope _ps(e);
+      CK(launch_k(seq_mean_pool_kernel, dim3(dim3(B, (H + 63) / 64)), dim3(256), 0, s, 1, tb.hid, d_cu, H, e->pooled_bf, H, d_pooled,
+                  s_last, ln.g, ln.b, 1e-12f));
+      CK(cudaGetLastError());
+    }
+    e->cur_cls = CLS_HEAD;
+    HeadPlan* hp;
+    TRY(get_head_plan(e, B, &hp));
+    TRY(launch_gemm(e, hp->proj_txt, s));
+    if (d_z_txt) TRY(launch_cvt(e, e->zcat + e->d_img, e->d_img + e->d_txt, B, e->d_txt, d_z_txt, s));
+    return 0;
+  }
   TRY(launch_embed(e, d_ids, d_pos, d_tt, T, H, e->word, e->ptab, e->ttab, e->emb_ln.g, e->emb_ln.b, 1e-12f, tb.hid, s,
                    e->vocab, e->max_pos, e->type_vocab));
   for (int l = 0; l < e->n_layers; ++l) {
@@ -1879,7 +2048,8 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   e->cur_cls = CLS_POOL;
   {
     ProfScope _ps(e);
-    CK(launch_k(seq_mean_pool_kernel, dim3(dim3(B, (H + 63) / 64)), dim3(256), 0, s, 1, tb.hid, d_cu, H, e->pooled_bf, H, d_pooled));
+    CK(launch_k(seq_mean_pool_kernel, dim3(dim3(B, (H + 63) / 64)), dim3(256), 0, s, 1, tb.hid, d_cu, H, e->pooled_bf, H, d_pooled,
+                (const long long*)nullptr, (const float*)nullptr, (const float*)nullptr, 0.f));
     CK(cudaGetLastError());
   }
   e->cur_cls = CLS_HEAD;
@@ -2594,7 +2764,8 @@ extern "C" int mmdx_op_seq_mean_pool(mmdx_engine* e, const void* d_h, const int3
   REQUIRE(e && hidden % 8 == 0, "hidden % 8");
   ProfScope _ps(e);
   CK(launch_k(seq_mean_pool_kernel, dim3(dim3(n_seq, (hidden + 63) / 64)), dim3(256), 0, (cudaStream_t)stream, 1, static_cast<const bf16*>(d_h), d_cu, hidden,
-                                                               static_cast<bf16*>(d_out_bf16), hidden, d_out_f32));
+                                                               static_cast<bf16*>(d_out_bf16), hidden, d_out_f32,
+                                                               (const long long*)nullptr, (const float*)nullptr, (const float*)nullptr, 0.f));
   CK(cudaGetLastError());
   return 0;
 }
@@ -2619,6 +2790,23 @@ extern "C" int mmdx_profile_begin(mmdx_engine* e) {
   e->prof.clear();
   e->profiling = true;
   return 0;
+}
+// Per-launch variant of mmdx_profile_end: device time and class of every launch since mmdx_profile_begin, in launch
+// order (tools/launch_times.py).  Returns the number of launches written (<= cap), or -1.
+extern "C" int mmdx_profile_end_list(mmdx_engine* e, float* ms, int32_t* cls, int cap) {
+  if (!e || !ms || !cls) return -1;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+  int n = 0;
+  for (auto& r : e->prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (n < cap) { ms[n] = t; cls[n] = r.cls; ++n; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  e->prof.clear();
+  e->profiling = false;
+  return n;
 }
 extern "C" int mmdx_profile_end(mmdx_engine* e, float* ms_by_class, int64_t* launches_by_class, int n_classes) {
   REQUIRE(e && ms_by_class && launches_by_class && n_classes >= CLS_COUNT, "bad argument");

@@ -78,7 +78,34 @@ struct alignas(64) GemmParams {
   const float* ln_beta;        // [N]
   __nv_bfloat16* ln_out;       // [M, ld_ln]; may alias `out` (in place)
   long long ld_ln;
+  // Folded LayerNorm (text encoder; DESIGN.md "LayerNorm folded into the GEMMs"): the activation tensor in memory is the
+  // PRE-LayerNorm tensor x with its per-row sums (sum x, sum x^2 as 2^24 fixed-point int64, so that atomic accumulation
+  // is order-independent and the result deterministic).  With mu, rstd from those sums:
+  //   consumer GEMM  LN(x) W^T + b      = rstd (x W"^T) + c2,   W" = (gamma o W)(I - 11^T / n): the mean is projected out
+  //                  by the weights themselves (x W"^T = (x - mu) (gamma o W)^T since mu = x 1 / n),  c2 = W beta + b
+  //   residual GEMM  A W^T + b + LN(x)  = rstd ((A / rstd) W^T + x diag(gamma) - mu gamma) + (b + beta)
+  //                  (the producer of A has already scaled its rows by 1 / rstd; x diag(gamma) is the residual MMA with
+  //                   diag(gamma) blocks in place of the identity)
+  // i.e. consumer epilogue v = rstd_row * D + bias[n] (one FMA per element, like a plain bias add); residual epilogue
+  // v = rstd_row * (D - mu_row * c1[n]) + bias[n], c1 = gamma.
+  int lnf;                     // 1: epilogue as above (bias = c2)
+  int lnf_post;                // 1: after the activation multiply by 1 / rstd_row (FFN1: its output feeds a residual GEMM)
+  int lnf_diag;                // 1: residual MMAs take diag(gamma) blocks from tmI (rows = output columns) through the ring
+  float lnf_inv_n;             // 1 / width of the LayerNorm
+  const float* lnf_c1;         // [N]
+  const long long* lnf_stats;  // [M][2]
+  unsigned long long* stat_out;   // [M][2] or null: row sums of THIS GEMM's output are accumulated here (zeroed by the host)
 };
+
+constexpr float kStatScale = 16777216.0f;     // 2^24 fixed point of the row sums
+
+__device__ __forceinline__ void ln_row_coeffs(const long long* st, float inv_n, float eps, float& mu, float& rstd) {
+  const float s1 = static_cast<float>(static_cast<double>(st[0]) * (1.0 / 16777216.0));
+  const float s2 = static_cast<float>(static_cast<double>(st[1]) * (1.0 / 16777216.0));
+  mu = s1 * inv_n;
+  const float var = fmaxf(s2 * inv_n - mu * mu, 0.0f);
+  rstd = rsqrtf(var + eps);
+}
 
 // Persistent schedule.  Default: tile = group + i * num_groups.  Item-major: group g owns items g, g + num_groups, ...
 // and walks each item's n_tiles tiles consecutively (tile = item * n_tiles + n).
@@ -174,14 +201,15 @@ __device__ __forceinline__ void ln_two_rows(const __nv_bfloat16* x, long long ld
 // group) is already being converted and written into the other one, and one named barrier per chunk is enough.
 // RES = the GEMM can add a residual on the tensor core (needs the resident identity block).  The ring takes whatever
 // shared memory is left (at most 8 stages).
-template <int BN, int BK, int CG, int EB, int RES>
+template <int BN, int BK, int CG, int EB, int RES, int LNF = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;     // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = kEpiGroups * EB * kEpiBufBytes + (RES ? kIdentBytes : 0);
-  static constexpr int BIAS_BYTES = 2 * BN * 4;          // bias slice of the current tile, double-buffered
-  static constexpr int BAR_BYTES = 512 + BIAS_BYTES;
+  static constexpr int BIAS_BYTES = (LNF ? 4 : 2) * BN * 4;   // bias (and c1) slices of two tiles in flight
+  static constexpr int ROW_BYTES = LNF ? 2 * 128 * 8 : 0;     // folded LayerNorm: (rstd, -rstd * mu) of the 128 rows, two tiles
+  static constexpr int BAR_BYTES = 512 + BIAS_BYTES + ROW_BYTES;
   static constexpr int FIXED = STG_BYTES + BAR_BYTES + 1024;                // +1024: manual alignment slack
   static constexpr int STAGES = (232448 - FIXED) / STAGE_BYTES > 8 ? 8 : (232448 - FIXED) / STAGE_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
@@ -206,9 +234,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return t;
 }
 
-template <int BN, int BK, int CG, int EB, int RES, int LN = 0>
+// LNF (folded LayerNorm, see GemmParams::lnf): 0 = off (every conv and head GEMM: the code below is compiled out),
+// 1 = consumer GEMM (QKV), 2 = consumer + rows scaled by 1 / rstd after the activation (FFN1), 3 = residual GEMM with
+// diag(gamma) residual MMAs + row sums of the output (attention output, FFN2).
+template <int BN, int BK, int CG, int EB, int RES, int LN = 0, int LNF = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-  using L = GemmSmem<BN, BK, CG, EB, RES>;
+  using L = GemmSmem<BN, BK, CG, EB, RES, LNF>;
   constexpr int STAGES = L::STAGES;
   constexpr int SWZ = BK * 2;                 // swizzle span = one K-chunk row (128 B or 64 B)
   constexpr uint32_t IDESC = make_idesc_bf16(128 * CG, BN);
@@ -218,6 +249,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert(BK == 64 || BK == 32, "BK");
 
+  static_assert(LNF == 0 || (BK == 64 && LN == 0 && (LNF == 3) == (RES == 1)), "folded LayerNorm variants");
+  constexpr bool kDiag = LNF == 3;      // residual B operand = diag(gamma) block through the ring (else the resident identity)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + L::RING_BYTES;
@@ -226,8 +259,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* ident_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ident_bar + 1);
-  float* sbias = reinterpret_cast<float*>(stg + L::STG_BYTES + 512);       // [2][BN]
+  uint64_t* cfull_bar = ident_bar + 1;        // tile coefficients (bias / c1 slices, row coefficients) staged  (coef warps -> epilogue)
+  uint64_t* cempty_bar = cfull_bar + 2;       // ... and no longer read                                             (epilogue -> coef warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty_bar + 2);
+  static_assert((2 * 8 + 9) * 8 + 4 <= 512, "barrier area");
+  float* sbias = reinterpret_cast<float*>(stg + L::STG_BYTES + 512);       // [2][BN] bias, then [2][BN] c1 (folded LN)
+  float2* srow = reinterpret_cast<float2*>(stg + L::STG_BYTES + 512 + L::BIAS_BYTES);   // [2][128] (LNF only)
   uint8_t* ident = stg + kEpiGroups * EB * kEpiBufBytes;      // 1024-byte aligned (RES only)
 
   const int warp = threadIdx.x >> 5;
@@ -251,6 +288,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       mbar_init(&tempty_bar[s], kEpiWarps * CG);        // epilogue warps of every CTA of the group
     }
     mbar_init(ident_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&cfull_bar[s], 64);                      // every thread of the two coefficient warps
+      mbar_init(&cempty_bar[s], kEpiWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -263,6 +304,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // the kernel that produced A / the residual has completed (everything above overlapped it)
   pdl_trigger();
+  // (setmaxnreg note: registers can only be redistributed INSIDE the CTA's launch allocation, 640 x 96 = 61440; the
+  // epilogue warp groups could gain at most 8 registers (128 x 64 + 512 x 104) and an .inc beyond the pool never
+  // returns - measured as a hang - so the kernel keeps the uniform 96.)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0;
       // CG = 2: completion is tracked by the LEADER's full barriers (shared::cluster addresses of rank 0)
       const uint32_t full0 = CG == 2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0;
-      if (RES && BK == 64 && p.res_blocks > 0) {        // identity block (this CTA's rows of it): loaded once, stays resident
+      if (RES && BK == 64 && p.res_blocks > 0 && !kDiag) {   // identity block (this CTA's rows of it): loaded once, stays resident
         if constexpr (CG == 2) {
           if (rank == 0) mbar_arrive_expect_tx(ident_bar, kIdentBytes);      // both halves
           tma_load_2d_pair(ident, &p.tmI, mapa_rank(smem_u32(ident_bar), 0), 0, rank * 32);
@@ -308,13 +352,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           for (int j = 0; j < p.res_blocks; ++j) {      // residual tile as extra A blocks + identity B block
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            // folded LN: the B operand of this residual block is diag(gamma[64 b .. 64 b + 63]), rows 64 b.. of tmI
+            constexpr uint32_t dg = kDiag ? static_cast<uint32_t>(kIdentBytes / CG) : 0u;
+            const int drow = t.n_t * BN + j * 64;
             if constexpr (CG == 2) {
               const uint32_t fb = full0 + stage * 8;
-              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(p.a_box_bytes));
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (static_cast<uint32_t>(p.a_box_bytes) + dg));
               tma_load_4d_pair(sa, &p.tmR, fb, t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+              if (dg) tma_load_2d_pair(sb, &p.tmI, fb, 0, drow + rank * 32);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes));
+              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.a_box_bytes) + dg);
               tma_load_4d(sa, &p.tmR, &full_bar[stage], t.n_t * BN + j * 64, t.w0, t.h0, t.n0);
+              if (dg) tma_load_2d(sb, &p.tmI, &full_bar[stage], 0, drow);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -340,7 +390,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0, soff = 0;              // soff = stage * STAGE_STEP
       int it = 0;
-      if (RES && BK == 64 && p.res_blocks > 0) mbar_wait(ident_bar, 0);
+      if (RES && BK == 64 && p.res_blocks > 0 && !kDiag) mbar_wait(ident_bar, 0);
       const int nkb = p.num_k_blocks, nres = (BK == 64 && RES) ? p.res_blocks : 0;
       for (int tile = first_tile(p, group); tile < p.num_tiles; tile = next_tile(p, tile, num_groups), ++it) {
         const int as = it & 1;
@@ -375,7 +425,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_words<CG == 2>(tmem_d + j * 64, a_lo0 + soff + 2 * k, HI128, id_lo + 2 * k, HI128, IDESC64, 1u);
+                umma_bf16_words<CG == 2>(tmem_d + j * 64, a_lo0 + soff + 2 * k, HI128,
+                                         (kDiag ? b_lo0 + soff : id_lo) + 2 * k, HI128, IDESC64, 1u);
               commit(&empty_bar[stage]);
               if (j == nres - 1) commit(&tfull_bar[as]);
             }
@@ -384,6 +435,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (++stage == STAGES) { stage = 0; phase ^= 1; soff = 0; }
           }
         }
+      }
+    }
+  } else if (warp < 4) {
+    // ================= coefficient warps 2, 3 =================
+    // Everything the epilogue of a tile needs from global memory - the bias (and, folded LayerNorm, c1) slice of its
+    // columns and the (rstd, -rstd * mu) pair of each of its 128 rows - is fetched here, up to two tiles ahead, and
+    // handed over through shared memory: the epilogue warps never wait for a global load.
+    if (p.epi_mode == EPI_TMA) {
+      const int ct = threadIdx.x - 64;        // 0..63
+      int it = 0;
+      for (int tile = first_tile(p, group); tile < p.num_tiles; tile = next_tile(p, tile, num_groups), ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const TileCoord t = decode_tile(p, tile, rank);
+        float vb[BN / 64], vc[BN / 64];
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) {
+          vb[j] = p.bias != nullptr ? __ldg(p.bias + t.n_t * BN + ct + 64 * j) : 0.0f;
+          if constexpr (LNF == 3) vc[j] = __ldg(p.lnf_c1 + t.n_t * BN + ct + 64 * j);
+        }
+        float2 rc[2];
+        if constexpr (LNF > 0) {
+          // plain GEMM: global rows of this CTA's tile (not t.w0: the past-the-end m-tile of an odd pair decodes to w0 = 0
+          // of the next "image" - its loads are zero-filled and its stores clipped, but its rows must stay past the end)
+          const int row0 = (((p.reverse ? p.num_tiles - 1 - tile : tile) / p.n_tiles) * CG + rank) * 128;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float mu, rstd;
+            ln_row_coeffs(p.lnf_stats + 2 * static_cast<size_t>(min(row0 + ct + 64 * j, p.OW - 1)), p.lnf_inv_n, p.ln_eps, mu, rstd);
+            rc[j] = make_float2(rstd, -rstd * mu);
+          }
+        }
+        mbar_wait(&cempty_bar[as], aphase ^ 1);          // the epilogue of two tiles ago has finished with this slot
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) {
+          sbias[as * BN + ct + 64 * j] = vb[j];
+          if constexpr (LNF == 3) sbias[(2 + as) * BN + ct + 64 * j] = vc[j];
+        }
+        if constexpr (LNF > 0) { srow[as * 128 + ct] = rc[0]; srow[as * 128 + ct + 64] = rc[1]; }
+        mbar_arrive(&cfull_bar[as]);
       }
     }
   } else if (warp >= 4) {
@@ -410,19 +501,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const TileCoord t = decode_tile(p, tile, rank);
+      // plain GEMM: global row of this thread (see the coefficient warps for why this is not t.w0 + r)
+      const int grow = (((p.reverse ? p.num_tiles - 1 - tile : tile) / p.n_tiles) * CG + rank) * 128 + r;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + hh * TW;
 
       if (p.epi_mode == EPI_TMA) {
         const int sw = (r >> 1) & 3;          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
-        // bias slice of this tile -> shared memory (once per tile, instead of dependent global loads per chunk).
-        // The barrier also orders this write after every thread's reads of the same slot two tiles ago.
-        float* sb = sbias + as * BN;
-        {
-          const int et = e * 32 + lane;       // 0..511
-          if (et < BN) sb[et] = p.bias != nullptr ? __ldg(p.bias + t.n_t * BN + et) : 0.0f;
-          named_bar_sync(3, 32 * kEpiWarps);
+        // bias (and c1) slices of this tile and - folded LayerNorm - the row coefficients were staged by the coefficient warps
+        const float* sb = sbias + as * BN;
+        const float* sc = sbias + (2 + as) * BN;
+        mbar_wait(&cfull_bar[as], aphase);
+        // folded LayerNorm: this thread's row coefficients  v = ra * D + (rb * c1[n] + c2[n])
+        float ra = 1.0f, rb = 0.0f, rsig = 1.0f;
+        uint64_t st_sum = 0, st_sq = 0;       // packed (even, odd column) sums of v and v^2 over this thread's share of the row (LNF 3)
+        if constexpr (LNF > 0) {
+          const float2 rc = srow[as * 128 + r];
+          ra = rc.x; rb = rc.y;
+          if constexpr (LNF == 2) rsig = 1.0f / ra;
         }
         uint32_t v[TW];
         tmem_ld_32x16(tbase + g * kEpiCW, v);
@@ -441,7 +538,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             __syncwarp();
             if (lane == 0) release_acc(as);
           }
-          {
+          if constexpr (LNF == 1 || LNF == 2) {
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW + hh * TW);
+            const uint64_t ra2 = pack_f32x2(ra, ra);
+#pragma unroll
+            for (int j = 0; j < TW / 4; ++j) {              // v = ra * D + c2, two columns per instruction
+              const float4 b = b4[j];
+              unpack_f32x2(fma_f32x2(ra2, pack_f32x2(x[4 * j], x[4 * j + 1]), pack_f32x2(b.x, b.y)), x[4 * j], x[4 * j + 1]);
+              unpack_f32x2(fma_f32x2(ra2, pack_f32x2(x[4 * j + 2], x[4 * j + 3]), pack_f32x2(b.z, b.w)), x[4 * j + 2], x[4 * j + 3]);
+            }
+          } else if constexpr (LNF == 3) {
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW + hh * TW);
+            const float4* c4 = reinterpret_cast<const float4*>(sc + c * kEpiCW + hh * TW);
+            const uint64_t ra2 = pack_f32x2(ra, ra), rb2 = pack_f32x2(rb, rb);
+#pragma unroll
+            for (int j = 0; j < TW / 4; ++j) {              // v = ra * D + (rb * c1 + c2), two columns per instruction
+              const float4 b = b4[j], cc = c4[j];
+              unpack_f32x2(fma_f32x2(ra2, pack_f32x2(x[4 * j], x[4 * j + 1]),
+                                     fma_f32x2(rb2, pack_f32x2(cc.x, cc.y), pack_f32x2(b.x, b.y))), x[4 * j], x[4 * j + 1]);
+              unpack_f32x2(fma_f32x2(ra2, pack_f32x2(x[4 * j + 2], x[4 * j + 3]),
+                                     fma_f32x2(rb2, pack_f32x2(cc.z, cc.w), pack_f32x2(b.z, b.w))), x[4 * j + 2], x[4 * j + 3]);
+            }
+          } else {
             const float4* b4 = reinterpret_cast<const float4*>(sb + c * kEpiCW + hh * TW);
 #pragma unroll
             for (int j = 0; j < TW / 4; ++j) {              // packed adds: two columns per instruction
@@ -457,6 +575,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           } else if (p.act == ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < TW; j += 2) gelu_erf_x2(x[j], x[j + 1]);
+          }
+          if constexpr (LNF == 2) {
+            const uint64_t sg2 = pack_f32x2(rsig, rsig);
+#pragma unroll
+            for (int j = 0; j < TW; j += 2) unpack_f32x2(mul_f32x2(pack_f32x2(x[j], x[j + 1]), sg2), x[j], x[j + 1]);
+          }
+          if constexpr (LNF == 3) {
+#pragma unroll
+            for (int j = 0; j < TW; j += 2) {
+              const uint64_t xx = pack_f32x2(x[j], x[j + 1]);
+              st_sum = add_f32x2(st_sum, xx);
+              st_sq = fma_f32x2(xx, xx, st_sq);
+            }
           }
           if constexpr (EB == 1) {
             if (issuer) tma_store_wait_read<0>();   // the previous store has finished reading `buf`
@@ -478,6 +609,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           if (issuer) {
             tma_store_4d(&p.tmC, buf, col0, t.w0, t.h0, t.n0);
             tma_store_commit();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cempty_bar[as]);       // this warp no longer reads the tile's staged coefficients
+        if constexpr (LNF == 3) {
+          if (grow < p.OW) {
+            // this thread's share of the row sums of the tile it has just written; int64 fixed point: integer atomics
+            // commute, so the totals do not depend on the order in which tiles and threads arrive
+            float a0, a1, q0, q1;
+            unpack_f32x2(st_sum, a0, a1);
+            unpack_f32x2(st_sq, q0, q1);
+            atomicAdd(p.stat_out + 2 * static_cast<size_t>(grow), static_cast<unsigned long long>(__float2ll_rn((a0 + a1) * kStatScale)));
+            atomicAdd(p.stat_out + 2 * static_cast<size_t>(grow) + 1, static_cast<unsigned long long>(__float2ll_rn((q0 + q1) * kStatScale)));
           }
         }
         if constexpr (LN > 0) {

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
                                                         const __nv_bfloat16* __restrict__ word,
                                                         const __nv_bfloat16* __restrict__ ptab,
                                                         const __nv_bfloat16* __restrict__ ttab, int reverse,
-                                                        int n_word, int n_pos, int n_type) {
+                                                        int n_word, int n_pos, int n_type,
+                                                        long long* __restrict__ stats_out = nullptr) {
   pdl_wait();
   pdl_trigger();
   // R rows per warp: all their 16-byte loads are issued before the first reduction (R * N / 256 loads in flight
@@ -419,6 +420,33 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
           v[r][c][2 * j] = f.x; v[r][c][2 * j + 1] = f.y;
         }
       }
+  }
+  if (EMBED && stats_out != nullptr) {
+    // Folded-LayerNorm mode (gemm_tcgen05.cuh): the embedding sum itself is the stored tensor (bf16) and the LayerNorm is
+    // applied by its consumers from the row sums written here (of the ROUNDED values, i.e. of what the consumers read).
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pk[j] = pack_bf16(v[r][c][2 * j], v[r][c][2 * j + 1]);
+          const float2 f = unpack_bf16(pk[j]);
+          s1 += f.x + f.y;
+          s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+        }
+        if (row0 + r < rows)
+          reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * N)[c * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0 && row0 + r < rows) {
+        stats_out[2 * static_cast<size_t>(row0 + r)] = __float2ll_rn(s1 * 16777216.0f);
+        stats_out[2 * static_cast<size_t>(row0 + r) + 1] = __float2ll_rn(s2 * 16777216.0f);
+      }
+    }
+    return;
   }
   float mean[R], rstd[R];
 #pragma unroll
@@ -477,7 +505,12 @@ __global__ void __launch_bounds__(256, MINB) layernorm_kernel(const __nv_bfloat1
 __global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16* __restrict__ h,
                                                             const int* __restrict__ cu_seqlens, int hidden,
                                                             __nv_bfloat16* __restrict__ out, long long ldo,
-                                                            float* __restrict__ out_f32) {
+                                                            float* __restrict__ out_f32,
+                                                            const long long* __restrict__ row_stats = nullptr,
+                                                            const float* __restrict__ gamma = nullptr,
+                                                            const float* __restrict__ beta = nullptr, float eps = 0.f) {
+  // row_stats != null (folded LayerNorm): h is the PRE-LayerNorm tensor; the mean of LN(h_t) over the tokens is
+  // gamma * mean_t(rstd_t * (h_t - mu_t)) + beta.
   pdl_wait();
   pdl_trigger();
   __shared__ float part[32][64 + 1];
@@ -489,11 +522,19 @@ __global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16*
   if (col < hidden) {
     for (int t = t0 + tl; t < t1; t += 32) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + static_cast<size_t>(t) * hidden + col));
+      float ra = 1.0f, rb = 0.0f;
+      if (row_stats != nullptr) {
+        const float s1 = static_cast<float>(static_cast<double>(row_stats[2 * static_cast<size_t>(t)]) * (1.0 / 16777216.0));
+        const float s2 = static_cast<float>(static_cast<double>(row_stats[2 * static_cast<size_t>(t) + 1]) * (1.0 / 16777216.0));
+        const float mu = s1 / hidden;
+        ra = rsqrtf(fmaxf(s2 / hidden - mu * mu, 0.0f) + eps);
+        rb = -ra * mu;
+      }
       float2 f;
-      f = unpack_bf16(u.x); s[0] += f.x; s[1] += f.y;
-      f = unpack_bf16(u.y); s[2] += f.x; s[3] += f.y;
-      f = unpack_bf16(u.z); s[4] += f.x; s[5] += f.y;
-      f = unpack_bf16(u.w); s[6] += f.x; s[7] += f.y;
+      f = unpack_bf16(u.x); s[0] += fmaf(ra, f.x, rb); s[1] += fmaf(ra, f.y, rb);
+      f = unpack_bf16(u.y); s[2] += fmaf(ra, f.x, rb); s[3] += fmaf(ra, f.y, rb);
+      f = unpack_bf16(u.z); s[4] += fmaf(ra, f.x, rb); s[5] += fmaf(ra, f.y, rb);
+      f = unpack_bf16(u.w); s[6] += fmaf(ra, f.x, rb); s[7] += fmaf(ra, f.y, rb);
     }
   }
 #pragma unroll
@@ -506,6 +547,7 @@ __global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16*
 #pragma unroll
       for (int i = 0; i < 32; ++i) a += part[i][threadIdx.x];
       a *= 1.0f / fmaxf(static_cast<float>(t1 - t0), 1e-6f);
+      if (row_stats != nullptr) a = fmaf(a, gamma[c], beta[c]);
       out[static_cast<size_t>(seq) * ldo + c] = __float2bfloat16(a);
       if (out_f32 != nullptr) out_f32[static_cast<size_t>(seq) * hidden + c] = a;
     }
