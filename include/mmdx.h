@@ -150,6 +150,28 @@ int mmdx_tokenize_batch(mmdx_tokenizer* t, const char* text, const int64_t* offs
                         int32_t* ids, int32_t* lens, uint8_t* fallback);
 const char* mmdx_tokenizer_last_error(void);
 
+/* ---- KV-cached T5 decoder step (csrc/t5_decoder.cu) -------------------------------------------
+ * The model call inside the reference's report generation - FusionTransformerModel.generate -> HF
+ * T5ForConditionalGeneration.generate (training_pipeline.py:613-618, inference_pipeline.py:190-196) - as CUDA kernels: one
+ * new token for each of R = batch x beams rows over a private KV cache, fp32 weights and arithmetic.  The beam search stays
+ * HF's own code (mmdx_b200/t5_fast.py replaces only the forward inside it), so the generated tokens are HF's.
+ * Weights: one mmdx_t5_load_tensor per key of T5ForConditionalGeneration.state_dict() that the decoder uses
+ * ("shared.weight", "decoder.block.N.layer.*", "decoder.final_layer_norm.weight", "lm_head.weight" when untied).
+ * mmdx_t5_begin: d_enc [R, n_enc, d_model] conditioning tokens per row (mmdx_cond_tokens, repeated over the beams);
+ * h_bias [max_steps][n_heads] = relative-position bias by distance (host; the caller evaluates HF's bucket formula).
+ * mmdx_t5_step: d_tokens int32 [R] -> d_logits fp32 [R, vocab].  mmdx_t5_reorder: row r continues row d_beam_idx[r]. */
+typedef struct mmdx_t5 mmdx_t5;
+int mmdx_t5_create(int device, int d_model, int n_heads, int d_kv, int d_ff, int n_layers, int vocab, float eps,
+                   int tied_embeddings, mmdx_t5** out);
+void mmdx_t5_destroy(mmdx_t5* t);
+int mmdx_t5_load_tensor(mmdx_t5* t, const char* name, const float* h_data, int64_t n_elems);
+int mmdx_t5_finalize(mmdx_t5* t);
+int mmdx_t5_begin(mmdx_t5* t, const float* d_enc, int R, int n_enc, int max_steps, const float* h_bias, void* stream);
+int mmdx_t5_reorder(mmdx_t5* t, const int32_t* d_beam_idx, void* stream);
+int mmdx_t5_step(mmdx_t5* t, const int32_t* d_tokens, float* d_logits, void* stream);
+int64_t mmdx_t5_launch_count(mmdx_t5* t);
+const char* mmdx_t5_last_error(void);
+
 /* ---- single-kernel entry points (parity tests call the hot kernels one at a time) ---------- */
 /* out[M,N] = act(A[M,K] * Wt[N,K]^T + bias (+ residual)); bf16 A/Wt/residual, bf16 or fp32 out. */
 int mmdx_op_gemm(mmdx_engine* e, const void* d_a, int64_t lda, const void* d_w, const float* d_bias,

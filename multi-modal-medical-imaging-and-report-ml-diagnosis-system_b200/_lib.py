@@ -70,6 +70,15 @@ SIGNATURES = {
     "mmdx_tokenizer_destroy": [_p],
     "mmdx_tokenize_batch": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
     "mmdx_tokenizer_last_error": [],
+    "mmdx_t5_create": [_i, _i, _i, _i, _i, _i, _i, _f, _i, C.POINTER(_p)],
+    "mmdx_t5_destroy": [_p],
+    "mmdx_t5_load_tensor": [_p, C.c_char_p, _p, _i64],
+    "mmdx_t5_finalize": [_p],
+    "mmdx_t5_begin": [_p, _p, _i, _i, _i, _p, _p],
+    "mmdx_t5_reorder": [_p, _p, _p],
+    "mmdx_t5_step": [_p, _p, _p, _p],
+    "mmdx_t5_launch_count": [_p],
+    "mmdx_t5_last_error": [],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_gemm_ln": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _f, _p, _i64, _i, _i, _i, _p],
     "mmdx_op_conv": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -88,6 +97,7 @@ SIGNATURES = {
 }
 _RESTYPE = {"mmdx_last_error": C.c_char_p, "mmdx_version": C.c_char_p, "mmdx_destroy": None,
             "mmdx_tokenizer_last_error": C.c_char_p, "mmdx_tokenizer_destroy": None,
+            "mmdx_t5_last_error": C.c_char_p, "mmdx_t5_destroy": None, "mmdx_t5_launch_count": C.c_int64,
             "mmdx_launch_count": C.c_int64}
 
 _lib = None

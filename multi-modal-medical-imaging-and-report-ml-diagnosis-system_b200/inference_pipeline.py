@@ -115,6 +115,27 @@ def _to_u8(img) -> np.ndarray:
 
 
 _TOKENIZERS: dict = {}
+_REPORT_GENS: dict = {}
+
+
+def fast_report_generator(fusion, dev):
+    """`t5_fast.FastT5Generator` on the CUDA decoder-step kernels for the bundle's report model (built once per module and
+    device), or None when that model is not a ReLU T5 (then HF's own generate runs unchanged)."""
+    rm = getattr(fusion, "report_model", None)
+    if rm is None:
+        return None
+    key = (id(rm), dev.index)
+    with _LOCK:
+        hit = _REPORT_GENS.get(key)
+        if hit is not None and hit[1] is rm:
+            return hit[0]
+        try:
+            from .t5_fast import FastT5Generator, MmdxStep
+            gen = FastT5Generator(rm, MmdxStep(rm, dev))
+        except Exception:      # noqa: BLE001 - unsupported decoder: not an error, HF does the work
+            gen = None
+        _REPORT_GENS[key] = (gen, rm)
+        return gen
 
 
 def native_tokenizer(model_bundle):
@@ -235,7 +256,14 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
             from transformers.modeling_outputs import BaseModelOutput
             cond = torch.from_numpy(cond_out).to(dev).view(B, fusion.n_cond, fusion.h_dec)
             cond = cond.to(next(fusion.report_model.parameters()).dtype)
-            gen_ids = fusion.report_model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **gen_attributes)
+            fast = fast_report_generator(fusion, dev) if model_bundle.get("fast_report", True) else None
+            if fast is not None and gen_attributes.get("max_new_tokens"):
+                # HF's beam search with the model call replaced by the KV-cached CUDA decoder step (csrc/t5_decoder.cu):
+                # same tokens, a small fraction of the time
+                with eng.lock:
+                    gen_ids = fast.generate(cond, **gen_attributes)
+            else:
+                gen_ids = fusion.report_model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **gen_attributes)
         else:
             gen_ids = fusion.generate(torch.from_numpy(z_img_out).to(dev), torch.from_numpy(z_txt_out).to(dev),
                                       **gen_attributes)

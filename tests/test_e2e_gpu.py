@@ -662,3 +662,31 @@ def test_concurrent_callers_default_report_path(bundle, g1):
         t.join()
     assert not errs, errs
     assert len(got) == 32 and all(res == want[i] for i, res in got.values())
+
+
+def test_batching_queue_in_front_of_the_engine(bundle, g1):
+    """concurrent single-study callers (what predict_view does per HTTP request) go through
+    serving.BatchingQueue and are served by a few batched engine calls; everyone gets the result inference() gives."""
+    import threading
+    from PIL import Image
+    from mmdx_b200.serving import BatchingQueue
+    pils = [Image.fromarray(np.repeat(g1["gray"][i][..., None], 3, axis=-1)) for i in range(2)]
+    want = [ip.inference(bundle, pils[i], str(g1["details"][i]), device="cuda", gen_kwargs=False) for i in range(2)]
+    with BatchingQueue.for_bundle(bundle, device="cuda", max_batch=64, max_delay_ms=50) as q:
+        got = {}
+
+        def worker(k):
+            got[k] = q.infer(pils[k % 2], str(g1["details"][k % 2]))
+
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(48)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert q.studies == 48 and q.batches < 24 and q.largest > 2
+    for k, r in got.items():
+        w = want[k % 2]
+        pa, pb = np.array(list(r["disease_probs"].values())), np.array(list(w["disease_probs"].values()))
+        assert np.abs(pa - pb).max() < 4e-3 and r["model_version"] == w["model_version"]
+        decided = np.abs(pb - 0.5) > 4e-3
+        assert np.array_equal(np.array(r["disease_vector"])[decided], np.array(w["disease_vector"])[decided])
