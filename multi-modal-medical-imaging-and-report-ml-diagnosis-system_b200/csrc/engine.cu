@@ -256,6 +256,7 @@ struct mmdx_engine {
   std::map<std::string, HostGraph> host_graphs;
   // Workspace generation: every reallocation of an arena a captured graph points into (img_ws, txt_ws, head_ws, the
   // request slots) bumps it; a graph captured under another generation holds dangling pointers and is dropped.
+  int max_pass = 512;        // images of 224 x 224 per pass of the conv stack (MMDX_MAX_PASS, read at mmdx_create; 0 = no limit)
   int64_t ws_gen = 0;
   // Cross-call ordering: the activation / head workspaces are shared by every call, so a call on another stream than
   // the previous one waits for the previous call's last kernel (calls on one stream are ordered anyway).
@@ -908,6 +909,7 @@ extern "C" int mmdx_create(const mmdx_config* cfg, mmdx_engine** out) {
   e->cfg = *cfg;
   if (e->cfg.n_heads <= 0) e->cfg.n_heads = 12;
   if (const char* v = getenv("MMDX_KEEP_FP32")) e->cfg.keep_fp32 = atoi(v);
+  if (const char* v = getenv("MMDX_MAX_PASS")) e->max_pass = atoi(v);
   e->num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1943,11 +1945,45 @@ static int order_end(mmdx_engine* e, cudaStream_t s) {
   return 0;
 }
 
+// Images per pass of the conv stack.  Beyond ~512 images of 224 x 224 the activation tensors of a pass outgrow what the
+// 126 MB L2 can hold between producer and consumer kernels and throughput falls (BASELINE config C5: 104.9 k img/s at
+// B = 512, 100.5 k at B = 1024 in one pass): larger batches run as several passes over the same workspace, so
+// throughput is monotone in B and the workspace stops growing.  MMDX_MAX_PASS overrides (0 = one pass).
+static int max_pass_images(const mmdx_engine* e, int H, int W) {
+  const int cap = e->max_pass;
+  if (cap <= 0) return 1 << 30;
+  const long long px = (long long)H * W;
+  long long n = (long long)cap * 224 * 224 / (px > 0 ? px : 1);      // same activation volume for other image sizes
+  return (int)(n < 16 ? 16 : n);
+}
+
+static int image_backbone_locked(mmdx_engine* e, const uint8_t* d_images, int B0, int B, int H, int W, int C, float* d_feats,
+                                 cudaStream_t s);
+
 static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, int H, int W, int C, float* d_feats,
                                float* d_z_img, cudaStream_t s) {
   REQUIRE(e->finalized, "weights not finalized");
   REQUIRE(B > 0 && H > 0 && W > 0, "bad image batch");
+  REQUIRE(C == 1 || C == 3, "images must have 1 or 3 channels");
   TRY(ensure_head_buffers(e, B));
+  PreGeom pg;
+  TRY(pre_geometry(e, H, W, &pg));
+  const int cap = max_pass_images(e, pg.crop_h, pg.crop_w);
+  for (int b0 = 0; b0 < B; b0 += cap) {
+    const int bc = B - b0 < cap ? B - b0 : cap;
+    TRY(image_backbone_locked(e, d_images + (size_t)b0 * H * W * C, b0, bc, H, W, C, d_feats, s));
+  }
+  e->cur_cls = CLS_HEAD;
+  HeadPlan* hp;
+  TRY(get_head_plan(e, B, &hp));
+  TRY(launch_gemm(e, hp->proj_img, s));
+  if (d_z_img) TRY(launch_cvt(e, e->zcat, e->d_img + e->d_txt, B, e->d_img, d_z_img, s));
+  return 0;
+}
+
+// preprocess + stem + 16 bottlenecks + avgpool of images [B0, B0 + B) of the batch: rows B0.. of the feature buffers
+static int image_backbone_locked(mmdx_engine* e, const uint8_t* d_images, int B0, int B, int H, int W, int C, float* d_feats,
+                                 cudaStream_t s) {
   ImagePlan* pl;
   TRY(get_image_plan(e, B, H, W, C, &pl));
   PreGeom g{0, 0, pl->off_y, pl->off_x, pl->crop_h, pl->crop_w, pl->has_x, pl->has_y};
@@ -1969,14 +2005,10 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
   {
     const int n = B * (e->feat_dim / 8);
     ProfScope _ps(e);
-    CK(launch_k(avgpool_kernel, dim3((n + 255) / 256), dim3(256), 0, s, 1, pl->last, B, pl->last_hw, e->feat_dim, e->feats_bf, d_feats));
+    CK(launch_k(avgpool_kernel, dim3((n + 255) / 256), dim3(256), 0, s, 1, pl->last, B, pl->last_hw, e->feat_dim,
+                e->feats_bf + (size_t)B0 * e->feat_dim, d_feats ? d_feats + (size_t)B0 * e->feat_dim : (float*)nullptr));
     CK(cudaGetLastError());
   }
-  e->cur_cls = CLS_HEAD;
-  HeadPlan* hp;
-  TRY(get_head_plan(e, B, &hp));
-  TRY(launch_gemm(e, hp->proj_img, s));
-  if (d_z_img) TRY(launch_cvt(e, e->zcat, e->d_img + e->d_txt, B, e->d_img, d_z_img, s));
   return 0;
 }
 

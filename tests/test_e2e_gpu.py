@@ -690,3 +690,26 @@ def test_batching_queue_in_front_of_the_engine(bundle, g1):
         assert np.abs(pa - pb).max() < 4e-3 and r["model_version"] == w["model_version"]
         decided = np.abs(pb - 0.5) > 4e-3
         assert np.array_equal(np.array(r["disease_vector"])[decided], np.array(w["disease_vector"])[decided])
+
+
+def test_large_batches_run_as_several_passes(bundle, eng):
+    """BASELINE config C5: beyond `max_pass` images the conv stack runs as several passes over the
+    same workspace.  With the cap lowered to 16, a batch of 40 (passes of 16 + 16 + 8) must equal the one-pass engine."""
+    import os
+    imgs = synth.synth_images(40, 224, seed=61)
+    ids, mask = synth.synth_token_ids(40, 64, seed=62, ragged=True)
+    want = _run_stages(eng, imgs, ids, mask)
+    os.environ["MMDX_MAX_PASS"] = "16"
+    try:
+        e2 = engine.Engine(ip._states_from_bundle(bundle))
+    finally:
+        del os.environ["MMDX_MAX_PASS"]
+    try:
+        got = _run_stages(e2, imgs, ids, mask)
+        assert np.abs(got["feats"] - want["feats"]).max() < 3e-2 * np.abs(want["feats"]).max()
+        assert np.abs(got["probs"] - want["probs"]).max() < 4e-3
+        # the first pass is a plain B = 16 call: bit-identical to running those 16 studies alone
+        alone = _run_stages(e2, imgs[:16], ids[:16], mask[:16])
+        assert np.array_equal(alone["feats"], got["feats"][:16])
+    finally:
+        e2.close()

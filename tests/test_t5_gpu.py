@@ -27,9 +27,12 @@ def t5():
 
 
 def test_step_logits_match_torch_step_with_reorder(t5):
+    """Ten steps of R = studies x beams rows, with two beam reorders (a hypothesis dropped, one duplicated - always inside
+    a study, as beam search does): logits of the CUDA step against the fp32 torch step on the same GPU."""
     torch.manual_seed(3)
-    for R in (1, 4, 12):
-        cond = torch.randn(R, 4, 512, device="cuda")
+    for studies, beams in ((1, 1), (1, 4), (3, 4)):
+        R = studies * beams
+        cond = torch.randn(studies, 4, 512, device="cuda").repeat_interleave(beams, 0)
         a, b = TorchStep(t5), MmdxStep(t5)
         a.begin(cond, R, 16)
         b.begin(cond, R, 16)
@@ -39,16 +42,12 @@ def test_step_logits_match_torch_step_with_reorder(t5):
             torch.cuda.synchronize()
             err = float((la - lb).abs().max() / la.abs().max())
             assert err < 2e-5, (R, t, err)
-            tok = la.argmax(-1)
-            if t in (3, 6) and R > 1:
-                idx = torch.randperm(R, device="cuda")
-                idx[0] = idx[-1]                              # a beam that is dropped and one that is duplicated
+            tok = la.topk(2, -1).indices[torch.arange(R), torch.arange(R) % 2]      # different continuations per beam
+            if t in (3, 6) and beams > 1:
+                idx = torch.cat([s0 * beams + torch.tensor([1, 1, 0, 3]) for s0 in range(studies)]).cuda()
                 a.reorder(idx)
                 b.reorder(idx)
                 tok = tok[idx]
-                a.ck = [k.index_select(0, idx) for k in a.ck]          # (TorchStep.reorder already did; cross K/V of the
-                a.cv = [v.index_select(0, idx) for v in a.cv]          #  CUDA backend are per study and stay in place)
-                break
         b.close()
 
 
