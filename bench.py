@@ -90,9 +90,12 @@ def gemm_bytes_per_step(B, L, hidden=768, ffn=3072, layers=12, d_img=1024, d_txt
 
 
 def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r01_traffic.json), or None."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/r02_traffic.json), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        with open(path) as f:
             t = json.load(f)
         ks = [t[k] for k in ("gemm_tcgen05_kernel", "bneck64_tcgen05_kernel") if k in t]
         n = sum(k["launches_per_step"] for k in ks)

@@ -177,14 +177,14 @@ class MmdxStep:
         with torch.cuda.device(self.dev):
             self._check(self._lib.mmdx_t5_begin(self._h, self._C.c_void_p(enc.data_ptr()), rows, enc.shape[1], int(max_steps),
                                                 self._C.c_void_p(bias.data_ptr()), self._stream()))
-            torch.cuda.current_stream(self.dev).synchronize()           # `enc` / `bias` may be freed by the caller
+        self._keep = [enc, bias]       # stream-ordered use: keep the operands alive instead of synchronising
         self.t = 0
 
     def reorder(self, beam_idx):
         idx = beam_idx.to(self.dev, torch.int32).contiguous()
         with torch.cuda.device(self.dev):
             self._check(self._lib.mmdx_t5_reorder(self._h, self._C.c_void_p(idx.data_ptr()), self._stream()))
-            torch.cuda.current_stream(self.dev).synchronize()
+        self._keep_idx = idx
 
     def step(self, tokens):
         tok = tokens.to(self.dev, torch.int32).contiguous()
@@ -192,6 +192,7 @@ class MmdxStep:
         with torch.cuda.device(self.dev):
             self._check(self._lib.mmdx_t5_step(self._h, self._C.c_void_p(tok.data_ptr()), self._C.c_void_p(logits.data_ptr()),
                                                self._stream()))
+        self._keep_tok = tok
         self.t += 1
         return logits
 

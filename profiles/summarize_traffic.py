@@ -27,5 +27,6 @@ print("\n| # | kernel | grid | block | us | DRAM MB |\n|---|---|---|---|---|---|
 for j,i in enumerate(ids):
     d=per[i]
     print(f"| {j} | {d['k'].split('(')[0].replace('void ','')} | {d['grid']} | {d['block']} | {d['gpu__time_duration.sum']:.1f} | {(d['dram__bytes_read.sum']+d['dram__bytes_write.sum'])/1e6:.1f} |")
-out["gemm_tcgen05_kernel"]["source"]="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over one bench.py step (B=256, L=128): profiles/r01_launches_v6.md; writes still dirty in L2 at kernel end are charged to later kernels"
+md = sys.argv[4] if len(sys.argv) > 4 else "profiles/r01_launches_v6.md"
+out["gemm_tcgen05_kernel"]["source"]="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over one bench.py step (B=256, L=128): " + md + "; writes still dirty in L2 at kernel end are charged to later kernels"
 json.dump(out,open(sys.argv[3],"w"),indent=1)
