@@ -446,6 +446,8 @@ __global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel
       if (id + stride < num_units) nxt = attn_short_unit(p, id + stride);     // prefetch: off the critical path
       const int len = min(u.len, 128);
       const bool active = q * 32 < len;               // warp-uniform: any valid query row in this quarter
+      // folded LayerNorm: this row's 1 / rstd is requested before waiting for S (its global loads hide under the wait)
+      const float sigma = (active && r < len) ? attn_row_sigma(p, u.tok0 + r) : 1.0f;
       mbar_wait(&s_full[g], n & 1);
       tc_fence_after();
       float l = 0.f;
@@ -501,7 +503,7 @@ __global__ void __launch_bounds__(ATS_THREADS, 1) attention_short_tcgen05_kernel
       mbar_wait(&o_full[g], n & 1);
       tc_fence_after();
       if (active) {
-        const float inv = (r < len ? attn_row_sigma(p, u.tok0 + r) : 1.0f) / l;
+        const float inv = sigma / l;
         uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<size_t>(u.tok0 + r) * p.hidden + u.head * 64);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
