@@ -201,6 +201,11 @@ int mmdx_op_bneck64(mmdx_engine* e, const void* d_t1, const void* d_res, const v
  * t2 [NB,OH,OW,Cmid], x [NB,H,W,Cin], out [NB,OH,OW,Cout], OH = (H-1)/stride + 1. */
 int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_x, const void* d_wcat, const float* d_bias, void* d_out,
                      int NB, int H, int W, int Cin, int Cmid, int Cout, int stride, void* stream);
+/* conv3 of a bottleneck and conv1 of the NEXT block as one two-GEMM launch (layers 2-3; csrc/gemm2_tcgen05.cuh):
+ * y [M,N1] = relu(t2 [M,K1] * w3^T + b3 + res [M,N1]); t1n [M,N2] = relu(y * w1n^T + b1n).  M = NB*H*W pixel rows (both convs
+ * are 1x1 over NHWC), bf16, BN folded; K1 % 64 == 0, N1 and N2 multiples of 128 (of 256 for the 256-wide variant). */
+int mmdx_op_conv3_conv1(mmdx_engine* e, const void* d_t2, const void* d_w3, const float* d_b3, const void* d_res, void* d_y,
+                        const void* d_w1n, const float* d_b1n, void* d_t1n, int64_t M, int K1, int N1, int N2, void* stream);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
  * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).

@@ -18,6 +18,7 @@
 #include "bneck64_tcgen05.cuh"
 #include "conv3x3_c64_tcgen05.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 #include "stem_tcgen05.cuh"
 #include "kernels.cuh"
 #include "fp32_kernels.cuh"
@@ -135,6 +136,7 @@ struct GemmLaunch {
   int ln = 0;                         // > 0: row LayerNorm fused behind the last N tile of every m-item (row width ln * 256)
   bool c64 = false; C64Params c;      // layer-1 style 3x3 64->64 conv: dedicated halo-tile kernel instead of the GEMM kernel
   int b64 = 0; Bneck64Params b;       // > 0: fused layer-1 bottleneck kernel, variant code (see build_b64)
+  int g2 = 0; Gemm2Params d;          // > 0 (= BN): conv3 + next conv1 as one two-GEMM launch (gemm2_tcgen05.cuh)
 };
 
 struct ConvW {      // one folded conv: weights [Cout][taps][Cin] bf16, bias fp32
@@ -728,6 +730,85 @@ static int launch_b64_inst(mmdx_engine* e, const Bneck64Params& p, cudaStream_t 
   return 0;
 }
 
+// conv3 (+ shortcut, ReLU) of a bottleneck and conv1 (+ ReLU) of the next block as one launch (gemm2_tcgen05.cuh).
+// MMDX_DUAL=0 keeps them as two launches.
+static bool dual_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("MMDX_DUAL"); on = (v && atoi(v) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static bool dual_applicable(const mmdx_engine* e, long long M, int K1, int N1, int N2) {
+  if (!dual_enabled() || K1 % 64 != 0 || N1 % 128 != 0 || N2 % 128 != 0) return false;
+  const int bn = (N2 % 256 == 0 && N1 % 256 == 0) ? 256 : 128;
+  if (N1 % bn != 0 || N2 % bn != 0) return false;
+  // item-major schedule: one item = 256 rows on one CTA pair; below ~2 items per pair the coarse items quantise worse
+  // than the two separate launches (layer 4 at B = 256: 49 items on 74 pairs)
+  return (M + 255) / 256 >= 2 * (e->num_sms / 2);
+}
+static int build_dual(mmdx_engine* e, GemmLaunch& g, const bf16* t2, int K1, const bf16* w3, const float* b3, const bf16* res,
+                      bf16* y, int N1, const bf16* w1n, const float* b1n, bf16* t1n, int N2, long long M) {
+  REQUIRE(K1 % 64 == 0 && N1 % 128 == 0 && N2 % 128 == 0 && M > 0 && M < (1ll << 31), "conv3 + conv1 shapes");
+  g.ln = 0; g.c64 = false; g.b64 = 0;
+  const int bn = (N2 % 256 == 0 && N1 % 256 == 0) ? 256 : 128;
+  g.g2 = bn;
+  Gemm2Params& p = g.d;
+  memset(&p, 0, sizeof p);
+  auto rows_map = [&](CUtensorMap* m, const void* base, int cols, int box_cols, int swz) -> int {
+    const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)M, 1, 1};
+    const uint64_t str[3] = {(uint64_t)cols * 2, (uint64_t)cols * 2 * (uint64_t)M, (uint64_t)cols * 2 * (uint64_t)M};
+    const uint32_t box[4] = {(uint32_t)box_cols, 128, 1, 1};
+    return make_tmap(e, m, base, 4, dims, str, box, swz);
+  };
+  auto w_map = [&](CUtensorMap* m, const void* base, int n, int k) -> int {
+    const uint64_t d[2] = {(uint64_t)k, (uint64_t)n};
+    const uint64_t st[1] = {(uint64_t)k * 2};
+    const uint32_t bx[2] = {64, (uint32_t)(bn / 2)};
+    return make_tmap(e, m, base, 2, d, st, bx, 128);
+  };
+  TRY(rows_map(&p.tmA1, t2, K1, 64, 128));
+  TRY(w_map(&p.tmB1, w3, N1, K1));
+  TRY(rows_map(&p.tmR, res, N1, 64, 128));
+  p.tmI = e->tm_ident_half;
+  TRY(rows_map(&p.tmC1, y, N1, kEpiCW, 64));
+  TRY(rows_map(&p.tmA2, y, N1, 64, 128));
+  TRY(w_map(&p.tmB2, w1n, N2, N1));
+  TRY(rows_map(&p.tmC2, t1n, N2, kEpiCW, 64));
+  p.bias1 = b3; p.bias2 = b1n;
+  p.kb1 = K1 / 64; p.nt1 = N1 / bn; p.kb2 = N1 / 64; p.nt2 = N2 / bn;
+  const long long m_tiles = (M + 127) / 128;
+  p.num_items = (int)((m_tiles + 1) / 2);
+  return 0;
+}
+template <int BN>
+static int launch_dual_inst(mmdx_engine* e, const Gemm2Params& p, cudaStream_t s, int reverse) {
+  static bool attr_set_[64] = {};
+  static int max_clusters_[64] = {};
+  bool& attr_set = attr_set_[cur_dev()];
+  int& max_clusters = max_clusters_[cur_dev()];
+  auto* kfn = gemm2_tcgen05_kernel<BN>;
+  constexpr int SMEM = GemmSmem<BN, 64, 2, 2, 1, 0>::TOTAL;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * 64, 1, 1); cfg.blockDim = dim3(kGemmThreads, 1, 1); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
+    REQUIRE(max_clusters > 0, "no CTA pair fits on this device");
+    attr_set = true;
+  }
+  int pairs = p.num_items < e->num_sms / 2 ? p.num_items : e->num_sms / 2;
+  if (pairs > max_clusters) pairs = max_clusters;
+  ProfScope _ps(e);
+  Gemm2Params prm = p;
+  prm.reverse = reverse;
+  CK(launch_k(kfn, dim3((unsigned)pairs * 2), dim3(kGemmThreads), SMEM, s, 2, prm));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // direction of this launch on its branch (and flip it for the next one)
 static int next_direction(mmdx_engine* e, cudaStream_t s) {
   if (!e->zigzag) return 0;
@@ -802,6 +883,8 @@ static int launch_gemm(mmdx_engine* e, const GemmLaunch& g, cudaStream_t s) {
     default: break;
   }
   if (g.c64) return launch_c64(e, g.c, s);
+  if (g.g2 == 256) return launch_dual_inst<256>(e, g.d, s, rv);
+  if (g.g2 == 128) return launch_dual_inst<128>(e, g.d, s, rv);
   const int max_groups = e->num_sms / g.cg;
   const int groups = g.p.num_tiles < max_groups ? g.p.num_tiles : max_groups;
   ProfScope _ps(e);
@@ -1687,7 +1770,15 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
       }
       pl->convs.push_back(gl);
       gl.c64 = false;
-      if (cat_ds) {
+      // conv3 (+ shortcut + ReLU) and the NEXT block's conv1 (+ ReLU) as one two-GEMM launch: y is read back by the
+      // second GEMM while it is still in L2 instead of from DRAM a launch later (gemm2_tcgen05.cuh)
+      const bool dual = !cat_ds && !bk.has_ds && nx && nx->c1.k == 1 && nx->c1.stride == 1 && nx->c1.cin == bk.c3.cout &&
+                        bk.c3.k == 1 && dual_applicable(e, (long long)B * oh * ow, bk.c3.cin, bk.c3.cout, nx->c1.cout);
+      if (dual) {
+        TRY(build_dual(e, gl, o2, bk.c3.cin, bk.c3.w, bk.c3.bias, idt, y, bk.c3.cout, nx->c1.w, nx->c1.bias, o1, nx->c1.cout,
+                       (long long)B * oh * ow));
+        have_t1 = true;              // o1 now holds the next block's conv1 output
+      } else if (cat_ds) {
         TRY(build_c3ds(e, gl, o2, B, oh, ow, bk.c3.cin, x, h, w, bk.ds.cin, s, bk.c3ds.w, bk.c3.cout));
         TRY(fill_epilogue(e, gl, bk.c3ds.bias, nullptr, 0, y, bk.c3.cout, ACT_RELU, 0));
       } else {
@@ -1695,6 +1786,7 @@ static int get_image_plan(mmdx_engine* e, int B, int H, int W, int C, ImagePlan*
         TRY(fill_epilogue(e, gl, bk.c3.bias, idt, bk.c3.cout, y, bk.c3.cout, ACT_RELU, 0));
       }
       pl->convs.push_back(gl);
+      gl.g2 = 0;
     }
     bf16* t = x; x = y; y = t;
     h = oh; w = ow;
@@ -2700,6 +2792,18 @@ extern "C" int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_
   TRY(build_c3ds(e, g, static_cast<const bf16*>(d_t2), NB, OH, OW, Cmid, static_cast<const bf16*>(d_x), H, W, Cin, stride,
                  static_cast<const bf16*>(d_wcat), Cout));
   TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, Cout, ACT_RELU, 0));
+  return launch_gemm(e, g, (cudaStream_t)stream);
+}
+extern "C" int mmdx_op_conv3_conv1(mmdx_engine* e, const void* d_t2, const void* d_w3, const float* d_b3, const void* d_res,
+                                   void* d_y, const void* d_w1n, const float* d_b1n, void* d_t1n, int64_t M, int K1, int N1,
+                                   int N2, void* stream) {
+  if (e) { e->cur_stream = (cudaStream_t)stream; e->cur_cls = CLS_MISC; }
+  REQUIRE(e && d_t2 && d_w3 && d_b3 && d_res && d_y && d_w1n && d_b1n && d_t1n, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->cfg.device));
+  GemmLaunch g;
+  TRY(build_dual(e, g, static_cast<const bf16*>(d_t2), K1, static_cast<const bf16*>(d_w3), d_b3, static_cast<const bf16*>(d_res),
+                 static_cast<bf16*>(d_y), N1, static_cast<const bf16*>(d_w1n), d_b1n, static_cast<bf16*>(d_t1n), N2, M));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
 extern "C" int mmdx_op_stem_pool(mmdx_engine* e, const void* d_in_padded, int NB, int H, int W, const void* d_w_packed,

@@ -415,3 +415,34 @@ def test_seq_mean_pool_and_head_tail(h):
     assert (zf - z).abs().max() < 1e-4 and (lg - l).abs().max() < 1e-4
     assert (pr - torch.sigmoid(l)).abs().max() < 1e-5
     assert torch.equal(vec, (pr >= thr).to(torch.uint8))
+
+
+# ---------------------------------------------------------------------------------------- conv3 + next conv1 (two-GEMM launch)
+@pytest.mark.parametrize("M,K1,N1,N2", [
+    (256, 128, 512, 128),          # one item
+    (1000, 128, 512, 128),         # ragged: odd number of m-tiles, partial last tile (layer-2 shape, BN 128)
+    (50176, 256, 1024, 256),       # layer 3 at B = 256 (BN 256): 196 items on 74 CTA pairs
+    (40000, 128, 512, 256),        # layer2.3 -> layer3.0 conv1 (BN 256 with N1 = 512)
+    (30011, 256, 1024, 512),       # layer3.5 -> layer4.0 conv1 (two G2 tiles per item), ragged
+    (100352, 128, 512, 128),       # layer 2 at B = 128: 392 items
+])
+def test_conv3_conv1_two_gemm_launch(h, M, K1, N1, N2):
+    """gemm2_tcgen05_kernel: y = relu(t2 W3^T + b3 + res), t1n = relu(y W1n^T + b1n) in one launch, against fp32 torch on
+    the same bf16 inputs (the second GEMM consumes the bf16-rounded y, like the two-launch path)."""
+    g = torch.Generator(device="cuda").manual_seed(M + K1 + N1 + N2)
+    t2 = bf(torch.randn(M, K1, generator=g, device="cuda").abs())
+    res = bf(torch.randn(M, N1, generator=g, device="cuda"))
+    w3 = bf(torch.randn(N1, K1, generator=g, device="cuda") * (K1 ** -0.5))
+    w1 = bf(torch.randn(N2, N1, generator=g, device="cuda") * (N1 ** -0.5))
+    b3 = torch.randn(N1, generator=g, device="cuda") * 0.1
+    b1 = torch.randn(N2, generator=g, device="cuda") * 0.1
+    y = torch.full((M, N1), float("nan"), dtype=torch.bfloat16, device="cuda")
+    t1n = torch.full((M, N2), float("nan"), dtype=torch.bfloat16, device="cuda")
+    for rep in range(2):                      # twice: the second launch walks the items in the other direction (zigzag)
+        _lib.check(_lib.lib().mmdx_op_conv3_conv1(h.handle, P(t2), P(w3), P(b3), P(res), P(y), P(w1), P(b1), P(t1n), M, K1, N1, N2, S()))
+        torch.cuda.synchronize()
+        y_ref = torch.relu(t2.float() @ w3.float().t() + b3 + res.float())
+        assert rel_err(y, y_ref) < 1e-2, (rep, rel_err(y, y_ref))
+        t_ref = torch.relu(y.float() @ w1.float().t() + b1)          # from the kernel's own (bf16) y
+        assert rel_err(t1n, t_ref) < 1e-2, (rep, rel_err(t1n, t_ref))
+        y.fill_(float("nan")); t1n.fill_(float("nan"))
