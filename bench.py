@@ -76,8 +76,11 @@ def gemm_bytes_per_step(B, L, hidden=768, ffn=3072, layers=12, d_img=1024, d_txt
                 if b == 0:
                     img += cin * cout * 2
             else:
+                # conv1 that follows a plain (non-downsample) block of layers 2-3 runs inside that block's conv3 launch
+                # (gemm2_tcgen05.cuh) and reads its input from L2, not DRAM: only its output and weights count
+                fused_c1 = (li == 1 and b >= 2) or (li == 2 and (b == 0 or b >= 2)) or (li == 3 and b == 0)
                 if not (li == 1 and b == 0):                                                        # layer2.0 conv1: done above
-                    img += B * hw * hw * (cin + mid) * 2 + cin * mid * 2                            # conv1 1x1
+                    img += B * hw * hw * ((0 if fused_c1 else cin) + mid) * 2 + cin * mid * 2       # conv1 1x1
                 img += B * (hw * hw + ho * ho) * mid * 2 + 9 * mid * mid * 2                        # conv2 3x3 (stride s)
                 if b == 0:      # conv3 + downsample as one GEMM over [t2 | x strided]
                     img += B * ho * ho * (mid + cin + cout) * 2 + (mid + cin) * cout * 2
@@ -97,7 +100,7 @@ def measured_traffic():
             path = os.path.join(ROOT, "profiles", "r01_traffic.json")
         with open(path) as f:
             t = json.load(f)
-        ks = [t[k] for k in ("gemm_tcgen05_kernel", "bneck64_tcgen05_kernel") if k in t]
+        ks = [t[k] for k in ("gemm_tcgen05_kernel", "gemm2_tcgen05_kernel", "bneck64_tcgen05_kernel") if k in t]
         n = sum(k["launches_per_step"] for k in ks)
         return sum(k["dram_bytes_read"] + k["dram_bytes_write"] for k in ks) / n, t["gemm_tcgen05_kernel"].get("source")
     except (OSError, KeyError, ValueError):
