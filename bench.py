@@ -119,8 +119,8 @@ def class_rooflines(by_class, B, L, peaks, hidden=768, layers=12):
         # global avgpool (7x7x2048 bf16 in) + masked mean pool (T x 768 bf16 in)
         "pooling": ("hbm", B * 49 * 2048 * 2 + T * hidden * 2),
         "attention": ("tensor", B * 36_864 * L * L),
-        # 24 LayerNorms (read + write T x 768 bf16) + embedding gather/LN (3 table rows read, 1 row written per token)
-        "layernorm_embed": ("hbm", 2 * layers * 2 * T * hidden * 2 + 4 * T * hidden * 2),
+        # embedding gather (3 table rows read, 1 row + its row sums written per token); the 24 LayerNorms are folded into the GEMMs
+        "layernorm_embed": ("hbm", 4 * T * hidden * 2 + 16 * T),
     }
     out = {}
     for name, (bound, amount) in work.items():

@@ -5,8 +5,10 @@
         (ii) the reference's faithful transform (Resize 256 + CenterCrop 224) on 512x512 inputs - 104.81 GFLOP/study
   C5  image-only branch (K_pre + stem + 52 convs + avgpool + proj), batch 1 ... 1024: latency and images/s
 
-Timing: CUDA events on the launch stream, 3 warm-up + `reps` timed passes, inputs rotate over distinct device buffers
-larger than L2 where the batch is small.  Prints one JSON object (kept under profiles/ per round)."""
+Timing: CUDA events on the launch stream, 3 warm-up passes, then every point is timed for the SAME duration (>= 1 s, at least
+`reps` passes): the board is power-limited, a 40 ms burst runs at higher clocks than a 90 ms one, and round 1's sweep - a
+fixed number of passes per point - showed that as a throughput drop from B = 512 to B = 1024.
+Inputs rotate over distinct device buffers larger than L2 where the batch is small.  Prints one JSON object."""
 import json
 import os
 import sys
@@ -24,11 +26,20 @@ if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(_
                                           "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", PEAK_TF)
 
 
+MIN_SECONDS = 1.0
+
+
 def timed(fn, reps, warm=3):
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(3):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    reps = max(reps, int(MIN_SECONDS * 1e3 / max(a.elapsed_time(b) / 3, 1e-3)))
     a.record()
     for i in range(reps):
         fn(i)
