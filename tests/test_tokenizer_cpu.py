@@ -11,6 +11,12 @@ from mmdx_b200 import synth
 from mmdx_b200.tokenizer import NativeBertTokenizer
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from mmdx_b200 import _lib
+    _lib.build()                         # no-op when libmmdx.so is up to date (host-only code: no GPU needed)
+
+
 @pytest.fixture(scope="module")
 def toks():
     hf = synth.make_bert_tokenizer()
