@@ -713,3 +713,24 @@ def test_large_batches_run_as_several_passes(bundle, eng):
         assert np.array_equal(alone["feats"], got["feats"][:16])
     finally:
         e2.close()
+
+
+@pytest.mark.parametrize("B,L,ragged", [(31, 128, False), (3, 128, True), (5, 77, False), (17, 200, False), (1, 9, False),
+                                         (2, 129, False), (64, 33, False)])
+def test_text_encoder_shapes_vs_oracle(bundle, eng, B, L, ragged):
+    """The folded-LayerNorm text path over token counts that exercise every tile shape and both attention kernels: odd
+    numbers of 128-row tiles (a CTA pair with a past-the-end half - the case that once corrupted the row sums of rows
+    0..127), a single partial tile, T just over a tile, L > 128 (flash attention)."""
+    ids, mask = synth.synth_token_ids(B, L, seed=1000 + B + L, ragged=ragged)
+    pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask, None, eng.table_sizes)
+    t = [torch.from_numpy(x).cuda() for x in (pi, pp, pt, cu)]
+    pooled, z_txt = eng.text_encode(t[0], t[1], t[2], t[3], mlen)
+    torch.cuda.synchronize()
+    ref_pooled, ref_z = R.text_encode(torch.from_numpy(ids), torch.from_numpy(mask), None, bundle["text_state"])
+    assert np.isfinite(pooled.cpu().numpy()).all()
+    assert _rel(pooled.cpu().numpy(), ref_pooled.numpy()) < REL_TOL, (B, L, _rel(pooled.cpu().numpy(), ref_pooled.numpy()))
+    assert _rel(z_txt.cpu().numpy(), ref_z.numpy()) < REL_TOL
+    # run-to-run determinism of the integer-atomic row sums
+    pooled2, _ = eng.text_encode(t[0], t[1], t[2], t[3], mlen)
+    torch.cuda.synchronize()
+    assert torch.equal(pooled, pooled2)
