@@ -7,10 +7,10 @@ length penalty, early stopping, min-length and no-repeat-n-gram processors are u
 construction - and only the model call inside the loop is replaced: `FastT5Generator` swaps the report model's
 `forward` for one decoder step over a private KV cache.
 
-Two step backends with the same interface:
-  * `TorchStep`  - plain fp32 torch restatement of the HF T5 decoder step (CPU or GPU); the checker of the CUDA backend
-                   and what the CPU tests run (tests/test_t5_cpu.py: token-identical to stock HF generate);
-  * `MmdxStep`   - hand-written CUDA kernels through the C ABI (csrc/t5_decoder.cu, `mmdx_t5_*`).
+The step backend of the product is `MmdxStep`: hand-written CUDA kernels through the C ABI (csrc/t5_decoder.cu,
+`mmdx_t5_*`); there is no CPU step here.  Its checker - a plain fp32 torch restatement of the HF T5 decoder step with the
+same interface, which is also what the CPU tests drive `FastT5Generator` with - lives in oracle/t5_step_ref.py (test
+infrastructure).
 """
 from __future__ import annotations
 
@@ -19,98 +19,17 @@ import math
 import torch
 
 
-class TorchStep:
-    """One T5 decoder step for R = batch * beams rows, fp32, KV-cached.  Mirrors HF modeling_t5 (T5Stack decoder):
-    x = E[tok]; per block: x += SelfAttn(RMSNorm(x)) ; x += CrossAttn(RMSNorm(x), enc) ; x += Wo relu(Wi RMSNorm(x));
-    logits = (RMSNorm(x) * d_model^-0.5) E^T (tied embeddings).  T5 attention has no 1/sqrt(d) scaling; the
-    self-attention adds the learned relative-position bias of block 0 in every block; cross-attention adds none."""
-
-    def __init__(self, model, device=None):
-        cfg = model.config
-        self.cfg = cfg
-        dev = torch.device(device) if device is not None else next(model.parameters()).device
-        self.dev = dev
-        sd = {k: v.detach().to(dev, torch.float32) for k, v in model.state_dict().items()}
-        self.E = sd["shared.weight"]
-        self.lm = sd.get("lm_head.weight", self.E)
-        self.tied = bool(cfg.tie_word_embeddings)
-        self.blocks = []
-        for i in range(cfg.num_decoder_layers):
-            p = f"decoder.block.{i}.layer."
-            self.blocks.append({
-                "ln0": sd[p + "0.layer_norm.weight"],
-                "sq": sd[p + "0.SelfAttention.q.weight"], "sk": sd[p + "0.SelfAttention.k.weight"],
-                "sv": sd[p + "0.SelfAttention.v.weight"], "so": sd[p + "0.SelfAttention.o.weight"],
-                "ln1": sd[p + "1.layer_norm.weight"],
-                "cq": sd[p + "1.EncDecAttention.q.weight"], "ck": sd[p + "1.EncDecAttention.k.weight"],
-                "cv": sd[p + "1.EncDecAttention.v.weight"], "co": sd[p + "1.EncDecAttention.o.weight"],
-                "ln2": sd[p + "2.layer_norm.weight"],
-                "wi": sd[p + "2.DenseReluDense.wi.weight"], "wo": sd[p + "2.DenseReluDense.wo.weight"],
-            })
-        self.final_ln = sd["decoder.final_layer_norm.weight"]
-        self.rel = sd["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"]     # [buckets, heads]
-        self.eps = cfg.layer_norm_epsilon
-        self.H, self.dk = cfg.num_heads, cfg.d_kv
-        if cfg.feed_forward_proj != "relu":
-            raise ValueError("only the ReLU feed-forward of t5-small / T5Config() is implemented")
-        self.t = 0
-
-    # -- relative position bias for distance d = query_pos - key_pos >= 0 (decoder: bidirectional=False)
-    def bias_table(self, n):
-        nb, md = self.cfg.relative_attention_num_buckets, self.cfg.relative_attention_max_distance
-        rp = torch.arange(n, device=self.dev)
-        max_exact = nb // 2
-        large = max_exact + (torch.log(rp.float() / max_exact) / math.log(md / max_exact) * (nb - max_exact)).to(torch.long)
-        large = torch.min(large, torch.full_like(large, nb - 1))
-        bucket = torch.where(rp < max_exact, rp, large)
-        return self.rel[bucket]                                   # [n, heads]
-
-    def _rms(self, x, w):
-        var = x.pow(2).mean(-1, keepdim=True)
-        return x * torch.rsqrt(var + self.eps) * w
-
-    def begin(self, enc, rows, max_steps):
-        """enc: [rows, n_enc, d_model] encoder states per row (already expanded over beams)."""
-        R, H, dk = rows, self.H, self.dk
-        self.t = 0
-        self.bias = self.bias_table(max_steps + 1)
-        self.sk = [torch.zeros(R, H, max_steps + 1, dk, device=self.dev) for _ in self.blocks]
-        self.sv = [torch.zeros(R, H, max_steps + 1, dk, device=self.dev) for _ in self.blocks]
-        enc = enc.to(self.dev, torch.float32)
-        self.ck = [(enc @ b["ck"].t()).view(R, -1, H, dk).transpose(1, 2) for b in self.blocks]
-        self.cv = [(enc @ b["cv"].t()).view(R, -1, H, dk).transpose(1, 2) for b in self.blocks]
-
-    def reorder(self, beam_idx):
-        idx = beam_idx.to(self.dev, torch.long)
-        self.sk = [k.index_select(0, idx) for k in self.sk]
-        self.sv = [v.index_select(0, idx) for v in self.sv]
-        self.ck = [k.index_select(0, idx) for k in self.ck]
-        self.cv = [v.index_select(0, idx) for v in self.cv]
-
-    def step(self, tokens):
-        """tokens: [R] int64 -> logits [R, vocab] fp32; appends this position to the cache."""
-        R, H, dk, t = tokens.shape[0], self.H, self.dk, self.t
-        x = self.E[tokens.to(self.dev)]
-        for i, b in enumerate(self.blocks):
-            h = self._rms(x, b["ln0"])
-            q = (h @ b["sq"].t()).view(R, H, 1, dk)
-            self.sk[i][:, :, t] = (h @ b["sk"].t()).view(R, H, dk)
-            self.sv[i][:, :, t] = (h @ b["sv"].t()).view(R, H, dk)
-            s = q @ self.sk[i][:, :, :t + 1].transpose(-1, -2)                    # [R,H,1,t+1]
-            s = s + self.bias[torch.arange(t, -1, -1, device=self.dev)].t().view(1, H, 1, t + 1)
-            a = torch.softmax(s.float(), -1) @ self.sv[i][:, :, :t + 1]
-            x = x + a.transpose(1, 2).reshape(R, H * dk) @ b["so"].t()
-            h = self._rms(x, b["ln1"])
-            q = (h @ b["cq"].t()).view(R, H, 1, dk)
-            a = torch.softmax((q @ self.ck[i].transpose(-1, -2)).float(), -1) @ self.cv[i]
-            x = x + a.transpose(1, 2).reshape(R, H * dk) @ b["co"].t()
-            h = self._rms(x, b["ln2"])
-            x = x + torch.relu(h @ b["wi"].t()) @ b["wo"].t()
-        x = self._rms(x, self.final_ln)
-        if self.tied:
-            x = x * (self.cfg.d_model ** -0.5)
-        self.t += 1
-        return x @ self.lm.t()
+def relative_position_bias_table(cfg, rel_weight, n, device="cpu"):
+    """Relative-position bias of the decoder self-attention by distance d = query_pos - key_pos in [0, n): rows of
+    `rel_weight` [buckets, heads] picked with HF's bucket arithmetic (T5Attention._relative_position_bucket with
+    bidirectional=False), evaluated with the same torch float32 ops so that bucket boundaries fall where HF puts them."""
+    nb, md = cfg.relative_attention_num_buckets, cfg.relative_attention_max_distance
+    rp = torch.arange(n, device=device)
+    max_exact = nb // 2
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(md / max_exact) * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    bucket = torch.where(rp < max_exact, rp, large)
+    return rel_weight.to(device)[bucket]                              # [n, heads]
 
 
 class MmdxStep:
@@ -141,7 +60,6 @@ class MmdxStep:
                 self._check(self._lib.mmdx_t5_load_tensor(self._h, k.encode(), C.c_void_p(t.data_ptr()), t.numel()))
         self._check(self._lib.mmdx_t5_finalize(self._h))
         self._rel = model.state_dict()["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"].detach().float().cpu()
-        self._bias_src = TorchStep.bias_table                     # HF's bucket arithmetic, evaluated once per generation
         self.t = 0
 
     def _check(self, rc):
@@ -167,10 +85,7 @@ class MmdxStep:
         return self._C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def begin(self, enc, rows, max_steps):
-        class _B:      # bias_table() only needs cfg / rel / dev
-            pass
-        b = _B(); b.cfg, b.rel, b.dev = self.cfg, self._rel, torch.device("cpu")
-        bias = TorchStep.bias_table(b, max_steps).contiguous()            # [max_steps, heads] fp32 on the host
+        bias = relative_position_bias_table(self.cfg, self._rel, max_steps).contiguous()      # [max_steps, heads] fp32, host
         enc = enc.to(self.dev, torch.float32).contiguous()
         self._vocab = self.cfg.vocab_size
         self._rows = rows
@@ -222,9 +137,11 @@ class _StepCache:
 class FastT5Generator:
     """`generate(cond, **gen_kwargs)`: HF's generate on `model` with the model call replaced by `backend.step`."""
 
-    def __init__(self, model, backend=None):
+    def __init__(self, model, backend):
+        """backend: an object with begin(enc, rows, max_steps) / step(tokens) -> logits / reorder(beam_idx) and a step
+        counter `t` - `MmdxStep` in the product, oracle.t5_step_ref.TorchStep in the CPU tests."""
         self.model = model
-        self.backend = backend if backend is not None else TorchStep(model)
+        self.backend = backend
 
     @torch.no_grad()
     def generate(self, cond, **gen_kwargs):

@@ -10,7 +10,8 @@ from transformers import T5Config, T5ForConditionalGeneration
 from transformers.modeling_outputs import BaseModelOutput
 
 from conftest import load_golden
-from mmdx_b200.t5_fast import FastT5Generator, TorchStep
+from mmdx_b200.t5_fast import FastT5Generator
+from oracle.t5_step_ref import TorchStep
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +33,7 @@ def test_generate_token_identical_to_hf(t5, kw):
     cond = torch.randn(3, 4, 512)
     with torch.no_grad():
         want = t5.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
-    got = FastT5Generator(t5).generate(cond, **kw)
+    got = FastT5Generator(t5, TorchStep(t5)).generate(cond, **kw)
     assert torch.equal(want, got)
     # the model is untouched afterwards (forward restored): a second stock call gives the same tokens
     with torch.no_grad():
@@ -46,7 +47,7 @@ def test_generate_from_the_reference_conditioning_tokens(t5):
     kw = dict(REF_KW, max_new_tokens=16, min_new_tokens=12)
     with torch.no_grad():
         want = t5.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
-    assert torch.equal(FastT5Generator(t5).generate(cond, **kw), want)
+    assert torch.equal(FastT5Generator(t5, TorchStep(t5)).generate(cond, **kw), want)
 
 
 def test_step_logits_match_hf_decoder(t5):

@@ -15,7 +15,8 @@ from transformers.modeling_outputs import BaseModelOutput               # noqa: 
 from conftest import load_golden                                        # noqa: E402
 from mmdx_b200 import synth                                             # noqa: E402
 from mmdx_b200 import inference_pipeline as ip                          # noqa: E402
-from mmdx_b200.t5_fast import FastT5Generator, MmdxStep, TorchStep      # noqa: E402
+from mmdx_b200.t5_fast import FastT5Generator, MmdxStep                 # noqa: E402
+from oracle.t5_step_ref import TorchStep                                # noqa: E402
 
 REF_KW = dict(num_beams=4, no_repeat_ngram_size=3, length_penalty=1.1, early_stopping=True, eos_token_id=1, pad_token_id=0)
 
