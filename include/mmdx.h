@@ -157,6 +157,9 @@ const char* mmdx_tokenizer_last_error(void);
  * HF's own code (mmdx_b200/t5_fast.py replaces only the forward inside it), so the generated tokens are HF's.
  * Weights: one mmdx_t5_load_tensor per key of T5ForConditionalGeneration.state_dict() that the decoder uses
  * ("shared.weight", "decoder.block.N.layer.*", "decoder.final_layer_norm.weight", "lm_head.weight" when untied).
+ * tied_embeddings: 1 = LM head tied to the embedding and decoder output scaled by d_model^-0.5 (the T5 default), 0 = separate
+ * lm_head.weight, no scaling (transformers 4.x with tie_word_embeddings=False), 2 = tied but unscaled (transformers 5.x with
+ * tie_word_embeddings=False, where only the scaling is switched off).
  * mmdx_t5_begin: d_enc [R, n_enc, d_model] conditioning tokens per row (mmdx_cond_tokens, repeated over the beams);
  * h_bias [max_steps][n_heads] = relative-position bias by distance (host; the caller evaluates HF's bucket formula).
  * mmdx_t5_step: d_tokens int32 [R] -> d_logits fp32 [R, vocab].  mmdx_t5_reorder: row r continues row d_beam_idx[r]. */
@@ -169,6 +172,11 @@ int mmdx_t5_finalize(mmdx_t5* t);
 int mmdx_t5_begin(mmdx_t5* t, const float* d_enc, int R, int n_enc, int max_steps, const float* h_bias, void* stream);
 int mmdx_t5_reorder(mmdx_t5* t, const int32_t* d_beam_idx, void* stream);
 int mmdx_t5_step(mmdx_t5* t, const int32_t* d_tokens, float* d_logits, void* stream);
+/* Beam-search scoring of the logits of the last step (native search, t5_fast.NativeBeamSearch): per study the k <= 8 best
+ * (row, token) continuations of log_softmax(logits) + beam_score, EOS (ban_eos) and the per-row banned tokens (int32
+ * [R, max_ban], -1 padded) masked to -inf (written into d_logits); outputs [R / num_beams, k], descending, idx = row_in_study * vocab + token. */
+int mmdx_t5_score_topk(mmdx_t5* t, float* d_logits, const float* d_beam_scores, const int32_t* d_banned, int max_ban,
+                       int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores, int32_t* d_out_idx, void* stream);
 int64_t mmdx_t5_launch_count(mmdx_t5* t);
 const char* mmdx_t5_last_error(void);
 

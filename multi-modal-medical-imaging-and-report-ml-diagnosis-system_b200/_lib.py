@@ -77,6 +77,7 @@ SIGNATURES = {
     "mmdx_t5_begin": [_p, _p, _i, _i, _i, _p, _p],
     "mmdx_t5_reorder": [_p, _p, _p],
     "mmdx_t5_step": [_p, _p, _p, _p],
+    "mmdx_t5_score_topk": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "mmdx_t5_launch_count": [_p],
     "mmdx_t5_last_error": [],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],

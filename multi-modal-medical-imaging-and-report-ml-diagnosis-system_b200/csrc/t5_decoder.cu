@@ -204,6 +204,104 @@ __global__ void t5_reorder_kernel(const float* __restrict__ src, float* __restri
   for (int i = threadIdx.x; i < t * dk / 4; i += blockDim.x) b[i] = a[i];
 }
 
+// ---- beam-search scoring (native search, mmdx_b200/t5_fast.py NativeBeamSearch)
+// Row statistics of log_softmax: (max, log(sum exp(x - max))) per row, in HF's formulation lp = (x - max) - log(sum).
+__global__ void __launch_bounds__(1024) t5_row_lse_kernel(const float* __restrict__ logits, int V, float* __restrict__ stat) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + static_cast<size_t>(r) * V;
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += 1024) mx = fmaxf(mx, x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 32; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sm = 0.f;
+  for (int i = tid; i < V; i += 1024) sm += expf(x[i] - mx);
+  sm = warp_sum_f(sm);
+  if ((tid & 31) == 0) red[tid >> 5] = sm;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 32; ++i) t += red[i];
+    stat[2 * r] = mx; stat[2 * r + 1] = logf(t);
+  }
+}
+
+// Top-k continuations of one study over its `beams` rows: score(row, token) = log_softmax(logits)[row, token] + beam_score
+// [row], minus infinity for banned tokens (no-repeat-n-gram lists, -1 padded) and for EOS while below the minimum length.
+// One block per study; every thread keeps its own top-k (k <= 8) of a strided share, then k rounds of a block-wide arg-max
+// pop the winners in descending order (ties: the lower flat index first).  out_idx = row_in_study * V + token.
+// (The masks are written into the logits by t5_ban_kernel AFTER the row statistics were taken: HF applies its logits
+// processors to log_softmax(logits), not to the logits.)
+__global__ void t5_ban_kernel(float* __restrict__ logits, const int32_t* __restrict__ banned, int max_ban, int ban_eos, int eos,
+                              int V) {
+  const int r = blockIdx.x;
+  float* x = logits + static_cast<size_t>(r) * V;
+  if (ban_eos && threadIdx.x == 0) x[eos] = -INFINITY;
+  for (int q = threadIdx.x; q < max_ban; q += blockDim.x) {
+    const int bt = banned[static_cast<size_t>(r) * max_ban + q];
+    if (bt >= 0 && bt < V) x[bt] = -INFINITY;
+  }
+}
+
+constexpr int kTopK = 8;
+__global__ void __launch_bounds__(1024) t5_topk_kernel(const float* __restrict__ logits, const float* __restrict__ stat,
+                                                       const float* __restrict__ beam_scores, int beams, int V, int k,
+                                                       float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  __shared__ int s_win_thread;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float best[kTopK];
+  int bidx[kTopK];
+#pragma unroll
+  for (int j = 0; j < kTopK; ++j) { best[j] = -INFINITY; bidx[j] = 0x7fffffff; }
+  const int total = beams * V;
+  for (int i = tid; i < total; i += 1024) {
+    const int row = i / V, tok = i - row * V;
+    const int R = b * beams + row;
+    float v = (logits[static_cast<size_t>(R) * V + tok] - stat[2 * R]) - stat[2 * R + 1];
+    v += beam_scores[R];
+    if (v > best[kTopK - 1]) {               // strictly greater: an equal later (higher) index never displaces an earlier one
+      int j = kTopK - 1;
+      while (j > 0 && v > best[j - 1]) { best[j] = best[j - 1]; bidx[j] = bidx[j - 1]; --j; }
+      best[j] = v; bidx[j] = i;
+    }
+  }
+  int head = 0;                               // this thread's next candidate
+  for (int round = 0; round < k; ++round) {
+    float v = head < kTopK ? best[head] : -INFINITY;
+    int ix = head < kTopK ? bidx[head] : 0x7fffffff;
+    int th = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, th, o);
+      if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; th = ot; }
+    }
+    if ((tid & 31) == 0) { sv[tid >> 5] = v; si[tid >> 5] = ix; }
+    __shared__ int st[32];
+    if ((tid & 31) == 0) st[tid >> 5] = th;
+    __syncthreads();
+    if (tid == 0) {
+      float bv = sv[0]; int bi = si[0], bt = st[0];
+      for (int w = 1; w < 32; ++w)
+        if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; bt = st[w]; }
+      out_scores[b * k + round] = bv;
+      out_idx[b * k + round] = bi;
+      s_win_thread = bt;
+    }
+    __syncthreads();
+    if (tid == s_win_thread) ++head;
+    __syncthreads();
+  }
+}
+
 struct Block { float *ln0, *qkv, *so, *ln1, *cq, *ck, *cv, *co, *ln2, *wi, *wo; };
 
 }  // namespace
@@ -299,7 +397,7 @@ extern "C" int mmdx_t5_finalize(mmdx_t5* e) {
   const int d = e->d, inner = e->H * e->dk;
   if (get("shared.weight", (size_t)e->vocab * d, &e->E)) return 1;
   e->lm = e->E;
-  if (!e->tied && get("lm_head.weight", (size_t)e->vocab * d, &e->lm)) return 1;
+  if (e->tied == 0 && get("lm_head.weight", (size_t)e->vocab * d, &e->lm)) return 1;
   if (get("decoder.final_layer_norm.weight", d, &e->final_ln)) return 1;
   e->blocks.clear();
   for (int i = 0; i < e->L; ++i) {
@@ -421,10 +519,35 @@ extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits
     if (t5_linear(e, e->hid, e->ff, nullptr, 1.0f, b.wo, e->x, d, e->x, R, e->ff, d, 0, s)) return 1;
     e->launches += 2;
   }
-  const float sc = e->tied ? 1.0f / std::sqrt((float)d) : 1.0f;
+  const float sc = e->tied == 1 ? 1.0f / std::sqrt((float)d) : 1.0f;     // HF scales the decoder output only in the default tied setup
   if (t5_linear(e, e->x, d, e->final_ln, sc, e->lm, d_logits, e->vocab, nullptr, R, d, e->vocab, 0, s)) return 1;
   T5_CK(cudaGetLastError());
   e->t++;
+  return 0;
+}
+
+// Beam-search scoring of the logits mmdx_t5_step has just produced: per study the k best (row, token) continuations of
+// log_softmax(logits) + beam_score, with EOS and the per-row banned tokens (int32 [R, max_ban], -1 padded; may be null when
+// max_ban = 0) masked out.  d_out_scores / d_out_idx [R / num_beams, k], descending, idx = row_in_study * vocab + token.
+extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_beam_scores, const int32_t* d_banned,
+                                  int max_ban, int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores,
+                                  int32_t* d_out_idx, void* stream) {
+  T5_REQUIRE(e && d_logits && d_beam_scores && d_out_scores && d_out_idx, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  T5_REQUIRE(e->R > 0 && num_beams > 0 && e->R % num_beams == 0, "mmdx_t5_score_topk: rows must be studies x beams");
+  T5_REQUIRE(k >= 1 && k <= kTopK && (max_ban == 0 || d_banned != nullptr), "mmdx_t5_score_topk: 1 <= k <= 8");
+  T5_CK(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  float* stat = e->hid;                        // 2 floats per row: scratch that the next step overwrites anyway
+  t5_row_lse_kernel<<<e->R, 1024, 0, s>>>(d_logits, e->vocab, stat);
+  if (ban_eos || max_ban > 0) {
+    T5_REQUIRE(eos_id >= 0 && eos_id < e->vocab, "eos id outside the vocabulary");
+    t5_ban_kernel<<<e->R, 128, 0, s>>>(d_logits, d_banned, max_ban, ban_eos, eos_id, e->vocab);
+    e->launches++;
+  }
+  t5_topk_kernel<<<e->R / num_beams, 1024, 0, s>>>(d_logits, stat, d_beam_scores, num_beams, e->vocab, k, d_out_scores, d_out_idx);
+  e->launches += 2;
+  T5_CK(cudaGetLastError());
   return 0;
 }
 

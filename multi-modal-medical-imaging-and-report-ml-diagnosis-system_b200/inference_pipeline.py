@@ -259,9 +259,14 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
             fast = fast_report_generator(fusion, dev) if model_bundle.get("fast_report", True) else None
             if fast is not None and gen_attributes.get("max_new_tokens"):
                 # HF's beam search with the model call replaced by the KV-cached CUDA decoder step (csrc/t5_decoder.cu):
-                # same tokens, a small fraction of the time
+                # same tokens, a small fraction of the time.  fast_report = "native" also replaces HF's
+                # Python loop by the restated search over the device scoring / top-k kernels (another ~8x).
                 with eng.lock:
-                    gen_ids = fast.generate(cond, **gen_attributes)
+                    if model_bundle.get("fast_report") == "native":
+                        from .t5_fast import NativeBeamSearch
+                        gen_ids = NativeBeamSearch(fast.backend, fusion.report_model.config).generate(cond, **gen_attributes)
+                    else:
+                        gen_ids = fast.generate(cond, **gen_attributes)
             else:
                 gen_ids = fusion.report_model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **gen_attributes)
         else:

@@ -19,6 +19,17 @@ import math
 import torch
 
 
+def lm_head_setup(model):
+    """(weights tied?, decoder output scaled by d_model^-0.5?) of a T5ForConditionalGeneration.  transformers 4.x ties and
+    scales together (`tie_word_embeddings`); 5.x always ties and keeps the scaling as `scale_decoder_outputs`."""
+    cfg = model.config
+    sd = model.state_dict()
+    tied = "lm_head.weight" not in sd or sd["lm_head.weight"].data_ptr() == sd["shared.weight"].data_ptr() \
+        or bool(torch.equal(sd["lm_head.weight"], sd["shared.weight"]) and cfg.tie_word_embeddings)
+    scaled = bool(getattr(cfg, "scale_decoder_outputs", cfg.tie_word_embeddings))
+    return tied, scaled
+
+
 def relative_position_bias_table(cfg, rel_weight, n, device="cpu"):
     """Relative-position bias of the decoder self-attention by distance d = query_pos - key_pos in [0, n): rows of
     `rel_weight` [buckets, heads] picked with HF's bucket arithmetic (T5Attention._relative_position_bucket with
@@ -49,11 +60,14 @@ class MmdxStep:
         self.cfg = cfg
         self.blocks = range(cfg.num_decoder_layers)
         self._h = C.c_void_p()
+        tied, scaled = lm_head_setup(model)
         self._check(self._lib.mmdx_t5_create(dev.index or 0, cfg.d_model, cfg.num_heads, cfg.d_kv, cfg.d_ff, cfg.num_decoder_layers,
-                                             cfg.vocab_size, float(cfg.layer_norm_epsilon), 1 if cfg.tie_word_embeddings else 0,
+                                             cfg.vocab_size, float(cfg.layer_norm_epsilon), (1 if scaled else 2) if tied else 0,
                                              C.byref(self._h)))
+        if not tied and scaled:
+            raise ValueError("untied LM head with scaled decoder output is not a T5 configuration")
         for k, v in model.state_dict().items():
-            if k == "shared.weight" or k.startswith("decoder.") or (k == "lm_head.weight" and not cfg.tie_word_embeddings):
+            if k == "shared.weight" or k.startswith("decoder.") or (k == "lm_head.weight" and not tied):
                 if "relative_attention_bias" in k:
                     continue
                 t = v.detach().to("cpu", torch.float32).contiguous()
@@ -110,6 +124,139 @@ class MmdxStep:
         self._keep_tok = tok
         self.t += 1
         return logits
+
+
+    def score_topk(self, logits, beam_scores, banned, ban_eos, eos_id, num_beams, k):
+        """Per study the k best continuations of log_softmax(logits) + beam_scores with the masks applied
+        (`mmdx_t5_score_topk`): -> (scores fp32 [B, k], flat index int64 [B, k] = row_in_study * vocab + token), on the host."""
+        C = self._C
+        B = self._rows // num_beams
+        bs = beam_scores.to(self.dev, torch.float32).contiguous()
+        max_ban = 0 if banned is None else int(banned.shape[1])
+        bn = None if not max_ban else banned.to(self.dev, torch.int32).contiguous()
+        out_s = torch.empty(B, k, dtype=torch.float32, device=self.dev)
+        out_i = torch.empty(B, k, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self._check(self._lib.mmdx_t5_score_topk(self._h, C.c_void_p(logits.data_ptr()), C.c_void_p(bs.data_ptr()),
+                                                     C.c_void_p(bn.data_ptr() if bn is not None else 0), max_ban, 1 if ban_eos else 0,
+                                                     int(eos_id), int(num_beams), int(k), C.c_void_p(out_s.data_ptr()),
+                                                     C.c_void_p(out_i.data_ptr()), self._stream()))
+        return out_s.cpu(), out_i.cpu().to(torch.int64)
+
+
+class NativeBeamSearch:
+    """Beam search driven from here instead of from HF's Python loop: per token one decoder step, one scoring / top-k
+    launch pair on the device and ~30 tiny host tensor ops, instead of the ~2.7 ms of eager-mode bookkeeping HF spends per
+    token.  The algorithm is HF's `GenerationMixin._beam_search` (transformers 5.x) for `do_sample=False`,
+    `num_return_sequences=1`, one EOS id, with the two logits processors the reference's settings enable
+    (inference_pipeline.py:190: `min_new_tokens`, `no_repeat_ngram_size`) and its stopping rule (`early_stopping`,
+    `length_penalty`, `max_new_tokens`): top-2K continuations per study, unfinished ones continue, finished ones compete
+    on score / length ** length_penalty.  tests/test_t5_cpu.py and test_t5_gpu.py hold it to token identity with HF's own
+    `generate`.  Opt-in (`model_bundle["fast_report"] = "native"`): HF's loop over the CUDA step stays the default because
+    it is HF's search by construction, while this one agrees with it up to fp32 rounding of near-tied scores."""
+
+    def __init__(self, backend, cfg):
+        self.be, self.cfg = backend, cfg
+
+    @staticmethod
+    def _banned(seqs, cur_len, n):
+        """no_repeat_ngram_size = n: for every row the tokens that would repeat an n-gram already in seqs[row, :cur_len]
+        (HF NoRepeatNGramLogitsProcessor), as an int32 array padded with -1."""
+        import numpy as np
+        R = seqs.shape[0]
+        if n <= 0 or cur_len + 1 < n:
+            return None
+        S = seqs[:, :cur_len]
+        if n == 1:
+            return S.astype(np.int32)
+        m = np.ones((R, cur_len - n + 1), bool)
+        for j in range(n - 1):                                      # windows whose first n-1 tokens equal the current suffix
+            m &= S[:, j:cur_len - n + 1 + j] == S[:, cur_len - n + 1 + j:cur_len - n + 2 + j]
+        nxt = S[:, n - 1:]
+        width = max(int(m.sum(1).max()), 1)
+        out = np.full((R, width), -1, np.int32)
+        for r in range(R):
+            t = nxt[r][m[r]]
+            out[r, :len(t)] = t
+        return out
+
+    @torch.no_grad()
+    def generate(self, cond, max_new_tokens, min_new_tokens=0, num_beams=1, no_repeat_ngram_size=0, length_penalty=1.0,
+                 early_stopping=False, eos_token_id=1, pad_token_id=0, decoder_start_token_id=None, **unused):
+        import numpy as np
+        unsupported = {k: v for k, v in unused.items() if v not in (None, False) and k not in ("use_cache",)}
+        if unsupported:
+            raise ValueError(f"NativeBeamSearch does not implement {sorted(unsupported)}")
+        be, K = self.be, int(num_beams)
+        B = cond.shape[0]
+        V = self.cfg.vocab_size
+        start = self.cfg.decoder_start_token_id if decoder_start_token_id is None else decoder_start_token_id
+        eos, lp = int(eos_token_id), float(length_penalty)
+        prompt, max_length = 1, 1 + int(max_new_tokens)
+        K2 = 2 * K
+        fill = pad_token_id if pad_token_id else eos               # HF: `pad_token_id or eos_token_id[0]`
+        NEG = np.float32(-1.0e9)
+        be.begin(cond.repeat_interleave(K, 0), B * K, max_length)
+        run_seq = np.full((B, K, max_length), fill, np.int64)
+        run_seq[:, :, 0] = start
+        seqs = run_seq.copy()
+        run_len = np.zeros((B, K), np.int64)                        # generated tokens of every stored hypothesis
+        fin_len = np.zeros((B, K), np.int64)
+        run_scores = np.zeros((B, K), np.float32)
+        run_scores[:, 1:] = NEG
+        beam_scores = np.full((B, K), NEG, np.float32)
+        finished = np.zeros((B, K), bool)
+        unsat = np.ones((B, 1), bool)
+        top_mask = np.arange(K2) < K
+        cur_len = 1
+        bidx = np.arange(B)[:, None]
+        while True:
+            tokens = torch.from_numpy(run_seq[:, :, cur_len - 1].reshape(-1))
+            logits = be.step(tokens)
+            flat = run_seq.reshape(B * K, max_length)
+            banned = self._banned(flat, cur_len, int(no_repeat_ngram_size))
+            ban_eos = (cur_len - prompt) < int(min_new_tokens)
+            tk_scores, tk_idx = be.score_topk(logits, torch.from_numpy(run_scores.reshape(-1)),
+                                              None if banned is None else torch.from_numpy(banned), ban_eos, eos, K, K2)
+            tk_scores = tk_scores.numpy().astype(np.float32)
+            tk_idx = tk_idx.numpy()
+            src_beam, tok = tk_idx // V, tk_idx % V                 # [B, K2]
+            tk_seq = run_seq[bidx, src_beam]                        # [B, K2, max_length]
+            tk_seq[:, :, cur_len] = tok
+            tk_len = np.full((B, K2), cur_len + 1 - prompt, np.int64)
+            hits = (tok == eos) | (cur_len + 1 >= max_length)
+            # running beams of the next step: the best K continuations that did not stop
+            run_pool = tk_scores + hits.astype(np.float32) * NEG
+            nxt = torch.topk(torch.from_numpy(run_pool), K).indices.numpy()        # the selection HF makes, ties included
+            run_seq = tk_seq[bidx, nxt]
+            run_scores = run_pool[bidx, nxt]
+            run_len = tk_len[bidx, nxt]
+            beam_src = (src_beam[bidx, nxt] + np.arange(B)[:, None] * K).reshape(-1)
+            # finished hypotheses: only the top K of the 2K continuations may finish
+            just = hits & top_mask[None, :]
+            fs = tk_scores / np.float32((cur_len + 1 - prompt) ** lp)
+            full = finished.all(axis=1, keepdims=True) & (early_stopping is True)
+            fs = fs + full.astype(np.float32) * NEG
+            fs = fs + (~unsat).astype(np.float32) * NEG
+            fs = fs + (~just).astype(np.float32) * NEG
+            m_scores = np.concatenate([beam_scores, fs], 1)
+            m_seq = np.concatenate([seqs, tk_seq], 1)
+            m_fin = np.concatenate([finished, just], 1)
+            m_len = np.concatenate([fin_len, tk_len], 1)
+            top = torch.topk(torch.from_numpy(m_scores), K).indices.numpy()
+            seqs, beam_scores, finished, fin_len = m_seq[bidx, top], m_scores[bidx, top], m_fin[bidx, top], m_len[bidx, top]
+            be.reorder(torch.from_numpy(beam_src))
+            cur_len += 1
+            # can a running beam still beat the worst finished one?
+            best_len = (max_length - prompt) if (early_stopping == "never" and lp > 0.0) else (cur_len - prompt)
+            best_possible = run_scores[:, :1] / np.float32(best_len ** lp)
+            worst = np.where(finished, beam_scores.min(axis=1, keepdims=True), NEG)
+            unsat = unsat & (best_possible > worst).any(axis=1, keepdims=True)
+            go_on = unsat.any() and not (finished.all() and early_stopping is True) and not hits.all()
+            if not go_on:
+                break
+        out_len = prompt + int(fin_len[:, 0].max())
+        return torch.from_numpy(seqs[:, 0, :out_len].copy())
 
 
 class _StepCache:

@@ -28,7 +28,7 @@ class TorchStep:
         sd = {k: v.detach().to(dev, torch.float32) for k, v in model.state_dict().items()}
         self.E = sd["shared.weight"]
         self.lm = sd.get("lm_head.weight", self.E)
-        self.tied = bool(cfg.tie_word_embeddings)
+        self.tied = bool(getattr(cfg, "scale_decoder_outputs", cfg.tie_word_embeddings))     # = "scale the decoder output"
         self.blocks = []
         for i in range(cfg.num_decoder_layers):
             p = f"decoder.block.{i}.layer."
@@ -99,3 +99,17 @@ class TorchStep:
             x = x * (self.cfg.d_model ** -0.5)
         self.t += 1
         return x @ self.lm.t()
+
+    def score_topk(self, logits, beam_scores, banned, ban_eos, eos_id, num_beams, k):
+        """torch restatement of mmdx_t5_score_topk: log_softmax, masks, + beam score, top-k per study."""
+        R, V = logits.shape
+        lp = torch.log_softmax(logits.float(), -1)
+        if ban_eos:
+            lp[:, eos_id] = -float("inf")
+        if banned is not None:
+            for r in range(R):
+                b = banned[r][banned[r] >= 0].long()
+                lp[r, b] = -float("inf")
+        lp = (lp + beam_scores.to(lp.device).view(R, 1)).view(R // num_beams, num_beams * V)
+        s, i = torch.topk(lp, k)
+        return s.cpu(), i.cpu()

@@ -75,3 +75,71 @@ def test_step_logits_match_hf_decoder(t5):
             be.reorder(idx)
             seq = seq[idx]
             cond = cond[idx]
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(REF_KW, max_new_tokens=24, min_new_tokens=18)),
+    (2, dict(REF_KW, max_new_tokens=30, min_new_tokens=0)),
+    (3, dict(max_new_tokens=14, num_beams=1, eos_token_id=1, pad_token_id=0)),
+    (4, dict(max_new_tokens=12, num_beams=2, length_penalty=0.8, early_stopping=False, eos_token_id=1, pad_token_id=0)),
+    (5, dict(max_new_tokens=16, num_beams=3, no_repeat_ngram_size=2, length_penalty=2.0, early_stopping="never", eos_token_id=1,
+             pad_token_id=0)),
+])
+def test_native_beam_search_token_identical_to_hf(t5, seed, kw):
+    """The native search loop (NativeBeamSearch: HF's beam-search algorithm restated over the step + score/top-k
+    interface) against stock HF generate - here with the torch step and torch scoring, so this pins the search LOGIC."""
+    from mmdx_b200.t5_fast import NativeBeamSearch
+    torch.manual_seed(seed)
+    cond = torch.randn(3, 4, 512)
+    with torch.no_grad():
+        want = t5.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
+    got = NativeBeamSearch(TorchStep(t5), t5.config).generate(cond, **kw)
+    assert want.shape == got.shape and torch.equal(want, got), (want.tolist(), got.tolist())
+
+
+class _EosBiased:
+    """Step backend wrapper that raises the EOS logit by `b` (the HF side gets the same through a forward hook on lm_head):
+    with random-init weights EOS never wins on its own, and the interesting part of a beam search is what happens when
+    hypotheses finish at different lengths."""
+
+    def __init__(self, be, b):
+        self.be, self.b = be, b
+
+    def __getattr__(self, k):
+        return getattr(self.be, k)
+
+    def step(self, tok):
+        lg = self.be.step(tok)
+        lg[:, 1] += self.b
+        return lg
+
+
+@pytest.mark.parametrize("bias", [5.0, 6.5])
+def test_native_beam_search_with_finishing_hypotheses(t5, bias):
+    """EOS made likely: hypotheses finish at different steps, the finished pool fills up and competes on
+    score / length ** length_penalty, early stopping ends the search, shorter outputs are padded the way HF pads them
+    (with EOS when pad_token_id is 0).  Native search == HF generate == HF's loop over the same step, shapes included."""
+    from mmdx_b200.t5_fast import NativeBeamSearch
+
+    def hook(mod, inp, out):
+        out[..., 1] += bias
+        return out
+
+    n_eos = 0
+    for seed in range(6):
+        torch.manual_seed(100 + seed)
+        cond = torch.randn(2, 4, 512)
+        kw = dict(max_new_tokens=24, min_new_tokens=(0 if seed % 2 else 3), num_beams=4, length_penalty=1.1,
+                  early_stopping=(True if seed % 3 else False), eos_token_id=1, pad_token_id=0, no_repeat_ngram_size=3)
+        h = t5.lm_head.register_forward_hook(hook)
+        try:
+            with torch.no_grad():
+                want = t5.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
+        finally:
+            h.remove()
+        got = NativeBeamSearch(_EosBiased(TorchStep(t5), bias), t5.config).generate(cond, **kw)
+        assert want.shape == got.shape and torch.equal(want, got), (seed, want.tolist(), got.tolist())
+        got2 = FastT5Generator(t5, _EosBiased(TorchStep(t5), bias)).generate(cond, **kw)
+        assert torch.equal(want, got2)
+        n_eos += int((want == 1).any())
+    assert n_eos >= 3

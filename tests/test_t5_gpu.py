@@ -107,3 +107,58 @@ def test_inference_report_text_through_the_cuda_decoder(state_bundle, g1):
     slow = ip.inference(dict(b, fast_report=False), pil, str(g1["details"][0]), device="cuda", gen_kwargs=kw)
     assert fast["report_text"] == slow["report_text"] and len(fast["report_text"].split()) >= 17
     assert fast["disease_vector"] == g1["inf_vector"][0].tolist()
+
+
+def test_native_beam_search_on_the_cuda_kernels(t5):
+    """NativeBeamSearch over the CUDA step + the scoring / top-k kernels (mmdx_t5_score_topk) against stock HF generate on
+    the GPU, at the reference's full generation settings (inference_pipeline.py:190: 180 new tokens, 150 minimum, 4 beams,
+    no-repeat 3-gram, length penalty 1.1, early stopping) and at short ones; prints the three timings."""
+    from mmdx_b200.t5_fast import NativeBeamSearch
+    g = load_golden("g2_B8_L128_ragged")
+    for n_new, n_min, B in ((180, 150, 2), (32, 0, 3)):
+        cond = torch.from_numpy(g["cond"][:B]).cuda()
+        kw = dict(REF_KW, max_new_tokens=n_new, min_new_tokens=n_min)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            want = t5.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
+            torch.cuda.synchronize()
+            t_hf = time.perf_counter() - t0
+        step = MmdxStep(t5)
+        loop = FastT5Generator(t5, step)
+        t0 = time.perf_counter()
+        got_loop = loop.generate(cond, **kw)
+        torch.cuda.synchronize()
+        t_loop = time.perf_counter() - t0
+        nat = NativeBeamSearch(step, t5.config)
+        nat.generate(cond, **dict(kw, max_new_tokens=4, min_new_tokens=0))
+        t0 = time.perf_counter()
+        got = nat.generate(cond, **kw)
+        torch.cuda.synchronize()
+        t_nat = time.perf_counter() - t0
+        print(f"generate {n_new} tokens x 4 beams x {B} studies: HF eager {t_hf * 1e3:.0f} ms, HF loop over the CUDA step "
+              f"{t_loop * 1e3:.0f} ms, native search {t_nat * 1e3:.0f} ms")
+        assert torch.equal(want, got_loop)
+        assert want.shape == got.shape and torch.equal(want.cpu(), got), (want.tolist(), got.tolist())
+        step.close()
+
+
+def test_score_topk_kernel_vs_torch(t5):
+    """mmdx_t5_score_topk against the torch restatement: same candidates in the same order, scores to fp32 rounding."""
+    torch.manual_seed(5)
+    R, K, V = 12, 4, t5.config.vocab_size
+    a, b = TorchStep(t5), MmdxStep(t5)
+    cond = torch.randn(R // K, 4, 512, device="cuda").repeat_interleave(K, 0)
+    a.begin(cond, R, 4)
+    b.begin(cond, R, 4)
+    tok = torch.randint(0, V, (R,), device="cuda")
+    la, lb = a.step(tok), b.step(tok)
+    bs = torch.randn(R) * 3
+    banned = torch.full((R, 5), -1, dtype=torch.int32)
+    banned[:, 0] = la.argmax(-1).cpu().int()                    # ban every row's best token
+    banned[3, 1] = 17
+    for ban_eos in (False, True):
+        sa, ia = a.score_topk(la.clone(), bs, banned, ban_eos, 1, K, 8)
+        sb, ib = b.score_topk(lb.clone(), bs, banned, ban_eos, 1, K, 8)
+        assert torch.equal(ia, ib)
+        assert float((sa - sb).abs().max()) < 1e-4
+    b.close()
