@@ -107,6 +107,10 @@ def test_inference_report_text_through_the_cuda_decoder(state_bundle, g1):
     slow = ip.inference(dict(b, fast_report=False), pil, str(g1["details"][0]), device="cuda", gen_kwargs=kw)
     assert fast["report_text"] == slow["report_text"] and len(fast["report_text"].split()) >= 17
     assert fast["disease_vector"] == g1["inf_vector"][0].tolist()
+    native = ip.inference(dict(b, fast_report="native"), pil, str(g1["details"][0]), device="cuda", gen_kwargs=kw)
+    assert native["report_text"] == slow["report_text"] and native["disease_probs"] == fast["disease_probs"]
+    with pytest.raises(ValueError):
+        ip.inference(dict(b, fast_report="native"), pil, "x", device="cuda", gen_kwargs=dict(kw, do_sample=True))
 
 
 def test_native_beam_search_on_the_cuda_kernels(t5):
