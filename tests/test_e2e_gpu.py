@@ -734,3 +734,19 @@ def test_text_encoder_shapes_vs_oracle(bundle, eng, B, L, ragged):
     pooled2, _ = eng.text_encode(t[0], t[1], t[2], t[3], mlen)
     torch.cuda.synchronize()
     assert torch.equal(pooled, pooled2)
+
+
+@pytest.mark.parametrize("B", [150, 300])
+def test_image_branch_batch_sizes_around_the_two_gemm_threshold(eng, B):
+    """The conv3 + next-conv1 two-GEMM launch is used per layer only where a layer has >= 2 items per CTA pair: at B = 150
+    layer 2 takes it and layer 3 does not, at B = 300 both do (and B = 300 is not a multiple of the 256-row item).  A
+    study's features must not depend on which plan its batch got: the first and last studies equal a B = 4 run."""
+    imgs = synth.synth_images(B, 224, seed=71)
+    d = torch.from_numpy(imgs).cuda()
+    feats, z = eng.image_encode(d)
+    sel = [0, 1, B - 2, B - 1]
+    f4, z4 = eng.image_encode(torch.from_numpy(np.ascontiguousarray(imgs[sel])).cuda())
+    torch.cuda.synchronize()
+    assert np.isfinite(feats.cpu().numpy()).all()
+    assert _rel(feats[sel].cpu().numpy(), f4.cpu().numpy()) < 1e-2
+    assert _rel(z[sel].cpu().numpy(), z4.cpu().numpy()) < 1e-2
