@@ -15,8 +15,11 @@ infrastructure).
 from __future__ import annotations
 
 import math
+import threading
 
 import torch
+
+_PATCH_LOCK = threading.RLock()      # one generation at a time swaps a model's forward (and owns the step backend's cache)
 
 
 def lm_head_setup(model):
@@ -187,6 +190,13 @@ class NativeBeamSearch:
         unsupported = {k: v for k, v in unused.items() if v not in (None, False) and k not in ("use_cache",)}
         if unsupported:
             raise ValueError(f"NativeBeamSearch does not implement {sorted(unsupported)}")
+        with _PATCH_LOCK:                 # the step backend holds ONE generation's KV cache
+            return self._generate(cond, max_new_tokens, min_new_tokens, num_beams, no_repeat_ngram_size, length_penalty,
+                                  early_stopping, eos_token_id, pad_token_id, decoder_start_token_id)
+
+    def _generate(self, cond, max_new_tokens, min_new_tokens, num_beams, no_repeat_ngram_size, length_penalty, early_stopping,
+                  eos_token_id, pad_token_id, decoder_start_token_id):
+        import numpy as np
         be, K = self.be, int(num_beams)
         B = cond.shape[0]
         V = self.cfg.vocab_size
@@ -313,9 +323,10 @@ class FastT5Generator:
             logits = be.step(decoder_input_ids[:, -1])
             return Seq2SeqLMOutput(logits=logits[:, None, :].to(dev), past_key_values=state["cache"])
 
-        orig = model.forward
-        model.forward = fast_forward
-        try:
-            return model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), use_cache=True, **gen_kwargs)
-        finally:
-            model.forward = orig
+        with _PATCH_LOCK:
+            orig = model.forward
+            model.forward = fast_forward
+            try:
+                return model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), use_cache=True, **gen_kwargs)
+            finally:
+                model.forward = orig
