@@ -214,6 +214,9 @@ int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_x, const vo
  * are 1x1 over NHWC), bf16, BN folded; K1 % 64 == 0, N1 and N2 multiples of 128 (of 256 for the 256-wide variant). */
 int mmdx_op_conv3_conv1(mmdx_engine* e, const void* d_t2, const void* d_w3, const float* d_b3, const void* d_res, void* d_y,
                         const void* d_w1n, const float* d_b1n, void* d_t1n, int64_t M, int K1, int N1, int N2, void* stream);
+/* host-only: the static job schedule of the two-GEMM kernel for one CTA pair, (type 0|1, item, n_tile) triples into out[3*cap];
+ * returns the number of jobs */
+int mmdx_gemm2_schedule(int num_items, int nt1, int nt2, int reverse, int group, int num_groups, int32_t* out, int cap);
 int mmdx_padded_dims(int H, int W, int* hp, int* wp);
 /* Fused stem: conv 7x7/2 + bias + ReLU (+ MaxPool 3x3/2 pad 1 when pool != 0) over the same padded 4-channel image.
  * d_w_packed: 14336 bf16 (7 x 64 x 32) from mmdx_pack_stem_weights (host helper: fp32 [64,3,7,7] x optional per-channel scale).

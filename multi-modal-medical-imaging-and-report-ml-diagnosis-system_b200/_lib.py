@@ -86,6 +86,7 @@ SIGNATURES = {
     "mmdx_op_bneck64": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mmdx_op_conv3_ds": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_conv3_conv1": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p],
+    "mmdx_gemm2_schedule": [_i, _i, _i, _i, _i, _i, _p, _i],
     "mmdx_pack_stem_weights": [_p, _p, _p],
     "mmdx_op_stem_pool": [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p],
     "mmdx_op_preprocess": [_p, _p, _i, _i, _i, _i, _p, _ip, _ip, _p],

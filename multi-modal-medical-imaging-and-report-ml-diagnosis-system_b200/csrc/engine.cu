@@ -2794,6 +2794,20 @@ extern "C" int mmdx_op_conv3_ds(mmdx_engine* e, const void* d_t2, const void* d_
   TRY(fill_epilogue(e, g, d_bias, nullptr, 0, d_out, Cout, ACT_RELU, 0));
   return launch_gemm(e, g, (cudaStream_t)stream);
 }
+// Host-side enumeration of the two-GEMM kernel's static schedule (the SAME iterator the device roles run): the jobs of CTA
+// pair `group` of `num_groups`, as (type, item, n_tile) triples.  No GPU needed; tests/test_capi_cpu.py checks that every job
+// runs exactly once and that an item's second GEMM never precedes its first.  Returns the number of jobs (or -1).
+extern "C" int mmdx_gemm2_schedule(int num_items, int nt1, int nt2, int reverse, int group, int num_groups, int32_t* out, int cap) {
+  if (num_items < 0 || nt1 <= 0 || nt2 <= 0 || group < 0 || num_groups <= 0 || !out) return -1;
+  Gemm2Sched sch(num_items, nt1, nt2, reverse, group, num_groups);
+  Gemm2Job j;
+  int n = 0;
+  while (sch.next(j)) {
+    if (n < cap) { out[3 * n] = j.type; out[3 * n + 1] = j.item; out[3 * n + 2] = j.n_t; }
+    ++n;
+  }
+  return n;
+}
 extern "C" int mmdx_op_conv3_conv1(mmdx_engine* e, const void* d_t2, const void* d_w3, const float* d_b3, const void* d_res,
                                    void* d_y, const void* d_w1n, const float* d_b1n, void* d_t1n, int64_t M, int K1, int N1,
                                    int N2, void* stream) {

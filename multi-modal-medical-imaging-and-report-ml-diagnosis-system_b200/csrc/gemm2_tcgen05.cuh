@@ -45,14 +45,16 @@ struct Gemm2Job { int type, seq, n_t, item; };
 // Job sequence of one CTA pair over its n items: block b = [G1 tiles of item b (b < n)] then [G2 tiles of item b - 1 (b >= 1)]
 struct Gemm2Sched {
   int n, n1, n2, b = 0, r = 0, group, num_groups, num_items, reverse;
+  __host__ __device__ Gemm2Sched(int num_items_, int nt1, int nt2, int reverse_, int group_, int num_groups_)
+      : n(group_ < num_items_ ? (num_items_ - group_ + num_groups_ - 1) / num_groups_ : 0), n1(nt1), n2(nt2), group(group_),
+        num_groups(num_groups_), num_items(num_items_), reverse(reverse_) {}
   __device__ Gemm2Sched(const Gemm2Params& p, int group_, int num_groups_)
-      : n(group_ < p.num_items ? (p.num_items - group_ + num_groups_ - 1) / num_groups_ : 0), n1(p.nt1), n2(p.nt2), group(group_),
-        num_groups(num_groups_), num_items(p.num_items), reverse(p.reverse) {}
-  __device__ __forceinline__ int item_of(int seq) const {
+      : Gemm2Sched(p.num_items, p.nt1, p.nt2, p.reverse, group_, num_groups_) {}
+  __host__ __device__ __forceinline__ int item_of(int seq) const {
     const int it = group + seq * num_groups;
     return reverse ? num_items - 1 - it : it;
   }
-  __device__ __forceinline__ bool next(Gemm2Job& j) {
+  __host__ __device__ __forceinline__ bool next(Gemm2Job& j) {
     while (b <= n) {
       if (r < n1) {
         if (b < n) { j.type = 0; j.seq = b; j.n_t = r; j.item = item_of(b); ++r; return true; }

@@ -75,3 +75,31 @@ def test_no_cpu_fallback(lib):
     h = C.c_void_p()
     assert lib.mmdx_create(C.byref(cfg), C.byref(h)) != 0
     assert b"no CUDA device" in lib.mmdx_last_error()
+
+
+@pytest.mark.parametrize("num_items,nt1,nt2,groups,reverse", [(784, 4, 1, 74, 0), (196, 4, 1, 74, 1), (196, 4, 2, 74, 0),
+                                                              (5, 2, 1, 74, 0), (1, 4, 1, 1, 1), (75, 3, 2, 74, 1), (0, 4, 1, 4, 0)])
+def test_two_gemm_schedule_covers_every_job_once(lib, num_items, nt1, nt2, groups, reverse):
+    """The static schedule of gemm2_tcgen05_kernel (conv3 + next conv1 in one launch), enumerated by the same iterator the
+    device runs: every (GEMM, item, n-tile) job exactly once over all CTA pairs, an item's second GEMM after ALL tiles of
+    its first one in the same pair, and one item of look-ahead between them (so the stores have landed)."""
+    seen = {}
+    g_used = min(groups, max(num_items, 1))
+    for g in range(g_used):
+        buf = np.zeros(3 * 4096, np.int32)
+        n = lib.mmdx_gemm2_schedule(num_items, nt1, nt2, reverse, g, g_used, buf.ctypes.data, 4096)
+        jobs = buf[:3 * n].reshape(n, 3).tolist()
+        pos = {}
+        for i, (t, item, nt) in enumerate(jobs):
+            assert (t, item, nt) not in seen
+            seen[(t, item, nt)] = g
+            pos[(t, item, nt)] = i
+        items = sorted({j[1] for j in jobs}, key=lambda it: min(p for (t, i2, _), p in pos.items() if i2 == it))
+        for k, it in enumerate(items):
+            last_g1 = max(pos[(0, it, nt)] for nt in range(nt1))
+            first_g2 = min(pos[(1, it, nt)] for nt in range(nt2))
+            assert first_g2 > last_g1
+            if k + 1 < len(items):          # the next item's first GEMM is issued before this item's second one
+                assert pos[(0, items[k + 1], nt1 - 1)] < first_g2
+    assert len(seen) == num_items * (nt1 + nt2)
+    assert {k[1] for k in seen} == set(range(num_items))
