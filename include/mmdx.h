@@ -177,6 +177,14 @@ int mmdx_t5_step(mmdx_t5* t, const int32_t* d_tokens, float* d_logits, void* str
  * [R, max_ban], -1 padded) masked to -inf (written into d_logits); outputs [R / num_beams, k], descending, idx = row_in_study * vocab + token. */
 int mmdx_t5_score_topk(mmdx_t5* t, float* d_logits, const float* d_beam_scores, const int32_t* d_banned, int max_ban,
                        int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores, int32_t* d_out_idx, void* stream);
+/* The whole report generation in one call: HF's beam search (GenerationMixin._beam_search; do_sample = False, one EOS id,
+ * min_new_tokens and no_repeat_ngram_size processors, length_penalty, early_stopping 0 = False / 1 = True / 2 = "never") with
+ * the per-token bookkeeping on the host in C++.  d_cond [B, n_enc, d_model] (mmdx_cond_tokens), num_beams <= 4.
+ * h_out int32 [B, max_new_tokens + 1] starts with the decoder start token and is padded the way HF pads (pad id, or EOS when
+ * the pad id is 0); *h_out_len = the length of the tensor HF's generate would return. */
+int mmdx_t5_generate(mmdx_t5* t, const float* d_cond, int B, int n_enc, int num_beams, int max_new_tokens, int min_new_tokens,
+                     int no_repeat_ngram, float length_penalty, int early_stopping, int eos_id, int pad_id, int start_id,
+                     const float* h_bias, int32_t* h_out, int32_t* h_out_len, void* stream);
 int64_t mmdx_t5_launch_count(mmdx_t5* t);
 const char* mmdx_t5_last_error(void);
 

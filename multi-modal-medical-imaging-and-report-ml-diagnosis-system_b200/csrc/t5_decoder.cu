@@ -15,6 +15,7 @@
 // through mmdx_t5_reorder.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -309,7 +310,7 @@ struct Block { float *ln0, *qkv, *so, *ln1, *cq, *ck, *cv, *co, *ln2, *wi, *wo; 
 struct mmdx_t5 {
   int device = 0, d = 512, H = 8, dk = 64, ff = 2048, L = 6, vocab = 32128, tied = 1;
   float eps = 1e-6f;
-  std::mutex mu;
+  std::recursive_mutex mu;         // recursive: mmdx_t5_generate drives begin / step / score / reorder under one lock
   std::map<std::string, std::vector<float>> host;
   bool finalized = false;
   float* arena = nullptr; size_t arena_floats = 0, used = 0;
@@ -435,7 +436,7 @@ extern "C" int mmdx_t5_finalize(mmdx_t5* e) {
 // caller with the reference's own bucket arithmetic).  Projects the cross-attention keys / values once.
 extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, int max_steps, const float* h_bias, void* stream) {
   T5_REQUIRE(e && d_enc && h_bias && R > 0 && n_enc > 0 && n_enc <= 64 && max_steps > 0 && max_steps <= 4096, "bad argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->finalized, "weights not finalized");
   T5_CK(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -480,7 +481,7 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
 // Beam reordering between steps: row r continues the hypothesis that lived in row d_beam_idx[r].
 extern "C" int mmdx_t5_reorder(mmdx_t5* e, const int32_t* d_beam_idx, void* stream) {
   T5_REQUIRE(e && d_beam_idx, "null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->R > 0, "mmdx_t5_reorder before mmdx_t5_begin");
   T5_CK(cudaSetDevice(e->device));
   if (e->t == 0) return 0;
@@ -498,7 +499,7 @@ extern "C" int mmdx_t5_reorder(mmdx_t5* e, const int32_t* d_beam_idx, void* stre
 // One decoder step: d_tokens [R] -> d_logits [R, vocab] fp32; the new position joins the cache.
 extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, void* stream) {
   T5_REQUIRE(e && d_tokens && d_logits, "null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->R > 0, "mmdx_t5_step before mmdx_t5_begin");
   T5_REQUIRE(e->t < e->Tmax, "more steps than mmdx_t5_begin reserved");
   T5_CK(cudaSetDevice(e->device));
@@ -533,7 +534,7 @@ extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_be
                                   int max_ban, int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores,
                                   int32_t* d_out_idx, void* stream) {
   T5_REQUIRE(e && d_logits && d_beam_scores && d_out_scores && d_out_idx, "null argument");
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->R > 0 && num_beams > 0 && e->R % num_beams == 0, "mmdx_t5_score_topk: rows must be studies x beams");
   T5_REQUIRE(k >= 1 && k <= kTopK && (max_ban == 0 || d_banned != nullptr), "mmdx_t5_score_topk: 1 <= k <= 8");
   T5_CK(cudaSetDevice(e->device));
@@ -548,6 +549,195 @@ extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_be
   t5_topk_kernel<<<e->R / num_beams, 1024, 0, s>>>(d_logits, stat, d_beam_scores, num_beams, e->vocab, k, d_out_scores, d_out_idx);
   e->launches += 2;
   T5_CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Whole generation in one call: the beam search of t5_fast.NativeBeamSearch (= HF GenerationMixin._beam_search for
+// do_sample = False, one EOS id, num_return_sequences = 1, with the min-new-tokens and no-repeat-n-gram processors) with
+// the per-token bookkeeping here on the host instead of in Python: per token one decoder step, the scoring / top-k
+// launches, one 2K-candidate read-back per study and a few dozen scalar operations.
+// early_stopping: 0 = False, 1 = True, 2 = "never".  h_out [B, max_new_tokens + 1] (start token first) is filled with HF's
+// fill value past each hypothesis; *h_out_len = the common output length HF would return (longest best hypothesis).
+__global__ void t5_repeat_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int K, long long row_elems) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * K * row_elems;
+  if (i >= total) return;
+  const long long r = i / row_elems, c = i - r * row_elems;
+  out[i] = in[(r / K) * row_elems + c];
+}
+
+extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_enc, int num_beams, int max_new_tokens,
+                                int min_new_tokens, int no_repeat_ngram, float length_penalty, int early_stopping, int eos_id,
+                                int pad_id, int start_id, const float* h_bias, int32_t* h_out, int32_t* h_out_len, void* stream) {
+  T5_REQUIRE(e && d_cond && h_bias && h_out && h_out_len, "null argument");
+  T5_REQUIRE(B > 0 && n_enc > 0 && num_beams >= 1 && 2 * num_beams <= kTopK && max_new_tokens >= 1 && max_new_tokens < 4096,
+             "mmdx_t5_generate: 1 <= num_beams <= 4, 1 <= max_new_tokens < 4096");
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  T5_REQUIRE(e->finalized, "weights not finalized");
+  T5_CK(cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int K = num_beams, K2 = 2 * K, R = B * K, V = e->vocab, prompt = 1, max_length = 1 + max_new_tokens;
+  const int fill = pad_id != 0 ? pad_id : eos_id;                 // HF: `pad_token_id or eos_token_id[0]`
+  const float NEG = -1.0e9f;
+  const double lp = (double)length_penalty;
+  // ---- device scratch of the search (freed on every exit path by the guard)
+  struct Scratch {
+    float *enc = nullptr, *logits = nullptr, *bscore = nullptr, *oscore = nullptr;
+    int32_t *tok = nullptr, *bidx = nullptr, *banned = nullptr, *oidx = nullptr;
+    float* h_oscore = nullptr; int32_t* h_oidx = nullptr;
+    ~Scratch() {
+      for (void* p : {(void*)enc, (void*)logits, (void*)bscore, (void*)oscore, (void*)tok, (void*)bidx, (void*)banned, (void*)oidx})
+        if (p) cudaFree(p);
+      if (h_oscore) cudaFreeHost(h_oscore);
+      if (h_oidx) cudaFreeHost(h_oidx);
+    }
+  } w;
+  const long long enc_row = (long long)n_enc * e->d;
+  const int max_ban = max_length;                                 // a row can ban at most one token per earlier position
+  T5_CK(cudaMalloc(&w.enc, (size_t)R * enc_row * 4));
+  T5_CK(cudaMalloc(&w.logits, (size_t)R * V * 4));
+  T5_CK(cudaMalloc(&w.bscore, (size_t)R * 4));
+  T5_CK(cudaMalloc(&w.oscore, (size_t)B * K2 * 4));
+  T5_CK(cudaMalloc(&w.tok, (size_t)R * 4));
+  T5_CK(cudaMalloc(&w.bidx, (size_t)R * 4));
+  T5_CK(cudaMalloc(&w.banned, (size_t)R * max_ban * 4));
+  T5_CK(cudaMalloc(&w.oidx, (size_t)B * K2 * 4));
+  T5_CK(cudaMallocHost(&w.h_oscore, (size_t)B * K2 * 4));
+  T5_CK(cudaMallocHost(&w.h_oidx, (size_t)B * K2 * 4));
+  {
+    const long long tot = (long long)R * enc_row;
+    t5_repeat_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_cond, w.enc, B, K, enc_row);
+    e->launches++;
+  }
+  if (mmdx_t5_begin(e, w.enc, R, n_enc, max_length, h_bias, s)) return 1;
+  // ---- host state (HF names): running = hypotheses still being extended, finished pool = `sequences` / `beam_scores`
+  std::vector<int32_t> run_seq((size_t)R * max_length, fill), seqs((size_t)R * max_length, fill);
+  std::vector<int32_t> tk_seq((size_t)B * K2 * max_length), m_seq((size_t)(K + K2) * max_length), new_run((size_t)R * max_length);
+  std::vector<float> run_scores(R, NEG), beam_scores(R, NEG);
+  std::vector<int> fin_len(R, 0);
+  std::vector<char> finished(R, 0), unsat(B, 1);
+  for (int b = 0; b < B; ++b) {
+    run_scores[b * K] = 0.f;
+    for (int k = 0; k < K; ++k) { run_seq[(size_t)(b * K + k) * max_length] = start_id; seqs[(size_t)(b * K + k) * max_length] = start_id; }
+  }
+  std::vector<int32_t> h_tok(R), h_bidx(R), h_banned((size_t)R * max_ban);
+  std::vector<float> h_bscore(R);
+  int cur_len = 1;
+  while (true) {
+    for (int r = 0; r < R; ++r) h_tok[r] = run_seq[(size_t)r * max_length + cur_len - 1];
+    T5_CK(cudaMemcpyAsync(w.tok, h_tok.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
+    if (mmdx_t5_step(e, w.tok, w.logits, s)) return 1;
+    // no-repeat-n-gram bans of every running row (HF NoRepeatNGramLogitsProcessor over the tokens generated so far)
+    int ban_w = 0;
+    const int n = no_repeat_ngram;
+    if (n > 0 && cur_len + 1 >= n) {
+      std::fill(h_banned.begin(), h_banned.end(), -1);
+      for (int r = 0; r < R; ++r) {
+        const int32_t* q = &run_seq[(size_t)r * max_length];
+        int cnt = 0;
+        for (int i = 0; i + n - 1 < cur_len; ++i) {              // window q[i .. i+n-2] against the current suffix
+          bool same = true;
+          for (int j = 0; j < n - 1 && same; ++j) same = q[i + j] == q[cur_len - n + 1 + j];
+          if (same) h_banned[(size_t)r * max_ban + cnt++] = q[i + n - 1];
+        }
+        ban_w = std::max(ban_w, cnt);
+      }
+      if (ban_w > 0) {
+        // repack to [R, ban_w]
+        std::vector<int32_t> packed((size_t)R * ban_w, -1);
+        for (int r = 0; r < R; ++r)
+          for (int c = 0; c < ban_w; ++c) packed[(size_t)r * ban_w + c] = h_banned[(size_t)r * max_ban + c];
+        T5_CK(cudaMemcpyAsync(w.banned, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, s));
+        T5_CK(cudaStreamSynchronize(s));                          // `packed` goes out of scope
+      }
+    }
+    const int ban_eos = (cur_len - prompt) < min_new_tokens ? 1 : 0;
+    for (int r = 0; r < R; ++r) h_bscore[r] = run_scores[r];
+    T5_CK(cudaMemcpyAsync(w.bscore, h_bscore.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
+    if (mmdx_t5_score_topk(e, w.logits, w.bscore, ban_w > 0 ? w.banned : nullptr, ban_w, ban_eos, eos_id, K, K2, w.oscore, w.oidx, s))
+      return 1;
+    T5_CK(cudaMemcpyAsync(w.h_oscore, w.oscore, (size_t)B * K2 * 4, cudaMemcpyDeviceToHost, s));
+    T5_CK(cudaMemcpyAsync(w.h_oidx, w.oidx, (size_t)B * K2 * 4, cudaMemcpyDeviceToHost, s));
+    T5_CK(cudaStreamSynchronize(s));
+    bool any_unsat = false, all_finished = true, all_hits = true;
+    for (int b = 0; b < B; ++b) {
+      const float* tks = w.h_oscore + (size_t)b * K2;
+      const int32_t* tki = w.h_oidx + (size_t)b * K2;
+      int src[kTopK], tokn[kTopK]; bool hit[kTopK]; float pool[kTopK];
+      for (int c = 0; c < K2; ++c) {
+        src[c] = tki[c] / V; tokn[c] = tki[c] % V;
+        int32_t* dst = &tk_seq[((size_t)b * K2 + c) * max_length];
+        std::copy_n(&run_seq[(size_t)(b * K + src[c]) * max_length], max_length, dst);
+        dst[cur_len] = tokn[c];
+        hit[c] = tokn[c] == eos_id || cur_len + 1 >= max_length;
+        pool[c] = tks[c] + (hit[c] ? 1.0f : 0.0f) * NEG;
+        all_hits = all_hits && hit[c];
+      }
+      // running beams of the next step: the best K continuations that did not stop (descending, ties: candidate order)
+      int order[kTopK];
+      for (int c = 0; c < K2; ++c) order[c] = c;
+      std::stable_sort(order, order + K2, [&](int a, int c2) { return pool[a] > pool[c2]; });
+      for (int k = 0; k < K; ++k) {
+        const int c = order[k];
+        std::copy_n(&tk_seq[((size_t)b * K2 + c) * max_length], max_length, &new_run[(size_t)(b * K + k) * max_length]);
+        run_scores[b * K + k] = pool[c];
+        h_bidx[b * K + k] = b * K + src[c];
+      }
+      // finished pool: only the top K of the 2K continuations may finish; merge with the stored ones, keep the best K
+      const float denom = (float)std::pow((double)(cur_len + 1 - prompt), lp);
+      bool full = true;
+      for (int k = 0; k < K; ++k) full = full && finished[b * K + k];
+      full = full && early_stopping == 1;
+      float m_scores[kTopK + 4]; char m_fin[kTopK + 4]; int m_len[kTopK + 4];
+      for (int k = 0; k < K; ++k) {
+        m_scores[k] = beam_scores[b * K + k]; m_fin[k] = finished[b * K + k]; m_len[k] = fin_len[b * K + k];
+        std::copy_n(&seqs[(size_t)(b * K + k) * max_length], max_length, &m_seq[(size_t)k * max_length]);
+      }
+      for (int c = 0; c < K2; ++c) {
+        const bool just = hit[c] && c < K;
+        float fs = tks[c] / denom;
+        fs = fs + (full ? 1.0f : 0.0f) * NEG;
+        fs = fs + (unsat[b] ? 0.0f : 1.0f) * NEG;
+        fs = fs + (just ? 0.0f : 1.0f) * NEG;
+        m_scores[K + c] = fs; m_fin[K + c] = just; m_len[K + c] = cur_len + 1 - prompt;
+        std::copy_n(&tk_seq[((size_t)b * K2 + c) * max_length], max_length, &m_seq[(size_t)(K + c) * max_length]);
+      }
+      int mo[kTopK + 4];
+      for (int c = 0; c < K + K2; ++c) mo[c] = c;
+      std::stable_sort(mo, mo + K + K2, [&](int a, int c2) { return m_scores[a] > m_scores[c2]; });
+      for (int k = 0; k < K; ++k) {
+        const int c = mo[k];
+        beam_scores[b * K + k] = m_scores[c]; finished[b * K + k] = m_fin[c]; fin_len[b * K + k] = m_len[c];
+        std::copy_n(&m_seq[(size_t)c * max_length], max_length, &seqs[(size_t)(b * K + k) * max_length]);
+      }
+    }
+    run_seq.swap(new_run);
+    T5_CK(cudaMemcpyAsync(w.bidx, h_bidx.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
+    if (mmdx_t5_reorder(e, w.bidx, s)) return 1;
+    ++cur_len;
+    // can a running beam still beat the worst finished hypothesis?
+    const int best_len = (early_stopping == 2 && lp > 0.0) ? (max_length - prompt) : (cur_len - prompt);
+    const float bden = (float)std::pow((double)best_len, lp);
+    for (int b = 0; b < B; ++b) {
+      const float best_possible = run_scores[b * K] / bden;
+      float mn = beam_scores[b * K];
+      for (int k = 1; k < K; ++k) mn = std::min(mn, beam_scores[b * K + k]);
+      bool any = false;
+      for (int k = 0; k < K; ++k) any = any || best_possible > (finished[b * K + k] ? mn : NEG);
+      unsat[b] = unsat[b] && any;
+      any_unsat = any_unsat || unsat[b];
+      for (int k = 0; k < K; ++k) all_finished = all_finished && finished[b * K + k];
+    }
+    const bool go_on = any_unsat && !(all_finished && early_stopping == 1) && !all_hits;
+    if (!go_on) break;
+  }
+  T5_CK(cudaStreamSynchronize(s));
+  int out_len = 0;
+  for (int b = 0; b < B; ++b) out_len = std::max(out_len, fin_len[b * K]);
+  out_len += prompt;
+  for (int b = 0; b < B; ++b) std::copy_n(&seqs[(size_t)(b * K) * max_length], max_length, h_out + (size_t)b * max_length);
+  *h_out_len = out_len;
   return 0;
 }
 

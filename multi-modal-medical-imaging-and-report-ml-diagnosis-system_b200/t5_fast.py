@@ -147,6 +147,26 @@ class MmdxStep:
         return out_s.cpu(), out_i.cpu().to(torch.int64)
 
 
+    def generate_native(self, cond, max_new_tokens, min_new_tokens, num_beams, no_repeat_ngram_size, length_penalty,
+                        early_stopping, eos_token_id, pad_token_id, decoder_start_token_id):
+        """The whole search in one C call (`mmdx_t5_generate`: the same algorithm as NativeBeamSearch, bookkeeping in C++)."""
+        C = self._C
+        B = cond.shape[0]
+        cond = cond.to(self.dev, torch.float32).contiguous()
+        bias = relative_position_bias_table(self.cfg, self._rel, int(max_new_tokens) + 1).contiguous()
+        out = torch.empty(B, int(max_new_tokens) + 1, dtype=torch.int32)
+        n = C.c_int32(0)
+        es = 1 if early_stopping is True else (2 if early_stopping == "never" else 0)
+        start = self.cfg.decoder_start_token_id if decoder_start_token_id is None else decoder_start_token_id
+        with torch.cuda.device(self.dev):
+            self._check(self._lib.mmdx_t5_generate(self._h, C.c_void_p(cond.data_ptr()), B, cond.shape[1], int(num_beams),
+                                                   int(max_new_tokens), int(min_new_tokens), int(no_repeat_ngram_size),
+                                                   float(length_penalty), es, int(eos_token_id), int(pad_token_id), int(start),
+                                                   C.c_void_p(bias.data_ptr()), C.c_void_p(out.data_ptr()), C.byref(n),
+                                                   self._stream()))
+        return out[:, :n.value].to(torch.int64)
+
+
 class NativeBeamSearch:
     """Beam search driven from here instead of from HF's Python loop: per token one decoder step, one scoring / top-k
     launch pair on the device and ~30 tiny host tensor ops, instead of the ~2.7 ms of eager-mode bookkeeping HF spends per
@@ -158,8 +178,10 @@ class NativeBeamSearch:
     `generate`.  Opt-in (`model_bundle["fast_report"] = "native"`): HF's loop over the CUDA step stays the default because
     it is HF's search by construction, while this one agrees with it up to fp32 rounding of near-tied scores."""
 
-    def __init__(self, backend, cfg):
-        self.be, self.cfg = backend, cfg
+    def __init__(self, backend, cfg, host_loop="auto"):
+        """host_loop: "python" keeps the bookkeeping in this file (what the CPU tests pin against HF); "auto" hands the whole
+        search to the backend's C++ loop when it has one (`MmdxStep.generate_native` -> `mmdx_t5_generate`, num_beams <= 4)."""
+        self.be, self.cfg, self.host_loop = backend, cfg, host_loop
 
     @staticmethod
     def _banned(seqs, cur_len, n):
@@ -191,6 +213,10 @@ class NativeBeamSearch:
         if unsupported:
             raise ValueError(f"NativeBeamSearch does not implement {sorted(unsupported)}")
         with _PATCH_LOCK:                 # the step backend holds ONE generation's KV cache
+            if self.host_loop == "auto" and hasattr(self.be, "generate_native") and int(num_beams) <= 4:
+                return self.be.generate_native(cond, max_new_tokens, min_new_tokens, num_beams, no_repeat_ngram_size,
+                                               length_penalty, early_stopping, eos_token_id, pad_token_id,
+                                               decoder_start_token_id)
             return self._generate(cond, max_new_tokens, min_new_tokens, num_beams, no_repeat_ngram_size, length_penalty,
                                   early_stopping, eos_token_id, pad_token_id, decoder_start_token_id)
 

@@ -133,17 +133,49 @@ def test_native_beam_search_on_the_cuda_kernels(t5):
         got_loop = loop.generate(cond, **kw)
         torch.cuda.synchronize()
         t_loop = time.perf_counter() - t0
-        nat = NativeBeamSearch(step, t5.config)
+        nat = NativeBeamSearch(step, t5.config, host_loop="python")
         nat.generate(cond, **dict(kw, max_new_tokens=4, min_new_tokens=0))
         t0 = time.perf_counter()
         got = nat.generate(cond, **kw)
         torch.cuda.synchronize()
         t_nat = time.perf_counter() - t0
+        cpp = NativeBeamSearch(step, t5.config)                      # bookkeeping in C++ (mmdx_t5_generate)
+        cpp.generate(cond, **dict(kw, max_new_tokens=4, min_new_tokens=0))
+        t0 = time.perf_counter()
+        got_cpp = cpp.generate(cond, **kw)
+        t_cpp = time.perf_counter() - t0
         print(f"generate {n_new} tokens x 4 beams x {B} studies: HF eager {t_hf * 1e3:.0f} ms, HF loop over the CUDA step "
-              f"{t_loop * 1e3:.0f} ms, native search {t_nat * 1e3:.0f} ms")
+              f"{t_loop * 1e3:.0f} ms, native search (python bookkeeping) {t_nat * 1e3:.0f} ms, (C++ bookkeeping) {t_cpp * 1e3:.0f} ms")
         assert torch.equal(want, got_loop)
         assert want.shape == got.shape and torch.equal(want.cpu(), got), (want.tolist(), got.tolist())
+        assert want.shape == got_cpp.shape and torch.equal(want.cpu(), got_cpp), (want.tolist(), got_cpp.tolist())
         step.close()
+
+
+def test_cpp_search_with_finishing_hypotheses(t5):
+    """mmdx_t5_generate against the Python bookkeeping (pinned against HF on the CPU) with EOS made likely - hypotheses
+    finishing at different lengths, early stopping, HF's padding - and across beam counts / penalties / stopping modes."""
+    import copy
+    from mmdx_b200.t5_fast import NativeBeamSearch
+    m = copy.deepcopy(t5)
+    torch.manual_seed(7)
+    with torch.no_grad():                      # an EOS row that scores well against typical decoder states
+        h = torch.randn(64, 512, device="cuda")
+        m.shared.weight[1] = 6.0 * m.shared.weight[torch.randint(0, 32128, (64,), device="cuda")].mean(0) + 0.25
+    step = MmdxStep(m)
+    n_short = 0
+    for seed in range(8):
+        torch.manual_seed(200 + seed)
+        cond = torch.randn(2, 4, 512, device="cuda")
+        kw = dict(max_new_tokens=28, min_new_tokens=(0 if seed % 2 else 3), num_beams=(4 if seed % 4 else 2),
+                  length_penalty=(1.1 if seed % 3 else 0.7), early_stopping=(True, False, "never")[seed % 3], eos_token_id=1,
+                  pad_token_id=0, no_repeat_ngram_size=(3 if seed % 2 else 2))
+        a = NativeBeamSearch(step, m.config, host_loop="python").generate(cond, **kw)
+        b = NativeBeamSearch(step, m.config).generate(cond, **kw)
+        assert a.shape == b.shape and torch.equal(a, b), (seed, a.tolist(), b.tolist())
+        n_short += int(a.shape[1] < 29 or bool((a[:, 1:] == 1).any()))
+    print("runs with an EOS / early finish:", n_short)
+    step.close()
 
 
 def test_score_topk_kernel_vs_torch(t5):
