@@ -131,9 +131,13 @@ __global__ void __launch_bounds__(128) t5_self_attn_kernel(const float* __restri
   __syncthreads();
   float mx = -INFINITY;
   for (int j = tid; j <= t; j += 128) {
-    const float* kj = kc + static_cast<size_t>(j) * dk;
+    const float4* kj = reinterpret_cast<const float4*>(kc + static_cast<size_t>(j) * dk);      // 16-byte loads of this key's row
+    const float4* q4 = reinterpret_cast<const float4*>(q);
     float s = 0.f;
-    for (int d = 0; d < dk; ++d) s = fmaf(q[d], kj[d], s);
+    for (int d = 0; d < dk / 4; ++d) {
+      const float4 kv = kj[d], qv = q4[d];
+      s = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, fmaf(qv.z, kv.z, fmaf(qv.w, kv.w, s))));
+    }
     s += bias[static_cast<size_t>(t - j) * H + h];
     p[j] = s;
     mx = fmaxf(mx, s);
@@ -150,11 +154,23 @@ __global__ void __launch_bounds__(128) t5_self_attn_kernel(const float* __restri
   if ((tid & 31) == 0) red[tid >> 5] = sum;
   __syncthreads();
   const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-  if (tid < dk) {
-    float o = 0.f;
-    for (int j = 0; j <= t; ++j) o = fmaf(p[j] * inv, vc[static_cast<size_t>(j) * dk + tid], o);
-    out[static_cast<size_t>(r) * inner + h * dk + tid] = o;
+  // P V: the two halves of the block take alternate keys (independent loads, four in flight), then meet in shared memory
+  __shared__ float part[64];
+  const int d = tid & 63, half = tid >> 6;
+  float o = 0.f;
+  if (d < dk) {
+    int j = half;
+    for (; j + 6 <= t; j += 8) {
+      const float v0 = vc[static_cast<size_t>(j) * dk + d], v1 = vc[static_cast<size_t>(j + 2) * dk + d];
+      const float v2 = vc[static_cast<size_t>(j + 4) * dk + d], v3 = vc[static_cast<size_t>(j + 6) * dk + d];
+      o = fmaf(p[j] * inv, v0, o); o = fmaf(p[j + 2] * inv, v1, o);
+      o = fmaf(p[j + 4] * inv, v2, o); o = fmaf(p[j + 6] * inv, v3, o);
+    }
+    for (; j <= t; j += 2) o = fmaf(p[j] * inv, vc[static_cast<size_t>(j) * dk + d], o);
   }
+  if (half == 1 && d < dk) part[d] = o;
+  __syncthreads();
+  if (half == 0 && d < dk) out[static_cast<size_t>(r) * inner + h * dk + d] = o + part[d];
 }
 
 // Cross-attention of the new token against the projected conditioning tokens: q [R, inner], K / V [R, H, n_enc, dk].

@@ -159,9 +159,15 @@ def test_cpp_search_with_finishing_hypotheses(t5):
     from mmdx_b200.t5_fast import NativeBeamSearch
     m = copy.deepcopy(t5)
     torch.manual_seed(7)
-    with torch.no_grad():                      # an EOS row that scores well against typical decoder states
-        h = torch.randn(64, 512, device="cuda")
-        m.shared.weight[1] = 6.0 * m.shared.weight[torch.randint(0, 32128, (64,), device="cuda")].mean(0) + 0.25
+    with torch.no_grad():
+        # random-init decoder states share a strong common direction; an EOS embedding along it makes EOS competitive at
+        # every step (tied LM head), so hypotheses finish at different lengths
+        ids = torch.randint(0, 32128, (4, 12), device="cuda")
+        out = m(decoder_input_ids=ids, encoder_outputs=BaseModelOutput(last_hidden_state=torch.randn(4, 4, 512, device="cuda")),
+                output_hidden_states=True)
+        u = out.decoder_hidden_states[-1].reshape(-1, 512)
+        v = (u / u.norm(dim=-1, keepdim=True)).mean(0)
+        m.shared.weight[1] = 14.0 * v / v.norm()
     step = MmdxStep(m)
     n_short = 0
     for seed in range(8):
@@ -175,6 +181,7 @@ def test_cpp_search_with_finishing_hypotheses(t5):
         assert a.shape == b.shape and torch.equal(a, b), (seed, a.tolist(), b.tolist())
         n_short += int(a.shape[1] < 29 or bool((a[:, 1:] == 1).any()))
     print("runs with an EOS / early finish:", n_short)
+    assert n_short >= 3
     step.close()
 
 
