@@ -186,6 +186,8 @@ int mmdx_t5_generate(mmdx_t5* t, const float* d_cond, int B, int n_enc, int num_
                      int no_repeat_ngram, float length_penalty, int early_stopping, int eos_id, int pad_id, int start_id,
                      const float* h_bias, int32_t* h_out, int32_t* h_out_len, void* stream);
 int64_t mmdx_t5_launch_count(mmdx_t5* t);
+/* Debug aid: globaltimer (ns) at the phase boundaries of the last decoder step (needs MMDX_T5_PROF=1 at the first step). */
+int mmdx_t5_step_profile(mmdx_t5* t, uint64_t* h_out, int cap, int* n_out);
 const char* mmdx_t5_last_error(void);
 
 /* ---- single-kernel entry points (parity tests call the hot kernels one at a time) ---------- */

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mmdx_t5_score_topk": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "mmdx_t5_generate": [_p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _p, _p, _p, _p],
     "mmdx_t5_launch_count": [_p],
+    "mmdx_t5_step_profile": [_p, _p, C.c_int, _p],
     "mmdx_t5_last_error": [],
     "mmdx_op_gemm": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "mmdx_op_gemm_ln": [_p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _f, _p, _i64, _i, _i, _i, _p],

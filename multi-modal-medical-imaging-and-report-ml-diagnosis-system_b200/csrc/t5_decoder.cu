@@ -4,20 +4,25 @@
 //
 // One step = one new token for each of R = batch x beams rows.  With R <= 64 every contraction is a skinny GEMV-like
 // product whose cost is reading the weights once (t5-small decoder + tied LM head: 41 M parameters, 165 MB fp32 per
-// step), so this is HBM-bound work on the CUDA cores: fp32 weights, fp32 arithmetic (the beam search compares sums of
-// log-probabilities; fp32 keeps the token sequence identical to HF's eager fp32 path), 50 launches per step:
+// step), so this is HBM/latency-bound work on the CUDA cores: fp32 weights, fp32 arithmetic (the beam search compares sums
+// of log-probabilities; fp32 keeps the token sequence identical to HF's eager fp32 path):
 //   x = E[token]
 //   per block:  qkv = RMSNorm(x) [Wq;Wk;Wv]^T ; self-attention over the cache (+ relative-position bias, no 1/sqrt(d)) ;
 //               x += attn Wo^T ; q = RMSNorm(x) Wq^T ; cross-attention over the projected conditioning tokens ;
 //               x += attn Wo^T ; x += relu(RMSNorm(x) Wi^T) Wo^T
 //   logits = (RMSNorm(x) * d_model^-0.5) E^T            (tied embeddings; lm_head.weight when untied)
-// The beam search itself stays HF's code (mmdx_b200/t5_fast.py swaps only the model call), which reorders the cache
-// through mmdx_t5_reorder.
+// The whole step is ONE cooperative launch (t5_step_mega_kernel: one 512-thread CTA per SM, the 50 dependent phases
+// separated by grid-wide barriers instead of kernel boundaries): at 8 rows a phase is a few microseconds of work, so 50
+// launches cost ~1 ms per token where the phases themselves need ~0.15 ms.  The self-attention cache is never moved by
+// the beam search: a hypothesis keeps, per position, the row slot that wrote that position (its ancestry), and
+// mmdx_t5_reorder permutes those small index rows instead of copying keys and values.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -47,13 +52,6 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-__global__ void t5_embed_kernel(const int32_t* __restrict__ tok, const float* __restrict__ E, int d, int vocab,
-                                float* __restrict__ x) {
-  const int r = blockIdx.x;
-  const int id = min(max(tok[r], 0), vocab - 1);
-  for (int i = threadIdx.x; i < d; i += blockDim.x) x[static_cast<size_t>(r) * d + i] = E[static_cast<size_t>(id) * d + i];
 }
 
 // out[r, n] (+= res) = act( (RMSNorm(x[r]) * in_scale) . W[n] ),  W [N, K] row-major, no bias (T5 Linear layers have none).
@@ -109,93 +107,320 @@ __global__ void __launch_bounds__(256) t5_linear_kernel(const float* __restrict_
   }
 }
 
-// Self-attention of the new token against the cache.  grid (heads, rows), 128 threads.
-// qkv [R, 3*inner] (q | k | v), cache_k / cache_v [R, H, Tmax, dk]; position t is written first.
-// scores[j] = q . k_j + bias[(t - j) * H + h]  (no scaling in T5), softmax in fp32, out [R, inner].
-__global__ void __launch_bounds__(128) t5_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ ck,
-                                                           float* __restrict__ cv, const float* __restrict__ bias, int H,
-                                                           int dk, int Tmax, int t, float* __restrict__ out) {
-  extern __shared__ float sm[];       // q[dk] | p[Tmax]
-  __shared__ float red[4];
-  float* q = sm;
-  float* p = sm + dk;
-  const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, inner = H * dk;
-  const float* row = qkv + static_cast<size_t>(r) * 3 * inner;
-  float* kc = ck + (static_cast<size_t>(r) * H + h) * Tmax * dk;
-  float* vc = cv + (static_cast<size_t>(r) * H + h) * Tmax * dk;
-  if (tid < dk) {
-    q[tid] = row[h * dk + tid];
-    kc[static_cast<size_t>(t) * dk + tid] = row[inner + h * dk + tid];
-    vc[static_cast<size_t>(t) * dk + tid] = row[2 * inner + h * dk + tid];
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int j = tid; j <= t; j += 128) {
-    const float4* kj = reinterpret_cast<const float4*>(kc + static_cast<size_t>(j) * dk);      // 16-byte loads of this key's row
-    const float4* q4 = reinterpret_cast<const float4*>(q);
-    float s = 0.f;
-    for (int d = 0; d < dk / 4; ++d) {
-      const float4 kv = kj[d], qv = q4[d];
-      s = fmaf(qv.x, kv.x, fmaf(qv.y, kv.y, fmaf(qv.z, kv.z, fmaf(qv.w, kv.w, s))));
-    }
-    s += bias[static_cast<size_t>(t - j) * H + h];
-    p[j] = s;
-    mx = fmaxf(mx, s);
-  }
+// ---- the decoder step as one cooperative kernel ---------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kMegaThreads = 512, kMegaWarps = kMegaThreads / 32;
+
+struct T5Layer {                      // device copy of one block's pointers
+  const float *ln0, *qkv, *so, *ln1, *cq, *co, *ln2, *wi, *wo;
+  float *sk, *sv;                     // self-attention cache [R, H, Tmax, dk]: slot (r, j) is written once, at step j, by row r
+  const float *ck, *cv;               // projected conditioning tokens [R, H, n_enc, dk]
+};
+
+struct T5StepArgs {
+  const int32_t* tok; float* logits;
+  const float *E, *lm, *final_ln, *bias;
+  const T5Layer* layers;
+  int32_t* anc;                       // [R, Tmax]: anc[r][j] = the row slot that holds position j of row r's hypothesis
+  float *x, *qkv, *att, *q, *hid;
+  float eps, lm_scale;
+  int R, d, H, dk, ff, L, vocab, Tmax, t, n_enc, kmax;
+  unsigned long long* prof;           // optional: globaltimer stamp per phase boundary, written by CTA 0 (mmdx_t5_step_profile)
+};
+
+__device__ __forceinline__ float dot4(const float4 w, const float4 v, float acc) {
+  return fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, acc))));
+}
+
+// One linear layer spread over the whole grid: out[r, c] (+= res) = act((RMSNorm(x[r]) * in_scale) . W[c]).  The NR rows of
+// x are staged (normalised) in every CTA's shared memory; a warp owns one column (two when there are more columns than
+// 2 x warps: the x reads from shared memory are then shared by both, which keeps the 65 MB LM head on the HBM side of
+// the shared-memory roofline), or a quarter of a column's K range when there are fewer columns than a quarter of the
+// warps (the four partial sums meet in shared memory, in a fixed order).  Columns are dealt round-robin over the CTAs so
+// that a narrow layer still streams through every SM.
+// The grid barrier that separates this phase from its producer sits INSIDE, behind the first batch of weight loads: the
+// weights do not depend on the previous phase, so their HBM / L2 latency runs under the barrier and the staging of x.
+template <int NR>
+__device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& grid, const float* x, long long ldx,
+                                         const float* __restrict__ ln_w, float in_scale, const float* __restrict__ W, float* out,
+                                         long long ldo, const float* res, int K, int N, int relu, bool stream_w, float* xs,
+                                         float* part) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nb = gridDim.x, bid = blockIdx.x;
+  const int GW = nb * kMegaWarps;
+  const int KS = (N * 4 <= GW && K % 512 == 0) ? 4 : 1;
+  const int NC = N >= 2 * GW ? 2 : 1;
+  const int slots = kMegaWarps / KS, slot = warp / KS, kp = warp % KS;
+  const int kq = K / 4 / KS;                                     // float4 per warp task (a multiple of 32)
+  const int groups = (N + slots * NC - 1) / (slots * NC);
+  float4 wa[4], wb[4];
+  auto load_batch = [&](int c0, int i0) {                        // four independent 16-byte loads per column in flight
+    const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<size_t>(c0) * K) + kp * kq;
+    const bool two = NC == 2 && c0 + 1 < N;
+    const float4* w1 = w0 + (two ? K / 4 : 0);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  __syncthreads();
-  float sum = 0.f;
-  for (int j = tid; j <= t; j += 128) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
-  sum = warp_sum_f(sum);
-  if ((tid & 31) == 0) red[tid >> 5] = sum;
-  __syncthreads();
-  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-  // P V: the two halves of the block take alternate keys (independent loads, four in flight), then meet in shared memory
-  __shared__ float part[64];
-  const int d = tid & 63, half = tid >> 6;
-  float o = 0.f;
-  if (d < dk) {
-    int j = half;
-    for (; j + 6 <= t; j += 8) {
-      const float v0 = vc[static_cast<size_t>(j) * dk + d], v1 = vc[static_cast<size_t>(j + 2) * dk + d];
-      const float v2 = vc[static_cast<size_t>(j + 4) * dk + d], v3 = vc[static_cast<size_t>(j + 6) * dk + d];
-      o = fmaf(p[j] * inv, v0, o); o = fmaf(p[j + 2] * inv, v1, o);
-      o = fmaf(p[j + 4] * inv, v2, o); o = fmaf(p[j + 6] * inv, v3, o);
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < kq) {
+        wa[u] = stream_w ? __ldcs(w0 + i) : __ldg(w0 + i);
+        if (two) wb[u] = stream_w ? __ldcs(w1 + i) : __ldg(w1 + i);
+      }
     }
-    for (; j <= t; j += 2) o = fmaf(p[j] * inv, vc[static_cast<size_t>(j) * dk + d], o);
+  };
+  bool preloaded = false;
+  if (bid < groups && (bid * slots + slot) * NC < N) { load_batch((bid * slots + slot) * NC, lane); preloaded = true; }
+  constexpr int XR = 4;                                          // float4 per lane of a row kept in registers (K <= 512)
+  float4 gw[XR];                                                 // the norm weights are constants too
+  const bool in_regs = ln_w != nullptr && K <= XR * 128;
+  if (in_regs) {
+#pragma unroll
+    for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) gw[u] = __ldg(reinterpret_cast<const float4*>(ln_w) + lane + 32 * u);
   }
-  if (half == 1 && d < dk) part[d] = o;
-  __syncthreads();
-  if (half == 0 && d < dk) out[static_cast<size_t>(r) * inner + h * dk + d] = o + part[d];
+  grid.sync();
+  for (int r0 = 0; r0 < a.R; r0 += NR) {
+    __syncthreads();                                             // the previous readers of xs are done
+    if (ln_w == nullptr) {                                       // plain copy (x in_scale): every thread, independent 16-byte loads
+      const int k4 = K / 4, tot = NR * k4;
+#pragma unroll 4
+      for (int i = tid; i < tot; i += kMegaThreads) {
+        const int r = i / k4, k = i - r * k4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < a.R) v = reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * ldx)[k];
+        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+        reinterpret_cast<float4*>(xs)[i] = v;
+      }
+    }
+    for (int r = warp; r < NR && ln_w != nullptr; r += kMegaWarps) {
+      float4* dst = reinterpret_cast<float4*>(xs + static_cast<size_t>(r) * K);
+      if (r0 + r >= a.R) { for (int k = lane; k < K / 4; k += 32) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+      const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * ldx);
+      if (in_regs) {                  // T5LayerNorm: x * rsqrt(mean(x^2) + eps) * w  (no mean subtraction, no bias); one read of x
+        float4 xv4[XR];
+        float q = 0.f;
+#pragma unroll
+        for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) xv4[u] = src[lane + 32 * u];
+#pragma unroll
+        for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) q = dot4(xv4[u], xv4[u], q);
+        const float sc = in_scale * rsqrtf(warp_sum_f(q) / K + a.eps);
+#pragma unroll
+        for (int u = 0; u < XR; ++u) {
+          if (lane + 32 * u < K / 4) {
+            float4 v = xv4[u];
+            v.x = v.x * sc * gw[u].x; v.y = v.y * sc * gw[u].y; v.z = v.z * sc * gw[u].z; v.w = v.w * sc * gw[u].w;
+            dst[lane + 32 * u] = v;
+          }
+        }
+        continue;
+      }
+      float sc = in_scale;
+      if (ln_w != nullptr) {
+        float q = 0.f;
+        for (int k = lane; k < K / 4; k += 32) { const float4 v = src[k]; q = dot4(v, v, q); }
+        sc *= rsqrtf(warp_sum_f(q) / K + a.eps);
+      }
+      for (int k = lane; k < K / 4; k += 32) {
+        float4 v = src[k];
+        const float4 g = ln_w != nullptr ? reinterpret_cast<const float4*>(ln_w)[k] : make_float4(1.f, 1.f, 1.f, 1.f);
+        v.x = v.x * sc * g.x; v.y = v.y * sc * g.y; v.z = v.z * sc * g.z; v.w = v.w * sc * g.w;
+        dst[k] = v;
+      }
+    }
+    __syncthreads();
+    for (int g = bid; g < groups; g += nb) {                     // trip count is uniform over the CTA
+      const int c0 = (g * slots + slot) * NC;
+      const bool on = c0 < N, two = NC == 2 && c0 + 1 < N;
+      const int oc = c0 + lane / NR, orow = r0 + lane % NR;       // the output element this lane writes (kp == 0 warps)
+      const bool writes = on && kp == 0 && lane < NR * NC && oc < N && orow < a.R;
+      float resv = 0.f;
+      if (writes && res != nullptr) resv = res[static_cast<size_t>(orow) * ldo + oc];     // in flight under the products
+      float acc0[NR], acc1[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+      if (on) {
+        const float4* xv = reinterpret_cast<const float4*>(xs) + kp * kq;
+        for (int i0 = lane; i0 < kq; i0 += 128) {
+          if (!(preloaded && i0 == lane)) load_batch(c0, i0);
+          preloaded = false;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < kq) {
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                const float4 v = xv[static_cast<size_t>(r) * (K / 4) + i];
+                acc0[r] = dot4(wa[u], v, acc0[r]);
+                if (two) acc1[r] = dot4(wb[u], v, acc1[r]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { acc0[r] = warp_sum_f(acc0[r]); if (NC == 2) acc1[r] = warp_sum_f(acc1[r]); }
+      float v = 0.f;                                             // lane l holds (column l / NR, row l % NR)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { if (lane == r) v = acc0[r]; if (lane == NR + r) v = acc1[r]; }
+      if (KS > 1) {
+        if (lane < NR) part[warp * NR + lane] = v;
+        __syncthreads();
+        if (kp == 0 && lane < NR) {
+          v = part[warp * NR + lane];
+          for (int q = 1; q < KS; ++q) v += part[(warp + q) * NR + lane];
+        }
+        __syncthreads();
+      }
+      if (writes) {
+        if (relu) v = fmaxf(v, 0.f);
+        out[static_cast<size_t>(orow) * ldo + oc] = v + resv;
+      }
+    }
+  }
+}
+
+// Self-attention of the new token against the cache, one (row, head) per CTA.  qkv [R, 3*inner] (q | k | v); position t is
+// written into the row's own slot first; key j < t is read from slot anc[r][j].  scores[j] = q . k_j + bias[(t - j) * H + h]
+// (no scaling in T5), softmax in fp32, out [R, inner].
+__device__ void mega_self_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
+  float* q = sm;                      // [64]
+  float* red = sm + 64;               // [32]
+  float* part = sm + 96;              // [32 key groups][64]
+  float* p = sm + 96 + 2048;          // [Tmax]
+  int* slot = reinterpret_cast<int*>(p + a.Tmax);      // [Tmax]: row slot of every position of this hypothesis
+  const int tid = threadIdx.x, H = a.H, dk = a.dk, Tmax = a.Tmax, t = a.t, inner = H * dk;
+  for (int item = blockIdx.x; item < a.R * H; item += gridDim.x) {
+    const int r = item / H, h = item - r * H;
+    __syncthreads();
+    const float* row = a.qkv + static_cast<size_t>(r) * 3 * inner;
+    const int32_t* an = a.anc + static_cast<size_t>(r) * Tmax;
+    for (int j = tid; j <= t; j += kMegaThreads) slot[j] = j == t ? r : an[j];
+    if (tid < dk) {
+      const size_t own = ((static_cast<size_t>(r) * H + h) * Tmax + t) * dk + tid;
+      q[tid] = row[h * dk + tid];
+      L.sk[own] = row[inner + h * dk + tid];
+      L.sv[own] = row[2 * inner + h * dk + tid];
+    }
+    if (h == 0 && tid == 0) a.anc[static_cast<size_t>(r) * Tmax + t] = r;
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = tid; j <= t; j += kMegaThreads) {
+      const float4* kj = reinterpret_cast<const float4*>(L.sk + ((static_cast<size_t>(slot[j]) * H + h) * Tmax + j) * dk);
+      const float4* q4 = reinterpret_cast<const float4*>(q);
+      float s = 0.f;
+#pragma unroll 4
+      for (int d = 0; d < dk / 4; ++d) s = dot4(q4[d], kj[d], s);
+      s += a.bias[static_cast<size_t>(t - j) * H + h];
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < kMegaWarps; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j <= t; j += kMegaThreads) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
+    sum = warp_sum_f(sum);
+    if ((tid & 31) == 0) red[tid >> 5] = sum;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < kMegaWarps; ++w) tot += red[w];
+    const float inv = 1.0f / tot;
+    // P V: 32 groups of 16 threads (four dims each, 16-byte loads) take every 32nd key; partial sums meet in shared memory
+    const int d4 = tid & 15, g = tid >> 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d4 * 4 < dk) {
+#pragma unroll 4
+      for (int j = g; j <= t; j += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(L.sv + ((static_cast<size_t>(slot[j]) * H + h) * Tmax + j) * dk + d4 * 4);
+        const float w = p[j] * inv;
+        o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y); o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
+      }
+    }
+    reinterpret_cast<float4*>(part)[g * 16 + d4] = o;
+    __syncthreads();
+    if (tid < dk) {
+      float v = part[tid];
+      for (int q8 = 1; q8 < 32; ++q8) v += part[q8 * 64 + tid];
+      a.att[static_cast<size_t>(r) * inner + h * dk + tid] = v;
+    }
+  }
 }
 
 // Cross-attention of the new token against the projected conditioning tokens: q [R, inner], K / V [R, H, n_enc, dk].
-__global__ void __launch_bounds__(64) t5_cross_attn_kernel(const float* __restrict__ qm, const float* __restrict__ K,
-                                                           const float* __restrict__ V, int H, int dk, int n_enc,
-                                                           float* __restrict__ out) {
-  __shared__ float p[64];
-  const int h = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, inner = H * dk;
-  const float* q = qm + static_cast<size_t>(r) * inner + h * dk;
-  const float* kc = K + (static_cast<size_t>(r) * H + h) * n_enc * dk;
-  const float* vc = V + (static_cast<size_t>(r) * H + h) * n_enc * dk;
-  if (tid < n_enc) {
-    float s = 0.f;
-    for (int d = 0; d < dk; ++d) s = fmaf(q[d], kc[static_cast<size_t>(tid) * dk + d], s);
-    p[tid] = s;
+__device__ void mega_cross_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
+  float* p = sm;                      // [64]
+  const int tid = threadIdx.x, H = a.H, dk = a.dk, n_enc = a.n_enc, inner = H * dk;
+  for (int item = blockIdx.x; item < a.R * H; item += gridDim.x) {
+    const int r = item / H, h = item - r * H;
+    __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(a.q + static_cast<size_t>(r) * inner + h * dk);
+    const float* kc = L.ck + (static_cast<size_t>(r) * H + h) * n_enc * dk;
+    const float* vc = L.cv + (static_cast<size_t>(r) * H + h) * n_enc * dk;
+    if (tid < n_enc) {
+      const float4* kj = reinterpret_cast<const float4*>(kc + static_cast<size_t>(tid) * dk);
+      float s = 0.f;
+      for (int d = 0; d < dk / 4; ++d) s = dot4(q4[d], kj[d], s);
+      p[tid] = s;
+    }
+    __syncthreads();
+    if (tid < dk) {
+      float mx = -INFINITY, sum = 0.f;
+      for (int j = 0; j < n_enc; ++j) mx = fmaxf(mx, p[j]);
+      for (int j = 0; j < n_enc; ++j) sum += expf(p[j] - mx);
+      float o = 0.f;
+      for (int j = 0; j < n_enc; ++j) o = fmaf(expf(p[j] - mx) / sum, vc[static_cast<size_t>(j) * dk + tid], o);
+      a.att[static_cast<size_t>(r) * inner + h * dk + tid] = o;
+    }
   }
-  __syncthreads();
-  float mx = -INFINITY, sum = 0.f;
-  for (int j = 0; j < n_enc; ++j) mx = fmaxf(mx, p[j]);
-  for (int j = 0; j < n_enc; ++j) sum += expf(p[j] - mx);
-  if (tid < dk) {
-    float o = 0.f;
-    for (int j = 0; j < n_enc; ++j) o = fmaf(expf(p[j] - mx) / sum, vc[static_cast<size_t>(j) * dk + tid], o);
-    out[static_cast<size_t>(r) * inner + h * dk + tid] = o;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kMegaThreads, 1) t5_step_mega_kernel(const T5StepArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float sm[];       // linear phases: xs [NR][kmax] | part [warps][NR]; attention phases: see there
+  float* xs = sm;
+  float* part = sm + static_cast<size_t>(NR) * a.kmax;
+  const int d = a.d, inner = a.H * a.dk;
+  int np = 0;
+  auto stamp = [&]() {
+    if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+      a.prof[np] = tns;
+    }
+    ++np;
+  };
+  stamp();
+  for (int i = blockIdx.x * kMegaThreads + threadIdx.x; i < a.R * d; i += gridDim.x * kMegaThreads) {
+    const int r = i / d, k = i - r * d;
+    const int id = min(max(a.tok[r], 0), a.vocab - 1);
+    a.x[i] = a.E[static_cast<size_t>(id) * d + k];
   }
+  for (int l = 0; l < a.L; ++l) {                                // every mega_linear starts with the barrier behind its producer
+    const T5Layer& L = a.layers[l];
+    mega_linear<NR>(a, grid, a.x, d, L.ln0, 1.0f, L.qkv, a.qkv, 3 * inner, nullptr, d, 3 * inner, 0, false, xs, part);
+    stamp();
+    grid.sync();
+    mega_self_attn(a, L, sm);
+    stamp();
+    mega_linear<NR>(a, grid, a.att, inner, nullptr, 1.0f, L.so, a.x, d, a.x, inner, d, 0, false, xs, part);
+    stamp();
+    mega_linear<NR>(a, grid, a.x, d, L.ln1, 1.0f, L.cq, a.q, inner, nullptr, d, inner, 0, false, xs, part);
+    stamp();
+    grid.sync();
+    mega_cross_attn(a, L, sm);
+    stamp();
+    mega_linear<NR>(a, grid, a.att, inner, nullptr, 1.0f, L.co, a.x, d, a.x, inner, d, 0, false, xs, part);
+    stamp();
+    mega_linear<NR>(a, grid, a.x, d, L.ln2, 1.0f, L.wi, a.hid, a.ff, nullptr, d, a.ff, 1, false, xs, part);
+    stamp();
+    mega_linear<NR>(a, grid, a.hid, a.ff, nullptr, 1.0f, L.wo, a.x, d, a.x, a.ff, d, 0, false, xs, part);
+    stamp();
+  }
+  // the LM head streams 65 MB once per step: evict-first loads keep the 88 MB of layer weights in the 126 MB L2
+  mega_linear<NR>(a, grid, a.x, d, a.final_ln, a.lm_scale, a.lm, a.logits, a.vocab, nullptr, d, a.vocab, 0, true, xs, part);
+  stamp();
 }
 
 // enc-side K / V: proj [R * n_enc, inner] -> [R, H, n_enc, dk]
@@ -211,84 +436,72 @@ __global__ void t5_split_heads_kernel(const float* __restrict__ in, int R, int n
   out[i] = in[(static_cast<size_t>(r) * n_enc + j) * H * dk + h * dk + d];
 }
 
-// beam reordering of the self-attention cache: dst[r] = src[idx[r]] for positions [0, t)
-__global__ void t5_reorder_kernel(const float* __restrict__ src, float* __restrict__ dst, const int32_t* __restrict__ idx, int H,
-                                  int Tmax, int dk, int t, int R) {
-  const int r = blockIdx.y, h = blockIdx.x;
+// beam reordering: row r continues the hypothesis of row idx[r] - only the ancestry rows move, positions [0, t)
+__global__ void t5_reorder_anc_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const int32_t* __restrict__ idx,
+                                      int Tmax, int t, int R) {
+  const int r = blockIdx.x;
   const int s = min(max(idx[r], 0), R - 1);
-  const float4* a = reinterpret_cast<const float4*>(src + (static_cast<size_t>(s) * H + h) * Tmax * dk);
-  float4* b = reinterpret_cast<float4*>(dst + (static_cast<size_t>(r) * H + h) * Tmax * dk);
-  for (int i = threadIdx.x; i < t * dk / 4; i += blockDim.x) b[i] = a[i];
+  for (int j = threadIdx.x; j < t; j += blockDim.x) dst[static_cast<size_t>(r) * Tmax + j] = src[static_cast<size_t>(s) * Tmax + j];
 }
 
-// ---- beam-search scoring (native search, mmdx_b200/t5_fast.py NativeBeamSearch)
-// Row statistics of log_softmax: (max, log(sum exp(x - max))) per row, in HF's formulation lp = (x - max) - log(sum).
-__global__ void __launch_bounds__(1024) t5_row_lse_kernel(const float* __restrict__ logits, int V, float* __restrict__ stat) {
-  __shared__ float red[32];
-  const int r = blockIdx.x, tid = threadIdx.x;
-  const float* x = logits + static_cast<size_t>(r) * V;
+// ---- beam-search scoring (native search, mmdx_b200/t5_fast.py NativeBeamSearch / mmdx_t5_generate)
+// score(row, token) = log_softmax(logits)[row, token] + beam_score[row] in HF's formulation ((x - max) - log(sum)) + score,
+// minus infinity for banned tokens (no-repeat-n-gram lists, -1 padded) and for EOS while below the minimum length; per study
+// the k best (row, token) pairs over its `beams` rows, descending, ties to the lower flat index row_in_study * V + token.
+// Three small launches over kScoreChunks slices of the vocabulary (one CTA scanning 4 x 32128 logits took 115 us):
+//   t5_lse_ban_kernel  (chunk, row)   : partial (max, sum exp) of the slice, THEN the row's bans inside the slice are written
+//                                       into the logits (HF applies its processors to log_softmax(logits), not to the logits)
+//   t5_topk_chunk_kernel (chunk, study): row statistics from the partials, thread-local top-k of the slice, k block-wide pops
+//   t5_topk_merge_kernel (study)      : k pops over the chunks' candidates - the same total order, so the same result as one pass
+constexpr int kTopK = 8;
+constexpr int kScoreChunks = 32;
+constexpr int kScoreThreads = 256;
+
+__device__ __forceinline__ int score_chunk_width(int V) { return (V + kScoreChunks - 1) / kScoreChunks; }
+
+__global__ void __launch_bounds__(kScoreThreads) t5_lse_ban_kernel(float* __restrict__ logits, int V, float* __restrict__ part,
+                                                                   const int32_t* __restrict__ banned, int max_ban, int ban_eos,
+                                                                   int eos) {
+  __shared__ float red[kScoreThreads / 32];
+  const int c = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
+  const int cw = score_chunk_width(V), lo = c * cw, hi = min(V, lo + cw);
+  float* x = logits + static_cast<size_t>(r) * V;
   float mx = -INFINITY;
-  for (int i = tid; i < V; i += 1024) mx = fmaxf(mx, x[i]);
+  for (int i = lo + tid; i < hi; i += kScoreThreads) mx = fmaxf(mx, x[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) red[tid >> 5] = mx;
   __syncthreads();
   mx = red[0];
-  for (int i = 1; i < 32; ++i) mx = fmaxf(mx, red[i]);
+  for (int i = 1; i < kScoreThreads / 32; ++i) mx = fmaxf(mx, red[i]);
   __syncthreads();
   float sm = 0.f;
-  for (int i = tid; i < V; i += 1024) sm += expf(x[i] - mx);
+  for (int i = lo + tid; i < hi; i += kScoreThreads) sm += expf(x[i] - mx);
   sm = warp_sum_f(sm);
   if ((tid & 31) == 0) red[tid >> 5] = sm;
-  __syncthreads();
+  __syncthreads();                                   // also: every read of the slice is done before the bans are written
   if (tid == 0) {
     float t = 0.f;
-    for (int i = 0; i < 32; ++i) t += red[i];
-    stat[2 * r] = mx; stat[2 * r + 1] = logf(t);
+    for (int i = 0; i < kScoreThreads / 32; ++i) t += red[i];
+    part[(static_cast<size_t>(r) * kScoreChunks + c) * 2] = mx;
+    part[(static_cast<size_t>(r) * kScoreChunks + c) * 2 + 1] = t;
   }
-}
-
-// Top-k continuations of one study over its `beams` rows: score(row, token) = log_softmax(logits)[row, token] + beam_score
-// [row], minus infinity for banned tokens (no-repeat-n-gram lists, -1 padded) and for EOS while below the minimum length.
-// One block per study; every thread keeps its own top-k (k <= 8) of a strided share, then k rounds of a block-wide arg-max
-// pop the winners in descending order (ties: the lower flat index first).  out_idx = row_in_study * V + token.
-// (The masks are written into the logits by t5_ban_kernel AFTER the row statistics were taken: HF applies its logits
-// processors to log_softmax(logits), not to the logits.)
-__global__ void t5_ban_kernel(float* __restrict__ logits, const int32_t* __restrict__ banned, int max_ban, int ban_eos, int eos,
-                              int V) {
-  const int r = blockIdx.x;
-  float* x = logits + static_cast<size_t>(r) * V;
-  if (ban_eos && threadIdx.x == 0) x[eos] = -INFINITY;
-  for (int q = threadIdx.x; q < max_ban; q += blockDim.x) {
+  if (ban_eos && tid == 0 && eos >= lo && eos < hi) x[eos] = -INFINITY;
+  for (int q = tid; q < max_ban; q += kScoreThreads) {
     const int bt = banned[static_cast<size_t>(r) * max_ban + q];
-    if (bt >= 0 && bt < V) x[bt] = -INFINITY;
+    if (bt >= lo && bt < hi) x[bt] = -INFINITY;
   }
 }
 
-constexpr int kTopK = 8;
-__global__ void __launch_bounds__(1024) t5_topk_kernel(const float* __restrict__ logits, const float* __restrict__ stat,
-                                                       const float* __restrict__ beam_scores, int beams, int V, int k,
-                                                       float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
-  __shared__ float sv[32];
-  __shared__ int si[32];
+// k rounds of a block-wide arg-max over the threads' sorted candidate lists: pops the winners in descending order (ties:
+// the lower index first).  kScoreThreads threads.
+__device__ void block_pop_topk(const float (&best)[kTopK], const int (&bidx)[kTopK], int k, float* __restrict__ out_scores,
+                               int32_t* __restrict__ out_idx) {
+  constexpr int W = kScoreThreads / 32;
+  __shared__ float sv[W];
+  __shared__ int si[W], st[W];
   __shared__ int s_win_thread;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  float best[kTopK];
-  int bidx[kTopK];
-#pragma unroll
-  for (int j = 0; j < kTopK; ++j) { best[j] = -INFINITY; bidx[j] = 0x7fffffff; }
-  const int total = beams * V;
-  for (int i = tid; i < total; i += 1024) {
-    const int row = i / V, tok = i - row * V;
-    const int R = b * beams + row;
-    float v = (logits[static_cast<size_t>(R) * V + tok] - stat[2 * R]) - stat[2 * R + 1];
-    v += beam_scores[R];
-    if (v > best[kTopK - 1]) {               // strictly greater: an equal later (higher) index never displaces an earlier one
-      int j = kTopK - 1;
-      while (j > 0 && v > best[j - 1]) { best[j] = best[j - 1]; bidx[j] = bidx[j - 1]; --j; }
-      best[j] = v; bidx[j] = i;
-    }
-  }
+  const int tid = threadIdx.x;
   int head = 0;                               // this thread's next candidate
   for (int round = 0; round < k; ++round) {
     float v = head < kTopK ? best[head] : -INFINITY;
@@ -301,22 +514,71 @@ __global__ void __launch_bounds__(1024) t5_topk_kernel(const float* __restrict__
       const int ot = __shfl_xor_sync(0xffffffffu, th, o);
       if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; th = ot; }
     }
-    if ((tid & 31) == 0) { sv[tid >> 5] = v; si[tid >> 5] = ix; }
-    __shared__ int st[32];
-    if ((tid & 31) == 0) st[tid >> 5] = th;
+    if ((tid & 31) == 0) { sv[tid >> 5] = v; si[tid >> 5] = ix; st[tid >> 5] = th; }
     __syncthreads();
     if (tid == 0) {
       float bv = sv[0]; int bi = si[0], bt = st[0];
-      for (int w = 1; w < 32; ++w)
+      for (int w = 1; w < W; ++w)
         if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; bt = st[w]; }
-      out_scores[b * k + round] = bv;
-      out_idx[b * k + round] = bi;
+      out_scores[round] = bv;
+      out_idx[round] = bi;
       s_win_thread = bt;
     }
     __syncthreads();
     if (tid == s_win_thread) ++head;
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(kScoreThreads) t5_topk_chunk_kernel(const float* __restrict__ logits, const float* __restrict__ part,
+                                                                      const float* __restrict__ beam_scores, int beams, int V,
+                                                                      int k, float* __restrict__ cand_s, int32_t* __restrict__ cand_i) {
+  extern __shared__ float stat[];             // [beams][3]: row max, log(sum exp), beam score
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int row = warp; row < beams; row += kScoreThreads / 32) {
+    const int R = b * beams + row;
+    static_assert(kScoreChunks == 32, "one partial per lane");
+    const float m = part[(static_cast<size_t>(R) * kScoreChunks + lane) * 2];
+    const float sc = part[(static_cast<size_t>(R) * kScoreChunks + lane) * 2 + 1];
+    float M = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    const float S = warp_sum_f(sc > 0.f ? sc * expf(m - M) : 0.f);
+    if (lane == 0) { stat[3 * row] = M; stat[3 * row + 1] = logf(S); stat[3 * row + 2] = beam_scores[R]; }
+  }
+  __syncthreads();
+  float best[kTopK];
+  int bidx[kTopK];
+#pragma unroll
+  for (int j = 0; j < kTopK; ++j) { best[j] = -INFINITY; bidx[j] = 0x7fffffff; }
+  const int cw = score_chunk_width(V), lo = c * cw, n = max(0, min(V, lo + cw) - lo);
+  for (int i = tid; i < beams * n; i += kScoreThreads) {     // ascending flat index per thread
+    const int row = i / n, tok = lo + (i - row * n);
+    float v = (logits[(static_cast<size_t>(b) * beams + row) * V + tok] - stat[3 * row]) - stat[3 * row + 1];
+    v += stat[3 * row + 2];
+    if (v > best[kTopK - 1]) {               // strictly greater: an equal later (higher) index never displaces an earlier one
+      int j = kTopK - 1;
+      while (j > 0 && v > best[j - 1]) { best[j] = best[j - 1]; bidx[j] = bidx[j - 1]; --j; }
+      best[j] = v; bidx[j] = row * V + tok;
+    }
+  }
+  const size_t o = (static_cast<size_t>(b) * kScoreChunks + c) * k;
+  block_pop_topk(best, bidx, k, cand_s + o, cand_i + o);
+}
+
+__global__ void __launch_bounds__(kScoreThreads) t5_topk_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
+                                                                      int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float best[kTopK];
+  int bidx[kTopK];
+#pragma unroll
+  for (int j = 0; j < kTopK; ++j) { best[j] = -INFINITY; bidx[j] = 0x7fffffff; }
+  static_assert(kScoreChunks * kTopK <= kScoreThreads, "one candidate per thread");
+  if (tid < kScoreChunks * k) {
+    best[0] = cand_s[static_cast<size_t>(b) * kScoreChunks * k + tid];
+    bidx[0] = cand_i[static_cast<size_t>(b) * kScoreChunks * k + tid];
+  }
+  block_pop_topk(best, bidx, k, out_scores + static_cast<size_t>(b) * k, out_idx + static_cast<size_t>(b) * k);
 }
 
 struct Block { float *ln0, *qkv, *so, *ln1, *cq, *ck, *cv, *co, *ln2, *wi, *wo; };
@@ -335,9 +597,15 @@ struct mmdx_t5 {
   // per generation
   int R = 0, n_enc = 0, Tmax = 0, t = 0;
   float* ws = nullptr; size_t ws_floats = 0;
-  float *x = nullptr, *qkv = nullptr, *att = nullptr, *q = nullptr, *hid = nullptr, *bias = nullptr;
-  std::vector<float*> sk[2], sv[2], ck, cv;
-  int cur = 0;                        // which of the two self-attention cache copies is live
+  float *x = nullptr, *qkv = nullptr, *att = nullptr, *q = nullptr, *hid = nullptr, *bias = nullptr, *score_ws = nullptr;
+  std::vector<float*> sk, sv, ck, cv;
+  int32_t* anc[2] = {nullptr, nullptr};   // ancestry rows [R, Tmax], double-buffered for the permutation
+  int cur = 0;                        // which ancestry copy is live
+  T5Layer* d_layers = nullptr;        // device copy of the per-block pointers (refreshed by mmdx_t5_begin)
+  unsigned long long* prof = nullptr; // device stamps of the last step (MMDX_T5_PROF=1)
+  int mega_blocks = 0;                // co-resident CTAs of the step kernel (one per SM)
+  float* gen_dev = nullptr; size_t gen_dev_words = 0;       // mmdx_t5_generate scratch (device / pinned host), grow-only
+  float* gen_host = nullptr; size_t gen_host_words = 0;
   int64_t launches = 0;
 };
 
@@ -380,6 +648,9 @@ extern "C" void mmdx_t5_destroy(mmdx_t5* e) {
   cudaDeviceSynchronize();
   if (e->arena) cudaFree(e->arena);
   if (e->ws) cudaFree(e->ws);
+  if (e->prof) cudaFree(e->prof);
+  if (e->gen_dev) cudaFree(e->gen_dev);
+  if (e->gen_host) cudaFreeHost(e->gen_host);
   delete e;
 }
 
@@ -458,8 +729,10 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
   cudaStream_t s = (cudaStream_t)stream;
   const int d = e->d, inner = e->H * e->dk;
   const size_t cache = (size_t)R * e->H * max_steps * e->dk, cross = (size_t)R * e->H * n_enc * e->dk;
-  const size_t need = (size_t)R * (d + 3 * inner + inner + inner + e->ff) + (size_t)max_steps * e->H + (size_t)e->L * (4 * cache + 2 * cross) +
-                      (size_t)R * n_enc * inner + 1024;
+  const size_t anc_words = ((size_t)R * max_steps + 3) / 4 * 4;          // int32 rows, kept 16-byte aligned
+  const size_t layer_words = (sizeof(T5Layer) * e->L + 15) / 16 * 4;
+  const size_t need = (size_t)R * (d + 3 * inner + inner + inner + e->ff) + (size_t)max_steps * e->H + 4 + (size_t)e->L * (2 * cache + 2 * cross) +
+                      (size_t)R * n_enc * inner + 2 * anc_words + layer_words + (size_t)R * kScoreChunks * (2 + 2 * kTopK) + 1024;
   if (need > e->ws_floats) {
     if (e->ws) { T5_CK(cudaDeviceSynchronize()); cudaFree(e->ws); e->ws = nullptr; }
     T5_CK(cudaMalloc(&e->ws, need * 4));
@@ -471,15 +744,24 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
   e->att = p; p += (size_t)R * inner;
   e->q = p; p += (size_t)R * inner;
   e->hid = p; p += (size_t)R * e->ff;
-  e->bias = p; p += (size_t)max_steps * e->H;
+  e->bias = p; p += ((size_t)max_steps * e->H + 3) / 4 * 4;
   float* tmp = p; p += (size_t)R * n_enc * inner;
-  for (int c = 0; c < 2; ++c) { e->sk[c].clear(); e->sv[c].clear(); }
-  e->ck.clear(); e->cv.clear();
+  e->sk.clear(); e->sv.clear(); e->ck.clear(); e->cv.clear();
+  std::vector<T5Layer> hl(e->L);
   for (int l = 0; l < e->L; ++l) {
-    for (int c = 0; c < 2; ++c) { e->sk[c].push_back(p); p += cache; e->sv[c].push_back(p); p += cache; }
+    e->sk.push_back(p); p += cache;
+    e->sv.push_back(p); p += cache;
     e->ck.push_back(p); p += cross;
     e->cv.push_back(p); p += cross;
+    const Block& b = e->blocks[l];
+    hl[l] = T5Layer{b.ln0, b.qkv, b.so, b.ln1, b.cq, b.co, b.ln2, b.wi, b.wo, e->sk[l], e->sv[l], e->ck[l], e->cv[l]};
   }
+  e->anc[0] = reinterpret_cast<int32_t*>(p); p += anc_words;
+  e->anc[1] = reinterpret_cast<int32_t*>(p); p += anc_words;
+  e->d_layers = reinterpret_cast<T5Layer*>(p); p += layer_words;
+  e->score_ws = p; p += (size_t)R * kScoreChunks * (2 + 2 * kTopK);
+  T5_CK(cudaMemcpyAsync(e->d_layers, hl.data(), sizeof(T5Layer) * e->L, cudaMemcpyHostToDevice, s));
+  T5_CK(cudaStreamSynchronize(s));                                  // `hl` is pageable and goes out of scope
   e->R = R; e->n_enc = n_enc; e->Tmax = max_steps; e->t = 0; e->cur = 0;
   T5_CK(cudaMemcpyAsync(e->bias, h_bias, (size_t)max_steps * e->H * 4, cudaMemcpyHostToDevice, s));
   const long long tot = (long long)R * n_enc * inner;
@@ -502,11 +784,8 @@ extern "C" int mmdx_t5_reorder(mmdx_t5* e, const int32_t* d_beam_idx, void* stre
   T5_CK(cudaSetDevice(e->device));
   if (e->t == 0) return 0;
   const int nxt = e->cur ^ 1;
-  for (int l = 0; l < e->L; ++l) {
-    t5_reorder_kernel<<<dim3(e->H, e->R), 128, 0, (cudaStream_t)stream>>>(e->sk[e->cur][l], e->sk[nxt][l], d_beam_idx, e->H, e->Tmax, e->dk, e->t, e->R);
-    t5_reorder_kernel<<<dim3(e->H, e->R), 128, 0, (cudaStream_t)stream>>>(e->sv[e->cur][l], e->sv[nxt][l], d_beam_idx, e->H, e->Tmax, e->dk, e->t, e->R);
-    e->launches += 2;
-  }
+  t5_reorder_anc_kernel<<<e->R, 128, 0, (cudaStream_t)stream>>>(e->anc[e->cur], e->anc[nxt], d_beam_idx, e->Tmax, e->t, e->R);
+  e->launches++;
   e->cur = nxt;
   T5_CK(cudaGetLastError());
   return 0;
@@ -521,23 +800,32 @@ extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits
   T5_CK(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int R = e->R, d = e->d, inner = e->H * e->dk;
-  t5_embed_kernel<<<R, 128, 0, s>>>(d_tokens, e->E, d, e->vocab, e->x);
-  e->launches++;
-  for (int l = 0; l < e->L; ++l) {
-    const Block& b = e->blocks[l];
-    if (t5_linear(e, e->x, d, b.ln0, 1.0f, b.qkv, e->qkv, 3 * inner, nullptr, R, d, 3 * inner, 0, s)) return 1;
-    t5_self_attn_kernel<<<dim3(e->H, R), 128, (size_t)(e->dk + e->Tmax) * 4, s>>>(e->qkv, e->sk[e->cur][l], e->sv[e->cur][l], e->bias, e->H,
-                                                                                  e->dk, e->Tmax, e->t, e->att);
-    if (t5_linear(e, e->att, inner, nullptr, 1.0f, b.so, e->x, d, e->x, R, inner, d, 0, s)) return 1;
-    if (t5_linear(e, e->x, d, b.ln1, 1.0f, b.cq, e->q, inner, nullptr, R, d, inner, 0, s)) return 1;
-    t5_cross_attn_kernel<<<dim3(e->H, R), 64, 0, s>>>(e->q, e->ck[l], e->cv[l], e->H, e->dk, e->n_enc, e->att);
-    if (t5_linear(e, e->att, inner, nullptr, 1.0f, b.co, e->x, d, e->x, R, inner, d, 0, s)) return 1;
-    if (t5_linear(e, e->x, d, b.ln2, 1.0f, b.wi, e->hid, e->ff, nullptr, R, d, e->ff, 1, s)) return 1;
-    if (t5_linear(e, e->hid, e->ff, nullptr, 1.0f, b.wo, e->x, d, e->x, R, e->ff, d, 0, s)) return 1;
-    e->launches += 2;
+  T5StepArgs a{};
+  a.tok = d_tokens; a.logits = d_logits; a.E = e->E; a.lm = e->lm; a.final_ln = e->final_ln; a.bias = e->bias;
+  a.layers = e->d_layers; a.anc = e->anc[e->cur];
+  a.x = e->x; a.qkv = e->qkv; a.att = e->att; a.q = e->q; a.hid = e->hid;
+  a.eps = e->eps;
+  a.lm_scale = e->tied == 1 ? 1.0f / std::sqrt((float)d) : 1.0f;     // HF scales the decoder output only in the default tied setup
+  a.R = R; a.d = d; a.H = e->H; a.dk = e->dk; a.ff = e->ff; a.L = e->L; a.vocab = e->vocab; a.Tmax = e->Tmax; a.t = e->t;
+  a.n_enc = e->n_enc; a.kmax = std::max(std::max(d, inner), e->ff);
+  a.prof = e->prof;
+  const int NR = R <= 4 ? 4 : 8;
+  const size_t smem = std::max((size_t)NR * a.kmax + (size_t)kMegaWarps * NR, (size_t)96 + 2048 + 2 * (size_t)e->Tmax) * 4;
+  T5_REQUIRE(smem <= 200 * 1024, "step: d_ff / max_steps too large for the shared-memory staging");
+  void* fn = NR == 4 ? (void*)t5_step_mega_kernel<4> : (void*)t5_step_mega_kernel<8>;
+  if (e->mega_blocks == 0) {
+    cudaDeviceProp prop;
+    T5_CK(cudaGetDeviceProperties(&prop, e->device));
+    T5_REQUIRE(prop.cooperativeLaunch, "device lacks cooperative launch");
+    e->mega_blocks = prop.multiProcessorCount;
+    T5_CK(cudaFuncSetAttribute(t5_step_mega_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    T5_CK(cudaFuncSetAttribute(t5_step_mega_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const char* pf = std::getenv("MMDX_T5_PROF");
+    if (pf && pf[0] == '1') { T5_CK(cudaMalloc(&e->prof, 1024 * 8)); T5_CK(cudaMemset(e->prof, 0, 1024 * 8)); }
   }
-  const float sc = e->tied == 1 ? 1.0f / std::sqrt((float)d) : 1.0f;     // HF scales the decoder output only in the default tied setup
-  if (t5_linear(e, e->x, d, e->final_ln, sc, e->lm, d_logits, e->vocab, nullptr, R, d, e->vocab, 0, s)) return 1;
+  void* args[] = {&a};
+  T5_CK(cudaLaunchCooperativeKernel(fn, dim3(e->mega_blocks), dim3(kMegaThreads), args, smem, s));
+  e->launches++;
   T5_CK(cudaGetLastError());
   e->t++;
   return 0;
@@ -555,15 +843,16 @@ extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_be
   T5_REQUIRE(k >= 1 && k <= kTopK && (max_ban == 0 || d_banned != nullptr), "mmdx_t5_score_topk: 1 <= k <= 8");
   T5_CK(cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
-  float* stat = e->hid;                        // 2 floats per row: scratch that the next step overwrites anyway
-  t5_row_lse_kernel<<<e->R, 1024, 0, s>>>(d_logits, e->vocab, stat);
-  if (ban_eos || max_ban > 0) {
-    T5_REQUIRE(eos_id >= 0 && eos_id < e->vocab, "eos id outside the vocabulary");
-    t5_ban_kernel<<<e->R, 128, 0, s>>>(d_logits, d_banned, max_ban, ban_eos, eos_id, e->vocab);
-    e->launches++;
-  }
-  t5_topk_kernel<<<e->R / num_beams, 1024, 0, s>>>(d_logits, stat, d_beam_scores, num_beams, e->vocab, k, d_out_scores, d_out_idx);
-  e->launches += 2;
+  T5_REQUIRE(!(ban_eos || max_ban > 0) || (eos_id >= 0 && eos_id < e->vocab), "eos id outside the vocabulary");
+  const int B = e->R / num_beams;
+  float* part = e->score_ws;                                          // [R][chunks][2]
+  float* cand_s = part + (size_t)e->R * kScoreChunks * 2;             // [B][chunks][k]
+  int32_t* cand_i = reinterpret_cast<int32_t*>(cand_s + (size_t)e->R * kScoreChunks * kTopK);
+  t5_lse_ban_kernel<<<dim3(kScoreChunks, e->R), kScoreThreads, 0, s>>>(d_logits, e->vocab, part, d_banned, max_ban, ban_eos, eos_id);
+  t5_topk_chunk_kernel<<<dim3(kScoreChunks, B), kScoreThreads, (size_t)num_beams * 3 * 4, s>>>(d_logits, part, d_beam_scores, num_beams,
+                                                                                               e->vocab, k, cand_s, cand_i);
+  t5_topk_merge_kernel<<<B, kScoreThreads, 0, s>>>(cand_s, cand_i, k, d_out_scores, d_out_idx);
+  e->launches += 3;
   T5_CK(cudaGetLastError());
   return 0;
 }
@@ -598,29 +887,42 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
   const float NEG = -1.0e9f;
   const double lp = (double)length_penalty;
   // ---- device scratch of the search (freed on every exit path by the guard)
-  struct Scratch {
-    float *enc = nullptr, *logits = nullptr, *bscore = nullptr, *oscore = nullptr;
-    int32_t *tok = nullptr, *bidx = nullptr, *banned = nullptr, *oidx = nullptr;
-    float* h_oscore = nullptr; int32_t* h_oidx = nullptr;
-    ~Scratch() {
-      for (void* p : {(void*)enc, (void*)logits, (void*)bscore, (void*)oscore, (void*)tok, (void*)bidx, (void*)banned, (void*)oidx})
-        if (p) cudaFree(p);
-      if (h_oscore) cudaFreeHost(h_oscore);
-      if (h_oidx) cudaFreeHost(h_oidx);
-    }
-  } w;
+  // One pinned block goes up per token (beam indices of the last step | tokens | running scores | banned lists) and one
+  // comes back (2K candidate scores | indices per study): two copies and one synchronisation per token.  The buffers
+  // belong to the engine and only ever grow (a cudaMallocHost / cudaFree pair per call cost ~3 ms).
   const long long enc_row = (long long)n_enc * e->d;
   const int max_ban = max_length;                                 // a row can ban at most one token per earlier position
-  T5_CK(cudaMalloc(&w.enc, (size_t)R * enc_row * 4));
-  T5_CK(cudaMalloc(&w.logits, (size_t)R * V * 4));
-  T5_CK(cudaMalloc(&w.bscore, (size_t)R * 4));
-  T5_CK(cudaMalloc(&w.oscore, (size_t)B * K2 * 4));
-  T5_CK(cudaMalloc(&w.tok, (size_t)R * 4));
-  T5_CK(cudaMalloc(&w.bidx, (size_t)R * 4));
-  T5_CK(cudaMalloc(&w.banned, (size_t)R * max_ban * 4));
-  T5_CK(cudaMalloc(&w.oidx, (size_t)B * K2 * 4));
-  T5_CK(cudaMallocHost(&w.h_oscore, (size_t)B * K2 * 4));
-  T5_CK(cudaMallocHost(&w.h_oidx, (size_t)B * K2 * 4));
+  const size_t stage_words = (size_t)R * (3 + max_ban), cand_words = (size_t)2 * B * K2;
+  const size_t dev_words = (size_t)R * enc_row + (size_t)R * V + stage_words + cand_words + 64;
+  if (dev_words > e->gen_dev_words) {
+    if (e->gen_dev) { T5_CK(cudaDeviceSynchronize()); cudaFree(e->gen_dev); e->gen_dev = nullptr; e->gen_dev_words = 0; }
+    T5_CK(cudaMalloc(&e->gen_dev, dev_words * 4));
+    e->gen_dev_words = dev_words;
+  }
+  if (stage_words + cand_words > e->gen_host_words) {
+    if (e->gen_host) { T5_CK(cudaDeviceSynchronize()); cudaFreeHost(e->gen_host); e->gen_host = nullptr; e->gen_host_words = 0; }
+    T5_CK(cudaMallocHost(&e->gen_host, (stage_words + cand_words) * 4));
+    e->gen_host_words = stage_words + cand_words;
+  }
+  struct { float *enc, *logits; int32_t *stage, *cand, *h_stage, *h_cand; } w;
+  w.enc = e->gen_dev;
+  w.logits = w.enc + (size_t)R * enc_row;
+  w.stage = reinterpret_cast<int32_t*>(w.logits + (size_t)R * V);
+  w.cand = w.stage + (stage_words + 3) / 4 * 4;
+  w.h_stage = reinterpret_cast<int32_t*>(e->gen_host);
+  w.h_cand = w.h_stage + stage_words;
+  int32_t* const h_bidx = w.h_stage;
+  int32_t* const h_tok = w.h_stage + R;
+  float* const h_bscore = reinterpret_cast<float*>(w.h_stage + 2 * R);
+  int32_t* const h_ban = w.h_stage + 3 * R;
+  const int32_t* d_bidx = w.stage;
+  const int32_t* d_tok = w.stage + R;
+  const float* d_bscore = reinterpret_cast<const float*>(w.stage + 2 * R);
+  const int32_t* d_ban = w.stage + 3 * R;
+  float* d_oscore = reinterpret_cast<float*>(w.cand);
+  int32_t* d_oidx = w.cand + (size_t)B * K2;
+  const float* h_oscore = reinterpret_cast<const float*>(w.h_cand);
+  const int32_t* h_oidx = w.h_cand + (size_t)B * K2;
   {
     const long long tot = (long long)R * enc_row;
     t5_repeat_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_cond, w.enc, B, K, enc_row);
@@ -637,13 +939,11 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
     run_scores[b * K] = 0.f;
     for (int k = 0; k < K; ++k) { run_seq[(size_t)(b * K + k) * max_length] = start_id; seqs[(size_t)(b * K + k) * max_length] = start_id; }
   }
-  std::vector<int32_t> h_tok(R), h_bidx(R), h_banned((size_t)R * max_ban);
-  std::vector<float> h_bscore(R);
+  std::vector<int32_t> h_banned((size_t)R * max_ban);
+  for (int r = 0; r < R; ++r) h_bidx[r] = r;
   int cur_len = 1;
   while (true) {
-    for (int r = 0; r < R; ++r) h_tok[r] = run_seq[(size_t)r * max_length + cur_len - 1];
-    T5_CK(cudaMemcpyAsync(w.tok, h_tok.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
-    if (mmdx_t5_step(e, w.tok, w.logits, s)) return 1;
+    for (int r = 0; r < R; ++r) { h_tok[r] = run_seq[(size_t)r * max_length + cur_len - 1]; h_bscore[r] = run_scores[r]; }
     // no-repeat-n-gram bans of every running row (HF NoRepeatNGramLogitsProcessor over the tokens generated so far)
     int ban_w = 0;
     const int n = no_repeat_ngram;
@@ -659,27 +959,21 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
         }
         ban_w = std::max(ban_w, cnt);
       }
-      if (ban_w > 0) {
-        // repack to [R, ban_w]
-        std::vector<int32_t> packed((size_t)R * ban_w, -1);
-        for (int r = 0; r < R; ++r)
-          for (int c = 0; c < ban_w; ++c) packed[(size_t)r * ban_w + c] = h_banned[(size_t)r * max_ban + c];
-        T5_CK(cudaMemcpyAsync(w.banned, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, s));
-        T5_CK(cudaStreamSynchronize(s));                          // `packed` goes out of scope
-      }
+      for (int r = 0; r < R; ++r)                                 // repack to [R, ban_w]
+        for (int c = 0; c < ban_w; ++c) h_ban[(size_t)r * ban_w + c] = h_banned[(size_t)r * max_ban + c];
     }
+    T5_CK(cudaMemcpyAsync(w.stage, w.h_stage, ((size_t)3 * R + (size_t)R * ban_w) * 4, cudaMemcpyHostToDevice, s));
+    if (cur_len > 1 && mmdx_t5_reorder(e, d_bidx, s)) return 1;
+    if (mmdx_t5_step(e, d_tok, w.logits, s)) return 1;
     const int ban_eos = (cur_len - prompt) < min_new_tokens ? 1 : 0;
-    for (int r = 0; r < R; ++r) h_bscore[r] = run_scores[r];
-    T5_CK(cudaMemcpyAsync(w.bscore, h_bscore.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
-    if (mmdx_t5_score_topk(e, w.logits, w.bscore, ban_w > 0 ? w.banned : nullptr, ban_w, ban_eos, eos_id, K, K2, w.oscore, w.oidx, s))
+    if (mmdx_t5_score_topk(e, w.logits, d_bscore, ban_w > 0 ? d_ban : nullptr, ban_w, ban_eos, eos_id, K, K2, d_oscore, d_oidx, s))
       return 1;
-    T5_CK(cudaMemcpyAsync(w.h_oscore, w.oscore, (size_t)B * K2 * 4, cudaMemcpyDeviceToHost, s));
-    T5_CK(cudaMemcpyAsync(w.h_oidx, w.oidx, (size_t)B * K2 * 4, cudaMemcpyDeviceToHost, s));
+    T5_CK(cudaMemcpyAsync(w.h_cand, w.cand, cand_words * 4, cudaMemcpyDeviceToHost, s));
     T5_CK(cudaStreamSynchronize(s));
     bool any_unsat = false, all_finished = true, all_hits = true;
     for (int b = 0; b < B; ++b) {
-      const float* tks = w.h_oscore + (size_t)b * K2;
-      const int32_t* tki = w.h_oidx + (size_t)b * K2;
+      const float* tks = h_oscore + (size_t)b * K2;
+      const int32_t* tki = h_oidx + (size_t)b * K2;
       int src[kTopK], tokn[kTopK]; bool hit[kTopK]; float pool[kTopK];
       for (int c = 0; c < K2; ++c) {
         src[c] = tki[c] / V; tokn[c] = tki[c] % V;
@@ -728,9 +1022,7 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
         std::copy_n(&m_seq[(size_t)c * max_length], max_length, &seqs[(size_t)(b * K + k) * max_length]);
       }
     }
-    run_seq.swap(new_run);
-    T5_CK(cudaMemcpyAsync(w.bidx, h_bidx.data(), (size_t)R * 4, cudaMemcpyHostToDevice, s));
-    if (mmdx_t5_reorder(e, w.bidx, s)) return 1;
+    run_seq.swap(new_run);                                        // h_bidx goes up with the next token's block
     ++cur_len;
     // can a running beam still beat the worst finished hypothesis?
     const int best_len = (early_stopping == 2 && lp > 0.0) ? (max_length - prompt) : (cur_len - prompt);
@@ -758,3 +1050,18 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
 }
 
 extern "C" int64_t mmdx_t5_launch_count(mmdx_t5* e) { return e ? e->launches : 0; }
+
+// Phase boundaries of the LAST decoder step as globaltimer nanoseconds (CTA 0's view): entry, then one stamp behind every
+// phase (per block: qkv, self-attention, o, cross q, cross-attention, o, wi, wo; finally the LM head).  Needs MMDX_T5_PROF=1
+// in the environment when the first step runs; synchronises the device.
+extern "C" int mmdx_t5_step_profile(mmdx_t5* e, uint64_t* h_out, int cap, int* n_out) {
+  T5_REQUIRE(e && h_out && n_out, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(e->mu);
+  T5_REQUIRE(e->prof != nullptr, "mmdx_t5_step_profile: set MMDX_T5_PROF=1 before the first step");
+  const int n = std::min(cap, 2 + 8 * e->L);
+  T5_CK(cudaSetDevice(e->device));
+  T5_CK(cudaDeviceSynchronize());
+  T5_CK(cudaMemcpy(h_out, e->prof, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  *n_out = n;
+  return 0;
+}
