@@ -117,10 +117,13 @@ struct T5Layer {                      // device copy of one block's pointers
   const float *ck, *cv;               // projected conditioning tokens [R, H, n_enc, dk]
 };
 
+constexpr int kMaxT5Layers = 24;
+// Kernel parameters live in the constant bank: nothing here is reached through a pointer in local or global memory, because
+// every grid barrier flushes L1 and each such access would then cost an L2 round trip on the critical path of a phase.
 struct T5StepArgs {
   const int32_t* tok; float* logits;
   const float *E, *lm, *final_ln, *bias;
-  const T5Layer* layers;
+  T5Layer layers[kMaxT5Layers];
   int32_t* anc;                       // [R, Tmax]: anc[r][j] = the row slot that holds position j of row r's hypothesis
   float *x, *qkv, *att, *q, *hid;
   float eps, lm_scale;
@@ -141,7 +144,7 @@ __device__ __forceinline__ float dot4(const float4 w, const float4 v, float acc)
 // The grid barrier that separates this phase from its producer sits INSIDE, behind the first batch of weight loads: the
 // weights do not depend on the previous phase, so their HBM / L2 latency runs under the barrier and the staging of x.
 template <int NR>
-__device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& grid, const float* x, long long ldx,
+__device__ __noinline__ void mega_linear(const int R, const float eps, const float* x, long long ldx,
                                          const float* __restrict__ ln_w, float in_scale, const float* __restrict__ W, float* out,
                                          long long ldo, const float* res, int K, int N, int relu, bool stream_w, float* xs,
                                          float* part) {
@@ -175,8 +178,8 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
 #pragma unroll
     for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) gw[u] = __ldg(reinterpret_cast<const float4*>(ln_w) + lane + 32 * u);
   }
-  grid.sync();
-  for (int r0 = 0; r0 < a.R; r0 += NR) {
+  cg::this_grid().sync();
+  for (int r0 = 0; r0 < R; r0 += NR) {
     __syncthreads();                                             // the previous readers of xs are done
     if (ln_w == nullptr) {                                       // plain copy (x in_scale): every thread, independent 16-byte loads
       const int k4 = K / 4, tot = NR * k4;
@@ -184,14 +187,14 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
       for (int i = tid; i < tot; i += kMegaThreads) {
         const int r = i / k4, k = i - r * k4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r0 + r < a.R) v = reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * ldx)[k];
+        if (r0 + r < R) v = reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * ldx)[k];
         v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
         reinterpret_cast<float4*>(xs)[i] = v;
       }
     }
     for (int r = warp; r < NR && ln_w != nullptr; r += kMegaWarps) {
       float4* dst = reinterpret_cast<float4*>(xs + static_cast<size_t>(r) * K);
-      if (r0 + r >= a.R) { for (int k = lane; k < K / 4; k += 32) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+      if (r0 + r >= R) { for (int k = lane; k < K / 4; k += 32) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
       const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * ldx);
       if (in_regs) {                  // T5LayerNorm: x * rsqrt(mean(x^2) + eps) * w  (no mean subtraction, no bias); one read of x
         float4 xv4[XR];
@@ -200,7 +203,7 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
         for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) xv4[u] = src[lane + 32 * u];
 #pragma unroll
         for (int u = 0; u < XR; ++u) if (lane + 32 * u < K / 4) q = dot4(xv4[u], xv4[u], q);
-        const float sc = in_scale * rsqrtf(warp_sum_f(q) / K + a.eps);
+        const float sc = in_scale * rsqrtf(warp_sum_f(q) / K + eps);
 #pragma unroll
         for (int u = 0; u < XR; ++u) {
           if (lane + 32 * u < K / 4) {
@@ -215,7 +218,7 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
       if (ln_w != nullptr) {
         float q = 0.f;
         for (int k = lane; k < K / 4; k += 32) { const float4 v = src[k]; q = dot4(v, v, q); }
-        sc *= rsqrtf(warp_sum_f(q) / K + a.eps);
+        sc *= rsqrtf(warp_sum_f(q) / K + eps);
       }
       for (int k = lane; k < K / 4; k += 32) {
         float4 v = src[k];
@@ -229,7 +232,7 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
       const int c0 = (g * slots + slot) * NC;
       const bool on = c0 < N, two = NC == 2 && c0 + 1 < N;
       const int oc = c0 + lane / NR, orow = r0 + lane % NR;       // the output element this lane writes (kp == 0 warps)
-      const bool writes = on && kp == 0 && lane < NR * NC && oc < N && orow < a.R;
+      const bool writes = on && kp == 0 && lane < NR * NC && oc < N && orow < R;
       float resv = 0.f;
       if (writes && res != nullptr) resv = res[static_cast<size_t>(orow) * ldo + oc];     // in flight under the products
       float acc0[NR], acc1[NR];
@@ -279,7 +282,7 @@ __device__ __noinline__ void mega_linear(const T5StepArgs& a, cg::grid_group& gr
 // Self-attention of the new token against the cache, one (row, head) per CTA.  qkv [R, 3*inner] (q | k | v); position t is
 // written into the row's own slot first; key j < t is read from slot anc[r][j].  scores[j] = q . k_j + bias[(t - j) * H + h]
 // (no scaling in T5), softmax in fp32, out [R, inner].
-__device__ void mega_self_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
+__device__ __forceinline__ void mega_self_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
   float* q = sm;                      // [64]
   float* red = sm + 64;               // [32]
   float* part = sm + 96;              // [32 key groups][64]
@@ -348,7 +351,7 @@ __device__ void mega_self_attn(const T5StepArgs& a, const T5Layer& L, float* sm)
 }
 
 // Cross-attention of the new token against the projected conditioning tokens: q [R, inner], K / V [R, H, n_enc, dk].
-__device__ void mega_cross_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
+__device__ __forceinline__ void mega_cross_attn(const T5StepArgs& a, const T5Layer& L, float* sm) {
   float* p = sm;                      // [64]
   const int tid = threadIdx.x, H = a.H, dk = a.dk, n_enc = a.n_enc, inner = H * dk;
   for (int item = blockIdx.x; item < a.R * H; item += gridDim.x) {
@@ -399,27 +402,27 @@ __global__ void __launch_bounds__(kMegaThreads, 1) t5_step_mega_kernel(const T5S
   }
   for (int l = 0; l < a.L; ++l) {                                // every mega_linear starts with the barrier behind its producer
     const T5Layer& L = a.layers[l];
-    mega_linear<NR>(a, grid, a.x, d, L.ln0, 1.0f, L.qkv, a.qkv, 3 * inner, nullptr, d, 3 * inner, 0, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.x, d, L.ln0, 1.0f, L.qkv, a.qkv, 3 * inner, nullptr, d, 3 * inner, 0, false, xs, part);
     stamp();
     grid.sync();
     mega_self_attn(a, L, sm);
     stamp();
-    mega_linear<NR>(a, grid, a.att, inner, nullptr, 1.0f, L.so, a.x, d, a.x, inner, d, 0, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.att, inner, nullptr, 1.0f, L.so, a.x, d, a.x, inner, d, 0, false, xs, part);
     stamp();
-    mega_linear<NR>(a, grid, a.x, d, L.ln1, 1.0f, L.cq, a.q, inner, nullptr, d, inner, 0, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.x, d, L.ln1, 1.0f, L.cq, a.q, inner, nullptr, d, inner, 0, false, xs, part);
     stamp();
     grid.sync();
     mega_cross_attn(a, L, sm);
     stamp();
-    mega_linear<NR>(a, grid, a.att, inner, nullptr, 1.0f, L.co, a.x, d, a.x, inner, d, 0, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.att, inner, nullptr, 1.0f, L.co, a.x, d, a.x, inner, d, 0, false, xs, part);
     stamp();
-    mega_linear<NR>(a, grid, a.x, d, L.ln2, 1.0f, L.wi, a.hid, a.ff, nullptr, d, a.ff, 1, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.x, d, L.ln2, 1.0f, L.wi, a.hid, a.ff, nullptr, d, a.ff, 1, false, xs, part);
     stamp();
-    mega_linear<NR>(a, grid, a.hid, a.ff, nullptr, 1.0f, L.wo, a.x, d, a.x, a.ff, d, 0, false, xs, part);
+    mega_linear<NR>(a.R, a.eps, a.hid, a.ff, nullptr, 1.0f, L.wo, a.x, d, a.x, a.ff, d, 0, false, xs, part);
     stamp();
   }
   // the LM head streams 65 MB once per step: evict-first loads keep the 88 MB of layer weights in the 126 MB L2
-  mega_linear<NR>(a, grid, a.x, d, a.final_ln, a.lm_scale, a.lm, a.logits, a.vocab, nullptr, d, a.vocab, 0, true, xs, part);
+  mega_linear<NR>(a.R, a.eps, a.x, d, a.final_ln, a.lm_scale, a.lm, a.logits, a.vocab, nullptr, d, a.vocab, 0, true, xs, part);
   stamp();
 }
 
@@ -601,7 +604,7 @@ struct mmdx_t5 {
   std::vector<float*> sk, sv, ck, cv;
   int32_t* anc[2] = {nullptr, nullptr};   // ancestry rows [R, Tmax], double-buffered for the permutation
   int cur = 0;                        // which ancestry copy is live
-  T5Layer* d_layers = nullptr;        // device copy of the per-block pointers (refreshed by mmdx_t5_begin)
+  std::vector<T5Layer> h_layers;      // per-block pointers (refreshed by mmdx_t5_begin), passed to the step kernel by value
   unsigned long long* prof = nullptr; // device stamps of the last step (MMDX_T5_PROF=1)
   int mega_blocks = 0;                // co-resident CTAs of the step kernel (one per SM)
   float* gen_dev = nullptr; size_t gen_dev_words = 0;       // mmdx_t5_generate scratch (device / pinned host), grow-only
@@ -633,7 +636,7 @@ extern "C" int mmdx_t5_create(int device, int d_model, int n_heads, int d_kv, in
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return t5_fail("mmdx_t5: no CUDA device (there is no CPU fallback)");
   T5_REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
-  T5_REQUIRE(d_model % 128 == 0 && d_ff % 128 == 0 && (n_heads * d_kv) % 128 == 0 && d_kv <= 64 && d_kv % 4 == 0 && n_layers > 0 &&
+  T5_REQUIRE(d_model % 128 == 0 && d_ff % 128 == 0 && (n_heads * d_kv) % 128 == 0 && d_kv <= 64 && d_kv % 4 == 0 && n_layers > 0 && n_layers <= kMaxT5Layers &&
                  vocab > 0, "unsupported T5 dimensions");
   mmdx_t5* e = new mmdx_t5();
   e->device = device; e->d = d_model; e->H = n_heads; e->dk = d_kv; e->ff = d_ff; e->L = n_layers; e->vocab = vocab; e->eps = eps;
@@ -758,10 +761,9 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
   }
   e->anc[0] = reinterpret_cast<int32_t*>(p); p += anc_words;
   e->anc[1] = reinterpret_cast<int32_t*>(p); p += anc_words;
-  e->d_layers = reinterpret_cast<T5Layer*>(p); p += layer_words;
+  (void)layer_words;
   e->score_ws = p; p += (size_t)R * kScoreChunks * (2 + 2 * kTopK);
-  T5_CK(cudaMemcpyAsync(e->d_layers, hl.data(), sizeof(T5Layer) * e->L, cudaMemcpyHostToDevice, s));
-  T5_CK(cudaStreamSynchronize(s));                                  // `hl` is pageable and goes out of scope
+  e->h_layers = hl;
   e->R = R; e->n_enc = n_enc; e->Tmax = max_steps; e->t = 0; e->cur = 0;
   T5_CK(cudaMemcpyAsync(e->bias, h_bias, (size_t)max_steps * e->H * 4, cudaMemcpyHostToDevice, s));
   const long long tot = (long long)R * n_enc * inner;
@@ -802,7 +804,8 @@ extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits
   const int R = e->R, d = e->d, inner = e->H * e->dk;
   T5StepArgs a{};
   a.tok = d_tokens; a.logits = d_logits; a.E = e->E; a.lm = e->lm; a.final_ln = e->final_ln; a.bias = e->bias;
-  a.layers = e->d_layers; a.anc = e->anc[e->cur];
+  for (int l = 0; l < e->L; ++l) a.layers[l] = e->h_layers[l];
+  a.anc = e->anc[e->cur];
   a.x = e->x; a.qkv = e->qkv; a.att = e->att; a.q = e->q; a.hid = e->hid;
   a.eps = e->eps;
   a.lm_scale = e->tied == 1 ? 1.0f / std::sqrt((float)d) : 1.0f;     // HF scales the decoder output only in the default tied setup
