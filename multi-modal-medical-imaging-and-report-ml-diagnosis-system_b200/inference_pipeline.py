@@ -258,12 +258,16 @@ def inference_batch(model_bundle, images, details=None, device=None, gen_kwargs=
             cond = cond.to(next(fusion.report_model.parameters()).dtype)
             fast = fast_report_generator(fusion, dev) if model_bundle.get("fast_report", True) else None
             if fast is not None and gen_attributes.get("max_new_tokens"):
-                # HF's beam search with the model call replaced by the KV-cached CUDA decoder step (csrc/t5_decoder.cu):
-                # same tokens, a small fraction of the time.  fast_report = "native" also replaces HF's
-                # Python loop by the restated search over the device scoring / top-k kernels (another ~8x).
+                # The KV-cached CUDA decoder step (csrc/t5_decoder.cu) under the report search.  Default:
+                # the whole beam search in one C call (mmdx_t5_generate - HF's algorithm restated, token-identical in the
+                # tests, ~20x faster than eager HF) when the generation arguments are the ones it restates, else HF's own
+                # beam search with only the model call replaced (same tokens by construction, ~3x).  fast_report = "hf"
+                # forces the latter, "native" the former (raising on arguments it does not implement).
+                from .t5_fast import NativeBeamSearch
+                mode = model_bundle.get("fast_report", True)
+                native = mode == "native" or (mode is True and NativeBeamSearch.supports(gen_attributes))
                 with eng.lock:
-                    if model_bundle.get("fast_report") == "native":
-                        from .t5_fast import NativeBeamSearch
+                    if native:
                         gen_ids = NativeBeamSearch(fast.backend, fusion.report_model.config).generate(cond, **gen_attributes)
                     else:
                         gen_ids = fast.generate(cond, **gen_attributes)

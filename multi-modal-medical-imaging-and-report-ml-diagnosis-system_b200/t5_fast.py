@@ -205,6 +205,18 @@ class NativeBeamSearch:
             out[r, :len(t)] = t
         return out
 
+    _KNOWN = ("max_new_tokens", "min_new_tokens", "num_beams", "no_repeat_ngram_size", "length_penalty", "early_stopping",
+              "eos_token_id", "pad_token_id", "decoder_start_token_id", "use_cache")
+
+    @classmethod
+    def supports(cls, gen_kwargs):
+        """True when these `generate` arguments are the ones this search restates (deterministic beam / greedy search,
+        one EOS id, at most 4 beams for the C++ host loop's top-8 kernel)."""
+        extra = {k: v for k, v in gen_kwargs.items() if k not in cls._KNOWN and v not in (None, False)}
+        eos = gen_kwargs.get("eos_token_id", 1)
+        return (not extra and bool(gen_kwargs.get("max_new_tokens")) and isinstance(eos, int)
+                and 1 <= int(gen_kwargs.get("num_beams", 1)) <= 4)
+
     @torch.no_grad()
     def generate(self, cond, max_new_tokens, min_new_tokens=0, num_beams=1, no_repeat_ngram_size=0, length_penalty=1.0,
                  early_stopping=False, eos_token_id=1, pad_token_id=0, decoder_start_token_id=None, **unused):
