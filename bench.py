@@ -268,6 +268,43 @@ def workload_config(B, L, world):
 MIN_TIMED_S = 2.0       # the timed region is extended to at least this long (power / clocks settle; >= 20 clock samples)
 
 
+def report_latency(local_rank):
+    """The other half of a real request (inference_pipeline.py:190-196): the 180-token, 4-beam T5 report for ONE study at
+    the reference's generation settings, through mmdx_t5_generate (the default report path of inference()), next to stock
+    HF generate (eager fp32) on the same GPU.  t5-small architecture, random-init weights, random conditioning tokens;
+    min_new_tokens = 150 as in the reference, so every run decodes at least 150 tokens."""
+    from transformers import T5Config, T5ForConditionalGeneration
+    from transformers.modeling_outputs import BaseModelOutput
+    from mmdx_b200.t5_fast import MmdxStep, NativeBeamSearch
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    m = T5ForConditionalGeneration(T5Config(decoder_start_token_id=0)).eval().to(dev)
+    cond = torch.randn(1, 4, 512, device=dev)
+    kw = dict(max_new_tokens=180, min_new_tokens=150, num_beams=4, no_repeat_ngram_size=3, length_penalty=1.1,
+              early_stopping=True, eos_token_id=1, pad_token_id=0)
+    step = MmdxStep(m, dev)
+    nat = NativeBeamSearch(step, m.config)
+    nat.generate(cond, **dict(kw, max_new_tokens=8, min_new_tokens=4))
+    ts = []
+    for _ in range(5):
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        got = nat.generate(cond, **kw)
+        ts.append(time.perf_counter() - t)
+    with torch.no_grad():
+        m.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **dict(kw, max_new_tokens=8, min_new_tokens=4))
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        want = m.generate(encoder_outputs=BaseModelOutput(last_hidden_state=cond), **kw)
+        torch.cuda.synchronize(dev)
+        t_hf = time.perf_counter() - t
+    step.close()
+    return {"ms_median": 1e3 * float(np.median(ts)), "tokens": int(got.shape[1] - 1),
+            "hf_generate_eager_gpu_ms": 1e3 * t_hf, "tokens_identical_to_hf": bool(torch.equal(want.cpu(), got.cpu())),
+            "shape": "1 study, 4 conditioning tokens, 4 beams, 180 new tokens (150 minimum), no-repeat 3-gram, length penalty 1.1",
+            "api": "mmdx_t5_generate (NativeBeamSearch): one cooperative decoder-step launch + 4 small launches per token"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +314,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-report-latency", action="store_true")
     ap.add_argument("--exact-steps", action="store_true", help="time exactly --steps steps (no extension to 2 s)")
     ap.add_argument("--profile-only", action="store_true", help="one warm pass + few steps, for ncu")
     args = ap.parse_args()
@@ -539,6 +577,11 @@ def main():
     if lat is not None:
         out["latency_b1_ms"] = lat["ms_median"]
         out["latency_b1"] = lat
+    if rank == 0 and world == 1 and not args.no_report_latency:
+        try:
+            out["report_b1"] = report_latency(local_rank)
+        except Exception as ex:      # noqa: BLE001 - informational: must never take the bench line down
+            out["report_b1"] = {"unavailable": repr(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_library_baseline:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))

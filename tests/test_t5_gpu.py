@@ -109,12 +109,14 @@ def test_inference_report_text_through_the_cuda_decoder(state_bundle, g1):
     assert fast["disease_vector"] == g1["inf_vector"][0].tolist()
     # the default is the native search (one C call per report); "hf" keeps HF's own beam search over the CUDA step, "native"
     # insists on the native search; arguments the native search does not restate fall back to the HF loop by default
-    launches0 = ip.fast_report_generator(b["fusion_model"], torch.device("cuda", 0)).backend.launch_count
+    def launches():
+        return sum(g[0].backend.launch_count for g in ip._REPORT_GENS.values() if g[0] is not None)
+    launches0 = launches()
     hf = ip.inference(dict(b, fast_report="hf"), pil, str(g1["details"][0]), device="cuda", gen_kwargs=kw)
     native = ip.inference(dict(b, fast_report="native"), pil, str(g1["details"][0]), device="cuda", gen_kwargs=kw)
     assert hf["report_text"] == slow["report_text"] and native["report_text"] == slow["report_text"]
     assert native["disease_probs"] == fast["disease_probs"]
-    assert ip.fast_report_generator(b["fusion_model"], torch.device("cuda", 0)).backend.launch_count > launches0
+    assert launches() > launches0
     sampled = ip.inference(b, pil, str(g1["details"][0]), device="cuda", gen_kwargs=dict(kw, repetition_penalty=1.3))
     want = ip.inference(dict(b, fast_report=False), pil, str(g1["details"][0]), device="cuda", gen_kwargs=dict(kw, repetition_penalty=1.3))
     assert sampled["report_text"] == want["report_text"]
