@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -115,6 +116,7 @@ struct T5Layer {                      // device copy of one block's pointers
   const float *ln0, *qkv, *so, *ln1, *cq, *co, *ln2, *wi, *wo;
   float *sk, *sv;                     // self-attention cache [R, H, Tmax, dk]: slot (r, j) is written once, at step j, by row r
   const float *ck, *cv;               // projected conditioning tokens [R, H, n_enc, dk]
+  const float *kq, *w2;               // cross-attention folded per generation (t5_cross_fold_kernel), or null
 };
 
 constexpr int kMaxT5Layers = 24;
@@ -125,9 +127,13 @@ struct T5StepArgs {
   const float *E, *lm, *final_ln, *bias;
   T5Layer layers[kMaxT5Layers];
   int32_t* anc;                       // [R, Tmax]: anc[r][j] = the row slot that holds position j of row r's hypothesis
+  const int32_t* anc_src;             // with bidx: the beam reordering happens here (anc[r] = anc_src[bidx[r]]), else unused
+  const int32_t* bidx;
+  const int32_t* copy_src; int32_t* copy_dst; int copy_n;     // optional: words the last CTA copies (mapped host -> device) for the scoring kernels
   float *x, *qkv, *att, *q, *hid;
   float eps, lm_scale;
   int R, d, H, dk, ff, L, vocab, Tmax, t, n_enc, kmax;
+  int xfold, xk;                      // cross-attention folded: xfold = R * H * n_enc score columns, xk = xfold padded to 128
   unsigned long long* prof;           // optional: globaltimer stamp per phase boundary, written by CTA 0 (mmdx_t5_step_profile)
 };
 
@@ -147,7 +153,7 @@ template <int NR>
 __device__ __noinline__ void mega_linear(const int R, const float eps, const float* x, long long ldx,
                                          const float* __restrict__ ln_w, float in_scale, const float* __restrict__ W, float* out,
                                          long long ldo, const float* res, int K, int N, int relu, bool stream_w, float* xs,
-                                         float* part) {
+                                         float* part, int bd_m = 0, int bd_nenc = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nb = gridDim.x, bid = blockIdx.x;
   const int GW = nb * kMegaWarps;
   const int KS = (N * 4 <= GW && K % 512 == 0) ? 4 : 1;
@@ -181,7 +187,25 @@ __device__ __noinline__ void mega_linear(const int R, const float eps, const flo
   cg::this_grid().sync();
   for (int r0 = 0; r0 < R; r0 += NR) {
     __syncthreads();                                             // the previous readers of xs are done
-    if (ln_w == nullptr) {                                       // plain copy (x in_scale): every thread, independent 16-byte loads
+    if (bd_m > 0) {
+      // folded cross-attention, second half: x holds the scores S [R, R * bd_m] of every row against every row's keys
+      // (only the diagonal blocks mean anything); the staged operand is the block-diagonal matrix of softmax(S) per
+      // head - row r carries its probabilities in columns [r * bd_m, (r + 1) * bd_m) and zeros elsewhere - so the
+      // product with W2 [N, K] (values x output projection, per row) is that row's cross-attention output.
+      for (int i = tid; i < NR * K; i += kMegaThreads) {
+        const int r = i / K, col = i - r * K, row = r0 + r;
+        float v = 0.f;
+        if (row < R && col >= row * bd_m && col < (row + 1) * bd_m) {
+          const int m = col - row * bd_m, h = m / bd_nenc;
+          const float* sc = x + static_cast<size_t>(row) * ldx + row * bd_m + h * bd_nenc;
+          float mx = -INFINITY, sum = 0.f;
+          for (int j = 0; j < bd_nenc; ++j) mx = fmaxf(mx, sc[j]);
+          for (int j = 0; j < bd_nenc; ++j) sum += expf(sc[j] - mx);
+          v = expf(sc[m - h * bd_nenc] - mx) / sum;
+        }
+        xs[i] = v;
+      }
+    } else if (ln_w == nullptr) {                                // plain copy (x in_scale): every thread, independent 16-byte loads
       const int k4 = K / 4, tot = NR * k4;
 #pragma unroll 4
       for (int i = tid; i < tot; i += kMegaThreads) {
@@ -238,6 +262,14 @@ __device__ __noinline__ void mega_linear(const int R, const float eps, const flo
       float acc0[NR], acc1[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+      if (stream_w && g + nb < groups) {                        // LM head: pull the next task's rows from HBM into L2 now
+        const int cn = ((g + nb) * slots + slot) * NC;
+        if (cn < N) {
+          const float4* n0 = reinterpret_cast<const float4*>(W + static_cast<size_t>(cn) * K) + kp * kq;
+          for (int i = lane * 8; i < kq * (NC == 2 && cn + 1 < N ? 2 : 1); i += 256)      // one prefetch per 128-byte line
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(n0 + i));
+        }
+      }
       if (on) {
         const float4* xv = reinterpret_cast<const float4*>(xs) + kp * kq;
         for (int i0 = lane; i0 < kq; i0 += 128) {
@@ -395,9 +427,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) t5_step_mega_kernel(const T5S
     ++np;
   };
   stamp();
+  // tok / bidx / copy_src may live in mapped host memory (mmdx_t5_generate): one PCIe read per warp or row, not per thread
+  if (a.bidx != nullptr) {            // beam reordering of the last search step; read two barriers later by layer 0's attention
+    __shared__ int s_src;
+    for (int r = blockIdx.x; r < a.R; r += gridDim.x) {
+      if (threadIdx.x == 0) s_src = min(max(a.bidx[r], 0), a.R - 1);
+      __syncthreads();
+      for (int j = threadIdx.x; j < a.t; j += kMegaThreads)
+        a.anc[static_cast<size_t>(r) * a.Tmax + j] = a.anc_src[static_cast<size_t>(s_src) * a.Tmax + j];
+      __syncthreads();
+    }
+  }
+  if (a.copy_n > 0 && blockIdx.x == gridDim.x - 1)
+    for (int i = threadIdx.x; i < a.copy_n; i += kMegaThreads) a.copy_dst[i] = a.copy_src[i];
   for (int i = blockIdx.x * kMegaThreads + threadIdx.x; i < a.R * d; i += gridDim.x * kMegaThreads) {
-    const int r = i / d, k = i - r * d;
-    const int id = min(max(a.tok[r], 0), a.vocab - 1);
+    const int r = i / d, k = i - r * d;                          // d % 128 == 0: a warp stays inside one row
+    int id = 0;
+    if ((threadIdx.x & 31) == 0) id = min(max(a.tok[r], 0), a.vocab - 1);
+    id = __shfl_sync(0xffffffffu, id, 0);
     a.x[i] = a.E[static_cast<size_t>(id) * d + k];
   }
   for (int l = 0; l < a.L; ++l) {                                // every mega_linear starts with the barrier behind its producer
@@ -409,13 +456,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) t5_step_mega_kernel(const T5S
     stamp();
     mega_linear<NR>(a.R, a.eps, a.att, inner, nullptr, 1.0f, L.so, a.x, d, a.x, inner, d, 0, false, xs, part);
     stamp();
-    mega_linear<NR>(a.R, a.eps, a.x, d, L.ln1, 1.0f, L.cq, a.q, inner, nullptr, d, inner, 0, false, xs, part);
-    stamp();
-    grid.sync();
-    mega_cross_attn(a, L, sm);
-    stamp();
-    mega_linear<NR>(a.R, a.eps, a.att, inner, nullptr, 1.0f, L.co, a.x, d, a.x, inner, d, 0, false, xs, part);
-    stamp();
+    if (a.xfold > 0) {
+      // cross-attention with the query projection folded into the keys and the output projection into the values (both are
+      // constants of the generation): scores = RMSNorm(x) . KQ, x += softmax(scores) . W2 - two phases instead of three
+      mega_linear<NR>(a.R, a.eps, a.x, d, L.ln1, 1.0f, L.kq, a.q, a.xfold, nullptr, d, a.xfold, 0, false, xs, part);
+      stamp();
+      stamp();
+      mega_linear<NR>(a.R, a.eps, a.q, a.xfold, nullptr, 1.0f, L.w2, a.x, d, a.x, a.xk, d, 0, false, xs, part, a.xfold / a.R, a.n_enc);
+      stamp();
+    } else {
+      mega_linear<NR>(a.R, a.eps, a.x, d, L.ln1, 1.0f, L.cq, a.q, inner, nullptr, d, inner, 0, false, xs, part);
+      stamp();
+      grid.sync();
+      mega_cross_attn(a, L, sm);
+      stamp();
+      mega_linear<NR>(a.R, a.eps, a.att, inner, nullptr, 1.0f, L.co, a.x, d, a.x, inner, d, 0, false, xs, part);
+      stamp();
+    }
     mega_linear<NR>(a.R, a.eps, a.x, d, L.ln2, 1.0f, L.wi, a.hid, a.ff, nullptr, d, a.ff, 1, false, xs, part);
     stamp();
     mega_linear<NR>(a.R, a.eps, a.hid, a.ff, nullptr, 1.0f, L.wo, a.x, d, a.x, a.ff, d, 0, false, xs, part);
@@ -437,6 +494,30 @@ __global__ void t5_split_heads_kernel(const float* __restrict__ in, int R, int n
   const int h = static_cast<int>(x % H);
   const int r = static_cast<int>(x / H);
   out[i] = in[(static_cast<size_t>(r) * n_enc + j) * H * dk + h * dk + d];
+}
+
+// Folds the two cross-attention projections into the per-generation constants (one CTA per (row, head, token)):
+//   kq [R * M, d]  : kq[r * M + m][k] = sum_dd Wq[h * dk + dd][k] * K[r, h, j, dd]          (m = h * n_enc + j, M = H * n_enc)
+//   w2 [d, xk]     : w2[c][r * M + m] = sum_dd Wo[c][h * dk + dd] * V[r, h, j, dd]          (columns >= R * M are zero)
+// so that scores = RMSNorm(x) . kq^T and output = softmax(scores) . w2^T need no q and no attention phase per token.
+__global__ void __launch_bounds__(256) t5_cross_fold_kernel(const float* __restrict__ Wq, const float* __restrict__ Wo,
+                                                            const float* __restrict__ Kc, const float* __restrict__ Vc, int H,
+                                                            int dk, int n_enc, int d, int xk, float* __restrict__ kq,
+                                                            float* __restrict__ w2) {
+  __shared__ float kv[64], vv[64];
+  const int M = H * n_enc, rm = blockIdx.x, r = rm / M, m = rm - r * M, h = m / n_enc, j = m - h * n_enc, inner = H * dk;
+  const size_t src = ((static_cast<size_t>(r) * H + h) * n_enc + j) * dk;
+  if (threadIdx.x < dk) { kv[threadIdx.x] = Kc[src + threadIdx.x]; vv[threadIdx.x] = Vc[src + threadIdx.x]; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int dd = 0; dd < dk; ++dd) {
+      a = fmaf(Wq[static_cast<size_t>(h * dk + dd) * d + k], kv[dd], a);
+      b = fmaf(Wo[static_cast<size_t>(k) * inner + h * dk + dd], vv[dd], b);
+    }
+    kq[static_cast<size_t>(rm) * d + k] = a;
+    w2[static_cast<size_t>(k) * xk + rm] = b;
+  }
 }
 
 // beam reordering: row r continues the hypothesis of row idx[r] - only the ancestry rows move, positions [0, t)
@@ -496,41 +577,55 @@ __global__ void __launch_bounds__(kScoreThreads) t5_lse_ban_kernel(float* __rest
   }
 }
 
-// k rounds of a block-wide arg-max over the threads' sorted candidate lists: pops the winners in descending order (ties:
-// the lower index first).  kScoreThreads threads.
+// The k best of the threads' sorted candidate lists, in descending order (ties: the lower index first).  Every warp pops
+// its own k winners with shuffles only (no block barrier per round), the 8 x k survivors meet in shared memory and warp 0
+// pops the final k from them.  The order is total, so the result equals k rounds of a block-wide arg-max.  kScoreThreads threads.
+__device__ __forceinline__ void warp_argmax(float& v, int& ix, int& th) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+    const int ot = __shfl_xor_sync(0xffffffffu, th, o);
+    if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; th = ot; }
+  }
+}
+
 __device__ void block_pop_topk(const float (&best)[kTopK], const int (&bidx)[kTopK], int k, float* __restrict__ out_scores,
                                int32_t* __restrict__ out_idx) {
   constexpr int W = kScoreThreads / 32;
-  __shared__ float sv[W];
-  __shared__ int si[W], st[W];
-  __shared__ int s_win_thread;
-  const int tid = threadIdx.x;
+  __shared__ float sv[W * kTopK];
+  __shared__ int si[W * kTopK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int head = 0;                               // this thread's next candidate
   for (int round = 0; round < k; ++round) {
-    float v = head < kTopK ? best[head] : -INFINITY;
-    int ix = head < kTopK ? bidx[head] : 0x7fffffff;
-    int th = tid;
+    float v = -INFINITY;
+    int ix = 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
-      const int ot = __shfl_xor_sync(0xffffffffu, th, o);
-      if (ov > v || (ov == v && oi < ix)) { v = ov; ix = oi; th = ot; }
-    }
-    if ((tid & 31) == 0) { sv[tid >> 5] = v; si[tid >> 5] = ix; st[tid >> 5] = th; }
-    __syncthreads();
-    if (tid == 0) {
-      float bv = sv[0]; int bi = si[0], bt = st[0];
-      for (int w = 1; w < W; ++w)
-        if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; bt = st[w]; }
-      out_scores[round] = bv;
-      out_idx[round] = bi;
-      s_win_thread = bt;
-    }
-    __syncthreads();
-    if (tid == s_win_thread) ++head;
-    __syncthreads();
+    for (int j = 0; j < kTopK; ++j) if (j == head) { v = best[j]; ix = bidx[j]; }
+    int th = lane;
+    warp_argmax(v, ix, th);
+    if (lane == th) ++head;
+    if (lane == 0) { sv[warp * kTopK + round] = v; si[warp * kTopK + round] = ix; }
   }
+  __syncthreads();
+  if (warp == 0) {                            // W * k <= 64 survivors: two per lane, each warp's list already sorted
+    float c0 = -INFINITY, c1 = -INFINITY;
+    int i0 = 0x7fffffff, i1 = 0x7fffffff;
+    const int a = lane, b = lane + 32;
+    if (a < W * kTopK && (a % kTopK) < k) { c0 = sv[a]; i0 = si[a]; }
+    if (b < W * kTopK && (b % kTopK) < k) { c1 = sv[b]; i1 = si[b]; }
+    if (c1 > c0 || (c1 == c0 && i1 < i0)) { const float tv = c0; c0 = c1; c1 = tv; const int ti = i0; i0 = i1; i1 = ti; }
+    int used = 0;                             // 0: c0 is next, 1: c1, 2: none left
+    for (int round = 0; round < k; ++round) {
+      float v = used == 0 ? c0 : (used == 1 ? c1 : -INFINITY);
+      int ix = used == 0 ? i0 : (used == 1 ? i1 : 0x7fffffff);
+      int th = lane;
+      warp_argmax(v, ix, th);
+      if (lane == th) ++used;
+      if (lane == 0) { out_scores[round] = v; out_idx[round] = ix; }
+    }
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kScoreThreads) t5_topk_chunk_kernel(const float* __restrict__ logits, const float* __restrict__ part,
@@ -555,14 +650,30 @@ __global__ void __launch_bounds__(kScoreThreads) t5_topk_chunk_kernel(const floa
 #pragma unroll
   for (int j = 0; j < kTopK; ++j) { best[j] = -INFINITY; bidx[j] = 0x7fffffff; }
   const int cw = score_chunk_width(V), lo = c * cw, n = max(0, min(V, lo + cw) - lo);
-  for (int i = tid; i < beams * n; i += kScoreThreads) {     // ascending flat index per thread
-    const int row = i / n, tok = lo + (i - row * n);
-    float v = (logits[(static_cast<size_t>(b) * beams + row) * V + tok] - stat[3 * row]) - stat[3 * row + 1];
-    v += stat[3 * row + 2];
-    if (v > best[kTopK - 1]) {               // strictly greater: an equal later (higher) index never displaces an earlier one
-      int j = kTopK - 1;
-      while (j > 0 && v > best[j - 1]) { best[j] = best[j - 1]; bidx[j] = bidx[j - 1]; --j; }
-      best[j] = v; bidx[j] = row * V + tok;
+  // rows outermost (no index divisions), tokens strided over the threads: ascending flat index per thread; the loads of a
+  // row are issued together, then the (data-dependent) insertions run as compare-exchanges on registers
+  for (int row = 0; row < beams; ++row) {
+    const float* x = logits + (static_cast<size_t>(b) * beams + row) * V + lo;
+    const float mx = stat[3 * row], ls = stat[3 * row + 1], bs = stat[3 * row + 2];
+    for (int t0 = tid; t0 < n; t0 += 4 * kScoreThreads) {
+      float x4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x4[u] = t0 + u * kScoreThreads < n ? x[t0 + u * kScoreThreads] : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v = (x4[u] - mx) - ls;
+        v += bs;
+        if (v > best[kTopK - 1]) {           // strictly greater: an equal later (higher) index never displaces an earlier one
+          best[kTopK - 1] = v; bidx[kTopK - 1] = row * V + lo + t0 + u * kScoreThreads;
+#pragma unroll
+          for (int j = kTopK - 1; j > 0; --j) {
+            if (best[j] > best[j - 1]) {     // bubble up past strictly smaller entries only
+              const float tv = best[j]; best[j] = best[j - 1]; best[j - 1] = tv;
+              const int ti = bidx[j]; bidx[j] = bidx[j - 1]; bidx[j - 1] = ti;
+            }
+          }
+        }
+      }
     }
   }
   const size_t o = (static_cast<size_t>(b) * kScoreChunks + c) * k;
@@ -570,7 +681,8 @@ __global__ void __launch_bounds__(kScoreThreads) t5_topk_chunk_kernel(const floa
 }
 
 __global__ void __launch_bounds__(kScoreThreads) t5_topk_merge_kernel(const float* __restrict__ cand_s, const int32_t* __restrict__ cand_i,
-                                                                      int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+                                                                      int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                                                                      int* __restrict__ done_ctr, volatile int* host_flag, int flag_value) {
   const int b = blockIdx.x, tid = threadIdx.x;
   float best[kTopK];
   int bidx[kTopK];
@@ -582,6 +694,13 @@ __global__ void __launch_bounds__(kScoreThreads) t5_topk_merge_kernel(const floa
     bidx[0] = cand_i[static_cast<size_t>(b) * kScoreChunks * k + tid];
   }
   block_pop_topk(best, bidx, k, out_scores + static_cast<size_t>(b) * k, out_idx + static_cast<size_t>(b) * k);
+  // mmdx_t5_generate: the outputs live in mapped host memory and the host spins on the studies' flags instead of
+  // synchronising the stream
+  (void)done_ctr;
+  if (host_flag != nullptr && tid == 0) {     // one flag per study: results, one system-scope fence, flag
+    __threadfence_system();
+    host_flag[b] = flag_value;
+  }
 }
 
 struct Block { float *ln0, *qkv, *so, *ln1, *cq, *ck, *cv, *co, *ln2, *wi, *wo; };
@@ -606,6 +725,7 @@ struct mmdx_t5 {
   int cur = 0;                        // which ancestry copy is live
   std::vector<T5Layer> h_layers;      // per-block pointers (refreshed by mmdx_t5_begin), passed to the step kernel by value
   unsigned long long* prof = nullptr; // device stamps of the last step (MMDX_T5_PROF=1)
+  int xfold = 0, xk = 0;              // folded cross-attention of the current generation (0 = off)
   int mega_blocks = 0;                // co-resident CTAs of the step kernel (one per SM)
   float* gen_dev = nullptr; size_t gen_dev_words = 0;       // mmdx_t5_generate scratch (device / pinned host), grow-only
   float* gen_host = nullptr; size_t gen_host_words = 0;
@@ -732,14 +852,21 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
   cudaStream_t s = (cudaStream_t)stream;
   const int d = e->d, inner = e->H * e->dk;
   const size_t cache = (size_t)R * e->H * max_steps * e->dk, cross = (size_t)R * e->H * n_enc * e->dk;
+  // cross-attention folding (see t5_cross_fold_kernel): worth it while the R x R score matrix stays narrow
+  const int xfold = R * e->H * n_enc <= inner && e->d == inner && std::getenv("MMDX_T5_NOFOLD") == nullptr ? R * e->H * n_enc : 0;
+  const int xk = (xfold + 127) / 128 * 128;
+  const size_t fold_words = xfold > 0 ? (size_t)xfold * d + (size_t)d * xk : 0;
   const size_t anc_words = ((size_t)R * max_steps + 3) / 4 * 4;          // int32 rows, kept 16-byte aligned
   const size_t layer_words = (sizeof(T5Layer) * e->L + 15) / 16 * 4;
   const size_t need = (size_t)R * (d + 3 * inner + inner + inner + e->ff) + (size_t)max_steps * e->H + 4 + (size_t)e->L * (2 * cache + 2 * cross) +
-                      (size_t)R * n_enc * inner + 2 * anc_words + layer_words + (size_t)R * kScoreChunks * (2 + 2 * kTopK) + 1024;
+                      (size_t)R * n_enc * inner + (size_t)e->L * fold_words + 2 * anc_words + layer_words + ((size_t)R * kScoreChunks * (2 + 2 * kTopK) + 4) + 1024;
   if (need > e->ws_floats) {
-    if (e->ws) { T5_CK(cudaDeviceSynchronize()); cudaFree(e->ws); e->ws = nullptr; }
-    T5_CK(cudaMalloc(&e->ws, need * 4));
-    e->ws_floats = need;
+    if (e->ws) { T5_CK(cudaDeviceSynchronize()); cudaFree(e->ws); e->ws = nullptr; e->ws_floats = 0; }
+    // headroom: a later generation with more rows or more steps should not have to free and reallocate (a device-wide
+    // synchronisation plus a cudaFree / cudaMalloc pair in the middle of serving)
+    const size_t grant = std::max(need + need / 2, (size_t)16 << 20);
+    T5_CK(cudaMalloc(&e->ws, grant * 4));
+    e->ws_floats = grant;
   }
   float* p = e->ws;
   e->x = p; p += (size_t)R * d;
@@ -757,12 +884,16 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
     e->ck.push_back(p); p += cross;
     e->cv.push_back(p); p += cross;
     const Block& b = e->blocks[l];
-    hl[l] = T5Layer{b.ln0, b.qkv, b.so, b.ln1, b.cq, b.co, b.ln2, b.wi, b.wo, e->sk[l], e->sv[l], e->ck[l], e->cv[l]};
+    float *kq = nullptr, *w2 = nullptr;
+    if (xfold > 0) { kq = p; p += (size_t)xfold * d; w2 = p; p += (size_t)d * xk; }
+    hl[l] = T5Layer{b.ln0, b.qkv, b.so, b.ln1, b.cq, b.co, b.ln2, b.wi, b.wo, e->sk[l], e->sv[l], e->ck[l], e->cv[l], kq, w2};
   }
+  e->xfold = xfold; e->xk = xk;
   e->anc[0] = reinterpret_cast<int32_t*>(p); p += anc_words;
   e->anc[1] = reinterpret_cast<int32_t*>(p); p += anc_words;
   (void)layer_words;
-  e->score_ws = p; p += (size_t)R * kScoreChunks * (2 + 2 * kTopK);
+  e->score_ws = p; p += ((size_t)R * kScoreChunks * (2 + 2 * kTopK) + 4);
+  T5_CK(cudaMemsetAsync(e->score_ws + (size_t)R * kScoreChunks * (2 + 2 * kTopK), 0, 16, s));      // the merge kernel's arrival counter
   e->h_layers = hl;
   e->R = R; e->n_enc = n_enc; e->Tmax = max_steps; e->t = 0; e->cur = 0;
   T5_CK(cudaMemcpyAsync(e->bias, h_bias, (size_t)max_steps * e->H * 4, cudaMemcpyHostToDevice, s));
@@ -773,6 +904,13 @@ extern "C" int mmdx_t5_begin(mmdx_t5* e, const float* d_enc, int R, int n_enc, i
     if (t5_linear(e, d_enc, d, nullptr, 1.0f, e->blocks[l].cv, tmp, inner, nullptr, R * n_enc, d, inner, 0, s)) return 1;
     t5_split_heads_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(tmp, R, n_enc, e->H, e->dk, e->cv[l]);
     e->launches += 2;
+    if (xfold > 0) {
+      float* w2 = const_cast<float*>(e->h_layers[l].w2);
+      if (xk > xfold) T5_CK(cudaMemsetAsync(w2, 0, (size_t)d * xk * 4, s));
+      t5_cross_fold_kernel<<<xfold, 256, 0, s>>>(e->blocks[l].cq, e->blocks[l].co, e->ck[l], e->cv[l], e->H, e->dk, n_enc, d, xk,
+                                                 const_cast<float*>(e->h_layers[l].kq), w2);
+      e->launches++;
+    }
   }
   T5_CK(cudaGetLastError());
   return 0;
@@ -793,8 +931,10 @@ extern "C" int mmdx_t5_reorder(mmdx_t5* e, const int32_t* d_beam_idx, void* stre
   return 0;
 }
 
-// One decoder step: d_tokens [R] -> d_logits [R, vocab] fp32; the new position joins the cache.
-extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, void* stream) {
+// One decoder step: d_tokens [R] -> d_logits [R, vocab] fp32; the new position joins the cache.  d_beam_idx (optional): the
+// beam reordering that precedes this step, done inside the same launch.
+static int t5_step_impl(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, const int32_t* d_beam_idx, void* stream,
+                        const int32_t* copy_src = nullptr, int32_t* copy_dst = nullptr, int copy_n = 0) {
   T5_REQUIRE(e && d_tokens && d_logits, "null argument");
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->R > 0, "mmdx_t5_step before mmdx_t5_begin");
@@ -806,12 +946,18 @@ extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits
   a.tok = d_tokens; a.logits = d_logits; a.E = e->E; a.lm = e->lm; a.final_ln = e->final_ln; a.bias = e->bias;
   for (int l = 0; l < e->L; ++l) a.layers[l] = e->h_layers[l];
   a.anc = e->anc[e->cur];
+  a.copy_src = copy_src; a.copy_dst = copy_dst; a.copy_n = copy_n;
+  if (d_beam_idx != nullptr && e->t > 0) {
+    a.anc_src = e->anc[e->cur]; a.anc = e->anc[e->cur ^ 1]; a.bidx = d_beam_idx;
+    e->cur ^= 1;
+  }
   a.x = e->x; a.qkv = e->qkv; a.att = e->att; a.q = e->q; a.hid = e->hid;
   a.eps = e->eps;
   a.lm_scale = e->tied == 1 ? 1.0f / std::sqrt((float)d) : 1.0f;     // HF scales the decoder output only in the default tied setup
   a.R = R; a.d = d; a.H = e->H; a.dk = e->dk; a.ff = e->ff; a.L = e->L; a.vocab = e->vocab; a.Tmax = e->Tmax; a.t = e->t;
   a.n_enc = e->n_enc; a.kmax = std::max(std::max(d, inner), e->ff);
   a.prof = e->prof;
+  a.xfold = e->xfold; a.xk = e->xk;
   const int NR = R <= 4 ? 4 : 8;
   const size_t smem = std::max((size_t)NR * a.kmax + (size_t)kMegaWarps * NR, (size_t)96 + 2048 + 2 * (size_t)e->Tmax) * 4;
   T5_REQUIRE(smem <= 200 * 1024, "step: d_ff / max_steps too large for the shared-memory staging");
@@ -834,12 +980,16 @@ extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits
   return 0;
 }
 
+extern "C" int mmdx_t5_step(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, void* stream) {
+  return t5_step_impl(e, d_tokens, d_logits, nullptr, stream);
+}
+
 // Beam-search scoring of the logits mmdx_t5_step has just produced: per study the k best (row, token) continuations of
 // log_softmax(logits) + beam_score, with EOS and the per-row banned tokens (int32 [R, max_ban], -1 padded; may be null when
 // max_ban = 0) masked out.  d_out_scores / d_out_idx [R / num_beams, k], descending, idx = row_in_study * vocab + token.
-extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_beam_scores, const int32_t* d_banned,
-                                  int max_ban, int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores,
-                                  int32_t* d_out_idx, void* stream) {
+static int t5_score_topk_impl(mmdx_t5* e, float* d_logits, const float* d_beam_scores, const int32_t* d_banned,
+                              int max_ban, int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores,
+                              int32_t* d_out_idx, int* d_host_flag, int flag_value, void* stream) {
   T5_REQUIRE(e && d_logits && d_beam_scores && d_out_scores && d_out_idx, "null argument");
   std::lock_guard<std::recursive_mutex> lk(e->mu);
   T5_REQUIRE(e->R > 0 && num_beams > 0 && e->R % num_beams == 0, "mmdx_t5_score_topk: rows must be studies x beams");
@@ -854,10 +1004,18 @@ extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_be
   t5_lse_ban_kernel<<<dim3(kScoreChunks, e->R), kScoreThreads, 0, s>>>(d_logits, e->vocab, part, d_banned, max_ban, ban_eos, eos_id);
   t5_topk_chunk_kernel<<<dim3(kScoreChunks, B), kScoreThreads, (size_t)num_beams * 3 * 4, s>>>(d_logits, part, d_beam_scores, num_beams,
                                                                                                e->vocab, k, cand_s, cand_i);
-  t5_topk_merge_kernel<<<B, kScoreThreads, 0, s>>>(cand_s, cand_i, k, d_out_scores, d_out_idx);
+  int* done_ctr = reinterpret_cast<int*>(cand_i + (size_t)e->R * kScoreChunks * kTopK);
+  t5_topk_merge_kernel<<<B, kScoreThreads, 0, s>>>(cand_s, cand_i, k, d_out_scores, d_out_idx, done_ctr, d_host_flag, flag_value);
   e->launches += 3;
   T5_CK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mmdx_t5_score_topk(mmdx_t5* e, float* d_logits, const float* d_beam_scores, const int32_t* d_banned,
+                                  int max_ban, int ban_eos, int eos_id, int num_beams, int k, float* d_out_scores,
+                                  int32_t* d_out_idx, void* stream) {
+  return t5_score_topk_impl(e, d_logits, d_beam_scores, d_banned, max_ban, ban_eos, eos_id, num_beams, k, d_out_scores, d_out_idx,
+                            nullptr, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -890,40 +1048,50 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
   const float NEG = -1.0e9f;
   const double lp = (double)length_penalty;
   // ---- device scratch of the search (freed on every exit path by the guard)
-  // One pinned block goes up per token (beam indices of the last step | tokens | running scores | banned lists) and one
-  // comes back (2K candidate scores | indices per study): two copies and one synchronisation per token.  The buffers
-  // belong to the engine and only ever grow (a cudaMallocHost / cudaFree pair per call cost ~3 ms).
+  // Per token the host writes one block (beam indices of the last step | tokens | running scores | banned lists) and reads
+  // one (2K candidate scores | indices per study | a sequence flag).  Both live in pinned host memory that the kernels
+  // read and write directly (zero-copy over PCIe: a few hundred bytes), and the host spins on the flag the merge kernel
+  // raises instead of synchronising the stream: no copy-engine launches and no stream synchronisation per token.  The
+  // buffers belong to the engine and only ever grow.
   const long long enc_row = (long long)n_enc * e->d;
   const int max_ban = max_length;                                 // a row can ban at most one token per earlier position
   const size_t stage_words = (size_t)R * (3 + max_ban), cand_words = (size_t)2 * B * K2;
-  const size_t dev_words = (size_t)R * enc_row + (size_t)R * V + stage_words + cand_words + 64;
+  const size_t dev_words = (size_t)R * enc_row + (size_t)R * V + (size_t)R * (1 + max_ban) + 64;
   if (dev_words > e->gen_dev_words) {
     if (e->gen_dev) { T5_CK(cudaDeviceSynchronize()); cudaFree(e->gen_dev); e->gen_dev = nullptr; e->gen_dev_words = 0; }
-    T5_CK(cudaMalloc(&e->gen_dev, dev_words * 4));
-    e->gen_dev_words = dev_words;
+    const size_t grant = std::max(dev_words + dev_words / 2, (size_t)4 << 20);
+    T5_CK(cudaMalloc(&e->gen_dev, grant * 4));
+    e->gen_dev_words = grant;
   }
-  if (stage_words + cand_words > e->gen_host_words) {
+  if (stage_words + cand_words + B + 16 > e->gen_host_words) {
     if (e->gen_host) { T5_CK(cudaDeviceSynchronize()); cudaFreeHost(e->gen_host); e->gen_host = nullptr; e->gen_host_words = 0; }
-    T5_CK(cudaMallocHost(&e->gen_host, (stage_words + cand_words) * 4));
-    e->gen_host_words = stage_words + cand_words;
+    const size_t grant = std::max(2 * (stage_words + cand_words + B + 16), (size_t)1 << 18);
+    T5_CK(cudaHostAlloc(&e->gen_host, grant * 4, cudaHostAllocMapped));
+    e->gen_host_words = grant;
   }
-  struct { float *enc, *logits; int32_t *stage, *cand, *h_stage, *h_cand; } w;
+  float* host_dev = nullptr;                                      // the device's view of the pinned block
+  T5_CK(cudaHostGetDevicePointer(&host_dev, e->gen_host, 0));
+  struct { float *enc, *logits; int32_t *h_stage, *h_cand, *score_in; } w;
   w.enc = e->gen_dev;
   w.logits = w.enc + (size_t)R * enc_row;
-  w.stage = reinterpret_cast<int32_t*>(w.logits + (size_t)R * V);
-  w.cand = w.stage + (stage_words + 3) / 4 * 4;
+  w.score_in = reinterpret_cast<int32_t*>(w.logits + (size_t)R * V);      // device copy of (running scores | banned lists)
   w.h_stage = reinterpret_cast<int32_t*>(e->gen_host);
   w.h_cand = w.h_stage + stage_words;
+  volatile int* h_flag = reinterpret_cast<volatile int*>(w.h_cand + cand_words);
+  for (int b = 0; b < B; ++b) h_flag[b] = 0;
+  int32_t* const dv_stage = reinterpret_cast<int32_t*>(host_dev);
+  int32_t* const dv_cand = dv_stage + stage_words;
+  int* const dv_flag = dv_cand + cand_words;
   int32_t* const h_bidx = w.h_stage;
   int32_t* const h_tok = w.h_stage + R;
   float* const h_bscore = reinterpret_cast<float*>(w.h_stage + 2 * R);
   int32_t* const h_ban = w.h_stage + 3 * R;
-  const int32_t* d_bidx = w.stage;
-  const int32_t* d_tok = w.stage + R;
-  const float* d_bscore = reinterpret_cast<const float*>(w.stage + 2 * R);
-  const int32_t* d_ban = w.stage + 3 * R;
-  float* d_oscore = reinterpret_cast<float*>(w.cand);
-  int32_t* d_oidx = w.cand + (size_t)B * K2;
+  const int32_t* d_bidx = dv_stage;
+  const int32_t* d_tok = dv_stage + R;
+  const float* d_bscore = reinterpret_cast<const float*>(w.score_in);
+  const int32_t* d_ban = w.score_in + R;
+  float* d_oscore = reinterpret_cast<float*>(dv_cand);
+  int32_t* d_oidx = dv_cand + (size_t)B * K2;
   const float* h_oscore = reinterpret_cast<const float*>(w.h_cand);
   const int32_t* h_oidx = w.h_cand + (size_t)B * K2;
   {
@@ -965,14 +1133,21 @@ extern "C" int mmdx_t5_generate(mmdx_t5* e, const float* d_cond, int B, int n_en
       for (int r = 0; r < R; ++r)                                 // repack to [R, ban_w]
         for (int c = 0; c < ban_w; ++c) h_ban[(size_t)r * ban_w + c] = h_banned[(size_t)r * max_ban + c];
     }
-    T5_CK(cudaMemcpyAsync(w.stage, w.h_stage, ((size_t)3 * R + (size_t)R * ban_w) * 4, cudaMemcpyHostToDevice, s));
-    if (cur_len > 1 && mmdx_t5_reorder(e, d_bidx, s)) return 1;
-    if (mmdx_t5_step(e, d_tok, w.logits, s)) return 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);          // the block is complete before the kernels are enqueued
+    if (t5_step_impl(e, d_tok, w.logits, cur_len > 1 ? d_bidx : nullptr, s, dv_stage + 2 * R, w.score_in, R + R * ban_w)) return 1;
     const int ban_eos = (cur_len - prompt) < min_new_tokens ? 1 : 0;
-    if (mmdx_t5_score_topk(e, w.logits, d_bscore, ban_w > 0 ? d_ban : nullptr, ban_w, ban_eos, eos_id, K, K2, d_oscore, d_oidx, s))
+    if (t5_score_topk_impl(e, w.logits, d_bscore, ban_w > 0 ? d_ban : nullptr, ban_w, ban_eos, eos_id, K, K2, d_oscore, d_oidx,
+                           dv_flag, cur_len, s))
       return 1;
-    T5_CK(cudaMemcpyAsync(w.h_cand, w.cand, cand_words * 4, cudaMemcpyDeviceToHost, s));
-    T5_CK(cudaStreamSynchronize(s));
+    auto all_flags = [&]() { for (int b = 0; b < B; ++b) if (h_flag[b] != cur_len) return false; return true; };
+    for (unsigned spins = 0; !all_flags(); ++spins) {             // the merge kernel raises a study's flag behind its results
+      if ((spins & 0xfff) == 0xfff) {
+        const cudaError_t q = cudaStreamQuery(s);
+        if (q == cudaSuccess && !all_flags()) return t5_fail("mmdx_t5_generate: the stream drained without the completion flags");
+        if (q != cudaSuccess && q != cudaErrorNotReady) return t5_fail(std::string("mmdx_t5_generate: ") + cudaGetErrorString(q));
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_seq_cst);
     bool any_unsat = false, all_finished = true, all_hits = true;
     for (int b = 0; b < B; ++b) {
       const float* tks = h_oscore + (size_t)b * K2;
