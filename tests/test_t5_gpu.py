@@ -52,6 +52,35 @@ def test_step_logits_match_torch_step_with_reorder(t5):
         b.close()
 
 
+@pytest.mark.parametrize("studies,beams,n_enc,nofold", [(1, 4, 7, False), (2, 4, 4, True), (5, 4, 4, False), (2, 3, 16, False)])
+def test_step_variants_match_torch_step(t5, monkeypatch, studies, beams, n_enc, nofold):
+    """The step kernel's other shapes against the fp32 torch step: a conditioning length whose folded cross-attention
+    matrix needs zero padding (1 x 4 rows x 8 heads x 7 tokens = 224 -> 256 columns), the unfolded cross-attention path
+    (forced, and chosen by itself at 20 rows where the folded score matrix would be too wide), three row chunks, and a
+    beam count that is not a power of two."""
+    if nofold:
+        monkeypatch.setenv("MMDX_T5_NOFOLD", "1")
+    torch.manual_seed(11)
+    R = studies * beams
+    cond = torch.randn(studies, n_enc, 512, device="cuda").repeat_interleave(beams, 0)
+    a, b = TorchStep(t5), MmdxStep(t5)
+    a.begin(cond, R, 12)
+    b.begin(cond, R, 12)
+    tok = torch.zeros(R, dtype=torch.long, device="cuda")
+    for t in range(8):
+        la, lb = a.step(tok), b.step(tok)
+        torch.cuda.synchronize()
+        err = float((la - lb).abs().max() / la.abs().max())
+        assert err < 2e-5, (R, t, err)
+        tok = la.topk(2, -1).indices[torch.arange(R), torch.arange(R) % 2]
+        if t == 4 and beams > 1:
+            idx = torch.cat([s0 * beams + torch.tensor(([1, 1, 0, 3] if beams == 4 else [2, 0, 0])) for s0 in range(studies)]).cuda()
+            a.reorder(idx)
+            b.reorder(idx)
+            tok = tok[idx]
+    b.close()
+
+
 @pytest.mark.parametrize("kw", [
     dict(REF_KW, max_new_tokens=40, min_new_tokens=30),
     dict(max_new_tokens=24, num_beams=1, eos_token_id=1, pad_token_id=0),
