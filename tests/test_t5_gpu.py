@@ -146,6 +146,15 @@ def test_inference_report_text_through_the_cuda_decoder(state_bundle, g1):
     assert hf["report_text"] == slow["report_text"] and native["report_text"] == slow["report_text"]
     assert native["disease_probs"] == fast["disease_probs"]
     assert launches() > launches0
+    # a whole request at the reference's default generation settings (gen_kwargs=None: 180 new tokens, 4 beams)
+    ip.inference(b, pil, str(g1["details"][0]), device="cuda")
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        full = ip.inference(b, pil, str(g1["details"][0]), device="cuda")
+        ts.append(time.perf_counter() - t0)
+    print(f"inference() with the default report settings: {min(ts) * 1e3:.1f} ms per request "
+          f"({len(full['report_text'].split())} report tokens)")
     sampled = ip.inference(b, pil, str(g1["details"][0]), device="cuda", gen_kwargs=dict(kw, repetition_penalty=1.3))
     want = ip.inference(dict(b, fast_report=False), pil, str(g1["details"][0]), device="cuda", gen_kwargs=dict(kw, repetition_penalty=1.3))
     assert sampled["report_text"] == want["report_text"]
