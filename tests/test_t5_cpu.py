@@ -143,3 +143,16 @@ def test_native_beam_search_with_finishing_hypotheses(t5, bias):
         assert torch.equal(want, got2)
         n_eos += int((want == 1).any())
     assert n_eos >= 3
+
+
+def test_native_search_argument_support():
+    """inference() sends a request to the native search only when every generation argument is one it restates
+    (NativeBeamSearch.supports); anything else keeps HF's own search code in the loop."""
+    from mmdx_b200.t5_fast import NativeBeamSearch
+    ref = dict(max_new_tokens=180, min_new_tokens=150, num_beams=4, no_repeat_ngram_size=3, length_penalty=1.1,
+               early_stopping=True, eos_token_id=1, pad_token_id=0)          # inference_pipeline.py:190
+    assert NativeBeamSearch.supports(ref)
+    assert NativeBeamSearch.supports(dict(ref, num_beams=1, early_stopping="never", do_sample=False, repetition_penalty=None))
+    for extra in (dict(do_sample=True), dict(repetition_penalty=1.2), dict(num_beams=5), dict(eos_token_id=[1, 2]),
+                  dict(max_new_tokens=None), dict(num_return_sequences=2), dict(top_k=50)):
+        assert not NativeBeamSearch.supports(dict(ref, **extra)), extra
