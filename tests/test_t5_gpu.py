@@ -254,3 +254,41 @@ def test_score_topk_kernel_vs_torch(t5):
         assert torch.equal(ia, ib)
         assert float((sa - sb).abs().max()) < 1e-4
     b.close()
+
+
+def test_decoder_c_abi_error_behaviour(t5):
+    """mmdx_t5_* misuse fails with a message instead of touching memory: steps before begin / beyond the reserved length,
+    more beams than the top-8 kernel serves, rows that are not studies x beams, an unfinished engine."""
+    import ctypes as C
+    from mmdx_b200._lib import MmdxError, lib
+    step = MmdxStep(t5)
+    tok = torch.zeros(4, dtype=torch.long, device="cuda")
+    with pytest.raises(MmdxError, match="before mmdx_t5_begin"):
+        step._rows, step._vocab = 4, 32128
+        step.step(tok)
+    step.begin(torch.randn(4, 4, 512, device="cuda"), 4, 2)
+    step.step(tok)
+    step.step(tok)
+    with pytest.raises(MmdxError, match="more steps"):
+        step.step(tok)
+    cond = torch.randn(1, 4, 512, device="cuda")
+    kw = dict(max_new_tokens=4, min_new_tokens=0, no_repeat_ngram_size=0, length_penalty=1.0, early_stopping=False,
+              eos_token_id=1, pad_token_id=0, decoder_start_token_id=0)
+    with pytest.raises(MmdxError, match="num_beams"):
+        step.generate_native(cond, num_beams=5, **kw)
+    step.begin(torch.randn(4, 4, 512, device="cuda"), 4, 4)
+    lg = step.step(tok)
+    with pytest.raises(MmdxError, match="studies x beams"):
+        step.score_topk(lg, torch.zeros(4), None, False, 1, 3, 6)
+    with pytest.raises(MmdxError, match="<= 8"):
+        step.score_topk(lg, torch.zeros(4), None, False, 1, 4, 9)
+    step.close()
+    h = C.c_void_p()
+    assert lib().mmdx_t5_create(0, 512, 8, 64, 2048, 6, 32128, 1e-6, 1, C.byref(h)) == 0
+    assert lib().mmdx_t5_finalize(h) != 0 and b"missing" in lib().mmdx_t5_last_error()
+    enc = torch.zeros(1, 4, 512, device="cuda")
+    bias = torch.zeros(4, 8)
+    assert lib().mmdx_t5_begin(h, C.c_void_p(enc.data_ptr()), 1, 4, 4, C.c_void_p(bias.data_ptr()), None) != 0
+    assert b"finalized" in lib().mmdx_t5_last_error()
+    assert lib().mmdx_t5_create(0, 500, 8, 64, 2048, 6, 32128, 1e-6, 1, C.byref(C.c_void_p())) != 0     # d_model % 128
+    lib().mmdx_t5_destroy(h)
