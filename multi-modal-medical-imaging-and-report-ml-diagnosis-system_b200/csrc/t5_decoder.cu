@@ -958,10 +958,10 @@ static int t5_step_impl(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, co
   a.n_enc = e->n_enc; a.kmax = std::max(std::max(d, inner), e->ff);
   a.prof = e->prof;
   a.xfold = e->xfold; a.xk = e->xk;
-  const int NR = R <= 4 ? 4 : 8;
+  const int NR = R <= 4 ? 4 : (R <= 8 ? 8 : 16);       // rows per pass over the weights
   const size_t smem = std::max((size_t)NR * a.kmax + (size_t)kMegaWarps * NR, (size_t)96 + 2048 + 2 * (size_t)e->Tmax) * 4;
   T5_REQUIRE(smem <= 200 * 1024, "step: d_ff / max_steps too large for the shared-memory staging");
-  void* fn = NR == 4 ? (void*)t5_step_mega_kernel<4> : (void*)t5_step_mega_kernel<8>;
+  void* fn = NR == 4 ? (void*)t5_step_mega_kernel<4> : (NR == 8 ? (void*)t5_step_mega_kernel<8> : (void*)t5_step_mega_kernel<16>);
   if (e->mega_blocks == 0) {
     cudaDeviceProp prop;
     T5_CK(cudaGetDeviceProperties(&prop, e->device));
@@ -969,6 +969,7 @@ static int t5_step_impl(mmdx_t5* e, const int32_t* d_tokens, float* d_logits, co
     e->mega_blocks = prop.multiProcessorCount;
     T5_CK(cudaFuncSetAttribute(t5_step_mega_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     T5_CK(cudaFuncSetAttribute(t5_step_mega_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    T5_CK(cudaFuncSetAttribute(t5_step_mega_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const char* pf = std::getenv("MMDX_T5_PROF");
     if (pf && pf[0] == '1') { T5_CK(cudaMalloc(&e->prof, 1024 * 8)); T5_CK(cudaMemset(e->prof, 0, 1024 * 8)); }
   }
