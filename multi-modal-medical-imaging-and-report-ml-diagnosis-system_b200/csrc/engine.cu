@@ -283,6 +283,10 @@ struct mmdx_engine {
   // head-side persistent buffers (capacity B)
   int head_cap = 0;
   bf16* feats_bf = nullptr; bf16* pooled_bf = nullptr; bf16* zcat = nullptr; float* fuse_h = nullptr;
+  bool defer_proj = false;    // inside mmdx_forward* at B <= kHeadFusedMaxB with head_mode 2: the encoders leave their projections to head_fused_kernel
+  bool fused_tail = false;    // inside mmdx_forward* at B <= kHeadFusedMaxB: fusion MLP + head tail as one launch
+  int head_mode = 2;          // MMDX_HEAD_FUSED at the first forward: 0 = four launches, 1 = F1 + O1 fused, 2 = I2 + T8 + F1 + O1 fused (default)
+  int head_cluster = 0;       // cluster size of head_fused_kernel on this device (16, else 8; -1 = unusable)
   bf16* zfuse_bf = nullptr;   // bf16 copy of z_fuse (A operand of cond_proj)
   float* thr_default = nullptr;
   // attention: tensor map over the packed qkv buffer, rebuilt when (pointer, T, hidden) changes
@@ -2065,6 +2069,7 @@ static int image_encode_locked(mmdx_engine* e, const uint8_t* d_images, int B, i
     const int bc = B - b0 < cap ? B - b0 : cap;
     TRY(image_backbone_locked(e, d_images + (size_t)b0 * H * W * C, b0, bc, H, W, C, d_feats, s));
   }
+  if (e->defer_proj) return 0;
   e->cur_cls = CLS_HEAD;
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
@@ -2144,6 +2149,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
                   s_last, ln.g, ln.b, 1e-12f));
       CK(cudaGetLastError());
     }
+    if (e->defer_proj) return 0;
     e->cur_cls = CLS_HEAD;
     HeadPlan* hp;
     TRY(get_head_plan(e, B, &hp));
@@ -2176,6 +2182,7 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
                 (const long long*)nullptr, (const float*)nullptr, (const float*)nullptr, 0.f));
     CK(cudaGetLastError());
   }
+  if (e->defer_proj) return 0;
   e->cur_cls = CLS_HEAD;
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
@@ -2184,11 +2191,71 @@ static int text_encode_locked(mmdx_engine* e, const int32_t* d_ids, const int32_
   return 0;
 }
 
+// K_head for the reference's request shape (B <= 2), MMDX_HEAD_FUSED read once per engine:
+//   2 (default)  both projections, the fusion MLP, LayerNorm, head, sigmoid and thresholds are ONE launch behind the join
+//                (I2 + T8 + F1 + O1 in one kernel);
+//   1            the projections stay GEMM + bias at the ends of their branches and only F1 + O1 are one launch;
+//   0            the four-launch tensor path everywhere.
+// B = 1 request latency, same box, two runs each (tools/latency_b1.py): 0.610 / 0.614 ms (0), 0.611 / 0.619 (1),
+// 0.623 / 0.617 (2) - the end of the chain is not what a request waits for; the launch count goes 111 -> 110 -> 108.
+static void head_fused_setup(mmdx_engine* e) {
+  if (e->head_cluster != 0) return;
+  e->head_cluster = -1;
+  { const char* v = getenv("MMDX_HEAD_FUSED"); e->head_mode = v ? atoi(v) : 2; }
+  if (e->head_mode <= 0 || e->feat_dim % 8 || e->hidden % 8 || (e->d_img + e->d_txt) % 8) return;
+  const size_t words = std::max<size_t>((size_t)kHeadFusedMaxB * std::max(e->feat_dim + e->hidden, e->d_img + e->d_txt), (size_t)e->d_fuse);
+  if (words * 4 > 48 * 1024) return;
+  for (int cs : {16, 8}) {
+    if (cs > 8) {
+      cudaFuncSetAttribute(head_fused_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(head_fused_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kHeadFusedThreads); cfg.dynamicSmemBytes = words * 4;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, head_fused_kernel<2>, &cfg) == cudaSuccess && n >= 1) { e->head_cluster = cs; break; }
+  }
+  cudaGetLastError();                // a refused cluster size is not an error of the engine
+}
+struct DeferProj {                   // scope of one mmdx_forward* call (under the engine mutex)
+  mmdx_engine* e;
+  DeferProj(mmdx_engine* e_, int B) : e(e_) {
+    head_fused_setup(e);
+    e->fused_tail = e->head_cluster > 0 && B <= kHeadFusedMaxB;
+    e->defer_proj = e->fused_tail && e->head_mode >= 2;
+  }
+  ~DeferProj() { e->defer_proj = false; e->fused_tail = false; }
+};
+
 static int head_locked(mmdx_engine* e, int B, const float* d_thr, float* d_z_fuse, float* d_logits, float* d_probs,
                        uint8_t* d_vector, cudaStream_t s) {
   REQUIRE(e->finalized && B > 0 && B <= e->head_cap, "head called before the encoders");
   REQUIRE(d_logits && d_probs && d_vector, "null output");
   e->cur_stream = s; e->cur_cls = CLS_HEAD;
+  if (e->fused_tail) {               // kernels.cuh head_fused_kernel: (projections +) fusion MLP + tail as one launch
+    HeadFusedParams p{};
+    p.feats = e->feats_bf; p.feat_dim = e->feat_dim; p.pooled = e->pooled_bf; p.hidden = e->hidden;
+    p.w_img = e->proj_img.w; p.b_img = e->proj_img.bias; p.d_img = e->d_img;
+    p.w_txt = e->proj_txt.w; p.b_txt = e->proj_txt.bias; p.d_txt = e->d_txt;
+    p.w_fuse = e->fuse.w; p.b_fuse = e->fuse.bias; p.d_fuse = e->d_fuse;
+    p.ln_g = e->fuse_ln.g; p.ln_b = e->fuse_ln.b; p.eps = 1e-5f;
+    p.w_head = e->head_w; p.b_head = e->head_b; p.n_cls = e->n_cls;
+    p.thr = d_thr ? d_thr : e->thr_default;
+    p.zcat = e->zcat; p.fuse_h = e->fuse_h;
+    p.z_fuse = d_z_fuse; p.logits = d_logits; p.probs = d_probs; p.vec = d_vector; p.z_fuse_bf = e->cond.w ? e->zfuse_bf : nullptr;
+    p.B = B; p.do_proj = e->defer_proj ? 1 : 0;
+    const int nr = B <= 1 ? 1 : 2;
+    const size_t words = std::max<size_t>((size_t)nr * std::max(e->feat_dim + e->hidden, e->d_img + e->d_txt), (size_t)e->d_fuse);
+    ProfScope _ps(e);
+    if (nr == 1) CK(launch_k(head_fused_kernel<1>, dim3(e->head_cluster), dim3(kHeadFusedThreads), words * 4, s, e->head_cluster, p));
+    else CK(launch_k(head_fused_kernel<2>, dim3(e->head_cluster), dim3(kHeadFusedThreads), words * 4, s, e->head_cluster, p));
+    CK(cudaGetLastError());
+    return 0;
+  }
   HeadPlan* hp;
   TRY(get_head_plan(e, B, &hp));
   TRY(launch_gemm(e, hp->fuse, s));
@@ -2259,6 +2326,7 @@ extern "C" int mmdx_forward(mmdx_engine* e, const uint8_t* d_images, int B, int 
     CK(cudaEventRecord(e->fork_ev, s));                 // inputs (and earlier work on `s`) are ready
     CK(cudaStreamWaitEvent(ts, e->fork_ev, 0));
   }
+  DeferProj _dp(e, B);
   TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, ts));
   if (fork) CK(cudaEventRecord(e->join_ev, ts));
   TRY(image_encode_locked(e, d_images, B, H, W, C, nullptr, nullptr, s));
@@ -2315,6 +2383,7 @@ static int forward_host_submit_locked(mmdx_engine* e, int slot, const uint8_t* h
   }
   CK(cudaStreamWaitEvent(ts, e->slot_tok_done[slot], 0));
   if (h_thr && fork) CK(cudaStreamWaitEvent(s, e->slot_tok_done[slot], 0));
+  DeferProj _dp(e, B);
   TRY(text_encode_locked(e, d_ids, d_pos, d_tt, d_cu, B, T, max_len, nullptr, nullptr, ts));
   if (fork) CK(cudaEventRecord(e->join_ev, ts));
   CK(cudaStreamWaitEvent(s, e->slot_copy_done[slot], 0));

@@ -559,47 +559,40 @@ __global__ void __launch_bounds__(256) seq_mean_pool_kernel(const __nv_bfloat16*
 // sigmoid; vector = probs >= thresholds  (training_pipeline.py:589-592, inference_pipeline.py:185-186).
 // One block (256 threads) per study; hidden width D <= 4096, D % 4 == 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict__ hdn, int D,
-                                                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
-                                                        float eps, const float* __restrict__ w_head,
-                                                        const float* __restrict__ b_head, int n_cls,
-                                                        const float* __restrict__ thresholds,
-                                                        float* __restrict__ z_fuse, float* __restrict__ logits,
-                                                        float* __restrict__ probs, uint8_t* __restrict__ vec,
-                                                        __nv_bfloat16* __restrict__ z_fuse_bf) {
-  pdl_wait();
-  pdl_trigger();
-  extern __shared__ float sz[];        // D floats
-  __shared__ float red[8];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* x = hdn + static_cast<size_t>(b) * D;
+// One study's head tail: LayerNorm(eps) of the D-wide fusion activation, the n_cls-way linear head, sigmoid and the
+// `probs >= thresholds` decision (fusion_mlp.3 + disease_head, training_pipeline.py:538-542; inference_pipeline.py:185-186).
+// Called by every thread of a CTA (blockDim a multiple of 32); sz = D floats of shared memory, red = 32 floats.
+__device__ __forceinline__ void head_tail_row(const float* __restrict__ x, int b, int D, const float* __restrict__ ln_g,
+                                              const float* __restrict__ ln_b, float eps, const float* __restrict__ w_head,
+                                              const float* __restrict__ b_head, int n_cls, const float* __restrict__ thresholds,
+                                              float* __restrict__ z_fuse, float* __restrict__ logits, float* __restrict__ probs,
+                                              uint8_t* __restrict__ vec, __nv_bfloat16* __restrict__ z_fuse_bf, float* sz, float* red) {
+  const int tid = threadIdx.x, nt = blockDim.x, nw = nt >> 5, warp = tid >> 5, lane = tid & 31;
   float s = 0.f;
-  for (int i = tid; i < D; i += 256) { const float v = x[i]; sz[i] = v; s += v; }
+  for (int i = tid; i < D; i += nt) { const float v = x[i]; sz[i] = v; s += v; }
   s = warp_sum(s);
   if (lane == 0) red[warp] = s;
   __syncthreads();
   float tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i];
+  for (int i = 0; i < nw; ++i) tot += red[i];
   const float mean = tot / D;
   __syncthreads();
   float q = 0.f;
-  for (int i = tid; i < D; i += 256) { const float d = sz[i] - mean; q += d * d; }
+  for (int i = tid; i < D; i += nt) { const float d = sz[i] - mean; q += d * d; }
   q = warp_sum(q);
   if (lane == 0) red[warp] = q;
   __syncthreads();
   tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i];
+  for (int i = 0; i < nw; ++i) tot += red[i];
   const float rstd = rsqrtf(tot / D + eps);
-  for (int i = tid; i < D; i += 256) {
+  for (int i = tid; i < D; i += nt) {
     const float z = (sz[i] - mean) * rstd * ln_g[i] + ln_b[i];
     sz[i] = z;
     if (z_fuse != nullptr) z_fuse[static_cast<size_t>(b) * D + i] = z;
     if (z_fuse_bf != nullptr) z_fuse_bf[static_cast<size_t>(b) * D + i] = __float2bfloat16(z);   // A operand of cond_proj
   }
   __syncthreads();
-  for (int c = warp; c < n_cls; c += 8) {
+  for (int c = warp; c < n_cls; c += nw) {
     const float* w = w_head + static_cast<size_t>(c) * D;
     float acc = 0.f;
     for (int i = lane; i < D; i += 32) acc += sz[i] * __ldg(w + i);
@@ -612,6 +605,134 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict_
       vec[b * n_cls + c] = pr >= thresholds[c] ? 1 : 0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) head_tail_kernel(const float* __restrict__ hdn, int D,
+                                                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                        float eps, const float* __restrict__ w_head,
+                                                        const float* __restrict__ b_head, int n_cls,
+                                                        const float* __restrict__ thresholds,
+                                                        float* __restrict__ z_fuse, float* __restrict__ logits,
+                                                        float* __restrict__ probs, uint8_t* __restrict__ vec,
+                                                        __nv_bfloat16* __restrict__ z_fuse_bf) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sz[];        // D floats
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  head_tail_row(hdn + static_cast<size_t>(b) * D, b, D, ln_g, ln_b, eps, w_head, b_head, n_cls, thresholds, z_fuse, logits, probs,
+                vec, z_fuse_bf, sz, red);
+}
+
+// ---- K_head for the reference's own request shape (B <= 2): both projections, the fusion MLP and the head tail in ONE
+// launch (I2 + T8 + F1 + O1; image proj training_pipeline.py:189,301, text proj :365,482, fusion :534-542,584-592,
+// post-processing inference_pipeline.py:185-186).  At one or two rows every layer is a GEMV: the work is streaming 7.8 MB of
+// bf16 weights once, and the tensor-core path spends it as four dependent launches on a handful of SMs.  Here one
+// thread-block cluster (16 CTAs, 8 if the device refuses) owns the request: a warp computes one output column - the 32
+// lanes split K (and the two rows), 16-byte weight loads, fp32 accumulation - the three dependent stages exchange their
+// small results through global memory and are separated by cluster barriers (release / acquire at cluster scope), and
+// CTA r < B finishes row r.  Rounding points are those of the tensor path (projections rounded to bf16 into zcat, the
+// fusion activation kept in fp32); only the summation order differs.
+struct HeadFusedParams {
+  const __nv_bfloat16* feats; int feat_dim;            // [B, feat_dim] pooled CNN features
+  const __nv_bfloat16* pooled; int hidden;             // [B, hidden]   pooled text states
+  const __nv_bfloat16* w_img; const float* b_img; int d_img;
+  const __nv_bfloat16* w_txt; const float* b_txt; int d_txt;
+  const __nv_bfloat16* w_fuse; const float* b_fuse; int d_fuse;
+  const float *ln_g, *ln_b; float eps;
+  const float *w_head, *b_head; int n_cls;
+  const float* thr;
+  __nv_bfloat16* zcat; float* fuse_h;                  // stage results, [B, d_img + d_txt] and [B, d_fuse]
+  float *z_fuse, *logits, *probs; uint8_t* vec; __nv_bfloat16* z_fuse_bf;
+  int B;
+  int do_proj;                                         // 0: zcat already holds the projections (GEMM + bias at the branch ends)
+};
+
+constexpr int kHeadFusedThreads = 512;
+constexpr int kHeadFusedMaxB = 2;
+
+__device__ __forceinline__ unsigned cluster_num_ctas() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+// y[r] = x[r] . w for the rows r < NR of xs (fp32, [NR][K] in shared memory): lanes = (32 / NR) K-groups x NR rows
+template <int NR>
+__device__ __forceinline__ float head_fused_dot(const __nv_bfloat16* __restrict__ w, const float* xs, int K, int lane) {
+  constexpr int KG = 32 / NR;
+  const int r = lane % NR, kg = lane / NR;
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  const float4* x4 = reinterpret_cast<const float4*>(xs + static_cast<size_t>(r) * K);
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = kg; i < K / 8; i += KG) {       // up to eight 16-byte weight loads per lane in flight
+    const uint4 q = __ldg(w4 + i);
+    const float4 a = x4[2 * i], b = x4[2 * i + 1];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float2 w0 = __bfloat1622float2(h[0]), w1 = __bfloat1622float2(h[1]), w2 = __bfloat1622float2(h[2]), w3 = __bfloat1622float2(h[3]);
+    acc = fmaf(w0.x, a.x, acc); acc = fmaf(w0.y, a.y, acc); acc = fmaf(w1.x, a.z, acc); acc = fmaf(w1.y, a.w, acc);
+    acc = fmaf(w2.x, b.x, acc); acc = fmaf(w2.y, b.y, acc); acc = fmaf(w3.x, b.z, acc); acc = fmaf(w3.y, b.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o >= NR; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // over the K-groups; lane r holds row r
+  return acc;
+}
+
+template <int NR>
+__global__ void __launch_bounds__(kHeadFusedThreads, 1) head_fused_kernel(const HeadFusedParams p) {
+  extern __shared__ float hs[];        // stage 1: feats [NR][feat_dim] | pooled [NR][hidden]; stage 2: zcat [NR][dz]; stage 3: D floats
+  __shared__ float red[32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = kHeadFusedThreads / 32;
+  const int rank = static_cast<int>(cluster_ctarank()), nc = static_cast<int>(cluster_num_ctas());
+  const int dz = p.d_img + p.d_txt;
+  // The weights are constants: while the producers of feats / pooled are still running (programmatic dependent launch
+  // starts this grid early), pull the rows this CTA will multiply from HBM into L2 - one prefetch per 128-byte line.
+  for (int c = rank * nw + warp; c < (p.do_proj ? dz : 0); c += nc * nw) {
+    const bool img = c < p.d_img;
+    const char* row = reinterpret_cast<const char*>(img ? p.w_img + static_cast<size_t>(c) * p.feat_dim
+                                                         : p.w_txt + static_cast<size_t>(c - p.d_img) * p.hidden);
+    for (int o = lane * 128; o < (img ? p.feat_dim : p.hidden) * 2; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+  }
+  for (int c = rank * nw + warp; c < p.d_fuse; c += nc * nw) {
+    const char* row = reinterpret_cast<const char*>(p.w_fuse + static_cast<size_t>(c) * dz);
+    for (int o = lane * 128; o < dz * 2; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+  }
+  pdl_wait();
+  pdl_trigger();
+  // ---- stage 1: zcat = [feats . Wimg^T + b | pooled . Wtxt^T + b], rounded to bf16
+  if (p.do_proj) {
+  float* xf = hs;
+  float* xp = hs + static_cast<size_t>(NR) * p.feat_dim;
+  for (int i = tid; i < NR * p.feat_dim; i += kHeadFusedThreads) {
+    const int r = i / p.feat_dim;
+    xf[i] = r < p.B ? __bfloat162float(p.feats[static_cast<size_t>(r) * p.feat_dim + (i - r * p.feat_dim)]) : 0.f;
+  }
+  for (int i = tid; i < NR * p.hidden; i += kHeadFusedThreads) {
+    const int r = i / p.hidden;
+    xp[i] = r < p.B ? __bfloat162float(p.pooled[static_cast<size_t>(r) * p.hidden + (i - r * p.hidden)]) : 0.f;
+  }
+  __syncthreads();
+  for (int c = rank * nw + warp; c < dz; c += nc * nw) {
+    const bool img = c < p.d_img;
+    const int cc = img ? c : c - p.d_img;
+    const float v = img ? head_fused_dot<NR>(p.w_img + static_cast<size_t>(cc) * p.feat_dim, xf, p.feat_dim, lane)
+                        : head_fused_dot<NR>(p.w_txt + static_cast<size_t>(cc) * p.hidden, xp, p.hidden, lane);
+    if (lane < NR && lane < p.B) p.zcat[static_cast<size_t>(lane) * dz + c] = __float2bfloat16(v + (img ? p.b_img[cc] : p.b_txt[cc]));
+  }
+  cluster_sync_all();
+  }
+  // ---- stage 2: fuse_h = GELU(zcat . Wfuse^T + b), fp32
+  for (int i = tid; i < NR * dz; i += kHeadFusedThreads) {
+    const int r = i / dz;
+    hs[i] = r < p.B ? __bfloat162float(p.zcat[static_cast<size_t>(r) * dz + (i - r * dz)]) : 0.f;
+  }
+  __syncthreads();
+  for (int c = rank * nw + warp; c < p.d_fuse; c += nc * nw) {
+    const float v = head_fused_dot<NR>(p.w_fuse + static_cast<size_t>(c) * dz, hs, dz, lane);
+    if (lane < NR && lane < p.B) p.fuse_h[static_cast<size_t>(lane) * p.d_fuse + c] = gelu_erf(v + p.b_fuse[c]);
+  }
+  cluster_sync_all();
+  // ---- stage 3: LayerNorm + head + sigmoid + thresholds, one CTA per study
+  if (rank < p.B)
+    head_tail_row(p.fuse_h + static_cast<size_t>(rank) * p.d_fuse, rank, p.d_fuse, p.ln_g, p.ln_b, p.eps, p.w_head, p.b_head, p.n_cls,
+                  p.thr, p.z_fuse, p.logits, p.probs, p.vec, p.z_fuse_bf, hs, red);
 }
 
 }  // namespace mmdx

@@ -750,3 +750,54 @@ def test_image_branch_batch_sizes_around_the_two_gemm_threshold(eng, B):
     assert np.isfinite(feats.cpu().numpy()).all()
     assert _rel(feats[sel].cpu().numpy(), f4.cpu().numpy()) < 1e-2
     assert _rel(z[sel].cpu().numpy(), z4.cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("B,mode", [(1, 2), (2, 2), (1, 1), (2, 1)])
+def test_single_request_head_fusion(bundle, eng, g1, B, mode):
+    """SURVEY.md 8a K_head: for the reference's own request shape (B <= 2) mmdx_forward runs both projections, the fusion
+    MLP, LayerNorm, head, sigmoid and thresholds (I2 + T8 + F1 + O1) as ONE cluster launch behind the join (mode 2, the
+    default), or only F1 + O1 with the projections left as GEMM + bias (MMDX_HEAD_FUSED=1).  Same rounding points
+    as the tensor-core path the staged calls use; only the summation order differs.  Checked against the staged path and,
+    for the reference's two sample studies, against the reference's own golden probabilities."""
+    import os
+    e2 = eng
+    if mode != 2:
+        os.environ["MMDX_HEAD_FUSED"] = str(mode)
+        try:
+            e2 = engine.Engine(ip._states_from_bundle(bundle))
+            pk0 = engine.pack_tokens(*synth.synth_token_ids(1, 16, seed=1, ragged=False))
+            d0 = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (synth.synth_images(1, 224, seed=1), *pk0[:4])]
+            e2.forward(d0[0], d0[1], d0[2], d0[3], d0[4], pk0[4])          # the mode is read at the first forward
+        finally:
+            del os.environ["MMDX_HEAD_FUSED"]
+    try:
+        imgs = synth.synth_images(B, 224, seed=4100 + B)
+        ids, mask = synth.synth_token_ids(B, 96, seed=4200 + B, ragged=True)
+        staged = _run_stages(e2, imgs, ids, mask)
+        pi, pp, pt, cu, mlen = engine.pack_tokens(ids, mask)
+        dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (imgs, pi, pp, pt, cu)]
+        n0 = e2.launch_count
+        lg, pr, vec = e2.forward(dev[0], dev[1], dev[2], dev[3], dev[4], mlen)
+        torch.cuda.synchronize()
+        n_fwd = e2.launch_count - n0
+        n0 = e2.launch_count
+        _run_stages(e2, imgs, ids, mask)
+        n_staged = e2.launch_count - n0
+        # staged: 2 projections + 2 conversions of z_img / z_txt + fusion GEMM + tail
+        assert n_fwd == n_staged - (3 if mode == 1 else 5), (n_fwd, n_staged)
+        assert np.abs(pr.cpu().numpy() - staged["probs"]).max() < 1e-3
+        assert np.abs(lg.cpu().numpy() - staged["logits"]).max() < 5e-3
+        decided = np.abs(staged["probs"] - 0.5) > 1e-3
+        assert np.array_equal(vec.cpu().numpy()[decided], staged["vector"][decided])
+        if B == 1:
+            for i in range(2):                                      # e1 / e2 of the reference, against its own forward
+                im = np.repeat(g1["gray"][i][None, ..., None], 3, axis=-1)
+                pk = engine.pack_tokens(g1["input_ids"][i:i + 1], g1["attention_mask"][i:i + 1])
+                d = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (im, pk[0], pk[1], pk[2], pk[3])]
+                _, p1, v1 = e2.forward(d[0], d[1], d[2], d[3], d[4], pk[4])
+                assert np.abs(p1.cpu().numpy()[0] - g1["probs"][i]).max() < PROB_TOL
+                acc = label_accounting(v1.cpu().numpy()[0], g1["probs"][i], g1["vector"][i], 2e-3)
+                assert acc["flips_decided"] == 0, acc
+    finally:
+        if e2 is not eng:
+            e2.close()
