@@ -267,8 +267,9 @@ def build_vocab(size: int = 30522) -> list:
 
 
 def make_bert_tokenizer():
-    """BertTokenizer (fast, WordPiece, lower-casing) over `build_vocab()` - the
-    offline replacement for `AutoTokenizer.from_pretrained("bert-base-uncased")`
-    (training_pipeline.py:323)."""
+    """HF `BertTokenizer` (WordPiece, lower-casing) over `build_vocab()` - the offline replacement for
+    `AutoTokenizer.from_pretrained("bert-base-uncased")` (training_pipeline.py:323).  It is the checker and the non-ASCII
+    fallback: the product path tokenises with the native `csrc/tokenizer.cpp` (tokenizer.py), which
+    tests/test_tokenizer_cpu.py holds to this tokenizer's ids bit for bit."""
     from transformers import BertTokenizer
     return BertTokenizer(vocab={w: i for i, w in enumerate(build_vocab())}, do_lower_case=True)
