@@ -153,8 +153,10 @@ const char* mmdx_tokenizer_last_error(void);
 /* ---- KV-cached T5 decoder step (csrc/t5_decoder.cu) -------------------------------------------
  * The model call inside the reference's report generation - FusionTransformerModel.generate -> HF
  * T5ForConditionalGeneration.generate (training_pipeline.py:613-618, inference_pipeline.py:190-196) - as CUDA kernels: one
- * new token for each of R = batch x beams rows over a private KV cache, fp32 weights and arithmetic.  The beam search stays
- * HF's own code (mmdx_b200/t5_fast.py replaces only the forward inside it), so the generated tokens are HF's.
+ * new token for each of R = batch x beams rows over a private KV cache, fp32 weights and arithmetic, ONE cooperative
+ * launch per token.  Two drivers: HF's own beam search with only the forward replaced (mmdx_b200/t5_fast.FastT5Generator:
+ * begin / step / reorder), or the whole search here (mmdx_t5_generate, the default of inference()); both reproduce HF's
+ * tokens in the tests.
  * Weights: one mmdx_t5_load_tensor per key of T5ForConditionalGeneration.state_dict() that the decoder uses
  * ("shared.weight", "decoder.block.N.layer.*", "decoder.final_layer_norm.weight", "lm_head.weight" when untied).
  * tied_embeddings: 1 = LM head tied to the embedding and decoder output scaled by d_model^-0.5 (the T5 default), 0 = separate
