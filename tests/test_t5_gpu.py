@@ -81,6 +81,35 @@ def test_step_variants_match_torch_step(t5, monkeypatch, studies, beams, n_enc, 
     b.close()
 
 
+def test_step_random_shapes_match_torch_step(t5):
+    """Fuzz: 20 random shapes of the decoder step (1-6 studies, 1-4 beams, 1-16 conditioning tokens, 4-24 positions, random
+    beam reorders inside every study) against the fp32 torch step; a 60-case run is kept in profiles/r02_t5_fuzz.log."""
+    g = torch.Generator().manual_seed(5)
+    a, b = TorchStep(t5), MmdxStep(t5)
+    for c in range(20):
+        studies = int(torch.randint(1, 7, (1,), generator=g))
+        beams = int(torch.randint(1, 5, (1,), generator=g))
+        n_enc = [1, 2, 3, 4, 4, 4, 5, 7, 9, 16][int(torch.randint(0, 10, (1,), generator=g))]
+        steps = int(torch.randint(4, 25, (1,), generator=g))
+        R = studies * beams
+        cond = torch.randn(studies, n_enc, 512, generator=g).cuda().repeat_interleave(beams, 0)
+        a.begin(cond, R, steps)
+        b.begin(cond, R, steps)
+        tok = torch.randint(0, 32128, (R,), generator=g).cuda()
+        for t in range(steps):
+            la, lb = a.step(tok), b.step(tok)
+            torch.cuda.synchronize()
+            err = float((la - lb).abs().max() / la.abs().max())
+            assert err < 2e-5, (c, studies, beams, n_enc, t, err)
+            tok = la.topk(3, -1).indices[torch.arange(R), torch.randint(0, 3, (R,), generator=g)]
+            if beams > 1 and t < steps - 1 and int(torch.randint(0, 3, (1,), generator=g)) == 0:
+                idx = torch.cat([s0 * beams + torch.randint(0, beams, (beams,), generator=g) for s0 in range(studies)]).cuda()
+                a.reorder(idx)
+                b.reorder(idx)
+                tok = tok[idx]
+    b.close()
+
+
 @pytest.mark.parametrize("kw", [
     dict(REF_KW, max_new_tokens=40, min_new_tokens=30),
     dict(max_new_tokens=24, num_beams=1, eos_token_id=1, pad_token_id=0),
