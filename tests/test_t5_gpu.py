@@ -321,3 +321,17 @@ def test_decoder_c_abi_error_behaviour(t5):
     assert b"finalized" in lib().mmdx_t5_last_error()
     assert lib().mmdx_t5_create(0, 500, 8, 64, 2048, 6, 32128, 1e-6, 1, C.byref(C.c_void_p())) != 0     # d_model % 128
     lib().mmdx_t5_destroy(h)
+
+
+def test_large_report_batches_are_row_independent(t5):
+    """33 studies x 4 beams = 132 rows (nine passes of 16 rows, unfolded cross-attention) through mmdx_t5_generate: the
+    reports of the first two studies equal what a 2-study call (8 rows, folded cross-attention) generates."""
+    torch.manual_seed(21)
+    step = MmdxStep(t5)
+    cond = torch.randn(33, 4, 512, device="cuda")
+    kw = dict(max_new_tokens=16, min_new_tokens=12, num_beams=4, no_repeat_ngram_size=3, length_penalty=1.1,
+              early_stopping=True, eos_token_id=1, pad_token_id=0, decoder_start_token_id=0)
+    big = step.generate_native(cond, **kw)
+    small = step.generate_native(cond[:2], **kw)
+    assert big.shape[0] == 33 and torch.equal(big[:2, :small.shape[1]], small)
+    step.close()
